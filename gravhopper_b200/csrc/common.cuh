@@ -1,0 +1,162 @@
+// common.cuh -- shared declarations of libgravhopper_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/gravhopper_b200.h"
+
+namespace gh {
+
+void set_error(const char *fmt, ...);
+int64_t &launch_counter();  // per-thread count of kernel launches (bench.py gpu_launches)
+
+#define GH_CUDA(call)                                                                       \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess) {                                                                \
+      gh::set_error("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));     \
+      return (e_ == cudaErrorMemoryAllocation) ? GH_ENOMEM : GH_ECUDA;                      \
+    }                                                                                       \
+  } while (0)
+
+#define GH_TRY(call)                 \
+  do {                               \
+    int rc_ = (call);                \
+    if (rc_ != GH_OK) return rc_;    \
+  } while (0)
+
+#define GH_LAUNCH_CHECK()            \
+  do {                               \
+    gh::launch_counter()++;          \
+    GH_CUDA(cudaGetLastError());     \
+  } while (0)
+
+// Grow-only device scratch buffer.
+struct DeviceBuffer {
+  void *ptr = nullptr;
+  size_t bytes = 0;
+  int reserve(size_t need) {
+    if (need <= bytes) return GH_OK;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+    size_t want = need + need / 8 + 256;
+    GH_CUDA(cudaMalloc(&ptr, want));
+    bytes = want;
+    return GH_OK;
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+  }
+  template <class T> T *as() const { return reinterpret_cast<T *>(ptr); }
+};
+
+// What a kernel does with a finished target acceleration a_i (raw units, G = 1).
+//   EP_ACC : acc_out[i] = a_i                                  (the _jbgrav entry points)
+//   EP_STEP: the kick and both drifts of gravhopper.py:414-416 (+ the next step's :409),
+//            with the unit factors of jbgrav.py:48; products and sums are rounded separately
+//            (__dmul_rn/__dadd_rn) exactly as numpy evaluates the reference expressions.
+enum { EP_ACC = 0, EP_STEP = 1 };
+
+struct Epilogue {
+  int mode;
+  // EP_ACC
+  double *acc_out;  // (nt,3)
+  // EP_STEP (all indexed by the local target index i)
+  const double *xhalf;   // (nt,3) x_half of this step
+  const double *v_in;    // (nt,3) v_n
+  double *x_out;         // (nt,3) x_{n+1}
+  double *v_out;         // (nt,3) v_{n+1}
+  double *xhalf_next;    // (nt,3) x_half of step n+1 (f64 source slice or private array)
+  float4 *src32_next;    // nullable: (nt) float4 (x_half_next - origin, mass) for the f32 path
+  const double *mass;    // (nt) masses of the owned targets (for src32_next.w)
+  const double *ext;     // nullable: (nt,3) external acceleration, km/s/Myr
+  double dt;
+  double origin[3];
+};
+
+__device__ __forceinline__ void apply_epilogue(const Epilogue &ep, int64_t i, double ax, double ay,
+                                               double az) {
+  if (ep.mode == EP_ACC) {
+    ep.acc_out[3 * i + 0] = ax;
+    ep.acc_out[3 * i + 1] = ay;
+    ep.acc_out[3 * i + 2] = az;
+    return;
+  }
+  double a[3] = {ax, ay, az};
+  double xn[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    double acc = __dmul_rn(a[k], GH_C_ACC);                               // jbgrav.py:48
+    if (ep.ext) acc = __dadd_rn(acc, ep.ext[3 * i + k]);                  // gravhopper.py:457
+    double vn = __dadd_rn(ep.v_in[3 * i + k], __dmul_rn(acc, ep.dt));     // :414
+    double hd = __dmul_rn(__dmul_rn(__dmul_rn(0.5, vn), ep.dt), GH_KPC_PER_KMS_MYR);
+    double x1 = __dadd_rn(ep.xhalf[3 * i + k], hd);                       // :416
+    ep.v_out[3 * i + k] = vn;
+    ep.x_out[3 * i + k] = x1;
+    xn[k] = __dadd_rn(x1, hd);                                            // next step's :409
+    ep.xhalf_next[3 * i + k] = xn[k];
+  }
+  if (ep.src32_next) {
+    ep.src32_next[i] = make_float4((float)(xn[0] - ep.origin[0]), (float)(xn[1] - ep.origin[1]),
+                                   (float)(xn[2] - ep.origin[2]), (float)ep.mass[i]);
+  }
+}
+
+// ---- direct summation (direct.cu) ----------------------------------------------------------
+struct DirectArgs {
+  int prec;  // GH_PREC_F32 / GH_PREC_F64
+  // sources: f64 -> pos (nj,3) + mass (nj); f32 -> src32 (nj) float4 (x - origin, mass)
+  const double *src_pos;
+  const double *src_mass;
+  const float4 *src32;
+  int64_t nj;
+  // targets: f64 -> tgt_pos (ni,3); f32 -> tgt32 (ni) float4 (x - origin, unused)
+  const double *tgt_pos;
+  const float4 *tgt32;
+  int64_t ni;
+  double eps;
+  Epilogue ep;
+};
+// Launches the force kernel (and a finalize kernel when the source range is split).  `ws` is
+// scratch for the per-split partial sums.  force_ms_events (nullable): two events recorded
+// around the dominant kernel.
+int launch_direct(const DirectArgs &a, DeviceBuffer &ws, cudaStream_t stream,
+                  cudaEvent_t *force_events);
+// pos (n,3) f64 [+ mass] -> float4 (x - origin, m)
+int launch_pack32(const double *pos, const double *mass, int64_t n, const double origin[3],
+                  float4 *out, cudaStream_t stream);
+// potential energy partial sums; out2 = {KE, PE} accumulated with atomics (must be zeroed)
+int launch_energy(const double *x, const double *v, const double *m_tgt, int64_t ni,
+                  const double *src_pos, const double *src_mass, int64_t nj, int64_t self_offset,
+                  double eps, double *out2, cudaStream_t stream);
+// x_half = x + ((0.5 v) dt) K   (gravhopper.py:409)
+int launch_half_drift(const double *x, const double *v, const double *mass, int64_t n, double dt,
+                      double *xhalf, float4 *src32, const double origin[3], cudaStream_t stream);
+
+// ---- tree (tree.cu) -------------------------------------------------------------------------
+struct TreeWorkspace;
+TreeWorkspace *tree_workspace_create();
+void tree_workspace_destroy(TreeWorkspace *);
+struct TreeArgs {
+  int prec;
+  const double *src_pos;   // (nj,3) device
+  const double *src_mass;  // (nj) device
+  const float4 *src32;     // alternative f32 sources (x - origin, m); then tgt32 are the targets
+  const float4 *tgt32;
+  int64_t nj;
+  const double *tgt_pos;   // (ni,3) device
+  int64_t ni;
+  bool targets_are_sources;  // tgt_pos == src_pos + 3*tgt_offset: reuse the Morton order
+  int64_t tgt_offset;
+  double eps, theta;
+  Epilogue ep;
+  bool want_stats;
+};
+int launch_tree(const TreeArgs &a, TreeWorkspace *ws, cudaStream_t stream,
+                cudaEvent_t *force_events);
+int tree_last_stats(TreeWorkspace *ws, int64_t out[5]);
+
+}  // namespace gh

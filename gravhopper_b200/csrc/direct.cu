@@ -1,0 +1,482 @@
+// direct.cu -- direct-summation force kernels for sm_100a (no tensor cores: the pair kernel is
+// not a contraction).  Replaces directsummation_workhorse / directsummation_position_workhorse
+// (/root/reference/gravhopper/_jbgrav.c:140-193, :299-353).
+//
+// Decomposition: grid.x tiles the targets (BLOCK*KI per CTA, KI targets per thread held in
+// registers), grid.y splits the sources into S contiguous chunks so that small problems still
+// fill 148 SMs and large ones have many more CTAs than SM slots (no wave tail).  Sources stream
+// through shared memory in tiles of BLOCK, double buffered; every thread reads the same source
+// (a shared-memory broadcast).  S == 1: the epilogue (plain store, or the fused kick+drift of
+// the leapfrog) runs inside the force kernel.  S > 1: per-chunk partial sums go to scratch and a
+// finalize kernel adds them in chunk order (deterministic) and runs the same epilogue.
+//
+// fp32 kernel: per source the tile holds x' = x s, y' = y s, z' = z s, s = m^-1/2, e = eps^2 s^2,
+// so that with d' = x' - x_i s (one FMA) and q = |d'|^2 + e (three FMAs), rsqrt(q)^3 d' =
+// m d / (r^2+eps^2)^{3/2}: 11 FP32 operations and one MUFU.RSQ per interaction.  Two sources
+// are processed per instruction with Blackwell's packed FFMA2/FMUL2 (one issue slot, two
+// lanes-worth of FMA), which is what makes room in the issue stream for the MUFU and LDS.
+// Accumulation is two-level: fp32 within a tile of BLOCK sources, fp64 across tiles (SURVEY
+// F10: plain fp32 accumulation fails the 1e-5 bar at N = 1M).
+//
+// fp64 kernel: d = x_j - x_i exactly as the reference forms it, s = |d|^2 + eps^2, and
+// s^-3/2 from MUFU.RSQ64H refined by one third-order step (error ~ 1e-19), then m s^-3/2 d
+// accumulated with DFMA in source order within a chunk.
+#include "common.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+
+namespace gh {
+
+// -------------------------------------------------------------------------------------------
+// fp32
+// -------------------------------------------------------------------------------------------
+// bare MUFU.RSQ (rsqrtf() without -ftz wraps it in three denormal-handling instructions)
+__device__ __forceinline__ float rsq_approx(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int BLOCK>
+struct Tile32 {
+  float4 a[BLOCK / 2];  // (x'0, x'1, y'0, y'1) per source pair
+  float4 b[BLOCK / 2];  // (z'0, z'1, s0, s1)
+  float2 c[BLOCK / 2];  // (e0, e1)
+};
+
+template <int BLOCK>
+__device__ __forceinline__ void store_tile32(Tile32<BLOCK> &t, int tid, float4 g, float eps2) {
+  // g = (x, y, z, m); m == 0 (padding or a massless tracer) contributes exactly zero
+  float s = g.w > 0.f ? rsqrtf(g.w) : 0.f;
+  float e = g.w > 0.f ? eps2 * s * s : 1.f;
+  float *pa = reinterpret_cast<float *>(&t.a[tid >> 1]);
+  float *pb = reinterpret_cast<float *>(&t.b[tid >> 1]);
+  float *pc = reinterpret_cast<float *>(&t.c[tid >> 1]);
+  int h = tid & 1;
+  pa[h] = g.x * s;
+  pa[2 + h] = g.y * s;
+  pb[h] = g.z * s;
+  pb[2 + h] = s;
+  pc[h] = e;
+}
+
+template <int BLOCK, int KI, bool GUARD>
+__global__ void __launch_bounds__(BLOCK)
+direct_f32_kernel(const float4 *__restrict__ src, int64_t nj, const float4 *__restrict__ tgt,
+                  int64_t ni, float eps2, int64_t jchunk, double *__restrict__ partial,
+                  Epilogue ep) {
+  __shared__ Tile32<BLOCK> tile[2];
+  const int tid = threadIdx.x;
+  const int64_t i0 = (int64_t)blockIdx.x * (BLOCK * KI);
+  const int64_t jb = (int64_t)blockIdx.y * jchunk;
+  const int64_t je = (jb + jchunk < nj) ? jb + jchunk : nj;
+  const int ntiles = (int)((je - jb + BLOCK - 1) / BLOCK);
+
+  float2 nx[KI], ny[KI], nz[KI];
+  double ax[KI], ay[KI], az[KI];
+#pragma unroll
+  for (int k = 0; k < KI; k++) {
+    int64_t i = i0 + tid + (int64_t)k * BLOCK;
+    float4 t = (i < ni) ? tgt[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    nx[k] = make_float2(-t.x, -t.x);
+    ny[k] = make_float2(-t.y, -t.y);
+    nz[k] = make_float2(-t.z, -t.z);
+    ax[k] = ay[k] = az[k] = 0.0;
+  }
+
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  {
+    int64_t j = jb + tid;
+    float4 g = (j < je) ? src[j] : zero4;
+    store_tile32<BLOCK>(tile[0], tid, g, eps2);
+  }
+  __syncthreads();
+
+  for (int t = 0; t < ntiles; t++) {
+    float4 g = zero4;
+    const bool more = (t + 1 < ntiles);
+    if (more) {
+      int64_t j = jb + (int64_t)(t + 1) * BLOCK + tid;
+      if (j < je) g = src[j];
+    }
+    const Tile32<BLOCK> &T = tile[t & 1];
+    float2 fx[KI], fy[KI], fz[KI];
+#pragma unroll
+    for (int k = 0; k < KI; k++) fx[k] = fy[k] = fz[k] = make_float2(0.f, 0.f);
+
+#pragma unroll 4
+    for (int p = 0; p < BLOCK / 2; p++) {
+      const float4 A = T.a[p];
+      const float4 B = T.b[p];
+      const float2 e = T.c[p];
+      const float2 xj = make_float2(A.x, A.y), yj = make_float2(A.z, A.w);
+      const float2 zj = make_float2(B.x, B.y), s = make_float2(B.z, B.w);
+#pragma unroll
+      for (int k = 0; k < KI; k++) {
+        float2 dx = __ffma2_rn(nx[k], s, xj);
+        float2 dy = __ffma2_rn(ny[k], s, yj);
+        float2 dz = __ffma2_rn(nz[k], s, zj);
+        float2 q = __ffma2_rn(dx, dx, e);
+        q = __ffma2_rn(dy, dy, q);
+        q = __ffma2_rn(dz, dz, q);
+        float2 r;
+        if (GUARD) {  // eps == 0: a source exactly at the target contributes zero
+          r.x = q.x > 0.f ? rsq_approx(q.x) : 0.f;
+          r.y = q.y > 0.f ? rsq_approx(q.y) : 0.f;
+        } else {
+          r.x = rsq_approx(q.x);
+          r.y = rsq_approx(q.y);
+        }
+        float2 r2 = __fmul2_rn(r, r);
+        float2 r3 = __fmul2_rn(r2, r);
+        fx[k] = __ffma2_rn(r3, dx, fx[k]);
+        fy[k] = __ffma2_rn(r3, dy, fy[k]);
+        fz[k] = __ffma2_rn(r3, dz, fz[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < KI; k++) {  // second accumulation level: fp64 across tiles
+      ax[k] += (double)(fx[k].x + fx[k].y);
+      ay[k] += (double)(fy[k].x + fy[k].y);
+      az[k] += (double)(fz[k].x + fz[k].y);
+    }
+    if (more) store_tile32<BLOCK>(tile[(t + 1) & 1], tid, g, eps2);
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int k = 0; k < KI; k++) {
+    int64_t i = i0 + tid + (int64_t)k * BLOCK;
+    if (i >= ni) continue;
+    if (partial) {
+      double *o = partial + ((int64_t)blockIdx.y * ni + i) * 3;
+      o[0] = ax[k];
+      o[1] = ay[k];
+      o[2] = az[k];
+    } else {
+      apply_epilogue(ep, i, ax[k], ay[k], az[k]);
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// fp64
+// -------------------------------------------------------------------------------------------
+// s^-1/2 to ~1e-19: MUFU.RSQ64H seed (relative error ~2^-20) + one third-order correction
+// y (1 + e/2 + 3e^2/8), e = 1 - s y^2; truncation 5e^3/16 ~ 1e-18.
+__device__ __forceinline__ double rsqrt64(double s) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
+  double t = s * y;
+  double e = fma(-t, y, 1.0);
+  double p = fma(0.375, e, 0.5);
+  double q = e * p;
+  return fma(y, q, y);
+}
+
+template <int BLOCK>
+struct Tile64 {
+  double4 s[BLOCK];  // (x, y, z, m)
+};
+
+template <int BLOCK, int KI, bool GUARD>
+__global__ void __launch_bounds__(BLOCK)
+direct_f64_kernel(const double *__restrict__ spos, const double *__restrict__ smass, int64_t nj,
+                  const double *__restrict__ tpos, int64_t ni, double eps2, int64_t jchunk,
+                  double *__restrict__ partial, Epilogue ep) {
+  __shared__ Tile64<BLOCK> tile[2];
+  const int tid = threadIdx.x;
+  const int64_t i0 = (int64_t)blockIdx.x * (BLOCK * KI);
+  const int64_t jb = (int64_t)blockIdx.y * jchunk;
+  const int64_t je = (jb + jchunk < nj) ? jb + jchunk : nj;
+  const int ntiles = (int)((je - jb + BLOCK - 1) / BLOCK);
+
+  double xi[KI], yi[KI], zi[KI], ax[KI], ay[KI], az[KI];
+#pragma unroll
+  for (int k = 0; k < KI; k++) {
+    int64_t i = i0 + tid + (int64_t)k * BLOCK;
+    if (i < ni) {
+      xi[k] = tpos[3 * i];
+      yi[k] = tpos[3 * i + 1];
+      zi[k] = tpos[3 * i + 2];
+    } else {
+      xi[k] = yi[k] = zi[k] = 0.0;
+    }
+    ax[k] = ay[k] = az[k] = 0.0;
+  }
+
+  auto fetch = [&](int64_t j) -> double4 {
+    if (j < je) return make_double4(spos[3 * j], spos[3 * j + 1], spos[3 * j + 2], smass[j]);
+    return make_double4(0.0, 0.0, 0.0, 0.0);  // zero mass: contributes exactly zero
+  };
+  tile[0].s[tid] = fetch(jb + tid);
+  __syncthreads();
+
+  for (int t = 0; t < ntiles; t++) {
+    const bool more = (t + 1 < ntiles);
+    double4 g = make_double4(0.0, 0.0, 0.0, 0.0);
+    if (more) g = fetch(jb + (int64_t)(t + 1) * BLOCK + tid);
+    const Tile64<BLOCK> &T = tile[t & 1];
+#pragma unroll 4
+    for (int p = 0; p < BLOCK; p++) {
+      const double4 sj = T.s[p];
+#pragma unroll
+      for (int k = 0; k < KI; k++) {
+        double dx = sj.x - xi[k];
+        double dy = sj.y - yi[k];
+        double dz = sj.z - zi[k];
+        double s = fma(dx, dx, eps2);
+        s = fma(dy, dy, s);
+        s = fma(dz, dz, s);
+        double y = rsqrt64(s);
+        if (GUARD) y = (s > 0.0) ? y : 0.0;  // _jbgrav.c:327-328
+        double w = sj.w * (y * y * y);
+        ax[k] = fma(w, dx, ax[k]);
+        ay[k] = fma(w, dy, ay[k]);
+        az[k] = fma(w, dz, az[k]);
+      }
+    }
+    if (more) tile[(t + 1) & 1].s[tid] = g;
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int k = 0; k < KI; k++) {
+    int64_t i = i0 + tid + (int64_t)k * BLOCK;
+    if (i >= ni) continue;
+    if (partial) {
+      double *o = partial + ((int64_t)blockIdx.y * ni + i) * 3;
+      o[0] = ax[k];
+      o[1] = ay[k];
+      o[2] = az[k];
+    } else {
+      apply_epilogue(ep, i, ax[k], ay[k], az[k]);
+    }
+  }
+}
+
+__global__ void finalize_kernel(const double *__restrict__ partial, int S, int64_t ni,
+                                Epilogue ep) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ni) return;
+  double ax = 0.0, ay = 0.0, az = 0.0;
+  for (int c = 0; c < S; c++) {  // fixed chunk order: results do not depend on scheduling
+    const double *o = partial + ((int64_t)c * ni + i) * 3;
+    ax += o[0];
+    ay += o[1];
+    az += o[2];
+  }
+  apply_epilogue(ep, i, ax, ay, az);
+}
+
+// -------------------------------------------------------------------------------------------
+// launch heuristics
+// -------------------------------------------------------------------------------------------
+static int env_int(const char *name, int dflt) {
+  const char *s = getenv(name);
+  return (s && *s) ? atoi(s) : dflt;
+}
+
+struct Split {
+  int S;
+  int64_t jchunk;
+  unsigned itiles;
+};
+
+static Split choose_split(int64_t ni, int64_t nj, int itile, int tj) {
+  // aim for >= GH_DIRECT_CTAS CTAs (default 148 SMs x 2 resident x 16) so the last wave is a small
+  // fraction of the run; never make a chunk shorter than 2 source tiles.
+  const int64_t want = env_int("GH_DIRECT_CTAS", 148 * 2 * 16);
+  Split sp;
+  sp.itiles = (unsigned)((ni + itile - 1) / itile);
+  int64_t ntiles = (nj + tj - 1) / tj;
+  int64_t S = (want + sp.itiles - 1) / sp.itiles;
+  int64_t maxS = (ntiles + 1) / 2;
+  if (S > maxS) S = maxS;
+  if (S > 65535) S = 65535;
+  if (S < 1) S = 1;
+  int64_t tiles_per = (ntiles + S - 1) / S;
+  sp.jchunk = tiles_per * tj;
+  sp.S = (int)((nj + sp.jchunk - 1) / sp.jchunk);
+  if (sp.S < 1) sp.S = 1;
+  return sp;
+}
+
+template <int BLOCK, int KI>
+static int run_f32(const DirectArgs &a, DeviceBuffer &ws, cudaStream_t st, cudaEvent_t *ev) {
+  Split sp = choose_split(a.ni, a.nj, BLOCK * KI, BLOCK);
+  double *partial = nullptr;
+  if (sp.S > 1) {
+    GH_TRY(ws.reserve(sizeof(double) * 3 * (size_t)sp.S * (size_t)a.ni));
+    partial = ws.as<double>();
+  }
+  dim3 grid(sp.itiles, sp.S);
+  float eps2 = (float)(a.eps * a.eps);
+  if (ev) GH_CUDA(cudaEventRecord(ev[0], st));
+  if (a.eps == 0.0)
+    direct_f32_kernel<BLOCK, KI, true><<<grid, BLOCK, 0, st>>>(a.src32, a.nj, a.tgt32, a.ni, eps2,
+                                                              sp.jchunk, partial, a.ep);
+  else
+    direct_f32_kernel<BLOCK, KI, false><<<grid, BLOCK, 0, st>>>(a.src32, a.nj, a.tgt32, a.ni, eps2,
+                                                               sp.jchunk, partial, a.ep);
+  GH_LAUNCH_CHECK();
+  if (ev) GH_CUDA(cudaEventRecord(ev[1], st));
+  if (partial) {
+    finalize_kernel<<<(unsigned)((a.ni + 255) / 256), 256, 0, st>>>(partial, sp.S, a.ni, a.ep);
+    GH_LAUNCH_CHECK();
+  }
+  return GH_OK;
+}
+
+template <int BLOCK, int KI>
+static int run_f64(const DirectArgs &a, DeviceBuffer &ws, cudaStream_t st, cudaEvent_t *ev) {
+  Split sp = choose_split(a.ni, a.nj, BLOCK * KI, BLOCK);
+  double *partial = nullptr;
+  if (sp.S > 1) {
+    GH_TRY(ws.reserve(sizeof(double) * 3 * (size_t)sp.S * (size_t)a.ni));
+    partial = ws.as<double>();
+  }
+  dim3 grid(sp.itiles, sp.S);
+  double eps2 = a.eps * a.eps;
+  if (ev) GH_CUDA(cudaEventRecord(ev[0], st));
+  if (a.eps == 0.0)
+    direct_f64_kernel<BLOCK, KI, true><<<grid, BLOCK, 0, st>>>(a.src_pos, a.src_mass, a.nj, a.tgt_pos,
+                                                              a.ni, eps2, sp.jchunk, partial, a.ep);
+  else
+    direct_f64_kernel<BLOCK, KI, false><<<grid, BLOCK, 0, st>>>(a.src_pos, a.src_mass, a.nj, a.tgt_pos,
+                                                               a.ni, eps2, sp.jchunk, partial, a.ep);
+  GH_LAUNCH_CHECK();
+  if (ev) GH_CUDA(cudaEventRecord(ev[1], st));
+  if (partial) {
+    finalize_kernel<<<(unsigned)((a.ni + 255) / 256), 256, 0, st>>>(partial, sp.S, a.ni, a.ep);
+    GH_LAUNCH_CHECK();
+  }
+  return GH_OK;
+}
+
+int launch_direct(const DirectArgs &a, DeviceBuffer &ws, cudaStream_t st, cudaEvent_t *ev) {
+  if (a.ni <= 0) return GH_OK;
+  if (a.prec == GH_PREC_F32) {
+    int ki = env_int("GH_F32_KI", 0);
+    if (ki == 0) ki = (a.ni >= 131072) ? 4 : (a.ni >= 16384 ? 2 : 1);
+    switch (ki) {
+      case 8: return run_f32<128, 8>(a, ws, st, ev);
+      case 4: return run_f32<256, 4>(a, ws, st, ev);
+      case 2: return run_f32<128, 2>(a, ws, st, ev);
+      default: return run_f32<128, 1>(a, ws, st, ev);
+    }
+  } else if (a.prec == GH_PREC_F64) {
+    int ki = env_int("GH_F64_KI", 0);
+    if (ki == 0) ki = (a.ni >= 65536) ? 2 : 1;
+    switch (ki) {
+      case 4: return run_f64<128, 4>(a, ws, st, ev);
+      case 2: return run_f64<256, 2>(a, ws, st, ev);
+      default: return run_f64<128, 1>(a, ws, st, ev);
+    }
+  }
+  set_error("launch_direct: bad precision %d", a.prec);
+  return GH_EINVAL;
+}
+
+// -------------------------------------------------------------------------------------------
+// small O(N) kernels
+// -------------------------------------------------------------------------------------------
+__global__ void pack32_kernel(const double *__restrict__ pos, const double *__restrict__ mass,
+                              int64_t n, double ox, double oy, double oz, float4 *__restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = make_float4((float)(pos[3 * i] - ox), (float)(pos[3 * i + 1] - oy),
+                       (float)(pos[3 * i + 2] - oz), mass ? (float)mass[i] : 0.f);
+}
+
+int launch_pack32(const double *pos, const double *mass, int64_t n, const double origin[3],
+                  float4 *out, cudaStream_t st) {
+  if (n <= 0) return GH_OK;
+  pack32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pos, mass, n, origin[0], origin[1],
+                                                           origin[2], out);
+  GH_LAUNCH_CHECK();
+  return GH_OK;
+}
+
+__global__ void half_drift_kernel(const double *__restrict__ x, const double *__restrict__ v,
+                                  const double *__restrict__ mass, int64_t n, double dt,
+                                  double *__restrict__ xhalf, float4 *__restrict__ src32, double ox,
+                                  double oy, double oz) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double h[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {  // gravhopper.py:409
+    double hd = __dmul_rn(__dmul_rn(__dmul_rn(0.5, v[3 * i + k]), dt), GH_KPC_PER_KMS_MYR);
+    h[k] = __dadd_rn(x[3 * i + k], hd);
+    xhalf[3 * i + k] = h[k];
+  }
+  if (src32)
+    src32[i] = make_float4((float)(h[0] - ox), (float)(h[1] - oy), (float)(h[2] - oz), (float)mass[i]);
+}
+
+int launch_half_drift(const double *x, const double *v, const double *mass, int64_t n, double dt,
+                      double *xhalf, float4 *src32, const double origin[3], cudaStream_t st) {
+  if (n <= 0) return GH_OK;
+  half_drift_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, v, mass, n, dt, xhalf, src32,
+                                                               origin[0], origin[1], origin[2]);
+  GH_LAUNCH_CHECK();
+  return GH_OK;
+}
+
+// Energy diagnostic (no reference code; consistent with _jbgrav.c:165-166).  Each target sums
+// m_j / sqrt(r^2+eps^2) over sources with global index > its own (i < j pairs).
+__global__ void energy_kernel(const double *__restrict__ x, const double *__restrict__ v,
+                              const double *__restrict__ mt, int64_t ni,
+                              const double *__restrict__ spos, const double *__restrict__ smass,
+                              int64_t nj, int64_t self_offset, double eps2, double *out2) {
+  __shared__ double4 sh[128];
+  __shared__ double red[2][128];
+  const int tid = threadIdx.x;
+  int64_t i = (int64_t)blockIdx.x * 128 + tid;
+  double xi = 0, yi = 0, zi = 0;
+  if (i < ni) { xi = x[3 * i]; yi = x[3 * i + 1]; zi = x[3 * i + 2]; }
+  const int64_t gi = i + self_offset;
+  double pot = 0.0;
+  // sources with index > the smallest target index of this block are the only ones needed
+  int64_t jstart = ((int64_t)blockIdx.x * 128 + self_offset) / 128 * 128;
+  for (int64_t j0 = jstart; j0 < nj; j0 += 128) {
+    int64_t j = j0 + tid;
+    sh[tid] = (j < nj) ? make_double4(spos[3 * j], spos[3 * j + 1], spos[3 * j + 2], smass[j])
+                       : make_double4(0, 0, 0, 0);
+    __syncthreads();
+    for (int p = 0; p < 128; p++) {
+      if (j0 + p > gi && j0 + p < nj) {
+        double dx = sh[p].x - xi, dy = sh[p].y - yi, dz = sh[p].z - zi;
+        pot += sh[p].w / sqrt(dx * dx + dy * dy + dz * dz + eps2);
+      }
+    }
+    __syncthreads();
+  }
+  double ke = 0.0, pe = 0.0;
+  if (i < ni) {
+    ke = 0.5 * mt[i] * (v[3 * i] * v[3 * i] + v[3 * i + 1] * v[3 * i + 1] + v[3 * i + 2] * v[3 * i + 2]);
+    pe = -GH_G * mt[i] * pot;
+  }
+  red[0][tid] = ke;
+  red[1][tid] = pe;
+  __syncthreads();
+  for (int s = 64; s > 0; s >>= 1) {
+    if (tid < s) { red[0][tid] += red[0][tid + s]; red[1][tid] += red[1][tid + s]; }
+    __syncthreads();
+  }
+  if (tid == 0) { atomicAdd(&out2[0], red[0][0]); atomicAdd(&out2[1], red[1][0]); }
+}
+
+int launch_energy(const double *x, const double *v, const double *m_tgt, int64_t ni,
+                  const double *src_pos, const double *src_mass, int64_t nj, int64_t self_offset,
+                  double eps, double *out2, cudaStream_t st) {
+  if (ni <= 0) return GH_OK;
+  energy_kernel<<<(unsigned)((ni + 127) / 128), 128, 0, st>>>(x, v, m_tgt, ni, src_pos, src_mass, nj,
+                                                            self_offset, eps * eps, out2);
+  GH_LAUNCH_CHECK();
+  return GH_OK;
+}
+
+}  // namespace gh

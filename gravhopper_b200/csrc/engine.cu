@@ -1,0 +1,640 @@
+// engine.cu -- the C ABI of libgravhopper_b200.so (include/gravhopper_b200.h): the four
+// stateless force entry points and the device-resident leapfrog engine.
+#include "common.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+namespace gh {
+
+static thread_local char g_err[512] = "";
+static thread_local int64_t g_launches = 0;
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int64_t &launch_counter() { return g_launches; }
+
+static int check_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    set_error("no CUDA device available (%s); libgravhopper_b200 has no CPU fallback",
+              e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    return GH_ECUDA;
+  }
+  return GH_OK;
+}
+
+// Per-thread scratch of the stateless entry points (grow-only, reused between calls).
+struct Stateless {
+  DeviceBuffer pos, mass, tpos, acc, src32, tgt32, ws, root, part;
+  TreeWorkspace *tw = nullptr;
+  cudaStream_t stream = nullptr;
+  int64_t tree_stats[5] = {0, 0, 0, 0, 0};
+  bool want_stats = false;
+};
+static thread_local Stateless *g_sl = nullptr;
+static Stateless *stateless() {
+  if (!g_sl) g_sl = new (std::nothrow) Stateless();
+  return g_sl;
+}
+
+// bbox midpoint of (pos) -> origin[3] on the device (for the f32 packing).  Two tiny kernels.
+__global__ void origin_stage1(const double *__restrict__ pos, int64_t n, double *__restrict__ part) {
+  __shared__ double sh[6][256];
+  double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    for (int k = 0; k < 3; k++) {
+      mn[k] = fmin(mn[k], pos[3 * i + k]);
+      mx[k] = fmax(mx[k], pos[3 * i + k]);
+    }
+  for (int k = 0; k < 3; k++) { sh[k][threadIdx.x] = mn[k]; sh[3 + k][threadIdx.x] = mx[k]; }
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s)
+      for (int k = 0; k < 3; k++) {
+        sh[k][threadIdx.x] = fmin(sh[k][threadIdx.x], sh[k][threadIdx.x + s]);
+        sh[3 + k][threadIdx.x] = fmax(sh[3 + k][threadIdx.x], sh[3 + k][threadIdx.x + s]);
+      }
+    __syncthreads();
+  }
+  if (threadIdx.x < 6) part[blockIdx.x * 6 + threadIdx.x] = sh[threadIdx.x][0];
+}
+__global__ void origin_stage2(const double *__restrict__ part, int nb, double *__restrict__ origin) {
+  if (threadIdx.x >= 3) return;
+  int k = threadIdx.x;
+  double mn = 1e300, mx = -1e300;
+  for (int b = 0; b < nb; b++) { mn = fmin(mn, part[b * 6 + k]); mx = fmax(mx, part[b * 6 + 3 + k]); }
+  origin[k] = 0.5 * (mn + mx);
+}
+__global__ void pack32_dev_origin(const double *__restrict__ pos, const double *__restrict__ mass,
+                                  int64_t n, const double *__restrict__ origin,
+                                  float4 *__restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = make_float4((float)(pos[3 * i] - origin[0]), (float)(pos[3 * i + 1] - origin[1]),
+                       (float)(pos[3 * i + 2] - origin[2]), mass ? (float)mass[i] : 0.f);
+}
+
+static int force_common(int alg, int prec, const double *pos, const double *mass, int64_t np,
+                        const double *fpos, int64_t nf, double eps, double theta, double *acc_out,
+                        int mem, void *stream) {
+  if (prec != GH_PREC_F32 && prec != GH_PREC_F64) { set_error("prec must be 32 or 64"); return GH_EINVAL; }
+  if (mem != GH_MEM_HOST && mem != GH_MEM_DEVICE) { set_error("mem must be GH_MEM_HOST or GH_MEM_DEVICE"); return GH_EINVAL; }
+  if (np < 0 || nf < 0) { set_error("negative particle count"); return GH_EINVAL; }
+  const bool self = (fpos == nullptr);
+  if (self) nf = np;
+  if (nf == 0) return GH_OK;
+  if (!pos || !mass || !acc_out) { set_error("null pointer argument"); return GH_EINVAL; }
+  if (!(eps >= 0.0)) { set_error("eps must be >= 0"); return GH_EINVAL; }
+  GH_TRY(check_device());
+  Stateless *s = stateless();
+  if (!s) { set_error("out of host memory"); return GH_ENOMEM; }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mem == GH_MEM_HOST && !st) {
+    if (!s->stream) GH_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    st = s->stream;
+  }
+  const double *dpos = pos, *dmass = mass, *dt = fpos;
+  double *dacc = acc_out;
+  if (mem == GH_MEM_HOST) {
+    GH_TRY(s->pos.reserve(sizeof(double) * 3 * (size_t)(np > 0 ? np : 1)));
+    GH_TRY(s->mass.reserve(sizeof(double) * (size_t)(np > 0 ? np : 1)));
+    GH_TRY(s->acc.reserve(sizeof(double) * 3 * (size_t)nf));
+    GH_CUDA(cudaMemcpyAsync(s->pos.ptr, pos, sizeof(double) * 3 * np, cudaMemcpyHostToDevice, st));
+    GH_CUDA(cudaMemcpyAsync(s->mass.ptr, mass, sizeof(double) * np, cudaMemcpyHostToDevice, st));
+    dpos = s->pos.as<double>();
+    dmass = s->mass.as<double>();
+    dacc = s->acc.as<double>();
+    if (!self) {
+      GH_TRY(s->tpos.reserve(sizeof(double) * 3 * (size_t)nf));
+      GH_CUDA(cudaMemcpyAsync(s->tpos.ptr, fpos, sizeof(double) * 3 * nf, cudaMemcpyHostToDevice, st));
+      dt = s->tpos.as<double>();
+    }
+  }
+  if (self) dt = dpos;
+
+  Epilogue ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.mode = EP_ACC;
+  ep.acc_out = dacc;
+
+  if (np == 0) {
+    GH_CUDA(cudaMemsetAsync(dacc, 0, sizeof(double) * 3 * nf, st));
+  } else if (alg == GH_ALG_DIRECT) {
+    DirectArgs a;
+    memset(&a, 0, sizeof(a));
+    a.prec = prec;
+    a.nj = np;
+    a.ni = nf;
+    a.eps = eps;
+    a.ep = ep;
+    if (prec == GH_PREC_F64) {
+      a.src_pos = dpos;
+      a.src_mass = dmass;
+      a.tgt_pos = dt;
+    } else {
+      // fp32 pair maths on coordinates taken relative to the sources' bbox midpoint
+      GH_TRY(s->src32.reserve(sizeof(float4) * (size_t)np));
+      GH_TRY(s->root.reserve(sizeof(double) * 4));
+      GH_TRY(s->part.reserve(sizeof(double) * 6 * 256));
+      int nb = (int)((np + 2047) / 2048);
+      if (nb > 256) nb = 256;
+      origin_stage1<<<nb, 256, 0, st>>>(dpos, np, s->part.as<double>());
+      GH_LAUNCH_CHECK();
+      origin_stage2<<<1, 32, 0, st>>>(s->part.as<double>(), nb, s->root.as<double>());
+      GH_LAUNCH_CHECK();
+      pack32_dev_origin<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(dpos, dmass, np, s->root.as<double>(),
+                                                                    s->src32.as<float4>());
+      GH_LAUNCH_CHECK();
+      a.src32 = s->src32.as<float4>();
+      if (self) {
+        a.tgt32 = a.src32;
+      } else {
+        GH_TRY(s->tgt32.reserve(sizeof(float4) * (size_t)nf));
+        pack32_dev_origin<<<(unsigned)((nf + 255) / 256), 256, 0, st>>>(dt, nullptr, nf, s->root.as<double>(),
+                                                                      s->tgt32.as<float4>());
+        GH_LAUNCH_CHECK();
+        a.tgt32 = s->tgt32.as<float4>();
+      }
+    }
+    GH_TRY(launch_direct(a, s->ws, st, nullptr));
+  } else {
+    if (!s->tw) s->tw = tree_workspace_create();
+    TreeArgs a;
+    memset(&a, 0, sizeof(a));
+    a.prec = prec;
+    a.src_pos = dpos;
+    a.src_mass = dmass;
+    a.nj = np;
+    a.tgt_pos = dt;
+    a.ni = nf;
+    a.targets_are_sources = self;
+    a.eps = eps;
+    a.theta = theta;
+    a.ep = ep;
+    a.want_stats = s->want_stats;
+    GH_TRY(launch_tree(a, s->tw, st, nullptr));
+    tree_last_stats(s->tw, s->tree_stats);
+  }
+  if (mem == GH_MEM_HOST) {
+    GH_CUDA(cudaMemcpyAsync(acc_out, dacc, sizeof(double) * 3 * nf, cudaMemcpyDeviceToHost, st));
+    GH_CUDA(cudaStreamSynchronize(st));
+  }
+  return GH_OK;
+}
+
+}  // namespace gh
+
+using namespace gh;
+
+// ---------------------------------------------------------------------------------------------
+// engine
+// ---------------------------------------------------------------------------------------------
+static constexpr int RING = 3;
+
+struct gh_engine {
+  int device = 0;
+  int64_t n = 0, ib = 0, ni = 0;
+  int prec = GH_PREC_F64;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  double *mass = nullptr;             // (n)
+  double *x[RING] = {nullptr}, *v[RING] = {nullptr};
+  int cur = 0;
+  cudaEvent_t copied[RING] = {nullptr};
+  bool copy_pending[RING] = {false};
+  cudaEvent_t step_done = nullptr;
+  bool external_src = false;
+  void *src[2] = {nullptr, nullptr};  // f64: double (n,3); f32: float4 (n)
+  int scur = 0;
+  double *xh_private = nullptr;       // f32: (ni,3) own x_half in float64
+  double origin[3] = {0, 0, 0};
+  double dt_built = 0.0;
+  bool uploaded = false, xhalf_valid = false;
+  DeviceBuffer ws, ext;
+  TreeWorkspace *tw = nullptr;
+  cudaEvent_t fev[2] = {nullptr, nullptr};
+  bool fev_valid = false;
+  int64_t launches = 0;
+  double *d_energy = nullptr;
+
+  double *xhalf_own(int b) const {
+    return prec == GH_PREC_F64 ? reinterpret_cast<double *>(src[b]) + 3 * ib : xh_private;
+  }
+  float4 *src32_own(int b) const {
+    return prec == GH_PREC_F32 ? reinterpret_cast<float4 *>(src[b]) + ib : nullptr;
+  }
+  size_t src_stride() const { return prec == GH_PREC_F64 ? 3 * sizeof(double) : sizeof(float4); }
+};
+
+struct LaunchScope {  // attribute this thread's kernel launches to the engine
+  gh_engine *e;
+  int64_t before;
+  explicit LaunchScope(gh_engine *e_) : e(e_), before(launch_counter()) {}
+  ~LaunchScope() { e->launches += launch_counter() - before; }
+};
+
+#define GH_ENGINE_GUARD(e)                                          \
+  if (!(e)) { set_error("null engine"); return GH_EINVAL; }         \
+  GH_CUDA(cudaSetDevice((e)->device));                              \
+  LaunchScope scope_(e)
+
+extern "C" {
+
+const char *gh_last_error(void) { return g_err; }
+int gh_version(void) { return 100; }
+
+int gh_device_count(int *n) {
+  if (!n) return GH_EINVAL;
+  *n = 0;
+  cudaError_t e = cudaGetDeviceCount(n);
+  if (e != cudaSuccess || *n <= 0) {
+    cudaGetLastError();
+    *n = 0;
+    set_error("no CUDA device available");
+    return GH_ECUDA;
+  }
+  return GH_OK;
+}
+
+int gh_direct_summation(int prec, const double *pos, const double *mass, int64_t np, double eps,
+                        double *acc_out, int mem, void *stream) {
+  return force_common(GH_ALG_DIRECT, prec, pos, mass, np, nullptr, np, eps, 0.0, acc_out, mem, stream);
+}
+int gh_direct_summation_position(int prec, const double *pos, const double *mass, int64_t np,
+                                 const double *force_pos, int64_t nf, double eps, double *acc_out,
+                                 int mem, void *stream) {
+  if (!force_pos && nf > 0) { set_error("null force_pos"); return GH_EINVAL; }
+  if (nf == 0) return GH_OK;
+  return force_common(GH_ALG_DIRECT, prec, pos, mass, np, force_pos, nf, eps, 0.0, acc_out, mem, stream);
+}
+int gh_tree_force(int prec, const double *pos, const double *mass, int64_t np, double eps,
+                  double theta, double *acc_out, int mem, void *stream) {
+  if (!(theta >= 0.0)) { set_error("theta must be >= 0"); return GH_EINVAL; }
+  return force_common(GH_ALG_TREE, prec, pos, mass, np, nullptr, np, eps, theta, acc_out, mem, stream);
+}
+int gh_tree_force_position(int prec, const double *pos, const double *mass, int64_t np,
+                           const double *force_pos, int64_t nf, double eps, double theta,
+                           double *acc_out, int mem, void *stream) {
+  if (!(theta >= 0.0)) { set_error("theta must be >= 0"); return GH_EINVAL; }
+  if (!force_pos && nf > 0) { set_error("null force_pos"); return GH_EINVAL; }
+  if (nf == 0) return GH_OK;
+  return force_common(GH_ALG_TREE, prec, pos, mass, np, force_pos, nf, eps, theta, acc_out, mem, stream);
+}
+int gh_tree_last_stats(int64_t out[5]) {
+  Stateless *s = stateless();
+  if (!s || !out) return GH_EINVAL;
+  for (int k = 0; k < 5; k++) out[k] = s->tree_stats[k];
+  return GH_OK;
+}
+int gh_set_tree_stats(int enable) {
+  Stateless *s = stateless();
+  if (!s) return GH_ENOMEM;
+  s->want_stats = enable != 0;
+  return GH_OK;
+}
+
+int gh_engine_create(gh_engine **out, int device, int64_t n_total, int64_t i_begin, int64_t i_count,
+                     int prec) {
+  if (!out) return GH_EINVAL;
+  *out = nullptr;
+  if (prec != GH_PREC_F32 && prec != GH_PREC_F64) { set_error("prec must be 32 or 64"); return GH_EINVAL; }
+  if (n_total <= 0 || i_begin < 0 || i_count <= 0 || i_begin + i_count > n_total) {
+    set_error("bad particle ranges n_total=%lld i_begin=%lld i_count=%lld", (long long)n_total,
+              (long long)i_begin, (long long)i_count);
+    return GH_EINVAL;
+  }
+  GH_TRY(check_device());
+  GH_CUDA(cudaSetDevice(device));
+  gh_engine *e = new (std::nothrow) gh_engine();
+  if (!e) return GH_ENOMEM;
+  e->device = device;
+  e->n = n_total;
+  e->ib = i_begin;
+  e->ni = i_count;
+  e->prec = prec;
+  auto fail = [&](int rc) { gh_engine_destroy(e); return rc; };
+#define E_CUDA(call)                                                                   \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess) {                                                           \
+      set_error("%s: %s", #call, cudaGetErrorString(e_));                              \
+      return fail(e_ == cudaErrorMemoryAllocation ? GH_ENOMEM : GH_ECUDA);             \
+    }                                                                                  \
+  } while (0)
+  E_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  E_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+  E_CUDA(cudaMalloc(&e->mass, sizeof(double) * n_total));
+  for (int r = 0; r < RING; r++) {
+    E_CUDA(cudaMalloc(&e->x[r], sizeof(double) * 3 * i_count));
+    E_CUDA(cudaMalloc(&e->v[r], sizeof(double) * 3 * i_count));
+    E_CUDA(cudaEventCreateWithFlags(&e->copied[r], cudaEventDisableTiming));
+  }
+  E_CUDA(cudaEventCreateWithFlags(&e->step_done, cudaEventDisableTiming));
+  E_CUDA(cudaEventCreate(&e->fev[0]));
+  E_CUDA(cudaEventCreate(&e->fev[1]));
+  for (int b = 0; b < 2; b++) {
+    E_CUDA(cudaMalloc(&e->src[b], e->src_stride() * n_total));
+    E_CUDA(cudaMemset(e->src[b], 0, e->src_stride() * n_total));
+  }
+  if (prec == GH_PREC_F32) E_CUDA(cudaMalloc(&e->xh_private, sizeof(double) * 3 * i_count));
+  E_CUDA(cudaMalloc(&e->d_energy, sizeof(double) * 2));
+#undef E_CUDA
+  e->tw = tree_workspace_create();
+  *out = e;
+  return GH_OK;
+}
+
+int gh_engine_destroy(gh_engine *e) {
+  if (!e) return GH_OK;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
+  cudaFree(e->mass);
+  for (int r = 0; r < RING; r++) {
+    cudaFree(e->x[r]);
+    cudaFree(e->v[r]);
+    if (e->copied[r]) cudaEventDestroy(e->copied[r]);
+  }
+  if (e->step_done) cudaEventDestroy(e->step_done);
+  if (e->fev[0]) cudaEventDestroy(e->fev[0]);
+  if (e->fev[1]) cudaEventDestroy(e->fev[1]);
+  if (!e->external_src) { cudaFree(e->src[0]); cudaFree(e->src[1]); }
+  cudaFree(e->xh_private);
+  cudaFree(e->d_energy);
+  e->ws.release();
+  e->ext.release();
+  tree_workspace_destroy(e->tw);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+  delete e;
+  return GH_OK;
+}
+
+int gh_engine_set_origin(gh_engine *e, const double origin[3]) {
+  if (!e || !origin) return GH_EINVAL;
+  for (int k = 0; k < 3; k++) e->origin[k] = origin[k];
+  e->xhalf_valid = false;
+  return GH_OK;
+}
+
+int gh_engine_upload(gh_engine *e, const double *pos, const double *vel, const double *mass_all) {
+  GH_ENGINE_GUARD(e);
+  if (!pos || !vel || !mass_all) { set_error("null pointer argument"); return GH_EINVAL; }
+  GH_CUDA(cudaStreamSynchronize(e->copy_stream));
+  for (int r = 0; r < RING; r++) e->copy_pending[r] = false;
+  GH_CUDA(cudaMemcpyAsync(e->x[e->cur], pos, sizeof(double) * 3 * e->ni, cudaMemcpyHostToDevice, e->stream));
+  GH_CUDA(cudaMemcpyAsync(e->v[e->cur], vel, sizeof(double) * 3 * e->ni, cudaMemcpyHostToDevice, e->stream));
+  GH_CUDA(cudaMemcpyAsync(e->mass, mass_all, sizeof(double) * e->n, cudaMemcpyHostToDevice, e->stream));
+  GH_CUDA(cudaStreamSynchronize(e->stream));
+  e->uploaded = true;
+  e->xhalf_valid = false;
+  return GH_OK;
+}
+
+int gh_engine_bind_sources(gh_engine *e, void *buf0, void *buf1) {
+  GH_ENGINE_GUARD(e);
+  if (!buf0 || !buf1 || buf0 == buf1) { set_error("need two distinct source buffers"); return GH_EINVAL; }
+  GH_CUDA(cudaStreamSynchronize(e->stream));
+  if (!e->external_src) { cudaFree(e->src[0]); cudaFree(e->src[1]); }
+  e->src[0] = buf0;
+  e->src[1] = buf1;
+  e->external_src = true;
+  e->xhalf_valid = false;
+  return GH_OK;
+}
+int gh_engine_source_index(gh_engine *e, int *idx) {
+  if (!e || !idx) return GH_EINVAL;
+  *idx = e->scur;
+  return GH_OK;
+}
+int gh_engine_source_stride_bytes(gh_engine *e, int64_t *bytes) {
+  if (!e || !bytes) return GH_EINVAL;
+  *bytes = (int64_t)e->src_stride();
+  return GH_OK;
+}
+
+// x_half for the next step from the current state (gravhopper.py:409), into the owned slice of
+// the current source buffer.
+int gh_engine_prepare(gh_engine *e, double dt) {
+  GH_ENGINE_GUARD(e);
+  if (!e->uploaded) { set_error("engine has no state: call gh_engine_upload first"); return GH_ESTATE; }
+  GH_TRY(launch_half_drift(e->x[e->cur], e->v[e->cur], e->mass + e->ib, e->ni, dt,
+                           e->xhalf_own(e->scur), e->src32_own(e->scur), e->origin, e->stream));
+  e->dt_built = dt;
+  e->xhalf_valid = true;
+  return GH_OK;
+}
+
+int gh_engine_set_dt(gh_engine *e, double dt) { return gh_engine_prepare(e, dt); }
+
+static int engine_step_impl(gh_engine *e, double dt, double eps, double theta, int algorithm,
+                            const double *ext_dev) {
+  if (!e->uploaded) { set_error("engine has no state: call gh_engine_upload first"); return GH_ESTATE; }
+  if (algorithm != GH_ALG_DIRECT && algorithm != GH_ALG_TREE) { set_error("unknown algorithm %d", algorithm); return GH_EINVAL; }
+  if (!e->xhalf_valid || dt != e->dt_built) {
+    if (e->n != e->ni) {
+      // multi-GPU: the caller must gh_engine_prepare + all-gather before stepping
+      set_error("sharded engine: call gh_engine_prepare(dt) and all-gather the sources before gh_engine_step");
+      return GH_ESTATE;
+    }
+    GH_TRY(gh_engine_prepare(e, dt));
+  }
+  const int nxt = (e->cur + 1) % RING;
+  if (e->copy_pending[nxt]) {
+    GH_CUDA(cudaStreamWaitEvent(e->stream, e->copied[nxt], 0));
+    e->copy_pending[nxt] = false;
+  }
+  Epilogue ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.mode = EP_STEP;
+  ep.xhalf = e->xhalf_own(e->scur);
+  ep.v_in = e->v[e->cur];
+  ep.x_out = e->x[nxt];
+  ep.v_out = e->v[nxt];
+  ep.xhalf_next = e->xhalf_own(e->scur ^ 1);
+  ep.src32_next = e->src32_own(e->scur ^ 1);
+  ep.mass = e->mass + e->ib;
+  ep.ext = ext_dev;
+  ep.dt = dt;
+  for (int k = 0; k < 3; k++) ep.origin[k] = e->origin[k];
+
+  if (e->n <= 1) {
+    // gravhopper.py:449-450: a single particle feels no N-body force; run the epilogue only
+    // through the direct kernel with zero sources is not possible (nj = 1 is fine: self term 0).
+  }
+  if (algorithm == GH_ALG_DIRECT) {
+    DirectArgs a;
+    memset(&a, 0, sizeof(a));
+    a.prec = e->prec;
+    a.nj = e->n;
+    a.ni = e->ni;
+    a.eps = eps;
+    a.ep = ep;
+    if (e->prec == GH_PREC_F64) {
+      a.src_pos = reinterpret_cast<const double *>(e->src[e->scur]);
+      a.src_mass = e->mass;
+      a.tgt_pos = a.src_pos + 3 * e->ib;
+    } else {
+      a.src32 = reinterpret_cast<const float4 *>(e->src[e->scur]);
+      a.tgt32 = a.src32 + e->ib;
+    }
+    GH_TRY(launch_direct(a, e->ws, e->stream, e->fev));
+  } else {
+    TreeArgs a;
+    memset(&a, 0, sizeof(a));
+    a.prec = e->prec;
+    a.nj = e->n;
+    a.ni = e->ni;
+    a.eps = eps;
+    a.theta = theta;
+    a.ep = ep;
+    a.targets_are_sources = true;
+    a.tgt_offset = e->ib;
+    if (e->prec == GH_PREC_F64) {
+      a.src_pos = reinterpret_cast<const double *>(e->src[e->scur]);
+      a.src_mass = e->mass;
+      a.tgt_pos = a.src_pos + 3 * e->ib;
+    } else {
+      a.src32 = reinterpret_cast<const float4 *>(e->src[e->scur]);
+      a.tgt32 = a.src32 + e->ib;
+    }
+    GH_TRY(launch_tree(a, e->tw, e->stream, e->fev));
+  }
+  e->fev_valid = true;
+  e->cur = nxt;
+  e->scur ^= 1;
+  return GH_OK;
+}
+
+int gh_engine_step(gh_engine *e, double dt, double eps, double theta, int algorithm,
+                   const double *ext_acc, int ext_mem) {
+  GH_ENGINE_GUARD(e);
+  const double *ext_dev = ext_acc;
+  if (ext_acc && ext_mem == GH_MEM_HOST) {
+    GH_TRY(e->ext.reserve(sizeof(double) * 3 * e->ni));
+    GH_CUDA(cudaMemcpyAsync(e->ext.ptr, ext_acc, sizeof(double) * 3 * e->ni, cudaMemcpyHostToDevice, e->stream));
+    ext_dev = e->ext.as<double>();
+  }
+  return engine_step_impl(e, dt, eps, theta, algorithm, ext_dev);
+}
+
+int gh_engine_run(gh_engine *e, int64_t nsteps, double dt, double eps, double theta, int algorithm,
+                  int64_t snapshot_every, double *pos_hist, double *vel_hist) {
+  GH_ENGINE_GUARD(e);
+  if (nsteps < 0 || snapshot_every < 0) { set_error("negative step count"); return GH_EINVAL; }
+  if (e->n != e->ni) { set_error("gh_engine_run is single-GPU only; drive sharded engines with gh_engine_step"); return GH_ESTATE; }
+  if (snapshot_every > 0 && (!pos_hist || !vel_hist)) { set_error("snapshot buffers are null"); return GH_EINVAL; }
+  const size_t row = sizeof(double) * 3 * (size_t)e->ni;
+  int64_t nsnap = 0;
+  if (snapshot_every > 0) nsnap = nsteps / snapshot_every + ((nsteps % snapshot_every) ? 1 : 0);
+  bool reg_p = false, reg_v = false;
+  if (nsnap > 0) {  // pin the caller's history arrays so the copies really overlap the steps
+    reg_p = cudaHostRegister(pos_hist, row * nsnap, cudaHostRegisterDefault) == cudaSuccess;
+    reg_v = cudaHostRegister(vel_hist, row * nsnap, cudaHostRegisterDefault) == cudaSuccess;
+    cudaGetLastError();
+  }
+  int rc = GH_OK;
+  int64_t k = 0;
+  for (int64_t s = 1; s <= nsteps && rc == GH_OK; s++) {
+    rc = engine_step_impl(e, dt, eps, theta, algorithm, nullptr);
+    if (rc != GH_OK) break;
+    if (snapshot_every > 0 && (s % snapshot_every == 0 || s == nsteps)) {
+      cudaError_t ce = cudaEventRecord(e->step_done, e->stream);
+      if (ce == cudaSuccess) ce = cudaStreamWaitEvent(e->copy_stream, e->step_done, 0);
+      if (ce == cudaSuccess) ce = cudaMemcpyAsync(pos_hist + 3 * e->ni * k, e->x[e->cur], row, cudaMemcpyDeviceToHost, e->copy_stream);
+      if (ce == cudaSuccess) ce = cudaMemcpyAsync(vel_hist + 3 * e->ni * k, e->v[e->cur], row, cudaMemcpyDeviceToHost, e->copy_stream);
+      if (ce == cudaSuccess) ce = cudaEventRecord(e->copied[e->cur], e->copy_stream);
+      if (ce != cudaSuccess) { set_error("snapshot copy: %s", cudaGetErrorString(ce)); rc = GH_ECUDA; break; }
+      e->copy_pending[e->cur] = true;
+      k++;
+    }
+  }
+  cudaError_t c1 = cudaStreamSynchronize(e->stream);
+  cudaError_t c2 = cudaStreamSynchronize(e->copy_stream);
+  for (int r = 0; r < RING; r++) e->copy_pending[r] = false;
+  if (reg_p) cudaHostUnregister(pos_hist);
+  if (reg_v) cudaHostUnregister(vel_hist);
+  if (rc == GH_OK && (c1 != cudaSuccess || c2 != cudaSuccess)) {
+    set_error("gh_engine_run: %s", cudaGetErrorString(c1 != cudaSuccess ? c1 : c2));
+    rc = GH_ECUDA;
+  }
+  return rc;
+}
+
+int gh_engine_download(gh_engine *e, double *pos, double *vel) {
+  GH_ENGINE_GUARD(e);
+  if (!e->uploaded) { set_error("engine has no state"); return GH_ESTATE; }
+  if (pos) GH_CUDA(cudaMemcpyAsync(pos, e->x[e->cur], sizeof(double) * 3 * e->ni, cudaMemcpyDeviceToHost, e->stream));
+  if (vel) GH_CUDA(cudaMemcpyAsync(vel, e->v[e->cur], sizeof(double) * 3 * e->ni, cudaMemcpyDeviceToHost, e->stream));
+  GH_CUDA(cudaStreamSynchronize(e->stream));
+  return GH_OK;
+}
+
+int gh_engine_download_xhalf(gh_engine *e, double *xhalf) {
+  GH_ENGINE_GUARD(e);
+  if (!e->uploaded || !e->xhalf_valid) { set_error("x_half not built: call gh_engine_prepare(dt)"); return GH_ESTATE; }
+  GH_CUDA(cudaMemcpyAsync(xhalf, e->xhalf_own(e->scur), sizeof(double) * 3 * e->ni, cudaMemcpyDeviceToHost, e->stream));
+  GH_CUDA(cudaStreamSynchronize(e->stream));
+  return GH_OK;
+}
+
+int gh_engine_energy(gh_engine *e, double eps, double out[2]) {
+  GH_ENGINE_GUARD(e);
+  if (!e->uploaded || !out) { set_error("engine has no state"); return GH_ESTATE; }
+  // sources: positions of ALL particles.  Single GPU: the state itself.  Sharded engines only
+  // hold x_half of the others, so the diagnostic is defined for single-GPU engines.
+  if (e->n != e->ni) { set_error("gh_engine_energy: single-GPU engines only"); return GH_ESTATE; }
+  GH_CUDA(cudaMemsetAsync(e->d_energy, 0, 2 * sizeof(double), e->stream));
+  GH_TRY(launch_energy(e->x[e->cur], e->v[e->cur], e->mass, e->ni, e->x[e->cur], e->mass, e->n, 0, eps,
+                       e->d_energy, e->stream));
+  GH_CUDA(cudaMemcpyAsync(out, e->d_energy, 2 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  GH_CUDA(cudaStreamSynchronize(e->stream));
+  return GH_OK;
+}
+
+int gh_engine_synchronize(gh_engine *e) {
+  GH_ENGINE_GUARD(e);
+  GH_CUDA(cudaStreamSynchronize(e->stream));
+  GH_CUDA(cudaStreamSynchronize(e->copy_stream));
+  return GH_OK;
+}
+
+int gh_engine_state_ptrs(gh_engine *e, double **pos_dev, double **vel_dev) {
+  if (!e) return GH_EINVAL;
+  if (pos_dev) *pos_dev = e->x[e->cur];
+  if (vel_dev) *vel_dev = e->v[e->cur];
+  return GH_OK;
+}
+int gh_engine_stream(gh_engine *e, void **stream) {
+  if (!e || !stream) return GH_EINVAL;
+  *stream = (void *)e->stream;
+  return GH_OK;
+}
+int gh_engine_launch_count(gh_engine *e, int64_t *count) {
+  if (!e || !count) return GH_EINVAL;
+  *count = e->launches;
+  return GH_OK;
+}
+int gh_engine_last_force_ms(gh_engine *e, float *ms) {
+  GH_ENGINE_GUARD(e);
+  if (!ms) return GH_EINVAL;
+  if (!e->fev_valid) { set_error("no step has run"); return GH_ESTATE; }
+  GH_CUDA(cudaEventSynchronize(e->fev[1]));
+  GH_CUDA(cudaEventElapsedTime(ms, e->fev[0], e->fev[1]));
+  return GH_OK;
+}
+int gh_engine_tree_stats(gh_engine *e, int64_t out[5]) {
+  if (!e || !out) return GH_EINVAL;
+  return tree_last_stats(e->tw, out);
+}
+
+}  // extern "C"

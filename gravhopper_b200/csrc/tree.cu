@@ -1,0 +1,676 @@
+// tree.cu -- Barnes-Hut octree on the GPU for sm_100a.  Replaces the pointer octree of
+// /root/reference/gravhopper/_jbgrav.c:360-558 and treeforce_workhorse (:737-806).
+//
+// The tree that is built is THE REFERENCE'S OCTREE, not an approximation of it: same root cube
+// (bbox midpoint, side per :764-769 including the eps padding quirk), same child assignment
+// (strict p > centre per axis, child centre = centre +- size/4 accumulated level by level in
+// the same floating-point order, :441-462,:406), one particle per leaf, a cell wherever two or
+// more particles share an octant path (chains of single-child cells included), monopole moments
+// (:432-435,:467-483).  The walk applies the reference's opening test per target (:502) and so
+// accepts exactly the reference's node set; only the order of floating-point additions differs
+// (sequential depth-first instead of child-subtotal), i.e. results agree to rounding (~1e-14).
+//
+// How it is built (all data-parallel, no pointers, no recursion, no per-node allocation):
+//   K3  bbox            two-stage min/max reduction -> root centre and side (device resident)
+//   K4  keys            per particle, descend up to 42 levels comparing against the running
+//                       cell centre exactly as gravoct_calc_subnode does; 3 bits per level,
+//                       z-major so that key order == the reference's branch order (:441-450);
+//                       levels 1-21 in `hi`, 22-42 in `lo`
+//   K5  sort            stable LSD radix sort of (lo, hi) with the particle index (CUB
+//                       DeviceRadixSort: library plumbing)
+//   K6a common levels   c[p] = number of octant levels shared by sorted neighbours p, p+1.
+//                       A cell of level l starts at p  <=>  c[p-1] < l <= c[p]; therefore the
+//                       depth-first (pre-order) position of every cell and leaf is a prefix sum
+//                       of (cells opened at p) + 1.
+//   K7  moments         double-double inclusive scan of (m, m x, m y, m z) in Morton order; a
+//                       cell covering sorted particles [p, b] has mass = P[b+1] - P[p] (the
+//                       double-double difference is exact to ~1e-30, so no cancellation)
+//   K6b emit            per particle: walk down its key, write one entry per opened cell
+//                       (centre, side, COM, mass, skip = pre-order index after the subtree, found
+//                       by galloping search for the end of the key-prefix run) and its leaf entry
+//   K8  walk            one warp per 32 Morton-consecutive targets; the warp scans the
+//                       pre-order array once, skipping a subtree when every lane has either
+//                       accepted the cell or is already past it; each lane applies ITS OWN
+//                       opening test and remembers the pre-order index up to which it has
+//                       accepted an ancestor.  Entry loads are warp-uniform (one L1 transaction).
+//                       The epilogue (store, or fused kick+drift) runs in the same kernel.
+// Cells deeper than 42 levels (|dx| < side * 2^-42) are not split: their particles become sibling
+// leaves, which is exact for the force and cannot loop forever on coincident particles (the
+// reference segfaults there, :401-413).
+#include "common.cuh"
+
+#include <cub/cub.cuh>
+#include <climits>
+#include <cstdlib>
+
+namespace gh {
+
+static constexpr int LEVELS_HI = 21;
+static constexpr int LEVELS_MAX = 42;
+
+// ---- source / target accessors --------------------------------------------------------------
+struct Src64 {
+  const double *pos;
+  const double *mass;
+  __device__ __forceinline__ void get(int64_t j, double &x, double &y, double &z) const {
+    x = pos[3 * j]; y = pos[3 * j + 1]; z = pos[3 * j + 2];
+  }
+  __device__ __forceinline__ double m(int64_t j) const { return mass[j]; }
+};
+struct Src32 {
+  const float4 *p;
+  __device__ __forceinline__ void get(int64_t j, double &x, double &y, double &z) const {
+    float4 t = p[j]; x = t.x; y = t.y; z = t.z;
+  }
+  __device__ __forceinline__ double m(int64_t j) const { return p[j].w; }
+};
+
+// root[0..2] centre, root[3] side, root[4..6] min, root[7..9] max
+static constexpr int ROOT_DOUBLES = 10;
+
+// ---- K3 bbox ----------------------------------------------------------------------------------
+template <class Src>
+__global__ void bbox_stage1(Src src, int64_t n, double *__restrict__ part) {
+  __shared__ double sh[6][256];
+  double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    double p[3];
+    src.get(i, p[0], p[1], p[2]);
+#pragma unroll
+    for (int k = 0; k < 3; k++) { mn[k] = fmin(mn[k], p[k]); mx[k] = fmax(mx[k], p[k]); }
+  }
+  for (int k = 0; k < 3; k++) { sh[k][threadIdx.x] = mn[k]; sh[3 + k][threadIdx.x] = mx[k]; }
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      for (int k = 0; k < 3; k++) {
+        sh[k][threadIdx.x] = fmin(sh[k][threadIdx.x], sh[k][threadIdx.x + s]);
+        sh[3 + k][threadIdx.x] = fmax(sh[3 + k][threadIdx.x], sh[3 + k][threadIdx.x + s]);
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < 6) part[blockIdx.x * 6 + threadIdx.x] = sh[threadIdx.x][0];
+}
+
+__global__ void bbox_stage2(const double *__restrict__ part, int nblocks, double eps,
+                            double *__restrict__ root) {
+  __shared__ double sh[6][256];
+  double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+  for (int b = threadIdx.x; b < nblocks; b += blockDim.x)
+    for (int k = 0; k < 3; k++) {
+      mn[k] = fmin(mn[k], part[b * 6 + k]);
+      mx[k] = fmax(mx[k], part[b * 6 + 3 + k]);
+    }
+  for (int k = 0; k < 3; k++) { sh[k][threadIdx.x] = mn[k]; sh[3 + k][threadIdx.x] = mx[k]; }
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      for (int k = 0; k < 3; k++) {
+        sh[k][threadIdx.x] = fmin(sh[k][threadIdx.x], sh[k][threadIdx.x + s]);
+        sh[3 + k][threadIdx.x] = fmax(sh[3 + k][threadIdx.x], sh[3 + k][threadIdx.x + s]);
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double mnv[3], mxv[3];
+    for (int k = 0; k < 3; k++) { mnv[k] = sh[k][0]; mxv[k] = sh[3 + k][0]; }
+    // _jbgrav.c:764-769: the un-padded extent is compared with the padded running value
+    double boxsize = __dadd_rn(__dadd_rn(mxv[0], -mnv[0]), eps);
+    for (int k = 1; k < 3; k++) {
+      double ext = __dadd_rn(mxv[k], -mnv[k]);
+      if (ext > boxsize) boxsize = __dadd_rn(ext, eps);
+    }
+    for (int k = 0; k < 3; k++) {
+      root[k] = __dmul_rn(0.5, __dadd_rn(mnv[k], mxv[k]));  // :770-772
+      root[4 + k] = mnv[k];
+      root[7 + k] = mxv[k];
+    }
+    root[3] = boxsize;
+  }
+}
+
+// ---- K4 keys ----------------------------------------------------------------------------------
+// One descent step of gravoct_calc_subnode/_branchnum + the child-centre update (:406,:441-462).
+__device__ __forceinline__ unsigned descend(const double p[3], double c[3], double quarter) {
+  unsigned d = 0;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    if (p[k] > c[k]) { d |= (1u << k); c[k] = __dadd_rn(c[k], quarter); }
+    else c[k] = __dadd_rn(c[k], -quarter);
+  }
+  return d;
+}
+
+template <class Src>
+__global__ void keys_kernel(Src src, int64_t n, const double *__restrict__ root, int levels,
+                            uint64_t *__restrict__ hi, uint64_t *__restrict__ lo,
+                            int *__restrict__ idx) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double p[3], c[3] = {root[0], root[1], root[2]};
+  src.get(i, p[0], p[1], p[2]);
+  double size = root[3];
+  uint64_t kh = 0, kl = 0;
+  for (int l = 1; l <= LEVELS_HI; l++) {
+    double quarter = __dmul_rn(0.5, __dmul_rn(0.5, size));  // 0.5 * halfsize (:406)
+    kh = (kh << 3) | descend(p, c, quarter);
+    size = __dmul_rn(0.5, size);
+  }
+  if (levels > LEVELS_HI) {
+    for (int l = LEVELS_HI + 1; l <= LEVELS_MAX; l++) {
+      double quarter = __dmul_rn(0.5, __dmul_rn(0.5, size));
+      kl = (kl << 3) | descend(p, c, quarter);
+      size = __dmul_rn(0.5, size);
+    }
+  }
+  hi[i] = kh;
+  if (lo) lo[i] = kl;
+  idx[i] = (int)i;
+}
+
+__global__ void gather_u64(const uint64_t *__restrict__ in, const int *__restrict__ idx, int64_t n,
+                           uint64_t *__restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[idx[i]];
+}
+
+// ---- K6a common levels --------------------------------------------------------------------------
+__device__ __forceinline__ int common_levels(uint64_t h0, uint64_t l0, uint64_t h1, uint64_t l1,
+                                             int levels) {
+  uint64_t x = h0 ^ h1;
+  if (x) return __clzll((long long)(x << 1)) / 3;
+  if (levels <= LEVELS_HI) return LEVELS_HI;
+  x = l0 ^ l1;
+  if (x) return LEVELS_HI + __clzll((long long)(x << 1)) / 3;
+  return LEVELS_MAX;
+}
+
+// cnt[p] = (cells opened at sorted position p) + 1 leaf;  clev[p] = c[p] (c[n-1] = -1)
+__global__ void levels_kernel(const uint64_t *__restrict__ hi, const uint64_t *__restrict__ lo,
+                              int64_t n, int levels, signed char *__restrict__ clev,
+                              int *__restrict__ cnt) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  int cprev = -1, c = -1;
+  if (p > 0) cprev = common_levels(hi[p - 1], lo ? lo[p - 1] : 0, hi[p], lo ? lo[p] : 0, levels);
+  if (p + 1 < n) c = common_levels(hi[p], lo ? lo[p] : 0, hi[p + 1], lo ? lo[p + 1] : 0, levels);
+  clev[p] = (signed char)c;
+  int open = c - cprev;
+  cnt[p] = (open > 0 ? open : 0) + 1;
+}
+
+// ---- K7 double-double moments -------------------------------------------------------------------
+struct DD4 {
+  double h[4];
+  double l[4];
+};
+__device__ __forceinline__ void dd_add(double ah, double al, double bh, double bl, double &rh,
+                                       double &rl) {
+  double s = __dadd_rn(ah, bh);
+  double bb = __dadd_rn(s, -ah);
+  double e = __dadd_rn(__dadd_rn(ah, -__dadd_rn(s, -bb)), __dadd_rn(bh, -bb));
+  e = __dadd_rn(e, __dadd_rn(al, bl));
+  rh = __dadd_rn(s, e);
+  rl = __dadd_rn(e, -__dadd_rn(rh, -s));
+}
+struct DD4Add {
+  __device__ __forceinline__ DD4 operator()(const DD4 &a, const DD4 &b) const {
+    DD4 r;
+#pragma unroll
+    for (int k = 0; k < 4; k++) dd_add(a.h[k], a.l[k], b.h[k], b.l[k], r.h[k], r.l[k]);
+    return r;
+  }
+};
+
+template <class Src>
+__global__ void moments_in_kernel(Src src, const int *__restrict__ idx, int64_t n,
+                                  DD4 *__restrict__ out /* n+1, out[0] = 0 */) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p > n) return;
+  DD4 r;
+  if (p == 0) {
+    for (int k = 0; k < 4; k++) r.h[k] = r.l[k] = 0.0;
+  } else {
+    int64_t j = idx[p - 1];
+    double x[3], m = src.m(j);
+    src.get(j, x[0], x[1], x[2]);
+    r.h[0] = m;
+    r.l[0] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      double pr = __dmul_rn(m, x[k]);
+      r.h[1 + k] = pr;
+      r.l[1 + k] = fma(m, x[k], -pr);
+    }
+  }
+  out[p] = r;
+}
+
+// ---- K6b emit -----------------------------------------------------------------------------------
+template <class Real> struct Vec4;
+template <> struct Vec4<double> { using type = double4; };
+template <> struct Vec4<float> { using type = float4; };
+
+template <class Real>
+struct Entries {
+  typename Vec4<Real>::type *com;  // (COM - origin, mass)
+  typename Vec4<Real>::type *cen;  // (centre - origin, side) ; side < 0 marks a leaf
+  int *skip;                       // pre-order index after this entry's subtree
+};
+
+__device__ __forceinline__ bool same_prefix(uint64_t h, uint64_t l, uint64_t h0, uint64_t l0,
+                                            int level) {
+  if (level <= LEVELS_HI) {
+    int sh = 3 * (LEVELS_HI - level);
+    return sh >= 64 ? true : ((h >> sh) == (h0 >> sh));  // level 0: sh = 63
+  }
+  if (h != h0) return false;
+  int sh = 3 * (LEVELS_MAX - level);
+  return (l >> sh) == (l0 >> sh);
+}
+
+template <class Src, class Real>
+__global__ void emit_kernel(Src src, const int *__restrict__ idx, const uint64_t *__restrict__ hi,
+                            const uint64_t *__restrict__ lo, const signed char *__restrict__ clev,
+                            const int *__restrict__ base /* n+1, exclusive scan of cnt */,
+                            const DD4 *__restrict__ P, int64_t n, const double *__restrict__ root,
+                            bool rel_origin, Entries<Real> E, int *__restrict__ maxlevel) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  using V4 = typename Vec4<Real>::type;
+  const double ox = rel_origin ? root[0] : 0.0, oy = rel_origin ? root[1] : 0.0,
+               oz = rel_origin ? root[2] : 0.0;
+  const int c = clev[p];
+  const int cprev = (p > 0) ? clev[p - 1] : -1;
+  const int64_t j = idx[p];
+  double x[3];
+  src.get(j, x[0], x[1], x[2]);
+  int e = base[p];
+  if (c > cprev) {
+    const uint64_t h0 = hi[p], l0 = lo ? lo[p] : 0;
+    double cc[3] = {root[0], root[1], root[2]};
+    double size = root[3];
+    int deepest = 0;
+    for (int level = 0; level <= c; level++) {
+      if (level > cprev) {
+        // this cell (level, centre cc, side size) starts at p.  Galloping + binary search for the
+        // last sorted particle b sharing `level` octant levels with p (p+1 does, since c >= level).
+        int64_t lo_i = p + 1, step = 1, hi_i;
+        for (;;) {
+          int64_t q = lo_i + step;
+          if (q >= n) { hi_i = n - 1; break; }
+          if (same_prefix(hi[q], lo ? lo[q] : 0, h0, l0, level)) { lo_i = q; step <<= 1; }
+          else { hi_i = q - 1; break; }
+        }
+        while (lo_i < hi_i) {
+          int64_t mid = (lo_i + hi_i + 1) >> 1;
+          if (same_prefix(hi[mid], lo ? lo[mid] : 0, h0, l0, level)) lo_i = mid;
+          else hi_i = mid - 1;
+        }
+        const int64_t b = lo_i;
+        double mh[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          double rh, rl;
+          dd_add(P[b + 1].h[k], P[b + 1].l[k], -P[p].h[k], -P[p].l[k], rh, rl);
+          mh[k] = rh;
+        }
+        V4 com, cen;
+        com.x = (Real)(mh[1] / mh[0] - ox);  // gravoct_finalize :477-479
+        com.y = (Real)(mh[2] / mh[0] - oy);
+        com.z = (Real)(mh[3] / mh[0] - oz);
+        com.w = (Real)mh[0];
+        cen.x = (Real)(cc[0] - ox);
+        cen.y = (Real)(cc[1] - oy);
+        cen.z = (Real)(cc[2] - oz);
+        cen.w = (Real)size;
+        E.com[e] = com;
+        E.cen[e] = cen;
+        E.skip[e] = base[b + 1];
+        e++;
+        deepest = level;
+      }
+      if (level < c) {  // descend one level along p's key (:406,:441-462)
+        const int l = level + 1;
+        unsigned d;
+        if (l <= LEVELS_HI) d = (unsigned)((h0 >> (3 * (LEVELS_HI - l))) & 7u);
+        else d = (unsigned)((l0 >> (3 * (LEVELS_MAX - l))) & 7u);
+        double quarter = __dmul_rn(0.5, __dmul_rn(0.5, size));
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+          cc[k] = __dadd_rn(cc[k], ((d >> k) & 1u) ? quarter : -quarter);
+        size = __dmul_rn(0.5, size);
+      }
+    }
+    atomicMax(maxlevel, deepest);
+  }
+  // the particle's own leaf: COM = particle position (:473-475), always accepted (:502)
+  V4 com, cen;
+  com.x = (Real)(x[0] - ox);
+  com.y = (Real)(x[1] - oy);
+  com.z = (Real)(x[2] - oz);
+  com.w = (Real)src.m(j);
+  cen.x = cen.y = cen.z = (Real)0;
+  cen.w = (Real)-1;
+  E.com[e] = com;
+  E.cen[e] = cen;
+  E.skip[e] = e + 1;
+}
+
+// ---- K8 walk ------------------------------------------------------------------------------------
+__device__ __forceinline__ double rsqrt64_t(double s) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
+  double t = s * y;
+  double e = fma(-t, y, 1.0);
+  double p = fma(0.375, e, 0.5);
+  double q = e * p;
+  return fma(y, q, y);
+}
+__device__ __forceinline__ double inv_cube(double s) {
+  double y = rsqrt64_t(s);
+  y = (s > 0.0) ? y : 0.0;  // _jbgrav.c:517-518
+  return y * y * y;
+}
+__device__ __forceinline__ float inv_cube(float s) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(s));
+  y = (s > 0.f) ? y : 0.f;
+  return y * y * y;
+}
+
+struct TargetsView {
+  const double *pos64;   // (ni,3) or null
+  const float4 *pos32;   // (ni) or null  (already relative to the f32 engine origin)
+  const int *order;      // sorted position -> local target index (null = identity)
+  int64_t order_offset;  // subtracted from order[] values (self case with a slice)
+};
+
+template <class Real, bool STATS>
+__global__ void __launch_bounds__(128)
+walk_kernel(Entries<Real> E, int nentries, TargetsView tv, int64_t ni,
+            const double *__restrict__ root, bool rel_origin, Real eps2, Real theta2, Epilogue ep,
+            unsigned long long *__restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t p = warp * 32 + lane;
+  const bool valid = p < ni;
+  int64_t ti = 0;
+  Real x = 0, y = 0, z = 0;
+  if (valid) {
+    ti = tv.order ? (int64_t)tv.order[p] - tv.order_offset : p;
+    if (tv.pos64) {
+      double ox = rel_origin ? root[0] : 0.0, oy = rel_origin ? root[1] : 0.0,
+             oz = rel_origin ? root[2] : 0.0;
+      x = (Real)(tv.pos64[3 * ti] - ox);
+      y = (Real)(tv.pos64[3 * ti + 1] - oy);
+      z = (Real)(tv.pos64[3 * ti + 2] - oz);
+    } else {
+      float4 t = tv.pos32[ti];
+      double ox = rel_origin ? root[0] : 0.0, oy = rel_origin ? root[1] : 0.0,
+             oz = rel_origin ? root[2] : 0.0;
+      x = (Real)((double)t.x - ox);
+      y = (Real)((double)t.y - oy);
+      z = (Real)((double)t.z - oz);
+    }
+  }
+  int until = valid ? 0 : INT_MAX;  // pre-order index up to which this lane has accepted an ancestor
+  Real ax = 0, ay = 0, az = 0;      // current accumulation block
+  double Ax = 0, Ay = 0, Az = 0;    // fp32 path: second-level fp64 accumulators
+  unsigned long long nacc = 0, nvis = 0;
+  int since_flush = 0;
+  int i = 0;
+  while (i < nentries) {
+    const auto cen = E.cen[i];
+    const auto com = E.com[i];
+    const int skip = E.skip[i];
+    const bool active = i >= until;
+    const Real dx = cen.x - x, dy = cen.y - y, dz = cen.z - z;
+    const Real d2 = dx * dx + dy * dy + dz * dz;
+    // (size / dist) < theta  <=>  size^2 < theta^2 dist^2 for size >= 0; leaves carry size < 0
+    const bool accept = (cen.w < (Real)0) || (cen.w * cen.w < theta2 * d2);
+    if (STATS && active) nvis++;
+    if (active && accept) {
+      const Real ex = com.x - x, ey = com.y - y, ez = com.z - z;
+      const Real s = ex * ex + ey * ey + ez * ez + eps2;
+      const Real w = com.w * inv_cube(s);
+      ax += w * ex;
+      ay += w * ey;
+      az += w * ez;
+      until = skip;
+      if (STATS) nacc++;
+    }
+    const bool open = active && !accept;
+    if (__any_sync(0xffffffffu, open)) i = i + 1;
+    else i = __reduce_min_sync(0xffffffffu, until);
+    if (sizeof(Real) == 4) {
+      if (++since_flush == 256) {
+        Ax += (double)ax; Ay += (double)ay; Az += (double)az;
+        ax = ay = az = 0;
+        since_flush = 0;
+      }
+    }
+  }
+  if (valid) {
+    double fx = (double)ax + Ax, fy = (double)ay + Ay, fz = (double)az + Az;
+    apply_epilogue(ep, ti, fx, fy, fz);
+  }
+  if (STATS) {
+    for (int o = 16; o > 0; o >>= 1) {
+      nacc += __shfl_down_sync(0xffffffffu, nacc, o);
+      nvis += __shfl_down_sync(0xffffffffu, nvis, o);
+    }
+    if (lane == 0) { atomicAdd(&stats[0], nacc); atomicAdd(&stats[1], nvis); }
+  }
+}
+
+// ---- workspace + orchestration --------------------------------------------------------------------
+struct TreeWorkspace {
+  DeviceBuffer root, part, hi, lo, hi2, lo2, idx, idx2, clev, cnt, base, P, Pin, cubtmp;
+  DeviceBuffer com, cen, skip, misc, thi, tidx, thi2, tidx2;
+  int64_t last_stats[5] = {0, 0, 0, 0, 0};
+  int *h_pinned = nullptr;  // [0] nentries, [1] maxlevel ; pinned for async readback
+  unsigned long long *h_stats = nullptr;
+};
+
+TreeWorkspace *tree_workspace_create() { return new TreeWorkspace(); }
+void tree_workspace_destroy(TreeWorkspace *w) {
+  if (!w) return;
+  DeviceBuffer *all[] = {&w->root, &w->part, &w->hi, &w->lo, &w->hi2, &w->lo2, &w->idx, &w->idx2,
+                         &w->clev, &w->cnt, &w->base, &w->P, &w->Pin, &w->cubtmp, &w->com, &w->cen,
+                         &w->skip, &w->misc, &w->thi, &w->tidx, &w->thi2, &w->tidx2};
+  for (auto *b : all) b->release();
+  if (w->h_pinned) cudaFreeHost(w->h_pinned);
+  if (w->h_stats) cudaFreeHost(w->h_stats);
+  delete w;
+}
+int tree_last_stats(TreeWorkspace *w, int64_t out[5]) {
+  for (int k = 0; k < 5; k++) out[k] = w->last_stats[k];
+  return GH_OK;
+}
+
+static inline unsigned nblk(int64_t n, int b) { return (unsigned)((n + b - 1) / b); }
+
+template <class Src, class Real>
+static int tree_impl(const TreeArgs &a, Src src, const float4 *tgt32, TreeWorkspace *w,
+                     cudaStream_t st, cudaEvent_t *ev) {
+  const int64_t n = a.nj, ni = a.ni;
+  if (n > (int64_t)INT_MAX / 48) { set_error("tree: too many particles (%lld)", (long long)n); return GH_EINVAL; }
+  const int levels = (sizeof(Real) == 8) ? LEVELS_MAX : LEVELS_HI;
+  const bool deep = levels > LEVELS_HI;
+  const bool rel_origin = (sizeof(Real) == 4);  // fp32 entries are stored relative to the root centre
+  if (!w->h_pinned) GH_CUDA(cudaMallocHost(&w->h_pinned, 4 * sizeof(int)));
+  if (!w->h_stats) GH_CUDA(cudaMallocHost(&w->h_stats, 2 * sizeof(unsigned long long)));
+
+  // K3
+  const int nb = (int)((n + 256 * 8 - 1) / (256 * 8) < 1024 ? (n + 256 * 8 - 1) / (256 * 8) : 1024);
+  GH_TRY(w->root.reserve(sizeof(double) * ROOT_DOUBLES));
+  GH_TRY(w->part.reserve(sizeof(double) * 6 * 1024));
+  GH_TRY(w->misc.reserve(64));
+  double *root = w->root.as<double>();
+  bbox_stage1<<<nb, 256, 0, st>>>(src, n, w->part.as<double>());
+  GH_LAUNCH_CHECK();
+  bbox_stage2<<<1, 256, 0, st>>>(w->part.as<double>(), nb, a.eps, root);
+  GH_LAUNCH_CHECK();
+
+  // K4
+  GH_TRY(w->hi.reserve(sizeof(uint64_t) * n));
+  GH_TRY(w->hi2.reserve(sizeof(uint64_t) * n));
+  GH_TRY(w->idx.reserve(sizeof(int) * n));
+  GH_TRY(w->idx2.reserve(sizeof(int) * n));
+  if (deep) {
+    GH_TRY(w->lo.reserve(sizeof(uint64_t) * n));
+    GH_TRY(w->lo2.reserve(sizeof(uint64_t) * n));
+  }
+  uint64_t *hi = w->hi.as<uint64_t>(), *hi2 = w->hi2.as<uint64_t>();
+  uint64_t *lo = deep ? w->lo.as<uint64_t>() : nullptr, *lo2 = deep ? w->lo2.as<uint64_t>() : nullptr;
+  int *idx = w->idx.as<int>(), *idx2 = w->idx2.as<int>();
+  keys_kernel<<<nblk(n, 256), 256, 0, st>>>(src, n, root, levels, hi, lo, idx);
+  GH_LAUNCH_CHECK();
+
+  // K5 (CUB radix sort; LSD over (lo, hi), stable)
+  size_t tmp_bytes = 0, tb;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, hi, hi2, idx, idx2, (int)n, 0, 63, st);
+  tb = 0;
+  cub::DeviceScan::InclusiveSum(nullptr, tb, (int *)nullptr, (int *)nullptr, (int)n + 1, st);
+  if (tb > tmp_bytes) tmp_bytes = tb;
+  tb = 0;
+  cub::DeviceScan::InclusiveScan(nullptr, tb, (DD4 *)nullptr, (DD4 *)nullptr, DD4Add(), (int)n + 1, st);
+  if (tb > tmp_bytes) tmp_bytes = tb;
+  GH_TRY(w->cubtmp.reserve(tmp_bytes));
+  void *tmp = w->cubtmp.ptr;
+  size_t tmpsz = w->cubtmp.bytes;
+  const uint64_t *shi, *slo = nullptr;
+  const int *sidx;
+  if (deep) {
+    // pass 1: by lo; pass 2: by hi gathered through the pass-1 order (stable)
+    GH_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmpsz, lo, lo2, idx, idx2, (int)n, 0, 63, st));
+    gather_u64<<<nblk(n, 256), 256, 0, st>>>(hi, idx2, n, hi2);
+    GH_LAUNCH_CHECK();
+    GH_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmpsz, hi2, hi, idx2, idx, (int)n, 0, 63, st));
+    // sorted: hi (keys), idx (order).  lo must be re-gathered from the unsorted lo... which pass 1
+    // left untouched in `lo` (SortPairs with separate in/out buffers does not modify its input).
+    gather_u64<<<nblk(n, 256), 256, 0, st>>>(lo, idx, n, lo2);
+    GH_LAUNCH_CHECK();
+    shi = hi; slo = lo2; sidx = idx;
+  } else {
+    GH_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmpsz, hi, hi2, idx, idx2, (int)n, 0, 63, st));
+    shi = hi2; sidx = idx2;
+  }
+
+  // K6a + scan
+  GH_TRY(w->clev.reserve(n));
+  GH_TRY(w->cnt.reserve(sizeof(int) * (n + 1)));
+  GH_TRY(w->base.reserve(sizeof(int) * (n + 1)));
+  signed char *clev = w->clev.as<signed char>();
+  int *cnt = w->cnt.as<int>(), *base = w->base.as<int>();
+  GH_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int), st));  // cnt is shifted by one: cnt[0] = 0
+  levels_kernel<<<nblk(n, 256), 256, 0, st>>>(shi, slo, n, levels, clev, cnt + 1);
+  GH_LAUNCH_CHECK();
+  GH_CUDA(cub::DeviceScan::InclusiveSum(tmp, tmpsz, cnt, base, (int)n + 1, st));  // base[p] = sum_{q<p}
+  GH_CUDA(cudaMemcpyAsync(&w->h_pinned[0], base + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+
+  // K7
+  GH_TRY(w->Pin.reserve(sizeof(DD4) * (n + 1)));
+  GH_TRY(w->P.reserve(sizeof(DD4) * (n + 1)));
+  moments_in_kernel<<<nblk(n + 1, 256), 256, 0, st>>>(src, sidx, n, w->Pin.as<DD4>());
+  GH_LAUNCH_CHECK();
+  GH_CUDA(cub::DeviceScan::InclusiveScan(tmp, tmpsz, w->Pin.as<DD4>(), w->P.as<DD4>(), DD4Add(),
+                                         (int)n + 1, st));
+
+  // entries: need the count on the host to size the arrays
+  GH_CUDA(cudaStreamSynchronize(st));
+  const int nentries = w->h_pinned[0];
+  using V4 = typename Vec4<Real>::type;
+  GH_TRY(w->com.reserve(sizeof(V4) * (size_t)nentries));
+  GH_TRY(w->cen.reserve(sizeof(V4) * (size_t)nentries));
+  GH_TRY(w->skip.reserve(sizeof(int) * (size_t)nentries));
+  Entries<Real> E{w->com.as<V4>(), w->cen.as<V4>(), w->skip.as<int>()};
+  int *maxlevel = w->misc.as<int>();
+  unsigned long long *dstats = reinterpret_cast<unsigned long long *>(w->misc.as<char>() + 16);
+  GH_CUDA(cudaMemsetAsync(w->misc.ptr, 0, 64, st));
+  emit_kernel<Src, Real><<<nblk(n, 128), 128, 0, st>>>(src, sidx, shi, slo, clev, base, w->P.as<DD4>(),
+                                                     n, root, rel_origin, E, maxlevel);
+  GH_LAUNCH_CHECK();
+
+  // targets: Morton order.  Self case: the source order restricted to the owned slice is the
+  // sorted order itself when the slice is everything; otherwise sort the targets' own keys.
+  TargetsView tv;
+  tv.pos64 = tgt32 ? nullptr : a.tgt_pos;
+  tv.pos32 = tgt32;
+  tv.order = nullptr;
+  tv.order_offset = 0;
+  if (a.targets_are_sources && ni == n) {
+    tv.order = sidx;
+  } else if (ni > 32) {
+    GH_TRY(w->thi.reserve(sizeof(uint64_t) * ni));
+    GH_TRY(w->thi2.reserve(sizeof(uint64_t) * ni));
+    GH_TRY(w->tidx.reserve(sizeof(int) * ni));
+    GH_TRY(w->tidx2.reserve(sizeof(int) * ni));
+    size_t need = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, need, w->thi.as<uint64_t>(), w->thi2.as<uint64_t>(),
+                                    w->tidx.as<int>(), w->tidx2.as<int>(), (int)ni, 0, 63, st);
+    GH_TRY(w->cubtmp.reserve(need > tmp_bytes ? need : tmp_bytes));
+    if (tgt32) {
+      Src32 ts{tgt32};
+      keys_kernel<<<nblk(ni, 256), 256, 0, st>>>(ts, ni, root, LEVELS_HI, w->thi.as<uint64_t>(),
+                                                (uint64_t *)nullptr, w->tidx.as<int>());
+    } else {
+      Src64 ts{a.tgt_pos, nullptr};
+      keys_kernel<<<nblk(ni, 256), 256, 0, st>>>(ts, ni, root, LEVELS_HI, w->thi.as<uint64_t>(),
+                                                (uint64_t *)nullptr, w->tidx.as<int>());
+    }
+    GH_LAUNCH_CHECK();
+    GH_CUDA(cub::DeviceRadixSort::SortPairs(w->cubtmp.ptr, w->cubtmp.bytes, w->thi.as<uint64_t>(),
+                                            w->thi2.as<uint64_t>(), w->tidx.as<int>(),
+                                            w->tidx2.as<int>(), (int)ni, 0, 63, st));
+    tv.order = w->tidx2.as<int>();
+  }
+
+  // K8
+  const Real eps2 = (Real)(a.eps * a.eps), theta2 = (Real)(a.theta * a.theta);
+  const int64_t nwarps = (ni + 31) / 32;
+  const unsigned blocks = (unsigned)((nwarps + 3) / 4);
+  if (ev) GH_CUDA(cudaEventRecord(ev[0], st));
+  if (a.want_stats)
+    walk_kernel<Real, true><<<blocks, 128, 0, st>>>(E, nentries, tv, ni, root, rel_origin, eps2, theta2,
+                                                   a.ep, dstats);
+  else
+    walk_kernel<Real, false><<<blocks, 128, 0, st>>>(E, nentries, tv, ni, root, rel_origin, eps2,
+                                                    theta2, a.ep, dstats);
+  GH_LAUNCH_CHECK();
+  if (ev) GH_CUDA(cudaEventRecord(ev[1], st));
+  GH_CUDA(cudaMemcpyAsync(&w->h_pinned[1], maxlevel, sizeof(int), cudaMemcpyDeviceToHost, st));
+  w->last_stats[0] = nentries;
+  w->last_stats[1] = nentries - n;
+  if (a.want_stats) {
+    GH_CUDA(cudaMemcpyAsync(w->h_stats, dstats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    GH_CUDA(cudaStreamSynchronize(st));
+    w->last_stats[2] = w->h_pinned[1];
+    w->last_stats[3] = (int64_t)w->h_stats[0];
+    w->last_stats[4] = (int64_t)w->h_stats[1];
+  }
+  return GH_OK;
+}
+
+int launch_tree(const TreeArgs &a, TreeWorkspace *w, cudaStream_t st, cudaEvent_t *ev) {
+  if (a.ni <= 0 || a.nj <= 0) return GH_OK;
+  if (a.prec == GH_PREC_F64) {
+    Src64 s{a.src_pos, a.src_mass};
+    return tree_impl<Src64, double>(a, s, nullptr, w, st, ev);
+  } else if (a.prec == GH_PREC_F32) {
+    if (a.src32) {  // f32 engine: sources and targets are float4 (x - origin, m)
+      Src32 s{a.src32};
+      return tree_impl<Src32, float>(a, s, a.tgt32, w, st, ev);
+    }
+    Src64 s{a.src_pos, a.src_mass};
+    return tree_impl<Src64, float>(a, s, nullptr, w, st, ev);
+  }
+  set_error("launch_tree: bad precision %d", a.prec);
+  return GH_EINVAL;
+}
+
+}  // namespace gh

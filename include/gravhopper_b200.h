@@ -1,0 +1,176 @@
+/*
+ * gravhopper_b200.h -- C ABI of libgravhopper_b200.so, the B200 (sm_100a) gravity engine that
+ * replaces GravHopper's C backend and step loop.
+ *
+ * What each entry point replaces in the reference (/root/reference, v1.2.0):
+ *
+ *   gh_direct_summation           gravhopper/_jbgrav.c:68-135   (wrapper) + :140-193 (workhorse)
+ *   gh_direct_summation_position  gravhopper/_jbgrav.c:200-294  (wrapper) + :299-353 (workhorse)
+ *   gh_tree_force                 gravhopper/_jbgrav.c:564-630  (wrapper) + :737-806, :360-558
+ *   gh_tree_force_position        gravhopper/_jbgrav.c:634-727  (wrapper) + :737-806, :360-558
+ *   gh_engine_*                   gravhopper/gravhopper.py:293-342 (Simulation.run / init_run),
+ *                                 :405-416 (perform_timestep, DKD leapfrog), :419-459
+ *                                 (calculate_acceleration incl. the external-force sum)
+ *
+ * Conventions (identical to the reference's _jbgrav level unless noted):
+ *   - positions are (N,3) row-major float64, masses (N,) float64, raw units kpc / Msun, G = 1;
+ *     accelerations come back as (N,3) row-major float64 in Msun/kpc^2;
+ *   - the engine works in GravHopper's internal units kpc, km/s, Msun, Myr (gravhopper.py:150-154)
+ *     and applies the two unit factors of jbgrav.py:48 and gravhopper.py:409 itself;
+ *   - `prec` selects the pair arithmetic: GH_PREC_F64 (reference-exact contract: <=1e-12) or
+ *     GH_PREC_F32 (fp32 pair maths, two-level fp32->fp64 accumulation: <=1e-5).  State, moments,
+ *     kick and drift are always float64;
+ *   - `mem` says where the caller's buffers live: GH_MEM_HOST (the library copies in and out) or
+ *     GH_MEM_DEVICE (pointers are CUDA device pointers on the current device, e.g. a torch
+ *     tensor's data_ptr(); nothing leaves the device);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the library's own stream / legacy
+ *     default).  With GH_MEM_DEVICE the call is asynchronous on that stream;
+ *   - every function returns 0 on success, a GH_E* code otherwise, and never calls exit();
+ *     gh_last_error() returns the calling thread's last message;
+ *   - inputs are never modified; the library never frees caller memory;
+ *   - one engine handle must be driven by one thread at a time; different handles are
+ *     independent.
+ *
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with
+ * GH_ECUDA.
+ */
+#ifndef GRAVHOPPER_B200_H
+#define GRAVHOPPER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GH_OK 0
+#define GH_EINVAL 1  /* bad argument (shape, precision, null pointer) */
+#define GH_ECUDA 2   /* CUDA runtime error or no device */
+#define GH_ENOMEM 3  /* allocation failed (the reference calls exit(209|435) here) */
+#define GH_ESTATE 4  /* engine used before upload, etc. */
+
+#define GH_PREC_F32 32
+#define GH_PREC_F64 64
+
+#define GH_MEM_HOST 0
+#define GH_MEM_DEVICE 1
+
+#define GH_ALG_DIRECT 0
+#define GH_ALG_TREE 1
+
+/* unit factors the engine applies (astropy CODATA-2018 definitions; jbgrav.py:40,48) */
+#define GH_C_ACC 4.398600412921223e-09           /* km/s/Myr per (Msun/kpc^2)  */
+#define GH_KPC_PER_KMS_MYR 1.022712165045695e-3  /* kpc per (km/s * Myr)       */
+#define GH_G 4.30091727003628e-06                /* kpc (km/s)^2 / Msun        */
+
+const char *gh_last_error(void);
+int gh_version(void);
+/* number of CUDA devices visible; *n = 0 and GH_ECUDA when there is none */
+int gh_device_count(int *n);
+
+/* ---- stateless force evaluation: the four _jbgrav entry points ---------------------------- */
+
+/* a_i = sum_{j != i} m_j (x_j - x_i) / (|x_j - x_i|^2 + eps^2)^{3/2}      (_jbgrav.c:140-193) */
+int gh_direct_summation(int prec, const double *pos, const double *mass, int64_t np, double eps,
+                        double *acc_out, int mem, void *stream);
+
+/* same at nf arbitrary target positions; a source exactly at a target with eps = 0 contributes
+ * zero (_jbgrav.c:299-353, zero guard :327-330) */
+int gh_direct_summation_position(int prec, const double *pos, const double *mass, int64_t np,
+                                 const double *force_pos, int64_t nf, double eps,
+                                 double *acc_out, int mem, void *stream);
+
+/* Barnes-Hut octree, one particle per leaf, monopole, opening test size/|x - cell centre| < theta
+ * (_jbgrav.c:487-541) on the octree the reference would build (_jbgrav.c:737-786). */
+int gh_tree_force(int prec, const double *pos, const double *mass, int64_t np, double eps,
+                  double theta, double *acc_out, int mem, void *stream);
+
+int gh_tree_force_position(int prec, const double *pos, const double *mass, int64_t np,
+                           const double *force_pos, int64_t nf, double eps, double theta,
+                           double *acc_out, int mem, void *stream);
+
+/* Statistics of the most recent tree evaluation made by the calling thread:
+ * out[0] = tree entries (cells + leaves), out[1] = cells, out[2] = deepest cell level,
+ * out[3] = accepted entries summed over targets, out[4] = visited entries summed over targets
+ * (out[3], out[4] only when the evaluation was made with gh_set_tree_stats(1)). */
+int gh_tree_last_stats(int64_t out[5]);
+int gh_set_tree_stats(int enable);
+
+/* ---- device-resident leapfrog engine: Simulation.run ------------------------------------- */
+
+typedef struct gh_engine gh_engine;
+
+/* Create an engine on CUDA device `device` for a system of n_total particles of which this
+ * engine integrates the targets [i_begin, i_begin + i_count) (single GPU: 0, n_total).
+ * All ranks of a multi-GPU run hold the full source set; see gh_engine_bind_sources. */
+int gh_engine_create(gh_engine **out, int device, int64_t n_total, int64_t i_begin,
+                     int64_t i_count, int prec);
+int gh_engine_destroy(gh_engine *e);
+
+/* Upload the state at a snapshot: pos/vel of the OWNED targets (i_count,3) in kpc and km/s, and
+ * the masses of ALL n_total particles in Msun (gravhopper.py:338-340).  Host pointers. */
+int gh_engine_upload(gh_engine *e, const double *pos, const double *vel, const double *mass_all);
+
+/* Multi-GPU only: use two caller-owned device buffers (e.g. torch tensors) as the double-buffered
+ * source array that an NCCL all-gather fills each step.  Layout per particle: 3 float64
+ * (x_half) for GH_PREC_F64, or one float4 (x_half - origin, mass) for GH_PREC_F32.  After
+ * upload, and after every gh_engine_step, the engine has written its own slice
+ * [i_begin, i_begin+i_count) of buffer gh_engine_source_index(); the caller all-gathers that
+ * buffer in place and then calls gh_engine_step. */
+int gh_engine_bind_sources(gh_engine *e, void *buf0, void *buf1);
+int gh_engine_source_index(gh_engine *e, int *idx);
+int gh_engine_source_stride_bytes(gh_engine *e, int64_t *bytes);
+
+/* Origin subtracted from positions before they are rounded to fp32 (GH_PREC_F32 engines only;
+ * default 0,0,0).  Every rank of a sharded run must set the same value. */
+int gh_engine_set_origin(gh_engine *e, const double origin[3]);
+
+/* Build x_half = x + ((0.5 v) dt) K for the next step from the current state
+ * (gravhopper.py:409) into the owned slice of source buffer gh_engine_source_index().  Single-GPU
+ * engines do this implicitly; sharded engines call it once after upload (and whenever dt
+ * changes), all-gather, then step. */
+int gh_engine_prepare(gh_engine *e, double dt);
+
+/* One DKD step (gravhopper.py:405-416): the sources hold x_half = x + 0.5 v dt; this computes
+ * a(x_half) [+ ext_acc], v += a dt, x = x_half + 0.5 v dt, and x_half of the NEXT step into the
+ * owned slice of the other source buffer (which becomes gh_engine_source_index()).
+ * ext_acc (nullable): (i_count,3) float64, km/s/Myr, the summed external accelerations the
+ * caller evaluated at x_half (gravhopper.py:455-457); ext_mem says where it lives.
+ * Asynchronous on the engine's stream. */
+int gh_engine_step(gh_engine *e, double dt, double eps, double theta, int algorithm,
+                   const double *ext_acc, int ext_mem);
+
+/* Single-GPU convenience: run nsteps steps back to back on the device.  Every `snapshot_every`
+ * steps (and always after the last one when snapshot_every > 0) the state is copied to
+ * pos_hist/vel_hist (host, (nsnap, i_count, 3) float64, row k = k-th snapshot taken); the copies
+ * overlap the following steps.  snapshot_every = 1 reproduces the reference's history arrays
+ * (gravhopper.py:330-336).  pos_hist/vel_hist may be NULL when snapshot_every = 0.
+ * Synchronous: returns when the last snapshot has landed. */
+int gh_engine_run(gh_engine *e, int64_t nsteps, double dt, double eps, double theta,
+                  int algorithm, int64_t snapshot_every, double *pos_hist, double *vel_hist);
+
+/* Copy the owned state (i_count,3)+(i_count,3) to host; synchronous. */
+int gh_engine_download(gh_engine *e, double *pos, double *vel);
+/* Copy the owned half-drifted positions x_half (i_count,3) to host (external-force hook). */
+int gh_engine_download_xhalf(gh_engine *e, double *xhalf);
+/* Change dt between steps: x_half is rebuilt from (x, v) with the new dt (= gh_engine_prepare). */
+int gh_engine_set_dt(gh_engine *e, double dt);
+/* Kinetic and potential energy (Msun (km/s)^2) of the owned targets against all sources, with the
+ * potential consistent with the softened force law; out = {KE, PE}.  Single GPU: the total. */
+int gh_engine_energy(gh_engine *e, double eps, double out[2]);
+int gh_engine_synchronize(gh_engine *e);
+/* Device pointers of the owned state, for zero-copy views (torch.from_dlpack-style) */
+int gh_engine_state_ptrs(gh_engine *e, double **pos_dev, double **vel_dev);
+/* The engine's cudaStream_t (as void*), e.g. to order an NCCL all-gather against the steps. */
+int gh_engine_stream(gh_engine *e, void **stream);
+/* Tree statistics of the engine's last tree step (layout as gh_tree_last_stats). */
+int gh_engine_tree_stats(gh_engine *e, int64_t out[5]);
+/* Kernel launches issued by this engine since creation (bench.py's gpu_launches). */
+int gh_engine_launch_count(gh_engine *e, int64_t *count);
+/* Device time (ms, CUDA events on the engine's stream) of the force kernel of the last step. */
+int gh_engine_last_force_ms(gh_engine *e, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

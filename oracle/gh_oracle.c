@@ -1,0 +1,436 @@
+/*
+ * gh_oracle.c -- CPU restatement of GravHopper's force path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * This file is the parity checker for gravhopper_b200.  It is NOT part of the product:
+ * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg
+ * may load it.  The product path (gravhopper_b200/) never imports, links or executes it.
+ *
+ * Every function restates, in plain C with the same IEEE-754 double operations in the same
+ * order, one function of the reference's C backend (/root/reference/gravhopper/_jbgrav.c,
+ * v1.2.0) or one method of its Python step loop (/root/reference/gravhopper/gravhopper.py).
+ * The restatement is pinned (tests/test_oracle.py, tests/golden/) against the reference's own
+ * compiled C extension (oracle/_ref, built from the untouched sources by oracle/Makefile):
+ * direct and tree results are BITWISE equal to the reference's on the golden inputs.
+ *
+ * Differences from the reference that do not change results:
+ *   - no O(N^2) scratch arrays (the reference stores every pair before summing; the values
+ *     summed, and their order, are identical -- see gho_direct below);
+ *   - 64-bit indices (the reference's int arithmetic overflows for N > 26,754);
+ *   - tree nodes come from one arena instead of one malloc each; OOM returns an error code
+ *     instead of exit(209|435);
+ *   - the per-target loops can run on several threads (OpenMP); each target's arithmetic is
+ *     untouched, so results do not depend on the thread count.
+ *
+ * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off; no -ffast-math, ever).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define GHO_OK 0
+#define GHO_ENOMEM 1
+#define GHO_EDEPTH 2
+
+static void gho_set_threads(int nthreads)
+{
+#ifdef _OPENMP
+	if (nthreads > 0) omp_set_num_threads(nthreads);
+#else
+	(void)nthreads;
+#endif
+}
+
+int gho_max_threads(void)
+{
+#ifdef _OPENMP
+	return omp_get_max_threads();
+#else
+	return 1;
+#endif
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Direct summation on the particles themselves.
+ * Follows directsummation_workhorse, _jbgrav.c:140-193.
+ *
+ * Reference pass 1 (:155-171) stores, for i<j, diff = x_i - x_j, dpos[i][j] = -diff,
+ * dpos[j][i] = +diff, and w = 1.0 / s / sqrt(s) with s = (((0+d0^2)+d1^2)+d2^2) + eps^2 for
+ * both (i,j) and (j,i).  -(x_i - x_j) == x_j - x_i exactly in IEEE arithmetic, and d^2 does
+ * not depend on the sign, so dpos[i][j] == x_j - x_i and w[i][j] == w[j][i] bit for bit
+ * whichever of i,j is smaller (only the sign of an exact zero can differ, which cannot
+ * change a sum that starts from +0.0 ... except to keep it +0.0; see test_oracle).
+ * Reference pass 2 (:174-185): acc starts at 0.0 and adds (mass[j]*dpos[i][j][k])*w[i][j]
+ * for j = 0..N-1, j != i, strictly in that order.  No zero guard (:166).
+ * ------------------------------------------------------------------------------------------ */
+int gho_direct(const double *pos, const double *mass, int64_t np, double eps, double *acc,
+               int nthreads)
+{
+	const double eps2 = eps * eps; /* :152 */
+	gho_set_threads(nthreads);
+#pragma omp parallel for schedule(static)
+	for (int64_t i = 0; i < np; i++) {
+		double a0 = 0.0, a1 = 0.0, a2 = 0.0; /* :177 */
+		const double xi = pos[3 * i], yi = pos[3 * i + 1], zi = pos[3 * i + 2];
+		for (int64_t j = 0; j < np; j++) {
+			if (i == j) continue; /* :179 */
+			/* value stored at dpos[i][j][k] (:160-161) */
+			double d0, d1, d2;
+			if (i < j) {
+				d0 = -(xi - pos[3 * j]);
+				d1 = -(yi - pos[3 * j + 1]);
+				d2 = -(zi - pos[3 * j + 2]);
+			} else {
+				d0 = pos[3 * j] - xi;
+				d1 = pos[3 * j + 1] - yi;
+				d2 = pos[3 * j + 2] - zi;
+			}
+			double dpos2 = 0.0; /* :157 */
+			dpos2 += d0 * d0;   /* :159,163 */
+			dpos2 += d1 * d1;
+			dpos2 += d2 * d2;
+			const double s = dpos2 + eps2;           /* :165 */
+			const double w = 1.0 / s / sqrt(s);      /* :166 */
+			const double m = mass[j];
+			a0 += m * d0 * w; /* :181-182, evaluated (m*d)*w */
+			a1 += m * d1 * w;
+			a2 += m * d2 * w;
+		}
+		acc[3 * i] = a0;
+		acc[3 * i + 1] = a1;
+		acc[3 * i + 2] = a2;
+	}
+	return GHO_OK;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Direct summation at arbitrary target positions.
+ * Follows directsummation_position_workhorse, _jbgrav.c:299-353: diff = target - source,
+ * stored value -diff (:318), zero guard s == 0.0 -> w = 0 (:327-330), no j is skipped
+ * (:343-346).
+ * ------------------------------------------------------------------------------------------ */
+int gho_direct_position(const double *pos, const double *mass, int64_t np, const double *fpos,
+                        int64_t nf, double eps, double *acc, int nthreads)
+{
+	const double eps2 = eps * eps; /* :311 */
+	gho_set_threads(nthreads);
+#pragma omp parallel for schedule(static)
+	for (int64_t i = 0; i < nf; i++) {
+		double a0 = 0.0, a1 = 0.0, a2 = 0.0; /* :342 */
+		const double xi = fpos[3 * i], yi = fpos[3 * i + 1], zi = fpos[3 * i + 2];
+		for (int64_t j = 0; j < np; j++) {
+			const double d0 = -(xi - pos[3 * j]); /* :316,318 */
+			const double d1 = -(yi - pos[3 * j + 1]);
+			const double d2 = -(zi - pos[3 * j + 2]);
+			double dpos2 = 0.0;
+			dpos2 += d0 * d0;
+			dpos2 += d1 * d1;
+			dpos2 += d2 * d2;
+			const double s = dpos2 + eps2; /* :321 */
+			double w;
+			if (s == 0.0) w = 0.0; /* :327-328 */
+			else w = 1.0 / s / sqrt(s); /* :330 */
+			const double m = mass[j];
+			a0 += m * d0 * w; /* :344-345 */
+			a1 += m * d1 * w;
+			a2 += m * d2 * w;
+		}
+		acc[3 * i] = a0;
+		acc[3 * i + 1] = a1;
+		acc[3 * i + 2] = a2;
+	}
+	return GHO_OK;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Barnes-Hut octree.  Node layout follows struct gravoct_node (_jbgrav.h:14-22); the fields
+ * the reference never reads (boxmin/boxmax, COMvalid) are dropped, child pointers are arena
+ * indices, and the leaf pointer is a particle index.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+	double center[3];
+	double size, halfsize;
+	double mass;
+	double firstmoment[3];
+	double COM[3];
+	int64_t branches[8]; /* -1 = NULL */
+	int64_t leaf;        /* particle index, -1 = NULL */
+	int empty;
+} gho_node;
+
+typedef struct {
+	gho_node *nodes;
+	int64_t n, cap;
+	const double *pos, *mass;
+	int err;
+	int64_t maxdepth;
+} gho_tree;
+
+/* gravoct_init, _jbgrav.c:360-384 */
+static int64_t gho_node_new(gho_tree *t, const double *center, double size)
+{
+	if (t->n == t->cap) {
+		int64_t ncap = t->cap * 2;
+		gho_node *nn = (gho_node *)realloc(t->nodes, sizeof(gho_node) * (size_t)ncap);
+		if (!nn) { t->err = GHO_ENOMEM; return -1; }
+		t->nodes = nn;
+		t->cap = ncap;
+	}
+	gho_node *r = &t->nodes[t->n];
+	r->size = size;            /* :366 */
+	r->halfsize = 0.5 * size;  /* :367 */
+	for (int i = 0; i < 3; i++) {
+		r->center[i] = center[i];
+		r->firstmoment[i] = 0.0;
+		r->COM[i] = 0.0;
+	}
+	for (int i = 0; i < 8; i++) r->branches[i] = -1;
+	r->mass = 0.0;
+	r->empty = 1;
+	r->leaf = -1;
+	return t->n++;
+}
+
+/* gravoct_calc_subnode + gravoct_calc_branchnum, _jbgrav.c:441-462: per axis +1 iff
+ * p > centre (strict); branch bit k set iff axis k is +. */
+static int gho_branch(const gho_node *nd, const double *p, int *subnode)
+{
+	int b = 0;
+	for (int i = 0; i < 3; i++) {
+		if (p[i] > nd->center[i]) { subnode[i] = 1; b += (1 << i); }
+		else subnode[i] = -1;
+	}
+	return b;
+}
+
+/* gravoct_add_particle, _jbgrav.c:387-437.  Recursion depth is capped (the reference
+ * recurses forever on coincident particles; we return GHO_EDEPTH instead of crashing). */
+#define GHO_MAXDEPTH 200
+static void gho_add(gho_tree *t, int64_t ni, int64_t p, int depth)
+{
+	if (t->err) return;
+	if (depth > GHO_MAXDEPTH) { t->err = GHO_EDEPTH; return; }
+	if (depth > t->maxdepth) t->maxdepth = depth;
+	const double *pp = &t->pos[3 * p];
+	const double pm = t->mass[p];
+	int subnode[3];
+	double subcenter[3];
+	gho_node *nd = &t->nodes[ni];
+	if (nd->empty) { /* :392-400 */
+		nd->empty = 0;
+		nd->leaf = p;
+		nd->mass = pm;
+		for (int i = 0; i < 3; i++) nd->firstmoment[i] = pm * pp[i];
+	} else if (nd->leaf >= 0) { /* :401-416 */
+		int64_t old = nd->leaf;
+		int bnum = gho_branch(nd, &t->pos[3 * old], subnode);
+		for (int i = 0; i < 3; i++) subcenter[i] = nd->center[i] + subnode[i] * 0.5 * nd->halfsize; /* :406 */
+		int64_t c = gho_node_new(t, subcenter, nd->halfsize); /* :409 */
+		if (c < 0) return;
+		nd = &t->nodes[ni]; /* arena may have moved */
+		nd->branches[bnum] = c;
+		gho_add(t, c, old, depth + 1); /* :410 */
+		nd = &t->nodes[ni];
+		nd->leaf = -1;                 /* :411 */
+		gho_add(t, ni, p, depth);      /* :413 */
+	} else { /* :417-436 */
+		int bnum = gho_branch(nd, pp, subnode);
+		if (nd->branches[bnum] >= 0) {
+			gho_add(t, nd->branches[bnum], p, depth + 1); /* :423 */
+		} else {
+			for (int i = 0; i < 3; i++) subcenter[i] = nd->center[i] + subnode[i] * 0.5 * nd->halfsize; /* :426-427 */
+			int64_t c = gho_node_new(t, subcenter, nd->halfsize);
+			if (c < 0) return;
+			nd = &t->nodes[ni];
+			nd->branches[bnum] = c;
+			gho_add(t, c, p, depth + 1); /* :430 */
+		}
+		nd = &t->nodes[ni];
+		nd->mass += pm; /* :432-435 */
+		for (int i = 0; i < 3; i++) nd->firstmoment[i] += pm * pp[i];
+	}
+}
+
+/* gravoct_finalize, _jbgrav.c:467-483, done eagerly for every node after the build (the
+ * reference does it lazily on first acceptance; same arithmetic, same value). */
+static void gho_finalize_all(gho_tree *t)
+{
+	for (int64_t k = 0; k < t->n; k++) {
+		gho_node *nd = &t->nodes[k];
+		if (nd->leaf >= 0) {
+			for (int i = 0; i < 3; i++) nd->COM[i] = t->pos[3 * nd->leaf + i]; /* :473-475 */
+		} else {
+			for (int i = 0; i < 3; i++) nd->COM[i] = nd->firstmoment[i] / nd->mass; /* :477-479 */
+		}
+	}
+}
+
+/* gravoct_calc_accel, _jbgrav.c:487-541.  counters[0] += accepted nodes, [1] += visited. */
+static void gho_accel(const gho_tree *t, int64_t ni, const double *pos, double eps, double theta,
+                      double *force, int64_t *counters)
+{
+	const gho_node *nd = &t->nodes[ni];
+	const double eps2 = eps * eps; /* :494 */
+	double node_dist = 0.0;
+	for (int i = 0; i < 3; i++)
+		node_dist += (nd->center[i] - pos[i]) * (nd->center[i] - pos[i]); /* :496-499 */
+	node_dist = sqrt(node_dist); /* :500 */
+	if (counters) counters[1]++;
+	if ((nd->leaf >= 0) || ((nd->size / node_dist) < theta)) { /* :502 */
+		double d_pos[3], dpos2 = 0.0, invdpos3;
+		for (int i = 0; i < 3; i++) {
+			double diff = nd->COM[i] - pos[i]; /* :508 */
+			d_pos[i] = diff;
+			dpos2 += diff * diff;
+		}
+		double s = dpos2 + eps2; /* :513 */
+		if (s == 0.0) invdpos3 = 0.0;          /* :517-518 */
+		else invdpos3 = 1.0 / s / sqrt(s);     /* :520 */
+		for (int i = 0; i < 3; i++) force[i] = d_pos[i] * nd->mass * invdpos3; /* :522-524 */
+		if (counters) counters[0]++;
+	} else {
+		double branchforce[3];
+		for (int i = 0; i < 3; i++) force[i] = 0.0; /* :527-529 */
+		for (int j = 0; j < 8; j++) { /* :530-537 */
+			if (nd->branches[j] >= 0) {
+				gho_accel(t, nd->branches[j], pos, eps, theta, branchforce, counters);
+				for (int i = 0; i < 3; i++) force[i] += branchforce[i];
+			}
+		}
+	}
+}
+
+/* treeforce_workhorse, _jbgrav.c:737-806.  stats (nullable) receives
+ * {nodes, max insert depth, accepted nodes summed over targets, visited nodes summed}. */
+int gho_tree_force(const double *pos, const double *mass, int64_t np, const double *fpos,
+                   int64_t nf, double eps, double theta, double *acc, int64_t *stats,
+                   int nthreads)
+{
+	double min[3], max[3], boxsize, boxcenter[3];
+	if (np < 1) return GHO_OK;
+	for (int i = 0; i < 3; i++) { min[i] = pos[i]; max[i] = min[i]; } /* :747-750 */
+	for (int64_t i = 1; i < np; i++) { /* :751-763 */
+		for (int j = 0; j < 3; j++) {
+			double q = pos[3 * i + j];
+			if (q < min[j]) min[j] = q;
+			if (q > max[j]) max[j] = q;
+		}
+	}
+	boxsize = max[0] - min[0] + eps; /* :764 */
+	for (int i = 1; i < 3; i++) {    /* :765-769: un-padded extent vs padded running value */
+		if ((max[i] - min[i]) > boxsize) boxsize = max[i] - min[i] + eps;
+	}
+	for (int i = 0; i < 3; i++) boxcenter[i] = 0.5 * (min[i] + max[i]); /* :770-772 */
+
+	gho_tree t;
+	t.cap = 2 * np + 64;
+	t.n = 0;
+	t.pos = pos;
+	t.mass = mass;
+	t.err = 0;
+	t.maxdepth = 0;
+	t.nodes = (gho_node *)malloc(sizeof(gho_node) * (size_t)t.cap);
+	if (!t.nodes) return GHO_ENOMEM;
+	int64_t root = gho_node_new(&t, boxcenter, boxsize); /* :775 */
+	for (int64_t i = 0; i < np && !t.err; i++) gho_add(&t, root, i, 0); /* :776-786 */
+	if (t.err) { free(t.nodes); return t.err; }
+	gho_finalize_all(&t);
+
+	int64_t acc_cnt = 0, vis_cnt = 0;
+	gho_set_threads(nthreads);
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : acc_cnt, vis_cnt)
+	for (int64_t i = 0; i < nf; i++) { /* :789-798 */
+		double f[3];
+		int64_t c[2] = {0, 0};
+		gho_accel(&t, root, &fpos[3 * i], eps, theta, f, c);
+		acc[3 * i] = f[0];
+		acc[3 * i + 1] = f[1];
+		acc[3 * i + 2] = f[2];
+		acc_cnt += c[0];
+		vis_cnt += c[1];
+	}
+	if (stats) { stats[0] = t.n; stats[1] = t.maxdepth; stats[2] = acc_cnt; stats[3] = vis_cnt; }
+	free(t.nodes); /* :801 */
+	return GHO_OK;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * One drift-kick-drift leapfrog step in the reference's internal units (kpc, km/s, Msun, Myr).
+ * Follows Simulation.perform_timestep, gravhopper.py:405-416, with the unit handling of
+ * jbgrav.py:38-48 made explicit:
+ *   x_half = x + ((0.5*v)*dt) * KPC_PER_KMS_MYR          (:409; astropy scales the product)
+ *   a      = C_ACC * force(x_half)  [+ ext]              (:413; jbgrav.py:48)
+ *   v_new  = v + a*dt                                    (:414)
+ *   x_new  = x_half + ((0.5*v_new)*dt) * KPC_PER_KMS_MYR (:416)
+ * algorithm: 0 = direct (gho_direct), 1 = tree (gho_tree_force on the particles themselves,
+ * theta as given; the reference always uses 0.7, gravhopper.py:446 + jbgrav.py:52).
+ * ext (nullable): extra acceleration (km/s/Myr) evaluated by the caller at x_half.
+ * xhalf_out (nullable) receives x_half.
+ * ------------------------------------------------------------------------------------------ */
+#define GHO_KPC_PER_KMS_MYR 1.022712165045695e-3
+#define GHO_C_ACC 4.398600412921223e-09
+
+void gho_half_drift(const double *x, const double *v, int64_t np, double dt, double *xhalf)
+{
+	for (int64_t q = 0; q < 3 * np; q++)
+		xhalf[q] = x[q] + ((0.5 * v[q]) * dt) * GHO_KPC_PER_KMS_MYR;
+}
+
+int gho_leapfrog_step(double *x, double *v, const double *mass, int64_t np, double dt, double eps,
+                      double theta, int algorithm, const double *ext, double *xhalf_out,
+                      int nthreads)
+{
+	double *xh = (double *)malloc(sizeof(double) * 3 * (size_t)np);
+	double *a = (double *)malloc(sizeof(double) * 3 * (size_t)np);
+	if (!xh || !a) { free(xh); free(a); return GHO_ENOMEM; }
+	int rc = GHO_OK;
+	gho_half_drift(x, v, np, dt, xh);
+	if (np > 1) { /* gravhopper.py:442 */
+		if (algorithm == 0) rc = gho_direct(xh, mass, np, eps, a, nthreads);
+		else rc = gho_tree_force(xh, mass, np, xh, np, eps, theta, a, NULL, nthreads);
+	} else {
+		for (int64_t q = 0; q < 3 * np; q++) a[q] = 0.0; /* gravhopper.py:449-450 */
+	}
+	if (rc == GHO_OK) {
+		for (int64_t q = 0; q < 3 * np; q++) {
+			double acc = a[q] * GHO_C_ACC;  /* jbgrav.py:48 */
+			if (ext) acc = acc + ext[q];    /* gravhopper.py:457 */
+			double vn = v[q] + acc * dt;    /* :414 */
+			v[q] = vn;
+			x[q] = xh[q] + ((0.5 * vn) * dt) * GHO_KPC_PER_KMS_MYR; /* :416 */
+		}
+		if (xhalf_out) memcpy(xhalf_out, xh, sizeof(double) * 3 * (size_t)np);
+	}
+	free(xh);
+	free(a);
+	return rc;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Energy diagnostic.  The reference has no energy routine; this is the energy consistent with
+ * its force law (_jbgrav.c:165-166): KE = 1/2 sum m v^2, PE = -G sum_{i<j} m_i m_j /
+ * sqrt(r_ij^2 + eps^2), G = 4.30091727003628e-06 kpc (km/s)^2 / Msun.  out = {KE, PE}.
+ * ------------------------------------------------------------------------------------------ */
+#define GHO_G 4.30091727003628e-06
+void gho_energy(const double *x, const double *v, const double *mass, int64_t np, double eps,
+                double *out, int nthreads)
+{
+	double ke = 0.0, pe = 0.0;
+	const double eps2 = eps * eps;
+	gho_set_threads(nthreads);
+#pragma omp parallel for schedule(dynamic, 16) reduction(+ : ke, pe)
+	for (int64_t i = 0; i < np; i++) {
+		ke += 0.5 * mass[i] * (v[3 * i] * v[3 * i] + v[3 * i + 1] * v[3 * i + 1] + v[3 * i + 2] * v[3 * i + 2]);
+		double p = 0.0;
+		for (int64_t j = i + 1; j < np; j++) {
+			double d0 = x[3 * j] - x[3 * i], d1 = x[3 * j + 1] - x[3 * i + 1], d2 = x[3 * j + 2] - x[3 * i + 2];
+			p += mass[j] / sqrt(d0 * d0 + d1 * d1 + d2 * d2 + eps2);
+		}
+		pe -= GHO_G * mass[i] * p;
+	}
+	out[0] = ke;
+	out[1] = pe;
+}
