@@ -45,11 +45,12 @@ struct Tile32 {
   float2 c[BLOCK / 2];  // (e0, e1)
 };
 
-template <int BLOCK>
+template <int BLOCK, int MODE>
 __device__ __forceinline__ void store_tile32(Tile32<BLOCK> &t, int tid, float4 g, float eps2) {
   // g = (x, y, z, m); m == 0 (padding or a massless tracer) contributes exactly zero
   float s = g.w > 0.f ? rsqrtf(g.w) : 0.f;
   float e = g.w > 0.f ? eps2 * s * s : 1.f;
+  if (MODE == 0) { s = 1.f; e = 0.f; }
   float *pa = reinterpret_cast<float *>(&t.a[tid >> 1]);
   float *pb = reinterpret_cast<float *>(&t.b[tid >> 1]);
   float *pc = reinterpret_cast<float *>(&t.c[tid >> 1]);
@@ -57,11 +58,15 @@ __device__ __forceinline__ void store_tile32(Tile32<BLOCK> &t, int tid, float4 g
   pa[h] = g.x * s;
   pa[2 + h] = g.y * s;
   pb[h] = g.z * s;
-  pb[2 + h] = s;
-  pc[h] = e;
+  pb[2 + h] = (MODE == 0) ? g.w : s;
+  if (MODE != 0) pc[h] = e;
 }
 
-template <int BLOCK, int KI, bool GUARD>
+// MODE 0: tile holds (x, y, z, m); d = x_j - x_i (FADD2), w = m r^3 (3 FMUL2): 12 FP32 ops.
+// MODE 1: per-source scaling described above: 11 FP32 ops, but d' of a source that coincides
+//         with the target is a rounding residue instead of an exact zero -> only usable when
+//         the caller knows targets never coincide with sources (kept for measurement).
+template <int BLOCK, int KI, bool GUARD, int MODE>
 __global__ void __launch_bounds__(BLOCK)
 direct_f32_kernel(const float4 *__restrict__ src, int64_t nj, const float4 *__restrict__ tgt,
                   int64_t ni, float eps2, int64_t jchunk, double *__restrict__ partial,
@@ -89,7 +94,7 @@ direct_f32_kernel(const float4 *__restrict__ src, int64_t nj, const float4 *__re
   {
     int64_t j = jb + tid;
     float4 g = (j < je) ? src[j] : zero4;
-    store_tile32<BLOCK>(tile[0], tid, g, eps2);
+    store_tile32<BLOCK, MODE>(tile[0], tid, g, eps2);
   }
   __syncthreads();
 
@@ -109,14 +114,23 @@ direct_f32_kernel(const float4 *__restrict__ src, int64_t nj, const float4 *__re
     for (int p = 0; p < BLOCK / 2; p++) {
       const float4 A = T.a[p];
       const float4 B = T.b[p];
-      const float2 e = T.c[p];
       const float2 xj = make_float2(A.x, A.y), yj = make_float2(A.z, A.w);
       const float2 zj = make_float2(B.x, B.y), s = make_float2(B.z, B.w);
+      float2 e;
+      if (MODE == 0) e = make_float2(eps2, eps2);
+      else e = T.c[p];
 #pragma unroll
       for (int k = 0; k < KI; k++) {
-        float2 dx = __ffma2_rn(nx[k], s, xj);
-        float2 dy = __ffma2_rn(ny[k], s, yj);
-        float2 dz = __ffma2_rn(nz[k], s, zj);
+        float2 dx, dy, dz;
+        if (MODE == 0) {
+          dx = __fadd2_rn(xj, nx[k]);
+          dy = __fadd2_rn(yj, ny[k]);
+          dz = __fadd2_rn(zj, nz[k]);
+        } else {
+          dx = __ffma2_rn(nx[k], s, xj);
+          dy = __ffma2_rn(ny[k], s, yj);
+          dz = __ffma2_rn(nz[k], s, zj);
+        }
         float2 q = __ffma2_rn(dx, dx, e);
         q = __ffma2_rn(dy, dy, q);
         q = __ffma2_rn(dz, dz, q);
@@ -130,6 +144,7 @@ direct_f32_kernel(const float4 *__restrict__ src, int64_t nj, const float4 *__re
         }
         float2 r2 = __fmul2_rn(r, r);
         float2 r3 = __fmul2_rn(r2, r);
+        if (MODE == 0) r3 = __fmul2_rn(r3, s);  // s holds the masses in MODE 0
         fx[k] = __ffma2_rn(r3, dx, fx[k]);
         fy[k] = __ffma2_rn(r3, dy, fy[k]);
         fz[k] = __ffma2_rn(r3, dz, fz[k]);
@@ -141,7 +156,7 @@ direct_f32_kernel(const float4 *__restrict__ src, int64_t nj, const float4 *__re
       ay[k] += (double)(fy[k].x + fy[k].y);
       az[k] += (double)(fz[k].x + fz[k].y);
     }
-    if (more) store_tile32<BLOCK>(tile[(t + 1) & 1], tid, g, eps2);
+    if (more) store_tile32<BLOCK, MODE>(tile[(t + 1) & 1], tid, g, eps2);
     __syncthreads();
   }
 
@@ -314,12 +329,16 @@ static int run_f32(const DirectArgs &a, DeviceBuffer &ws, cudaStream_t st, cudaE
   dim3 grid(sp.itiles, sp.S);
   float eps2 = (float)(a.eps * a.eps);
   if (ev) GH_CUDA(cudaEventRecord(ev[0], st));
+  const int mode = env_int("GH_F32_MODE", 0);
   if (a.eps == 0.0)
-    direct_f32_kernel<BLOCK, KI, true><<<grid, BLOCK, 0, st>>>(a.src32, a.nj, a.tgt32, a.ni, eps2,
-                                                              sp.jchunk, partial, a.ep);
+    direct_f32_kernel<BLOCK, KI, true, 0><<<grid, BLOCK, 0, st>>>(a.src32, a.nj, a.tgt32, a.ni, eps2,
+                                                                 sp.jchunk, partial, a.ep);
+  else if (mode == 1)
+    direct_f32_kernel<BLOCK, KI, false, 1><<<grid, BLOCK, 0, st>>>(a.src32, a.nj, a.tgt32, a.ni, eps2,
+                                                                  sp.jchunk, partial, a.ep);
   else
-    direct_f32_kernel<BLOCK, KI, false><<<grid, BLOCK, 0, st>>>(a.src32, a.nj, a.tgt32, a.ni, eps2,
-                                                               sp.jchunk, partial, a.ep);
+    direct_f32_kernel<BLOCK, KI, false, 0><<<grid, BLOCK, 0, st>>>(a.src32, a.nj, a.tgt32, a.ni, eps2,
+                                                                  sp.jchunk, partial, a.ep);
   GH_LAUNCH_CHECK();
   if (ev) GH_CUDA(cudaEventRecord(ev[1], st));
   if (partial) {

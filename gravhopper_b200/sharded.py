@@ -1,0 +1,180 @@
+"""Multi-GPU leapfrog: one process per GPU (torchrun), targets sharded evenly, sources all-gathered.
+
+SURVEY 8(e): the force on target i needs every source j, so each rank owns the state of a
+contiguous slice of particles, and each step ONE collective -- an in-place NCCL all-gather of the
+half-drifted positions over NVLink/NVSwitch -- gives every rank the full source array.  Direct
+summation then tiles all sources against the rank's own targets; the tree is built redundantly on
+every rank from the gathered sources and walked for the rank's own targets.  No reduction is
+needed: each rank produces final accelerations, kicks and drifts for its own particles.
+
+The source array is double buffered (two torch tensors bound into the engine with
+gh_engine_bind_sources): while step n reads buffer b, its epilogue writes the rank's slice of
+x_half(n+1) into buffer b^1, which the next all-gather completes.  Per step and rank the exchange
+moves N*24 B (fp64: x_half as 3 float64) or N*16 B (fp32: float4 x_half-origin, mass).
+
+``ShardedSimulation`` holds only host logic; the per-rank compute object (``CudaShard``) is the
+C-ABI engine.  Tests drive the same host logic over gloo on CPU with a stand-in shard.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def partition(n, world):
+    """Contiguous even split of n particles over `world` ranks: list of (begin, count).
+    The first n % world ranks get one extra particle."""
+    if world < 1 or n < world:
+        raise ValueError("need at least one particle per rank (n=%d, world=%d)" % (n, world))
+    base, rem = divmod(n, world)
+    out, b = [], 0
+    for r in range(world):
+        c = base + (1 if r < rem else 0)
+        out.append((b, c))
+        b += c
+    return out
+
+
+class CudaShard(object):
+    """One rank's gh_engine over torch-owned source buffers."""
+
+    def __init__(self, n_total, begin, count, precision, device):
+        import torch
+        self.torch = torch
+        self.n, self.begin, self.count = n_total, begin, count
+        self.precision = precision
+        self.device = torch.device("cuda", device)
+        self.lib = _lib.lib()
+        _lib.require_gpu()
+        h = C.c_void_p()
+        prec = _lib.GH_PREC_F64 if precision == "fp64" else _lib.GH_PREC_F32
+        _lib.check(self.lib.gh_engine_create(C.byref(h), device, n_total, begin, count, prec),
+                   "gh_engine_create")
+        self.h = h
+        cols, dtype = (3, torch.float64) if precision == "fp64" else (4, torch.float32)
+        self.bufs = [torch.zeros((n_total, cols), dtype=dtype, device=self.device) for _ in range(2)]
+        torch.cuda.synchronize(self.device)
+        _lib.check(self.lib.gh_engine_bind_sources(self.h, C.c_void_p(self.bufs[0].data_ptr()),
+                                                   C.c_void_p(self.bufs[1].data_ptr())),
+                   "gh_engine_bind_sources")
+        s = C.c_void_p()
+        _lib.check(self.lib.gh_engine_stream(self.h, C.byref(s)))
+        self.stream = torch.cuda.ExternalStream(s.value, device=self.device)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gh_engine_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def upload(self, pos_own, vel_own, mass_all, origin):
+        pos_own = np.ascontiguousarray(pos_own, dtype=np.float64)
+        vel_own = np.ascontiguousarray(vel_own, dtype=np.float64)
+        mass_all = np.ascontiguousarray(mass_all, dtype=np.float64)
+        origin = np.ascontiguousarray(origin, dtype=np.float64)
+        _lib.check(self.lib.gh_engine_set_origin(self.h, origin.ctypes.data_as(C.POINTER(C.c_double))))
+        _lib.check(self.lib.gh_engine_upload(self.h, C.c_void_p(pos_own.ctypes.data),
+                                             C.c_void_p(vel_own.ctypes.data),
+                                             C.c_void_p(mass_all.ctypes.data)), "gh_engine_upload")
+
+    def prepare(self, dt):
+        _lib.check(self.lib.gh_engine_prepare(self.h, dt), "gh_engine_prepare")
+
+    def source_index(self):
+        i = C.c_int()
+        _lib.check(self.lib.gh_engine_source_index(self.h, C.byref(i)))
+        return i.value
+
+    def step(self, dt, eps, theta, alg):
+        _lib.check(self.lib.gh_engine_step(self.h, dt, eps, theta, alg, None, _lib.GH_MEM_HOST),
+                   "gh_engine_step")
+
+    def download(self):
+        pos = np.empty((self.count, 3))
+        vel = np.empty((self.count, 3))
+        _lib.check(self.lib.gh_engine_download(self.h, C.c_void_p(pos.ctypes.data),
+                                               C.c_void_p(vel.ctypes.data)), "gh_engine_download")
+        return pos, vel
+
+    def synchronize(self):
+        _lib.check(self.lib.gh_engine_synchronize(self.h))
+
+    def launches(self):
+        n = C.c_int64()
+        _lib.check(self.lib.gh_engine_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def last_force_ms(self):
+        ms = C.c_float()
+        _lib.check(self.lib.gh_engine_last_force_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def stream_context(self):
+        return self.torch.cuda.stream(self.stream)
+
+
+class ShardedSimulation(object):
+    """Leapfrog over `world` ranks.  Every rank constructs it with the FULL initial conditions
+    (host arrays; synthetic ICs are generated identically on every rank) and keeps its slice."""
+
+    def __init__(self, pos, vel, mass, dt, eps, algorithm="direct", theta=0.7, precision="fp64",
+                 rank=0, world=1, device=0, group=None, shard_factory=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.rank, self.world, self.group = rank, world, group
+        self.n = int(np.shape(pos)[0])
+        self.parts = partition(self.n, world)
+        self.begin, self.count = self.parts[rank]
+        self.dt, self.eps, self.theta = float(dt), float(eps), float(theta)
+        if algorithm not in ("direct", "tree"):
+            raise ValueError("algorithm must be 'tree' or 'direct'.")
+        self.alg = _lib.GH_ALG_DIRECT if algorithm == "direct" else _lib.GH_ALG_TREE
+        self.uneven = len(set(c for _, c in self.parts)) > 1
+        factory = shard_factory or (lambda n, b, c: CudaShard(n, b, c, precision, device))
+        self.shard = factory(self.n, self.begin, self.count)
+        pos = np.asarray(pos, dtype=np.float64)
+        origin = pos.mean(axis=0)  # identical on every rank: all ranks hold the same ICs
+        sl = slice(self.begin, self.begin + self.count)
+        self.shard.upload(pos[sl], np.asarray(vel, dtype=np.float64)[sl], mass, origin)
+        self.shard.prepare(self.dt)
+        self.steps_done = 0
+
+    def _all_gather(self, buf):
+        """In-place all-gather: every rank contributes rows [begin, begin+count) of `buf`."""
+        if self.world == 1:
+            return
+        if not self.uneven:
+            own = buf[self.begin:self.begin + self.count]
+            self.dist.all_gather_into_tensor(buf, own, group=self.group)
+        else:
+            # uneven split (n % world != 0): one broadcast per owner; works on every backend
+            for r, (b, c) in enumerate(self.parts):
+                src = r if self.group is None else self.dist.get_global_rank(self.group, r)
+                self.dist.broadcast(buf[b:b + c], src=src, group=self.group)
+
+    def step(self):
+        buf = self.shard.bufs[self.shard.source_index()]
+        with self.shard.stream_context():
+            self._all_gather(buf)
+        self.shard.step(self.dt, self.eps, self.theta, self.alg)
+        self.steps_done += 1
+
+    def run(self, nsteps):
+        for _ in range(int(nsteps)):
+            self.step()
+
+    def local_state(self):
+        return self.shard.download()
+
+    def gather_state(self):
+        """Full (pos, vel) on every rank (host arrays) -- output cadence only."""
+        import torch
+        pos, vel = self.shard.download()
+        if self.world == 1:
+            return pos, vel
+        objs = [None] * self.world
+        self.dist.all_gather_object(objs, (pos, vel), group=self.group)
+        return (np.concatenate([o[0] for o in objs], axis=0),
+                np.concatenate([o[1] for o in objs], axis=0))

@@ -63,17 +63,19 @@ def time_dev(fn, n_iter=3):
 
 for N in (65536, 262144, 1048576):
     p, v, m = ic_raw.Plummer(N, 1e-3, 1e6, seed=42)
-    tp = torch.from_numpy(p).cuda(); tm = torch.from_numpy(m).cuda()
+    tp = torch.from_numpy(np.ascontiguousarray(p)).cuda(); tm = torch.from_numpy(m).cuda()
     for prec in ("fp32", "fp64"):
         if prec == "fp64" and N > 262144:
             continue
-        for ki in ([1, 2, 4, 8] if prec == "fp32" else [1, 2, 4]):
+        for mode in ([0, 1] if prec == "fp32" else [0]):
+          os.environ["GH_F32_MODE"] = str(mode)
+          for ki in ([1, 2, 4, 8] if prec == "fp32" else [1, 2, 4]):
             os.environ["GH_F32_KI" if prec == "fp32" else "GH_F64_KI"] = str(ki)
             ms = time_dev(lambda: J.direct_summation(tp, tm, 5e-5, precision=prec), 2)
             rate = N * N / (ms * 1e-3)
-            out["direct_%s_N%d_ki%d" % (prec, N, ki)] = dict(ms=ms, inter_per_s=rate, tflops20=rate * 20 / 1e12)
-            print("direct", prec, N, "ki", ki, "%.3f ms" % ms, "%.3e int/s" % rate, "%.1f TF(20)" % (rate * 20 / 1e12), flush=True)
-        os.environ.pop("GH_F32_KI", None); os.environ.pop("GH_F64_KI", None)
+            out["direct_%s_N%d_ki%d_mode%d" % (prec, N, ki, mode)] = dict(ms=ms, inter_per_s=rate, tflops20=rate * 20 / 1e12)
+            print("direct", prec, N, "mode", mode, "ki", ki, "%.3f ms" % ms, "%.3e int/s" % rate, "%.1f TF(20)" % (rate * 20 / 1e12), flush=True)
+        os.environ.pop("GH_F32_KI", None); os.environ.pop("GH_F64_KI", None); os.environ.pop("GH_F32_MODE", None)
     for prec in ("fp32", "fp64"):
         ms = time_dev(lambda: J.tree_force(tp, tm, 5e-5, 0.7, precision=prec), 2)
         out["tree_%s_N%d" % (prec, N)] = dict(ms=ms, part_per_s=N / (ms * 1e-3))
