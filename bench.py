@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path's headline number on B200, one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload direct|tree] [--impl reference]
+
+Default workload (BASELINE.json configs[2], the configuration the metric and the north_star
+target are quoted on): Plummer sphere N = 1,048,576, direct summation, fp32 pair arithmetic,
+one full DKD leapfrog step per "step" (force on all N particles from all N + kick + drift, state
+resident in HBM).  metric = pairwise interactions/s = N^2 per step.  With --gpus N > 1 (launched
+by torchrun, one rank per GPU) the targets are sharded N/P per rank and each step all-gathers the
+half-drifted positions (strong scaling: the total work is fixed).
+
+--workload tree: BASELINE.json configs[3]: Hernquist N = 4,194,304, Barnes-Hut theta = 0.7, fp32
+walk; metric = particle-steps/s.
+
+--impl reference: times the reference's own CPU implementation of the same path
+(oracle/_ref = the unmodified /root/reference/gravhopper/_jbgrav.c compiled by oracle/Makefile;
+falls back to the oracle port) on the host cores, on a bounded sample of the workload.
+
+Keys follow the driver's contract: value = whole-job throughput with inputs resident in HBM;
+e2e = the same metric through the public call with HOST buffers (pinned), H2D and D2H inside the
+timed region; roofline = the dominant kernel against the FP32 FMA peak (this path is FMA-pipe
+bound, not HBM or tensor bound: SURVEY 8d); cpu_baseline = reference C timed beside it.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+N_DIRECT = 1 << 20
+N_TREE = 1 << 22
+FLOP_PER_INTERACTION = 20  # north_star / GPU-Gems-3 convention
+SM_COUNT = 148
+FP32_LANES_PER_SM = 128
+
+
+def workload(kind):
+    from gravhopper_b200 import ic_raw
+    if kind == "direct":
+        x, v, m = ic_raw.Plummer(N_DIRECT, 1e-3, 1e6, seed=42)
+        return dict(x=np.ascontiguousarray(x), v=np.ascontiguousarray(v), m=m, eps=5e-5, dt=0.005,
+                    theta=0.7, alg="direct", prec="fp32",
+                    name="Plummer N=1048576 b=1pc M=1e6Msun eps=0.05pc dt=0.005Myr, direct summation fp32, "
+                         "1 DKD leapfrog step (BASELINE.json configs[2])")
+    x, v, m = ic_raw.Hernquist(N_TREE, 1.0, 1e10, seed=42)
+    return dict(x=np.ascontiguousarray(x), v=np.ascontiguousarray(v), m=m, eps=0.05, dt=1.0, theta=0.7,
+                alg="tree", prec="fp32",
+                name="Hernquist N=4194304 a=1kpc M=1e10Msun eps=0.05kpc dt=1Myr, Barnes-Hut theta=0.7 fp32 walk, "
+                     "1 DKD leapfrog step (BASELINE.json configs[3])")
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.p is None:
+            return None
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        for r in self.rows:
+            f = [c.strip() for c in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(power)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except ValueError:
+            pass
+    return {}
+
+
+def cpu_baseline_direct(w, seconds_target=12.0):
+    """Reference C (oracle/_ref) on ONE core (the reference is single threaded), bounded sample:
+    nf targets x all N sources through direct_summation_position (the only reference
+    entry point that can run at N = 2^20)."""
+    from oracle import oracle as O
+    ref = O.ref()
+    n = len(w["m"])
+    nf = 192  # 32*nf*np bytes of scratch inside the reference = 6.4 GB at N = 2^20
+    if ref is not None:
+        fn, kind = (lambda t: ref.direct_summation_position(w["x"], w["m"], t, w["eps"])), "reference"
+    else:
+        fn, kind = (lambda t: O.direct_summation_position(w["x"], w["m"], t, w["eps"], nthreads=1)), "port"
+    t0 = time.perf_counter()
+    fn(w["x"][:8])
+    est = (time.perf_counter() - t0) / 8
+    nf = int(max(16, min(nf, seconds_target / max(est, 1e-9))))
+    t0 = time.perf_counter()
+    fn(w["x"][:nf])
+    dt = time.perf_counter() - t0
+    return {"value": nf * n / dt, "unit": "interactions/s", "cores": 1, "kind": kind,
+            "sample": "%d targets x %d sources, direct_summation_position, %.1f s" % (nf, n, dt)}
+
+
+def cpu_baseline_tree(w, ntargets=16384):
+    from oracle import oracle as O
+    ref = O.ref()
+    sel = np.random.default_rng(0).choice(len(w["m"]), ntargets, replace=False)
+    t0 = time.perf_counter()
+    if ref is not None:
+        ref.tree_force_position(w["x"], w["m"], w["x"][sel], w["eps"], w["theta"])
+        kind = "reference"
+    else:
+        O.tree_force_position(w["x"], w["m"], w["x"][sel], w["eps"], w["theta"], nthreads=1)
+        kind = "port"
+    dt = time.perf_counter() - t0
+    # one evaluation = build (all N) + walk (sampled targets); extrapolate the walk to all N targets
+    return {"value": ntargets / dt, "unit": "particle-steps/s", "cores": 1, "kind": kind,
+            "sample": "tree build over %d sources + walk of %d targets, %.1f s (build included once)"
+                      % (len(w["m"]), ntargets, dt)}
+
+
+_W = None  # workload shared with forked reference workers (no per-step pickling of the sources)
+
+
+def _ref_worker(args):
+    kind, targets = args
+    x, m, eps, theta = _W["x"], _W["m"], _W["eps"], _W["theta"]
+    from oracle import oracle as O
+    ref = O.ref()
+    if kind == "direct":
+        if ref is not None:
+            ref.direct_summation_position(x, m, targets, eps)
+        else:
+            O.direct_summation_position(x, m, targets, eps, nthreads=1)
+    else:
+        if ref is not None:
+            ref.tree_force_position(x, m, targets, eps, theta)
+        else:
+            O.tree_force_position(x, m, targets, eps, theta, nthreads=1)
+    return len(targets)
+
+
+def run_reference(args):
+    """--impl reference: the reference C backend on all host cores (P processes, each evaluating a
+    slice of targets against all sources -- the only way the single-threaded reference can use
+    more than one core)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from oracle import oracle as O
+    global _W
+    w = workload(args.workload)
+    _W = w
+    n = len(w["m"])
+    cores = os.cpu_count() or 1
+    P = max(1, min(cores, 32))
+    kind = "reference" if O.ref() is not None else "port"
+    if args.workload == "direct":
+        per = 24  # targets per process per step: ~1.3 s of reference C, 0.8 GB scratch each
+    else:
+        per = 2048
+    rng = np.random.default_rng(1)
+    ctx = mp.get_context("fork")
+    times = []
+    with ctx.Pool(P) as pool:
+        for s in range(args.warmup + args.steps):
+            jobs = []
+            for p in range(P):
+                sel = rng.choice(n, per, replace=False)
+                jobs.append((args.workload, w["x"][sel]))
+            t0 = time.perf_counter()
+            pool.map(_ref_worker, jobs)
+            if s >= args.warmup:
+                times.append(time.perf_counter() - t0)
+    tot = sum(times)
+    units = (per * P * n) if args.workload == "direct" else (per * P)
+    value = units * args.steps / tot
+    unit = "interactions/s" if args.workload == "direct" else "particle-steps/s"
+    sample = ("%d processes x %d targets x %d sources per step (direct_summation_position)" % (P, per, n)
+              if args.workload == "direct" else
+              "%d processes, each: tree build over %d sources + walk of %d targets per step" % (P, n, per))
+    line = {"impl": "reference", "metric": "pairwise interactions/s" if args.workload == "direct" else "particle-steps/s",
+            "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["name"]},
+            "cpu_baseline": {"value": value, "unit": unit, "cores": P, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", choices=["direct", "tree"], default="direct")
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from gravhopper_b200 import _jbgrav as J, _lib
+    from gravhopper_b200.sharded import ShardedSimulation
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    _lib.require_gpu()
+
+    w = workload(args.workload)
+    n = len(w["m"])
+    sim = ShardedSimulation(w["x"], w["v"], w["m"], w["dt"], w["eps"], algorithm=w["alg"], theta=w["theta"],
+                            precision=w["prec"], rank=rank, world=world, device=local)
+    shard = sim.shard
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step():
+        with shard.stream_context():
+            flush.zero_()  # evict L2 between steps (the 16-24 MB source array would otherwise stay hot)
+        sim.step()
+
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    launches0 = shard.launches()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with shard.stream_context():
+        ev0.record()
+    for _ in range(args.steps):
+        one_step()
+    with shard.stream_context():
+        ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = shard.launches() - launches0
+    clocks = sampler.stop() if sampler else None
+    # per-kernel time of the dominant (force) kernel: events the engine records around it, last step
+    kernel_ms = shard.last_force_ms()
+    t = torch.tensor([ms_total, kernel_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, kernel_ms = float(t[0]), float(t[1])
+    ms_per_step = ms_total / args.steps
+
+    if args.workload == "direct":
+        units_per_step = float(n) * float(n)
+        metric, unit = "pairwise interactions/s", "interactions/s"
+    else:
+        units_per_step = float(n)
+        metric, unit = "particle-steps/s", "particle-steps/s"
+    value = units_per_step / (ms_per_step * 1e-3)
+
+    # ---- end to end through the reference-facing call with HOST (pinned) buffers, rank-local ----
+    e2e = None
+    if rank == 0:
+        hx = torch.from_numpy(w["x"]).pin_memory().numpy()
+        hm = torch.from_numpy(w["m"]).pin_memory().numpy()
+        if args.workload == "direct":
+            call = lambda: J.direct_summation(hx, hm, w["eps"], precision=w["prec"])  # noqa: E731
+        else:
+            call = lambda: J.tree_force(hx, hm, w["eps"], w["theta"], precision=w["prec"])  # noqa: E731
+        call()
+        reps = 3 if args.workload == "direct" else 5
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            out = call()
+        te = (time.perf_counter() - t0) / reps
+        e2e = {"value": units_per_step / te, "unit": unit, "h2d_bytes_per_step": int(hx.nbytes + hm.nbytes),
+               "d2h_bytes_per_step": int(out.nbytes), "ms_per_call": te * 1e3, "n_gpus_used": 1,
+               "call": "_jbgrav.%s(host ndarray pos, mass, eps%s) -> host ndarray" %
+                       ("direct_summation" if args.workload == "direct" else "tree_force",
+                        "" if args.workload == "direct" else ", theta")}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    peaks = measured_peaks()
+    sm_max = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
+    fp32_peak_tflops = SM_COUNT * FP32_LANES_PER_SM * 2 * sm_max * 1e6 / 1e12
+    if args.workload == "direct":
+        per_rank_units = units_per_step / world
+        achieved = per_rank_units * FLOP_PER_INTERACTION / (kernel_ms * 1e-3) / 1e12
+        roofline = {"bound": "fp32_fma", "achieved": achieved, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
+                    "frac": achieved / fp32_peak_tflops, "traffic": None,
+                    "kernel": "direct_f32_kernel", "kernel_ms": kernel_ms,
+                    "how": "20 flop/interaction x N_i x N_j per launch / CUDA-event time of the force kernel; "
+                           "peak = 148 SMs x 128 FP32 lanes x 2 flop x clocks.max.sm (%.0f MHz); no measured FP32 "
+                           "figure exists in MEASURED_PEAKS.json (it holds HBM GB/s and bf16 TF/s)" % sm_max}
+        if clocks:
+            roofline["frac_at_observed_clock"] = achieved / (fp32_peak_tflops * clocks["sm_mhz"] / sm_max)
+    else:
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        roofline = {"bound": "l2+fma (walk)", "achieved": None, "peak": hbm, "unit": "GB/s", "frac": None,
+                    "traffic": None, "kernel": "walk_kernel", "kernel_ms": kernel_ms,
+                    "how": "walk is latency/L2 bound; build is HBM bound (see DESIGN.md)"}
+
+    line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["name"], "n_particles": n, "precision": w["prec"],
+                       "parallelism": "targets sharded over %d rank(s), NCCL all-gather of x_half per step" % world,
+                       "l2": "256 MB flush write between steps"},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline_direct(w) if args.workload == "direct" else cpu_baseline_tree(w)
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,97 @@
+"""GPU tests at BASELINE.json's full sizes: sampled-target parity against the oracle plus
+size-independent properties (momentum conservation, permutation and translation invariance,
+entry-point equivalence)."""
+import numpy as np
+import pytest
+
+from gravhopper_b200 import _jbgrav as J, ic_raw
+
+pytestmark = pytest.mark.gpu
+
+
+def relerr(a, b):
+    return np.linalg.norm(a - b, axis=1) / np.linalg.norm(b, axis=1)
+
+
+@pytest.fixture(scope="module")
+def plummer_1m():
+    x, v, m = ic_raw.Plummer(1 << 20, 1e-3, 1e6, seed=42)
+    return np.ascontiguousarray(x), np.ascontiguousarray(v), m
+
+
+def test_direct_fp32_1m_sampled_targets(plummer_1m, oracle):
+    """Config 3: N = 2^20 fp32 on 4096 random targets vs the oracle's direct_summation_position."""
+    x, v, m = plummer_1m
+    eps = 5e-5
+    a = J.direct_summation(x, m, eps, precision="fp32")
+    sel = np.random.default_rng(0).choice(len(m), 4096, replace=False)
+    ref = oracle.direct_summation_position(x, m, x[sel], eps, nthreads=0)
+    e = relerr(a[sel], ref)
+    assert e.max() <= 1e-5, e.max()
+    assert np.median(e) <= 1e-6
+    # Newton's third law: sum m_i a_i vanishes (relative to sum m_i |a_i|)
+    p = (m[:, None] * a).sum(axis=0)
+    assert np.linalg.norm(p) <= 1e-6 * (m * np.linalg.norm(a, axis=1)).sum()
+    # the position entry point gives the same numbers on the same points
+    ap = J.direct_summation_position(x, m, x[sel], eps, precision="fp32")
+    assert relerr(ap, a[sel]).max() <= 1e-6
+
+
+def test_direct_fp64_sampled_targets_200k(oracle):
+    x, v, m = ic_raw.Hernquist(200000, 1.0, 1e10, seed=42)
+    x = np.ascontiguousarray(x)
+    sel = np.random.default_rng(1).choice(len(m), 2048, replace=False)
+    a = J.direct_summation_position(x, m, x[sel], 0.05)
+    ref = oracle.direct_summation_position(x, m, x[sel], 0.05, nthreads=0)
+    assert relerr(a, ref).max() <= 1e-12
+
+
+def test_direct_invariances():
+    x, v, m = ic_raw.Plummer(30000, 1e-3, 1e6, seed=5)
+    x = np.ascontiguousarray(x)
+    m = m * np.random.default_rng(2).uniform(0.5, 2.0, len(m))
+    eps = 5e-5
+    a = J.direct_summation(x, m, eps)
+    perm = np.random.default_rng(3).permutation(len(m))
+    ap = J.direct_summation(x[perm], m[perm], eps)
+    assert relerr(ap, a[perm]).max() <= 1e-12
+    shift = np.array([3.0, -7.0, 11.0])
+    ash = J.direct_summation(x + shift, m, eps)
+    assert relerr(ash, a).max() <= 1e-9  # limited by rounding of the shifted inputs
+    a32 = J.direct_summation(x + shift, m, eps, precision="fp32")  # origin handling
+    assert relerr(a32, a).max() <= 1e-5 * 50 and np.median(relerr(a32, a)) <= 1e-5
+    p = (m[:, None] * a).sum(axis=0)
+    assert np.linalg.norm(p) <= 1e-12 * (m * np.linalg.norm(a, axis=1)).sum()
+
+
+@pytest.mark.parametrize("prec", ["fp64", "fp32"])
+def test_tree_4m_hernquist_sampled(oracle, prec):
+    """Config 4: Hernquist N = 4M, theta = 0.7: 2048 sampled targets against the oracle's
+    reference tree (fp64: same node set -> 1e-12; fp32: error vs direct no worse than the
+    reference tree's)."""
+    n = 1 << 22
+    x, v, m = ic_raw.Hernquist(n, 1.0, 1e10, seed=42)
+    x = np.ascontiguousarray(x)
+    eps = 0.05
+    sel = np.random.default_rng(4).choice(n, 2048, replace=False)
+    a = J.tree_force(x, m, eps, 0.7, precision=prec)
+    reft = oracle.tree_force_position(x, m, x[sel], eps, 0.7, nthreads=0)
+    refd = oracle.direct_summation_position(x, m, x[sel], eps, nthreads=0)
+    if prec == "fp64":
+        assert relerr(a[sel], reft).max() <= 1e-12
+    else:
+        eref, egpu = relerr(reft, refd), relerr(a[sel], refd)
+        assert egpu.mean() <= eref.mean() * 1.02 + 1e-6
+        assert np.percentile(egpu, 99) <= np.percentile(eref, 99) * 1.05 + 1e-6
+        assert egpu.max() <= eref.max() * 1.1 + 1e-6
+
+
+def test_tree_galaxy_model_sampled(oracle):
+    """Config 5 analogue at 2M particles (two mass species, thin disk): fp64 tree == reference tree."""
+    n = 2_000_000
+    x, v, m = ic_raw.galaxy_model(n)
+    x = np.ascontiguousarray(x)
+    sel = np.random.default_rng(6).choice(n, 1024, replace=False)
+    a = J.tree_force(x, m, 0.05, 0.7)
+    reft = oracle.tree_force_position(x, m, x[sel], 0.05, 0.7, nthreads=0)
+    assert relerr(a[sel], reft).max() <= 1e-12
