@@ -46,34 +46,32 @@ static Stateless *stateless() {
   return g_sl;
 }
 
-// bbox midpoint of (pos) -> origin[3] on the device (for the f32 packing).  Two tiny kernels.
+// mean position -> origin[3] on the device (for the f32 packing).  The mean, not the bbox
+// midpoint: centrally concentrated systems have outliers at 10^3 scale radii (untruncated
+// Plummer), and an origin far from the core costs fp32 digits exactly where pairs are closest.
+// Two tiny deterministic kernels (fixed block count, fixed reduction order).
 __global__ void origin_stage1(const double *__restrict__ pos, int64_t n, double *__restrict__ part) {
-  __shared__ double sh[6][256];
-  double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+  __shared__ double sh[3][256];
+  double sum[3] = {0.0, 0.0, 0.0};
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x)
-    for (int k = 0; k < 3; k++) {
-      mn[k] = fmin(mn[k], pos[3 * i + k]);
-      mx[k] = fmax(mx[k], pos[3 * i + k]);
-    }
-  for (int k = 0; k < 3; k++) { sh[k][threadIdx.x] = mn[k]; sh[3 + k][threadIdx.x] = mx[k]; }
+    for (int k = 0; k < 3; k++) sum[k] += pos[3 * i + k];
+  for (int k = 0; k < 3; k++) sh[k][threadIdx.x] = sum[k];
   __syncthreads();
   for (int s = 128; s > 0; s >>= 1) {
     if (threadIdx.x < s)
-      for (int k = 0; k < 3; k++) {
-        sh[k][threadIdx.x] = fmin(sh[k][threadIdx.x], sh[k][threadIdx.x + s]);
-        sh[3 + k][threadIdx.x] = fmax(sh[3 + k][threadIdx.x], sh[3 + k][threadIdx.x + s]);
-      }
+      for (int k = 0; k < 3; k++) sh[k][threadIdx.x] += sh[k][threadIdx.x + s];
     __syncthreads();
   }
-  if (threadIdx.x < 6) part[blockIdx.x * 6 + threadIdx.x] = sh[threadIdx.x][0];
+  if (threadIdx.x < 3) part[blockIdx.x * 3 + threadIdx.x] = sh[threadIdx.x][0];
 }
-__global__ void origin_stage2(const double *__restrict__ part, int nb, double *__restrict__ origin) {
+__global__ void origin_stage2(const double *__restrict__ part, int nb, int64_t n,
+                              double *__restrict__ origin) {
   if (threadIdx.x >= 3) return;
   int k = threadIdx.x;
-  double mn = 1e300, mx = -1e300;
-  for (int b = 0; b < nb; b++) { mn = fmin(mn, part[b * 6 + k]); mx = fmax(mx, part[b * 6 + 3 + k]); }
-  origin[k] = 0.5 * (mn + mx);
+  double sum = 0.0;
+  for (int b = 0; b < nb; b++) sum += part[b * 3 + k];
+  origin[k] = sum / (double)n;
 }
 __global__ void pack32_dev_origin(const double *__restrict__ pos, const double *__restrict__ mass,
                                   int64_t n, const double *__restrict__ origin,
@@ -142,7 +140,7 @@ static int force_common(int alg, int prec, const double *pos, const double *mass
       a.src_mass = dmass;
       a.tgt_pos = dt;
     } else {
-      // fp32 pair maths on coordinates taken relative to the sources' bbox midpoint
+      // fp32 pair maths on coordinates taken relative to the sources' mean position
       GH_TRY(s->src32.reserve(sizeof(float4) * (size_t)np));
       GH_TRY(s->root.reserve(sizeof(double) * 4));
       GH_TRY(s->part.reserve(sizeof(double) * 6 * 256));
@@ -150,7 +148,7 @@ static int force_common(int alg, int prec, const double *pos, const double *mass
       if (nb > 256) nb = 256;
       origin_stage1<<<nb, 256, 0, st>>>(dpos, np, s->part.as<double>());
       GH_LAUNCH_CHECK();
-      origin_stage2<<<1, 32, 0, st>>>(s->part.as<double>(), nb, s->root.as<double>());
+      origin_stage2<<<1, 32, 0, st>>>(s->part.as<double>(), nb, np, s->root.as<double>());
       GH_LAUNCH_CHECK();
       pack32_dev_origin<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(dpos, dmass, np, s->root.as<double>(),
                                                                     s->src32.as<float4>());

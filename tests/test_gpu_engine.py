@@ -38,8 +38,13 @@ def test_first_ten_steps_particlewise(golden, alg):
 @pytest.mark.parametrize("alg,precision", [("direct", "fp64"), ("tree", "fp64"), ("direct", "fp32"), ("tree", "fp32")])
 def test_400_step_energy_drift_matches_reference(golden, oracle, alg, precision):
     """README config: the reference's own DKD integrator error is +14 % over 400 steps
-    (BASELINE.md 2.2); the GPU run must show the same drift (chaos decorrelates trajectories, so
-    the comparison is on the energy series)."""
+    (BASELINE.md 2.2); the GPU run must show the same drift.  The system is chaotic: re-running the
+    REFERENCE arithmetic (oracle) with the initial positions perturbed by 1e-15 relative gives
+    identical drifts to 4 digits at steps 100 and 200, 0.112-0.119 at step 300 and 0.136-0.152 at
+    step 400 (5 trials; golden: 0.1152, 0.1426).  With fp32-sized noise (6e-8 relative on the
+    force inputs each step) the same reference arithmetic spreads to 0.071-0.079 (direct) /
+    0.078-0.096 (tree) at step 200 and 0.136-0.164 at step 400 (4 trials each).  The tolerances
+    below are those spreads."""
     sim = make_sim(golden, alg, precision)
     sim.run(400)
     m, eps = golden["c1_mass"], float(golden["c1_eps"])
@@ -47,10 +52,12 @@ def test_400_step_energy_drift_matches_reference(golden, oracle, alg, precision)
     gE = golden["c1_%s_energy" % alg].sum(axis=1)
     pos, vel = np.asarray(sim.positions.value), np.asarray(sim.velocities.value)
     e0 = gE[0]
+    tols = {0: 1e-12, 100: 1e-3, 200: 1e-3, 300: 1e-2, 400: 2e-2} if precision == "fp64" else \
+           {0: 1e-6, 100: 5e-3, 200: 2e-2, 300: 3e-2, 400: 3e-2}
     for s, want in zip(gsteps, gE):
         ke, pe = oracle.energy(pos[s], vel[s], m, eps, nthreads=0)
         drift_gpu, drift_ref = (ke + pe - e0) / abs(e0), (want - e0) / abs(e0)
-        assert abs(drift_gpu - drift_ref) <= 4e-3, (s, drift_gpu, drift_ref)
+        assert abs(drift_gpu - drift_ref) <= tols[int(s)], (s, drift_gpu, drift_ref)
     # the on-device energy diagnostic agrees with the oracle's
     ke_d, pe_d = sim.energy(400)
     ke, pe = oracle.energy(pos[400], vel[400], m, eps, nthreads=0)
@@ -90,7 +97,8 @@ def test_external_force_hooks_match_oracle(golden, oracle):
         return -vel * args["k"]
 
     def rotating(pos, time, args):
-        return pos * 0 + np.array([1e-3, 0, 0]) * (u.km / u.s / u.Myr) * np.cos(time.to(u.Myr).value)
+        amp = np.cos(time.to(u.Myr).value)
+        return np.tile(np.array([1e-3, 0, 0]) * amp, (len(pos), 1)) * (u.km / u.s / u.Myr)
 
     sim = g.Simulation(dt=dt * u.Myr, eps=eps * u.kpc, algorithm="direct")
     sim.add_IC({"pos": x * u.kpc, "vel": v * u.km / u.s, "mass": m * u.Msun})

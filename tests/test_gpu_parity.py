@@ -160,8 +160,9 @@ def test_ragged_sizes_against_oracle(oracle, n):
     assert np.allclose(J.tree_force(x, m, 0.05, 0.6), oracle.tree_force(x, m, 0.05, 0.6), rtol=1e-12, atol=1e-13)
     assert np.allclose(J.tree_force_position(x, m, t, 0.05, 0.6),
                        oracle.tree_force_position(x, m, t, 0.05, 0.6), rtol=1e-12, atol=1e-13)
-    a32 = J.direct_summation(x, m, 0.05, precision="fp32")
-    assert np.allclose(a32, oracle.direct_summation(x, m, 0.05), rtol=1e-4, atol=1e-5)
+    if n > 1:
+        a32 = J.direct_summation(x, m, 0.05, precision="fp32")
+        assert relerr(a32, oracle.direct_summation(x, m, 0.05)).max() <= 1e-5
 
 
 def test_device_pointer_path_matches_host_path(golden):
