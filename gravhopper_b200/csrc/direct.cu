@@ -91,73 +91,122 @@ direct_f32_kernel(const float4 *__restrict__ src, int64_t nj, const float4 *__re
   }
 
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  // A tile whose BLOCK sources all carry the same mass m0 (the usual case: equal-mass
+  // components stored contiguously) skips the per-interaction mass multiply; its fp32 partial sum
+  // is scaled by m0 once, when it is promoted to fp64.  12 -> 11 FP32 operations per interaction.
+  float m0 = 0.f;
+  bool uni = false;
   {
     int64_t j = jb + tid;
     float4 g = (j < je) ? src[j] : zero4;
+    m0 = (jb < je) ? src[jb].w : 0.f;
     store_tile32<BLOCK, MODE>(tile[0], tid, g, eps2);
+    uni = __syncthreads_and(g.w == m0) != 0;
   }
-  __syncthreads();
 
   for (int t = 0; t < ntiles; t++) {
     float4 g = zero4;
+    float m0n = 0.f;
     const bool more = (t + 1 < ntiles);
     if (more) {
-      int64_t j = jb + (int64_t)(t + 1) * BLOCK + tid;
+      const int64_t jt = jb + (int64_t)(t + 1) * BLOCK;
+      int64_t j = jt + tid;
       if (j < je) g = src[j];
+      m0n = src[jt].w;
     }
     const Tile32<BLOCK> &T = tile[t & 1];
     float2 fx[KI], fy[KI], fz[KI];
 #pragma unroll
     for (int k = 0; k < KI; k++) fx[k] = fy[k] = fz[k] = make_float2(0.f, 0.f);
 
+    if (MODE == 0 && uni) {
 #pragma unroll 4
-    for (int p = 0; p < BLOCK / 2; p++) {
-      const float4 A = T.a[p];
-      const float4 B = T.b[p];
-      const float2 xj = make_float2(A.x, A.y), yj = make_float2(A.z, A.w);
-      const float2 zj = make_float2(B.x, B.y), s = make_float2(B.z, B.w);
-      float2 e;
-      if (MODE == 0) e = make_float2(eps2, eps2);
-      else e = T.c[p];
+      for (int p = 0; p < BLOCK / 2; p++) {
+        const float4 A = T.a[p];
+        const float2 zj = *reinterpret_cast<const float2 *>(&T.b[p]);
+        const float2 xj = make_float2(A.x, A.y), yj = make_float2(A.z, A.w);
+        const float2 e = make_float2(eps2, eps2);
+#pragma unroll
+        for (int k = 0; k < KI; k++) {
+          float2 dx = __fadd2_rn(xj, nx[k]);
+          float2 dy = __fadd2_rn(yj, ny[k]);
+          float2 dz = __fadd2_rn(zj, nz[k]);
+          float2 q = __ffma2_rn(dx, dx, e);
+          q = __ffma2_rn(dy, dy, q);
+          q = __ffma2_rn(dz, dz, q);
+          float2 r;
+          if (GUARD) {
+            r.x = q.x > 0.f ? rsq_approx(q.x) : 0.f;
+            r.y = q.y > 0.f ? rsq_approx(q.y) : 0.f;
+          } else {
+            r.x = rsq_approx(q.x);
+            r.y = rsq_approx(q.y);
+          }
+          float2 r2 = __fmul2_rn(r, r);
+          float2 r3 = __fmul2_rn(r2, r);
+          fx[k] = __ffma2_rn(r3, dx, fx[k]);
+          fy[k] = __ffma2_rn(r3, dy, fy[k]);
+          fz[k] = __ffma2_rn(r3, dz, fz[k]);
+        }
+      }
+      const double dm0 = (double)m0;
 #pragma unroll
       for (int k = 0; k < KI; k++) {
-        float2 dx, dy, dz;
-        if (MODE == 0) {
-          dx = __fadd2_rn(xj, nx[k]);
-          dy = __fadd2_rn(yj, ny[k]);
-          dz = __fadd2_rn(zj, nz[k]);
-        } else {
-          dx = __ffma2_rn(nx[k], s, xj);
-          dy = __ffma2_rn(ny[k], s, yj);
-          dz = __ffma2_rn(nz[k], s, zj);
+        ax[k] = fma((double)(fx[k].x + fx[k].y), dm0, ax[k]);
+        ay[k] = fma((double)(fy[k].x + fy[k].y), dm0, ay[k]);
+        az[k] = fma((double)(fz[k].x + fz[k].y), dm0, az[k]);
+      }
+    } else {
+#pragma unroll 4
+      for (int p = 0; p < BLOCK / 2; p++) {
+        const float4 A = T.a[p];
+        const float4 B = T.b[p];
+        const float2 xj = make_float2(A.x, A.y), yj = make_float2(A.z, A.w);
+        const float2 zj = make_float2(B.x, B.y), s = make_float2(B.z, B.w);
+        float2 e;
+        if (MODE == 0) e = make_float2(eps2, eps2);
+        else e = T.c[p];
+#pragma unroll
+        for (int k = 0; k < KI; k++) {
+          float2 dx, dy, dz;
+          if (MODE == 0) {
+            dx = __fadd2_rn(xj, nx[k]);
+            dy = __fadd2_rn(yj, ny[k]);
+            dz = __fadd2_rn(zj, nz[k]);
+          } else {
+            dx = __ffma2_rn(nx[k], s, xj);
+            dy = __ffma2_rn(ny[k], s, yj);
+            dz = __ffma2_rn(nz[k], s, zj);
+          }
+          float2 q = __ffma2_rn(dx, dx, e);
+          q = __ffma2_rn(dy, dy, q);
+          q = __ffma2_rn(dz, dz, q);
+          float2 r;
+          if (GUARD) {  // eps == 0: a source exactly at the target contributes zero
+            r.x = q.x > 0.f ? rsq_approx(q.x) : 0.f;
+            r.y = q.y > 0.f ? rsq_approx(q.y) : 0.f;
+          } else {
+            r.x = rsq_approx(q.x);
+            r.y = rsq_approx(q.y);
+          }
+          float2 r2 = __fmul2_rn(r, r);
+          float2 r3 = __fmul2_rn(r2, r);
+          if (MODE == 0) r3 = __fmul2_rn(r3, s);  // s holds the masses in MODE 0
+          fx[k] = __ffma2_rn(r3, dx, fx[k]);
+          fy[k] = __ffma2_rn(r3, dy, fy[k]);
+          fz[k] = __ffma2_rn(r3, dz, fz[k]);
         }
-        float2 q = __ffma2_rn(dx, dx, e);
-        q = __ffma2_rn(dy, dy, q);
-        q = __ffma2_rn(dz, dz, q);
-        float2 r;
-        if (GUARD) {  // eps == 0: a source exactly at the target contributes zero
-          r.x = q.x > 0.f ? rsq_approx(q.x) : 0.f;
-          r.y = q.y > 0.f ? rsq_approx(q.y) : 0.f;
-        } else {
-          r.x = rsq_approx(q.x);
-          r.y = rsq_approx(q.y);
-        }
-        float2 r2 = __fmul2_rn(r, r);
-        float2 r3 = __fmul2_rn(r2, r);
-        if (MODE == 0) r3 = __fmul2_rn(r3, s);  // s holds the masses in MODE 0
-        fx[k] = __ffma2_rn(r3, dx, fx[k]);
-        fy[k] = __ffma2_rn(r3, dy, fy[k]);
-        fz[k] = __ffma2_rn(r3, dz, fz[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < KI; k++) {  // second accumulation level: fp64 across tiles
+        ax[k] += (double)(fx[k].x + fx[k].y);
+        ay[k] += (double)(fy[k].x + fy[k].y);
+        az[k] += (double)(fz[k].x + fz[k].y);
       }
     }
-#pragma unroll
-    for (int k = 0; k < KI; k++) {  // second accumulation level: fp64 across tiles
-      ax[k] += (double)(fx[k].x + fx[k].y);
-      ay[k] += (double)(fy[k].x + fy[k].y);
-      az[k] += (double)(fz[k].x + fz[k].y);
-    }
     if (more) store_tile32<BLOCK, MODE>(tile[(t + 1) & 1], tid, g, eps2);
-    __syncthreads();
+    uni = __syncthreads_and(more && g.w == m0n) != 0;
+    m0 = m0n;
   }
 
 #pragma unroll
@@ -378,12 +427,23 @@ int launch_direct(const DirectArgs &a, DeviceBuffer &ws, cudaStream_t st, cudaEv
   if (a.ni <= 0) return GH_OK;
   if (a.prec == GH_PREC_F32) {
     int ki = env_int("GH_F32_KI", 0);
-    if (ki == 0) ki = (a.ni >= 131072) ? 4 : (a.ni >= 16384 ? 2 : 1);
-    switch (ki) {
-      case 8: return run_f32<128, 8>(a, ws, st, ev);
-      case 4: return run_f32<256, 4>(a, ws, st, ev);
-      case 2: return run_f32<128, 2>(a, ws, st, ev);
-      default: return run_f32<128, 1>(a, ws, st, ev);
+    int blk = env_int("GH_F32_BLOCK", 0);
+    // measured on B200 (profiles/r01_sweep_direct.txt): 8 targets/thread x 128 threads is the
+    // fastest shape once there are enough targets to fill the chip
+    if (ki == 0) ki = (a.ni >= 131072) ? 8 : (a.ni >= 16384 ? 2 : 1);
+    if (blk == 0) blk = 128;
+    switch (ki * 1000 + blk) {
+      case 8128: return run_f32<128, 8>(a, ws, st, ev);
+      case 8064: return run_f32<64, 8>(a, ws, st, ev);
+      case 4256: return run_f32<256, 4>(a, ws, st, ev);
+      case 4128: return run_f32<128, 4>(a, ws, st, ev);
+      case 4512: return run_f32<512, 4>(a, ws, st, ev);
+      case 2256: return run_f32<256, 2>(a, ws, st, ev);
+      case 2128: return run_f32<128, 2>(a, ws, st, ev);
+      case 1128: return run_f32<128, 1>(a, ws, st, ev);
+      default:
+        set_error("unsupported GH_F32_KI/GH_F32_BLOCK combination %d/%d", ki, blk);
+        return GH_EINVAL;
     }
   } else if (a.prec == GH_PREC_F64) {
     int ki = env_int("GH_F64_KI", 0);
