@@ -40,6 +40,8 @@
 #include "common.cuh"
 
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
 #include <climits>
 #include <cstdlib>
 
@@ -203,9 +205,13 @@ __global__ void levels_kernel(const uint64_t *__restrict__ hi, const uint64_t *_
 }
 
 // ---- K7 double-double moments -------------------------------------------------------------------
-struct DD4 {
-  double h[4];
-  double l[4];
+// Inclusive scans of m, m x, m y, m z over the Morton-sorted particles, in double-double
+// arithmetic (hi + lo, ~106 bits), so that the moments of a cell covering sorted particles
+// [p, b] are P[b+1] - P[p] without cancellation (errors ~1e-30 of the total).  One scan per
+// component on 16-byte elements; the inputs are produced on the fly by a transform iterator
+// (the products m x are formed exactly: hi = fl(m x), lo = fma(m, x, -hi)).
+struct DD {
+  double h, l;
 };
 __device__ __forceinline__ void dd_add(double ah, double al, double bh, double bl, double &rh,
                                        double &rl) {
@@ -216,38 +222,36 @@ __device__ __forceinline__ void dd_add(double ah, double al, double bh, double b
   rh = __dadd_rn(s, e);
   rl = __dadd_rn(e, -__dadd_rn(rh, -s));
 }
-struct DD4Add {
-  __device__ __forceinline__ DD4 operator()(const DD4 &a, const DD4 &b) const {
-    DD4 r;
-#pragma unroll
-    for (int k = 0; k < 4; k++) dd_add(a.h[k], a.l[k], b.h[k], b.l[k], r.h[k], r.l[k]);
+struct DDAdd {
+  __device__ __forceinline__ DD operator()(const DD &a, const DD &b) const {
+    DD r;
+    dd_add(a.h, a.l, b.h, b.l, r.h, r.l);
     return r;
   }
 };
-
-template <class Src>
-__global__ void moments_in_kernel(Src src, const int *__restrict__ idx, int64_t n,
-                                  DD4 *__restrict__ out /* n+1, out[0] = 0 */) {
-  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p > n) return;
-  DD4 r;
-  if (p == 0) {
-    for (int k = 0; k < 4; k++) r.h[k] = r.l[k] = 0.0;
-  } else {
-    int64_t j = idx[p - 1];
-    double x[3], m = src.m(j);
-    src.get(j, x[0], x[1], x[2]);
-    r.h[0] = m;
-    r.l[0] = 0.0;
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      double pr = __dmul_rn(m, x[k]);
-      r.h[1 + k] = pr;
-      r.l[1 + k] = fma(m, x[k], -pr);
+// element p of component C (0 = m, 1..3 = m x_k) of the shifted sequence: 0 for p = 0, else
+// the value of sorted particle p-1
+template <class Src, int C>
+struct MomentIn {
+  Src src;
+  const int *idx;
+  __device__ __forceinline__ DD operator()(int p) const {
+    DD r;
+    r.h = r.l = 0.0;
+    if (p == 0) return r;
+    const int64_t j = idx[p - 1];
+    const double m = src.m(j);
+    if (C == 0) {
+      r.h = m;
+    } else {
+      double x[3];
+      src.get(j, x[0], x[1], x[2]);
+      r.h = __dmul_rn(m, x[C - 1]);
+      r.l = fma(m, x[C - 1], -r.h);
     }
+    return r;
   }
-  out[p] = r;
-}
+};
 
 // ---- K6b emit -----------------------------------------------------------------------------------
 template <class Real> struct Vec4;
@@ -255,10 +259,14 @@ template <> struct Vec4<double> { using type = double4; };
 template <> struct Vec4<float> { using type = float4; };
 
 template <class Real>
+struct Node {
+  typename Vec4<Real>::type cen;  // (centre - origin, s2 = side^2 / theta^2); s2 = -1 marks a leaf
+  typename Vec4<Real>::type com;  // (COM - origin, mass)
+};
+template <class Real>
 struct Entries {
-  typename Vec4<Real>::type *com;  // (COM - origin, mass)
-  typename Vec4<Real>::type *cen;  // (centre - origin, side) ; side < 0 marks a leaf
-  int *skip;                       // pre-order index after this entry's subtree
+  Node<Real> *node;
+  int *skip;  // pre-order index after this entry's subtree
 };
 
 __device__ __forceinline__ bool same_prefix(uint64_t h, uint64_t l, uint64_t h0, uint64_t l0,
@@ -276,8 +284,10 @@ template <class Src, class Real>
 __global__ void emit_kernel(Src src, const int *__restrict__ idx, const uint64_t *__restrict__ hi,
                             const uint64_t *__restrict__ lo, const signed char *__restrict__ clev,
                             const int *__restrict__ base /* n+1, exclusive scan of cnt */,
-                            const DD4 *__restrict__ P, int64_t n, const double *__restrict__ root,
-                            bool rel_origin, Entries<Real> E, int *__restrict__ maxlevel) {
+                            const DD *__restrict__ P0, const DD *__restrict__ P1,
+                            const DD *__restrict__ P2, const DD *__restrict__ P3, int64_t n,
+                            const double *__restrict__ root, bool rel_origin, double inv_theta2,
+                            Entries<Real> E, int *__restrict__ maxlevel) {
   int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   using V4 = typename Vec4<Real>::type;
@@ -311,13 +321,11 @@ __global__ void emit_kernel(Src src, const int *__restrict__ idx, const uint64_t
           else hi_i = mid - 1;
         }
         const int64_t b = lo_i;
-        double mh[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          double rh, rl;
-          dd_add(P[b + 1].h[k], P[b + 1].l[k], -P[p].h[k], -P[p].l[k], rh, rl);
-          mh[k] = rh;
-        }
+        double mh[4], rl;
+        dd_add(P0[b + 1].h, P0[b + 1].l, -P0[p].h, -P0[p].l, mh[0], rl);
+        dd_add(P1[b + 1].h, P1[b + 1].l, -P1[p].h, -P1[p].l, mh[1], rl);
+        dd_add(P2[b + 1].h, P2[b + 1].l, -P2[p].h, -P2[p].l, mh[2], rl);
+        dd_add(P3[b + 1].h, P3[b + 1].l, -P3[p].h, -P3[p].l, mh[3], rl);
         V4 com, cen;
         com.x = (Real)(mh[1] / mh[0] - ox);  // gravoct_finalize :477-479
         com.y = (Real)(mh[2] / mh[0] - oy);
@@ -326,9 +334,10 @@ __global__ void emit_kernel(Src src, const int *__restrict__ idx, const uint64_t
         cen.x = (Real)(cc[0] - ox);
         cen.y = (Real)(cc[1] - oy);
         cen.z = (Real)(cc[2] - oz);
-        cen.w = (Real)size;
-        E.com[e] = com;
-        E.cen[e] = cen;
+        // (size / dist) < theta  <=>  size^2 / theta^2 < dist^2   (theta = 0: inf, never accepted)
+        cen.w = (Real)(__dmul_rn(__dmul_rn(size, size), inv_theta2));
+        E.node[e].cen = cen;
+        E.node[e].com = com;
         E.skip[e] = base[b + 1];
         e++;
         deepest = level;
@@ -355,8 +364,8 @@ __global__ void emit_kernel(Src src, const int *__restrict__ idx, const uint64_t
   com.w = (Real)src.m(j);
   cen.x = cen.y = cen.z = (Real)0;
   cen.w = (Real)-1;
-  E.com[e] = com;
-  E.cen[e] = cen;
+  E.node[e].cen = cen;
+  E.node[e].com = com;
   E.skip[e] = e + 1;
 }
 
@@ -370,15 +379,17 @@ __device__ __forceinline__ double rsqrt64_t(double s) {
   double q = e * p;
   return fma(y, q, y);
 }
+template <bool GUARD>
 __device__ __forceinline__ double inv_cube(double s) {
   double y = rsqrt64_t(s);
-  y = (s > 0.0) ? y : 0.0;  // _jbgrav.c:517-518
+  if (GUARD) y = (s > 0.0) ? y : 0.0;  // _jbgrav.c:517-518 (only reachable when eps == 0)
   return y * y * y;
 }
+template <bool GUARD>
 __device__ __forceinline__ float inv_cube(float s) {
   float y;
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(s));
-  y = (s > 0.f) ? y : 0.f;
+  if (GUARD) y = (s > 0.f) ? y : 0.f;
   return y * y * y;
 }
 
@@ -389,11 +400,19 @@ struct TargetsView {
   int64_t order_offset;  // subtracted from order[] values (self case with a slice)
 };
 
-template <class Real, bool STATS>
-__global__ void __launch_bounds__(128)
-walk_kernel(Entries<Real> E, int nentries, TargetsView tv, int64_t ni,
-            const double *__restrict__ root, bool rel_origin, Real eps2, Real theta2, Epilogue ep,
-            unsigned long long *__restrict__ stats) {
+// One warp per 32 Morton-consecutive targets.  `i` (warp-uniform) runs through the pre-order
+// entry array.  Per lane: `until` = pre-order index up to which this lane is covered by a cell it
+// already accepted.  A lane is active at entry i iff i >= until; an active lane accepts iff
+// s2 < |centre - x|^2 (leaves carry s2 = -1), adds the monopole and sets until = skip[i];
+// otherwise it must open the cell.  The warp advances to min over lanes of (open ? i+1 : until)
+// with one REDUX: the scan only touches entries some lane still needs.  Branch-free body.
+// fp32: plain fp32 accumulation (<= ~1e3 accepted terms per target; error ~1e-6, far below the
+// monopole error).
+template <class Real, bool STATS, bool GUARD>
+__global__ void __launch_bounds__(128, 8)
+walk_kernel(const Node<Real> *__restrict__ nodes, const int *__restrict__ skips, int nentries,
+            TargetsView tv, int64_t ni, const double *__restrict__ root, bool rel_origin, Real eps2,
+            Epilogue ep, unsigned long long *__restrict__ stats) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t p = warp * 32 + lane;
@@ -402,62 +421,45 @@ walk_kernel(Entries<Real> E, int nentries, TargetsView tv, int64_t ni,
   Real x = 0, y = 0, z = 0;
   if (valid) {
     ti = tv.order ? (int64_t)tv.order[p] - tv.order_offset : p;
+    const double ox = rel_origin ? root[0] : 0.0, oy = rel_origin ? root[1] : 0.0,
+                 oz = rel_origin ? root[2] : 0.0;
     if (tv.pos64) {
-      double ox = rel_origin ? root[0] : 0.0, oy = rel_origin ? root[1] : 0.0,
-             oz = rel_origin ? root[2] : 0.0;
       x = (Real)(tv.pos64[3 * ti] - ox);
       y = (Real)(tv.pos64[3 * ti + 1] - oy);
       z = (Real)(tv.pos64[3 * ti + 2] - oz);
     } else {
       float4 t = tv.pos32[ti];
-      double ox = rel_origin ? root[0] : 0.0, oy = rel_origin ? root[1] : 0.0,
-             oz = rel_origin ? root[2] : 0.0;
       x = (Real)((double)t.x - ox);
       y = (Real)((double)t.y - oy);
       z = (Real)((double)t.z - oz);
     }
   }
-  int until = valid ? 0 : INT_MAX;  // pre-order index up to which this lane has accepted an ancestor
-  Real ax = 0, ay = 0, az = 0;      // current accumulation block
-  double Ax = 0, Ay = 0, Az = 0;    // fp32 path: second-level fp64 accumulators
+  int until = valid ? 0 : INT_MAX;
+  Real ax = 0, ay = 0, az = 0;
   unsigned long long nacc = 0, nvis = 0;
-  int since_flush = 0;
   int i = 0;
   while (i < nentries) {
-    const auto cen = E.cen[i];
-    const auto com = E.com[i];
-    const int skip = E.skip[i];
-    const bool active = i >= until;
+    const auto cen = nodes[i].cen;
+    const auto com = nodes[i].com;
+    const int sk = skips[i];
     const Real dx = cen.x - x, dy = cen.y - y, dz = cen.z - z;
     const Real d2 = dx * dx + dy * dy + dz * dz;
-    // (size / dist) < theta  <=>  size^2 < theta^2 dist^2 for size >= 0; leaves carry size < 0
-    const bool accept = (cen.w < (Real)0) || (cen.w * cen.w < theta2 * d2);
-    if (STATS && active) nvis++;
-    if (active && accept) {
-      const Real ex = com.x - x, ey = com.y - y, ez = com.z - z;
-      const Real s = ex * ex + ey * ey + ez * ez + eps2;
-      const Real w = com.w * inv_cube(s);
-      ax += w * ex;
-      ay += w * ey;
-      az += w * ez;
-      until = skip;
-      if (STATS) nacc++;
-    }
-    const bool open = active && !accept;
-    if (__any_sync(0xffffffffu, open)) i = i + 1;
-    else i = __reduce_min_sync(0xffffffffu, until);
-    if (sizeof(Real) == 4) {
-      if (++since_flush == 256) {
-        Ax += (double)ax; Ay += (double)ay; Az += (double)az;
-        ax = ay = az = 0;
-        since_flush = 0;
-      }
-    }
+    const bool active = i >= until;
+    const bool pass = cen.w < d2;
+    const bool acc = active && pass;
+    const bool open = active && !pass;
+    const Real ex = com.x - x, ey = com.y - y, ez = com.z - z;
+    const Real s = ex * ex + ey * ey + ez * ez + eps2;
+    const Real w = acc ? com.w * inv_cube<GUARD>(s) : (Real)0;
+    ax += w * ex;
+    ay += w * ey;
+    az += w * ez;
+    until = acc ? sk : until;
+    if (STATS) { nvis += active; nacc += acc; }
+    const int next = open ? i + 1 : until;
+    i = __reduce_min_sync(0xffffffffu, next);
   }
-  if (valid) {
-    double fx = (double)ax + Ax, fy = (double)ay + Ay, fz = (double)az + Az;
-    apply_epilogue(ep, ti, fx, fy, fz);
-  }
+  if (valid) apply_epilogue(ep, ti, (double)ax, (double)ay, (double)az);
   if (STATS) {
     for (int o = 16; o > 0; o >>= 1) {
       nacc += __shfl_down_sync(0xffffffffu, nacc, o);
@@ -469,8 +471,8 @@ walk_kernel(Entries<Real> E, int nentries, TargetsView tv, int64_t ni,
 
 // ---- workspace + orchestration --------------------------------------------------------------------
 struct TreeWorkspace {
-  DeviceBuffer root, part, hi, lo, hi2, lo2, idx, idx2, clev, cnt, base, P, Pin, cubtmp;
-  DeviceBuffer com, cen, skip, misc, thi, tidx, thi2, tidx2;
+  DeviceBuffer root, part, hi, lo, hi2, lo2, idx, idx2, clev, cnt, base, P, cubtmp;
+  DeviceBuffer node, skip, misc, thi, tidx, thi2, tidx2;
   int64_t last_stats[5] = {0, 0, 0, 0, 0};
   int *h_pinned = nullptr;  // [0] nentries, [1] maxlevel ; pinned for async readback
   unsigned long long *h_stats = nullptr;
@@ -480,7 +482,7 @@ TreeWorkspace *tree_workspace_create() { return new TreeWorkspace(); }
 void tree_workspace_destroy(TreeWorkspace *w) {
   if (!w) return;
   DeviceBuffer *all[] = {&w->root, &w->part, &w->hi, &w->lo, &w->hi2, &w->lo2, &w->idx, &w->idx2,
-                         &w->clev, &w->cnt, &w->base, &w->P, &w->Pin, &w->cubtmp, &w->com, &w->cen,
+                         &w->clev, &w->cnt, &w->base, &w->P, &w->cubtmp, &w->node,
                          &w->skip, &w->misc, &w->thi, &w->tidx, &w->thi2, &w->tidx2};
   for (auto *b : all) b->release();
   if (w->h_pinned) cudaFreeHost(w->h_pinned);
@@ -538,7 +540,8 @@ static int tree_impl(const TreeArgs &a, Src src, const float4 *tgt32, TreeWorksp
   cub::DeviceScan::InclusiveSum(nullptr, tb, (int *)nullptr, (int *)nullptr, (int)n + 1, st);
   if (tb > tmp_bytes) tmp_bytes = tb;
   tb = 0;
-  cub::DeviceScan::InclusiveScan(nullptr, tb, (DD4 *)nullptr, (DD4 *)nullptr, DD4Add(), (int)n + 1, st);
+  cub::DeviceScan::InclusiveScan(nullptr, tb, (DD *)nullptr, (DD *)nullptr, DDAdd(), (int)n + 1, st);
+  tb += 4096;  // transform-iterator inputs may need a little more
   if (tb > tmp_bytes) tmp_bytes = tb;
   GH_TRY(w->cubtmp.reserve(tmp_bytes));
   void *tmp = w->cubtmp.ptr;
@@ -574,26 +577,36 @@ static int tree_impl(const TreeArgs &a, Src src, const float4 *tgt32, TreeWorksp
   GH_CUDA(cudaMemcpyAsync(&w->h_pinned[0], base + n, sizeof(int), cudaMemcpyDeviceToHost, st));
 
   // K7
-  GH_TRY(w->Pin.reserve(sizeof(DD4) * (n + 1)));
-  GH_TRY(w->P.reserve(sizeof(DD4) * (n + 1)));
-  moments_in_kernel<<<nblk(n + 1, 256), 256, 0, st>>>(src, sidx, n, w->Pin.as<DD4>());
-  GH_LAUNCH_CHECK();
-  GH_CUDA(cub::DeviceScan::InclusiveScan(tmp, tmpsz, w->Pin.as<DD4>(), w->P.as<DD4>(), DD4Add(),
-                                         (int)n + 1, st));
+  GH_TRY(w->P.reserve(sizeof(DD) * 4 * (size_t)(n + 1)));
+  DD *P[4];
+  for (int c = 0; c < 4; c++) P[c] = w->P.as<DD>() + (size_t)c * (size_t)(n + 1);
+  {
+    thrust::counting_iterator<int> cnt_it(0);
+    auto i0 = thrust::make_transform_iterator(cnt_it, MomentIn<Src, 0>{src, sidx});
+    auto i1 = thrust::make_transform_iterator(cnt_it, MomentIn<Src, 1>{src, sidx});
+    auto i2 = thrust::make_transform_iterator(cnt_it, MomentIn<Src, 2>{src, sidx});
+    auto i3 = thrust::make_transform_iterator(cnt_it, MomentIn<Src, 3>{src, sidx});
+    size_t need = 0;
+    cub::DeviceScan::InclusiveScan(nullptr, need, i1, P[1], DDAdd(), (int)n + 1, st);
+    if (need > w->cubtmp.bytes) { GH_TRY(w->cubtmp.reserve(need)); tmp = w->cubtmp.ptr; tmpsz = w->cubtmp.bytes; }
+    GH_CUDA(cub::DeviceScan::InclusiveScan(tmp, tmpsz, i0, P[0], DDAdd(), (int)n + 1, st));
+    GH_CUDA(cub::DeviceScan::InclusiveScan(tmp, tmpsz, i1, P[1], DDAdd(), (int)n + 1, st));
+    GH_CUDA(cub::DeviceScan::InclusiveScan(tmp, tmpsz, i2, P[2], DDAdd(), (int)n + 1, st));
+    GH_CUDA(cub::DeviceScan::InclusiveScan(tmp, tmpsz, i3, P[3], DDAdd(), (int)n + 1, st));
+  }
 
   // entries: need the count on the host to size the arrays
   GH_CUDA(cudaStreamSynchronize(st));
   const int nentries = w->h_pinned[0];
-  using V4 = typename Vec4<Real>::type;
-  GH_TRY(w->com.reserve(sizeof(V4) * (size_t)nentries));
-  GH_TRY(w->cen.reserve(sizeof(V4) * (size_t)nentries));
+  GH_TRY(w->node.reserve(sizeof(Node<Real>) * (size_t)nentries));
   GH_TRY(w->skip.reserve(sizeof(int) * (size_t)nentries));
-  Entries<Real> E{w->com.as<V4>(), w->cen.as<V4>(), w->skip.as<int>()};
+  Entries<Real> E{w->node.as<Node<Real>>(), w->skip.as<int>()};
+  const double inv_theta2 = 1.0 / (a.theta * a.theta);  // theta = 0 -> inf: cells are never accepted
   int *maxlevel = w->misc.as<int>();
   unsigned long long *dstats = reinterpret_cast<unsigned long long *>(w->misc.as<char>() + 16);
   GH_CUDA(cudaMemsetAsync(w->misc.ptr, 0, 64, st));
-  emit_kernel<Src, Real><<<nblk(n, 128), 128, 0, st>>>(src, sidx, shi, slo, clev, base, w->P.as<DD4>(),
-                                                     n, root, rel_origin, E, maxlevel);
+  emit_kernel<Src, Real><<<nblk(n, 128), 128, 0, st>>>(src, sidx, shi, slo, clev, base, P[0], P[1], P[2],
+                                                     P[3], n, root, rel_origin, inv_theta2, E, maxlevel);
   GH_LAUNCH_CHECK();
 
   // targets: Morton order.  Self case: the source order restricted to the owned slice is the
@@ -631,16 +644,17 @@ static int tree_impl(const TreeArgs &a, Src src, const float4 *tgt32, TreeWorksp
   }
 
   // K8
-  const Real eps2 = (Real)(a.eps * a.eps), theta2 = (Real)(a.theta * a.theta);
+  const Real eps2 = (Real)(a.eps * a.eps);
   const int64_t nwarps = (ni + 31) / 32;
   const unsigned blocks = (unsigned)((nwarps + 3) / 4);
   if (ev) GH_CUDA(cudaEventRecord(ev[0], st));
-  if (a.want_stats)
-    walk_kernel<Real, true><<<blocks, 128, 0, st>>>(E, nentries, tv, ni, root, rel_origin, eps2, theta2,
-                                                   a.ep, dstats);
-  else
-    walk_kernel<Real, false><<<blocks, 128, 0, st>>>(E, nentries, tv, ni, root, rel_origin, eps2,
-                                                    theta2, a.ep, dstats);
+  const bool guard = (a.eps == 0.0);
+#define GH_WALK(STATS, GUARD)                                                                      \
+  walk_kernel<Real, STATS, GUARD><<<blocks, 128, 0, st>>>(E.node, E.skip, nentries, tv, ni, root, \
+                                                         rel_origin, eps2, a.ep, dstats)
+  if (a.want_stats) { if (guard) GH_WALK(true, true); else GH_WALK(true, false); }
+  else { if (guard) GH_WALK(false, true); else GH_WALK(false, false); }
+#undef GH_WALK
   GH_LAUNCH_CHECK();
   if (ev) GH_CUDA(cudaEventRecord(ev[1], st));
   GH_CUDA(cudaMemcpyAsync(&w->h_pinned[1], maxlevel, sizeof(int), cudaMemcpyDeviceToHost, st));
