@@ -17,13 +17,14 @@
 //                       z-major so that key order == the reference's branch order (:441-450);
 //                       levels 1-21 in `hi`, 22-42 in `lo`
 //   K5  sort            stable LSD radix sort of (lo, hi) with the particle index (CUB
-//                       DeviceRadixSort: library plumbing)
+//                       DeviceRadixSort and one CUB int prefix sum: library plumbing)
 //   K6a common levels   c[p] = number of octant levels shared by sorted neighbours p, p+1.
 //                       A cell of level l starts at p  <=>  c[p-1] < l <= c[p]; therefore the
 //                       depth-first (pre-order) position of every cell and leaf is a prefix sum
 //                       of (cells opened at p) + 1.
-//   K7  moments         double-double inclusive scan of (m, m x, m y, m z) in Morton order; a
-//                       cell covering sorted particles [p, b] has mass = P[b+1] - P[p] (the
+//   K7  moments         sources gathered once into Morton order, then a fused, deterministic
+//                       three-phase double-double inclusive scan of (m, m x, m y, m z); a cell
+//                       covering sorted particles [p, b] has mass = P[b+1] - P[p] (the
 //                       double-double difference is exact to ~1e-30, so no cancellation)
 //   K6b emit            per particle: walk down its key, write one entry per opened cell
 //                       (centre, side, COM, mass, skip = pre-order index after the subtree, found
@@ -40,8 +41,6 @@
 #include "common.cuh"
 
 #include <cub/cub.cuh>
-#include <thrust/iterator/counting_iterator.h>
-#include <thrust/iterator/transform_iterator.h>
 #include <climits>
 #include <cstdlib>
 
@@ -207,9 +206,8 @@ __global__ void levels_kernel(const uint64_t *__restrict__ hi, const uint64_t *_
 // ---- K7 double-double moments -------------------------------------------------------------------
 // Inclusive scans of m, m x, m y, m z over the Morton-sorted particles, in double-double
 // arithmetic (hi + lo, ~106 bits), so that the moments of a cell covering sorted particles
-// [p, b] are P[b+1] - P[p] without cancellation (errors ~1e-30 of the total).  One scan per
-// component on 16-byte elements; the inputs are produced on the fly by a transform iterator
-// (the products m x are formed exactly: hi = fl(m x), lo = fma(m, x, -hi)).
+// [p, b] are P[b+1] - P[p] without cancellation (errors ~1e-30 of the total).  The products m x
+// are formed exactly: hi = fl(m x), lo = fma(m, x, -hi).
 struct DD {
   double h, l;
 };
@@ -222,36 +220,166 @@ __device__ __forceinline__ void dd_add(double ah, double al, double bh, double b
   rh = __dadd_rn(s, e);
   rl = __dadd_rn(e, -__dadd_rn(rh, -s));
 }
-struct DDAdd {
-  __device__ __forceinline__ DD operator()(const DD &a, const DD &b) const {
-    DD r;
-    dd_add(a.h, a.l, b.h, b.l, r.h, r.l);
-    return r;
-  }
+// sources gathered once into Morton order: (x, y, z, m) as double4, so that the moment scans,
+// the emit kernel and the walk's target loads are all coalesced
+template <class Src>
+__global__ void gather_sorted_kernel(Src src, const int *__restrict__ idx, int64_t n,
+                                     double4 *__restrict__ out) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const int64_t j = idx[p];
+  double x, y, z;
+  src.get(j, x, y, z);
+  out[p] = make_double4(x, y, z, src.m(j));
+}
+// Deterministic three-phase inclusive scan of the four double-double moment sequences, fused
+// (one read of the sorted double4 array per phase, fixed summation order -> bitwise reproducible
+// run to run, unlike a decoupled-look-back scan with a non-associative operator).
+//   phase 1: per-CTA totals of SCAN_CHUNK consecutive particles
+//   phase 2: one CTA scans the CTA totals (exclusive)
+//   phase 3: each CTA rescans its chunk from its offset and writes P_c[p+1], c = 0..3
+static constexpr int SCAN_THREADS = 256;
+static constexpr int SCAN_PER_THREAD = 8;
+static constexpr int SCAN_CHUNK = SCAN_THREADS * SCAN_PER_THREAD;
+
+struct DD4 {
+  DD c[4];
 };
-// element p of component C (0 = m, 1..3 = m x_k) of the shifted sequence: 0 for p = 0, else
-// the value of sorted particle p-1
-template <class Src, int C>
-struct MomentIn {
-  Src src;
-  const int *idx;
-  __device__ __forceinline__ DD operator()(int p) const {
-    DD r;
-    r.h = r.l = 0.0;
-    if (p == 0) return r;
-    const int64_t j = idx[p - 1];
-    const double m = src.m(j);
-    if (C == 0) {
-      r.h = m;
-    } else {
-      double x[3];
-      src.get(j, x[0], x[1], x[2]);
-      r.h = __dmul_rn(m, x[C - 1]);
-      r.l = fma(m, x[C - 1], -r.h);
+__device__ __forceinline__ DD4 dd4_zero() {
+  DD4 r;
+#pragma unroll
+  for (int k = 0; k < 4; k++) r.c[k].h = r.c[k].l = 0.0;
+  return r;
+}
+__device__ __forceinline__ DD4 dd4_add(const DD4 &a, const DD4 &b) {
+  DD4 r;
+#pragma unroll
+  for (int k = 0; k < 4; k++) dd_add(a.c[k].h, a.c[k].l, b.c[k].h, b.c[k].l, r.c[k].h, r.c[k].l);
+  return r;
+}
+__device__ __forceinline__ DD4 dd4_of(const double4 q) {
+  DD4 r;
+  r.c[0].h = q.w;
+  r.c[0].l = 0.0;
+  const double x[3] = {q.x, q.y, q.z};
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    r.c[1 + k].h = __dmul_rn(q.w, x[k]);
+    r.c[1 + k].l = fma(q.w, x[k], -r.c[1 + k].h);
+  }
+  return r;
+}
+__device__ __forceinline__ DD4 dd4_shfl_up(const DD4 &v, int d) {
+  DD4 r;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    r.c[k].h = __shfl_up_sync(0xffffffffu, v.c[k].h, d);
+    r.c[k].l = __shfl_up_sync(0xffffffffu, v.c[k].l, d);
+  }
+  return r;
+}
+// inclusive scan of one DD4 per thread across the CTA (warp shuffles + smem for warp totals);
+// returns the inclusive value; *total (all threads) receives the CTA total
+__device__ __forceinline__ DD4 block_scan_dd4(DD4 v, DD4 *total, DD4 *sh /* SCAN_THREADS/32 + 1 */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    DD4 o = dd4_shfl_up(v, d);
+    if (lane >= d) v = dd4_add(o, v);
+  }
+  if (lane == 31) sh[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    DD4 t = (lane < SCAN_THREADS / 32) ? sh[lane] : dd4_zero();
+#pragma unroll
+    for (int d = 1; d < SCAN_THREADS / 32; d <<= 1) {
+      DD4 o = dd4_shfl_up(t, d);
+      if (lane >= d) t = dd4_add(o, t);
     }
-    return r;
+    if (lane < SCAN_THREADS / 32) sh[lane] = t;  // inclusive warp totals
   }
-};
+  __syncthreads();
+  if (wid > 0) v = dd4_add(sh[wid - 1], v);
+  *total = sh[SCAN_THREADS / 32 - 1];
+  __syncthreads();
+  return v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+moments_phase1(const double4 *__restrict__ sp, int64_t n, DD4 *__restrict__ blocksum) {
+  __shared__ DD4 sh[SCAN_THREADS / 32 + 1];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_CHUNK + (int64_t)threadIdx.x * SCAN_PER_THREAD;
+  DD4 acc = dd4_zero();
+#pragma unroll
+  for (int k = 0; k < SCAN_PER_THREAD; k++)
+    if (base + k < n) acc = dd4_add(acc, dd4_of(sp[base + k]));
+  DD4 total;
+  block_scan_dd4(acc, &total, sh);
+  if (threadIdx.x == 0) blocksum[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(SCAN_THREADS)
+moments_phase2(DD4 *__restrict__ blocksum, int nblocks) {
+  // exclusive scan of blocksum in place; one CTA, each thread owns a contiguous run
+  __shared__ DD4 sh[SCAN_THREADS / 32 + 1];
+  const int per = (nblocks + SCAN_THREADS - 1) / SCAN_THREADS;
+  const int b0 = threadIdx.x * per;
+  DD4 acc = dd4_zero();
+  for (int k = 0; k < per; k++)
+    if (b0 + k < nblocks) acc = dd4_add(acc, blocksum[b0 + k]);
+  DD4 total;
+  DD4 incl = block_scan_dd4(acc, &total, sh);
+  // exclusive prefix of this thread's run = incl - acc, recomputed by re-adding to stay exact:
+  // walk the run again starting from the previous thread's inclusive value
+  DD4 prev = dd4_zero();
+  {
+    __shared__ DD4 inc_all[SCAN_THREADS];
+    inc_all[threadIdx.x] = incl;
+    __syncthreads();
+    if (threadIdx.x > 0) prev = inc_all[threadIdx.x - 1];
+  }
+  for (int k = 0; k < per; k++) {
+    if (b0 + k < nblocks) {
+      DD4 v = blocksum[b0 + k];
+      blocksum[b0 + k] = prev;
+      prev = dd4_add(prev, v);
+    }
+  }
+}
+__global__ void __launch_bounds__(SCAN_THREADS)
+moments_phase3(const double4 *__restrict__ sp, int64_t n, const DD4 *__restrict__ blockoff,
+               DD *__restrict__ P0, DD *__restrict__ P1, DD *__restrict__ P2, DD *__restrict__ P3) {
+  __shared__ DD4 sh[SCAN_THREADS / 32 + 1];
+  __shared__ DD4 inc_all[SCAN_THREADS];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_CHUNK + (int64_t)threadIdx.x * SCAN_PER_THREAD;
+  DD4 v[SCAN_PER_THREAD];
+  DD4 acc = dd4_zero();
+#pragma unroll
+  for (int k = 0; k < SCAN_PER_THREAD; k++) {
+    v[k] = (base + k < n) ? dd4_of(sp[base + k]) : dd4_zero();
+    acc = dd4_add(acc, v[k]);
+  }
+  DD4 total;
+  DD4 incl = block_scan_dd4(acc, &total, sh);
+  inc_all[threadIdx.x] = incl;
+  __syncthreads();
+  DD4 run = blockoff[blockIdx.x];
+  if (threadIdx.x > 0) run = dd4_add(run, inc_all[threadIdx.x - 1]);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    DD z;
+    z.h = z.l = 0.0;
+    P0[0] = z; P1[0] = z; P2[0] = z; P3[0] = z;
+  }
+#pragma unroll
+  for (int k = 0; k < SCAN_PER_THREAD; k++) {
+    if (base + k < n) {
+      run = dd4_add(run, v[k]);
+      P0[base + k + 1] = run.c[0];
+      P1[base + k + 1] = run.c[1];
+      P2[base + k + 1] = run.c[2];
+      P3[base + k + 1] = run.c[3];
+    }
+  }
+}
 
 // ---- K6b emit -----------------------------------------------------------------------------------
 template <class Real> struct Vec4;
@@ -281,7 +409,7 @@ __device__ __forceinline__ bool same_prefix(uint64_t h, uint64_t l, uint64_t h0,
 }
 
 template <class Src, class Real>
-__global__ void emit_kernel(Src src, const int *__restrict__ idx, const uint64_t *__restrict__ hi,
+__global__ void emit_kernel(const double4 *__restrict__ sp, const uint64_t *__restrict__ hi,
                             const uint64_t *__restrict__ lo, const signed char *__restrict__ clev,
                             const int *__restrict__ base /* n+1, exclusive scan of cnt */,
                             const DD *__restrict__ P0, const DD *__restrict__ P1,
@@ -295,9 +423,8 @@ __global__ void emit_kernel(Src src, const int *__restrict__ idx, const uint64_t
                oz = rel_origin ? root[2] : 0.0;
   const int c = clev[p];
   const int cprev = (p > 0) ? clev[p - 1] : -1;
-  const int64_t j = idx[p];
-  double x[3];
-  src.get(j, x[0], x[1], x[2]);
+  const double4 self = sp[p];
+  const double x[3] = {self.x, self.y, self.z};
   int e = base[p];
   if (c > cprev) {
     const uint64_t h0 = hi[p], l0 = lo ? lo[p] : 0;
@@ -309,13 +436,22 @@ __global__ void emit_kernel(Src src, const int *__restrict__ idx, const uint64_t
         // this cell (level, centre cc, side size) starts at p.  Galloping + binary search for the
         // last sorted particle b sharing `level` octant levels with p (p+1 does, since c >= level).
         int64_t lo_i = p + 1, step = 1, hi_i;
-        for (;;) {
+        // most cells hold a handful of particles: look at the next few common-level bytes first
+        // (sequential, cached) -- the cell ends at the first q > p with clev[q] < level
+        bool found = false;
+        for (int t = 0; t < 12 && lo_i < n; t++) {
+          if (clev[lo_i] < level) { found = true; break; }
+          lo_i++;
+        }
+        if (lo_i >= n) { lo_i = n - 1; found = true; }
+        hi_i = lo_i;
+        if (!found) for (;;) {
           int64_t q = lo_i + step;
           if (q >= n) { hi_i = n - 1; break; }
           if (same_prefix(hi[q], lo ? lo[q] : 0, h0, l0, level)) { lo_i = q; step <<= 1; }
           else { hi_i = q - 1; break; }
         }
-        while (lo_i < hi_i) {
+        while (!found && lo_i < hi_i) {
           int64_t mid = (lo_i + hi_i + 1) >> 1;
           if (same_prefix(hi[mid], lo ? lo[mid] : 0, h0, l0, level)) lo_i = mid;
           else hi_i = mid - 1;
@@ -361,7 +497,7 @@ __global__ void emit_kernel(Src src, const int *__restrict__ idx, const uint64_t
   com.x = (Real)(x[0] - ox);
   com.y = (Real)(x[1] - oy);
   com.z = (Real)(x[2] - oz);
-  com.w = (Real)src.m(j);
+  com.w = (Real)self.w;
   cen.x = cen.y = cen.z = (Real)0;
   cen.w = (Real)-1;
   E.node[e].cen = cen;
@@ -394,6 +530,7 @@ __device__ __forceinline__ float inv_cube(float s) {
 }
 
 struct TargetsView {
+  const double4 *sorted;  // non-null: target p IS sorted source p (self evaluation of all sources)
   const double *pos64;   // (ni,3) or null
   const float4 *pos32;   // (ni) or null  (already relative to the f32 engine origin)
   const int *order;      // sorted position -> local target index (null = identity)
@@ -423,7 +560,12 @@ walk_kernel(const Node<Real> *__restrict__ nodes, const int *__restrict__ skips,
     ti = tv.order ? (int64_t)tv.order[p] - tv.order_offset : p;
     const double ox = rel_origin ? root[0] : 0.0, oy = rel_origin ? root[1] : 0.0,
                  oz = rel_origin ? root[2] : 0.0;
-    if (tv.pos64) {
+    if (tv.sorted) {
+      const double4 q = tv.sorted[p];
+      x = (Real)(q.x - ox);
+      y = (Real)(q.y - oy);
+      z = (Real)(q.z - oz);
+    } else if (tv.pos64) {
       x = (Real)(tv.pos64[3 * ti] - ox);
       y = (Real)(tv.pos64[3 * ti + 1] - oy);
       z = (Real)(tv.pos64[3 * ti + 2] - oz);
@@ -472,7 +614,7 @@ walk_kernel(const Node<Real> *__restrict__ nodes, const int *__restrict__ skips,
 // ---- workspace + orchestration --------------------------------------------------------------------
 struct TreeWorkspace {
   DeviceBuffer root, part, hi, lo, hi2, lo2, idx, idx2, clev, cnt, base, P, cubtmp;
-  DeviceBuffer node, skip, misc, thi, tidx, thi2, tidx2;
+  DeviceBuffer node, skip, misc, thi, tidx, thi2, tidx2, sorted, bsum;
   int64_t last_stats[5] = {0, 0, 0, 0, 0};
   int *h_pinned = nullptr;  // [0] nentries, [1] maxlevel ; pinned for async readback
   unsigned long long *h_stats = nullptr;
@@ -482,7 +624,7 @@ TreeWorkspace *tree_workspace_create() { return new TreeWorkspace(); }
 void tree_workspace_destroy(TreeWorkspace *w) {
   if (!w) return;
   DeviceBuffer *all[] = {&w->root, &w->part, &w->hi, &w->lo, &w->hi2, &w->lo2, &w->idx, &w->idx2,
-                         &w->clev, &w->cnt, &w->base, &w->P, &w->cubtmp, &w->node,
+                         &w->clev, &w->cnt, &w->base, &w->P, &w->cubtmp, &w->node, &w->sorted, &w->bsum,
                          &w->skip, &w->misc, &w->thi, &w->tidx, &w->thi2, &w->tidx2};
   for (auto *b : all) b->release();
   if (w->h_pinned) cudaFreeHost(w->h_pinned);
@@ -539,10 +681,6 @@ static int tree_impl(const TreeArgs &a, Src src, const float4 *tgt32, TreeWorksp
   tb = 0;
   cub::DeviceScan::InclusiveSum(nullptr, tb, (int *)nullptr, (int *)nullptr, (int)n + 1, st);
   if (tb > tmp_bytes) tmp_bytes = tb;
-  tb = 0;
-  cub::DeviceScan::InclusiveScan(nullptr, tb, (DD *)nullptr, (DD *)nullptr, DDAdd(), (int)n + 1, st);
-  tb += 4096;  // transform-iterator inputs may need a little more
-  if (tb > tmp_bytes) tmp_bytes = tb;
   GH_TRY(w->cubtmp.reserve(tmp_bytes));
   void *tmp = w->cubtmp.ptr;
   size_t tmpsz = w->cubtmp.bytes;
@@ -577,22 +715,22 @@ static int tree_impl(const TreeArgs &a, Src src, const float4 *tgt32, TreeWorksp
   GH_CUDA(cudaMemcpyAsync(&w->h_pinned[0], base + n, sizeof(int), cudaMemcpyDeviceToHost, st));
 
   // K7
+  GH_TRY(w->sorted.reserve(sizeof(double4) * (size_t)n));
+  double4 *sp = w->sorted.as<double4>();
+  gather_sorted_kernel<<<nblk(n, 256), 256, 0, st>>>(src, sidx, n, sp);
+  GH_LAUNCH_CHECK();
   GH_TRY(w->P.reserve(sizeof(DD) * 4 * (size_t)(n + 1)));
   DD *P[4];
   for (int c = 0; c < 4; c++) P[c] = w->P.as<DD>() + (size_t)c * (size_t)(n + 1);
   {
-    thrust::counting_iterator<int> cnt_it(0);
-    auto i0 = thrust::make_transform_iterator(cnt_it, MomentIn<Src, 0>{src, sidx});
-    auto i1 = thrust::make_transform_iterator(cnt_it, MomentIn<Src, 1>{src, sidx});
-    auto i2 = thrust::make_transform_iterator(cnt_it, MomentIn<Src, 2>{src, sidx});
-    auto i3 = thrust::make_transform_iterator(cnt_it, MomentIn<Src, 3>{src, sidx});
-    size_t need = 0;
-    cub::DeviceScan::InclusiveScan(nullptr, need, i1, P[1], DDAdd(), (int)n + 1, st);
-    if (need > w->cubtmp.bytes) { GH_TRY(w->cubtmp.reserve(need)); tmp = w->cubtmp.ptr; tmpsz = w->cubtmp.bytes; }
-    GH_CUDA(cub::DeviceScan::InclusiveScan(tmp, tmpsz, i0, P[0], DDAdd(), (int)n + 1, st));
-    GH_CUDA(cub::DeviceScan::InclusiveScan(tmp, tmpsz, i1, P[1], DDAdd(), (int)n + 1, st));
-    GH_CUDA(cub::DeviceScan::InclusiveScan(tmp, tmpsz, i2, P[2], DDAdd(), (int)n + 1, st));
-    GH_CUDA(cub::DeviceScan::InclusiveScan(tmp, tmpsz, i3, P[3], DDAdd(), (int)n + 1, st));
+    const int nsb = (int)((n + SCAN_CHUNK - 1) / SCAN_CHUNK);
+    GH_TRY(w->bsum.reserve(sizeof(DD4) * (size_t)nsb));
+    moments_phase1<<<nsb, SCAN_THREADS, 0, st>>>(sp, n, w->bsum.as<DD4>());
+    GH_LAUNCH_CHECK();
+    moments_phase2<<<1, SCAN_THREADS, 0, st>>>(w->bsum.as<DD4>(), nsb);
+    GH_LAUNCH_CHECK();
+    moments_phase3<<<nsb, SCAN_THREADS, 0, st>>>(sp, n, w->bsum.as<DD4>(), P[0], P[1], P[2], P[3]);
+    GH_LAUNCH_CHECK();
   }
 
   // entries: need the count on the host to size the arrays
@@ -605,19 +743,21 @@ static int tree_impl(const TreeArgs &a, Src src, const float4 *tgt32, TreeWorksp
   int *maxlevel = w->misc.as<int>();
   unsigned long long *dstats = reinterpret_cast<unsigned long long *>(w->misc.as<char>() + 16);
   GH_CUDA(cudaMemsetAsync(w->misc.ptr, 0, 64, st));
-  emit_kernel<Src, Real><<<nblk(n, 128), 128, 0, st>>>(src, sidx, shi, slo, clev, base, P[0], P[1], P[2],
+  emit_kernel<Src, Real><<<nblk(n, 128), 128, 0, st>>>(sp, shi, slo, clev, base, P[0], P[1], P[2],
                                                      P[3], n, root, rel_origin, inv_theta2, E, maxlevel);
   GH_LAUNCH_CHECK();
 
   // targets: Morton order.  Self case: the source order restricted to the owned slice is the
   // sorted order itself when the slice is everything; otherwise sort the targets' own keys.
   TargetsView tv;
+  tv.sorted = nullptr;
   tv.pos64 = tgt32 ? nullptr : a.tgt_pos;
   tv.pos32 = tgt32;
   tv.order = nullptr;
   tv.order_offset = 0;
   if (a.targets_are_sources && ni == n) {
     tv.order = sidx;
+    tv.sorted = sp;
   } else if (ni > 32) {
     GH_TRY(w->thi.reserve(sizeof(uint64_t) * ni));
     GH_TRY(w->thi2.reserve(sizeof(uint64_t) * ni));
