@@ -351,10 +351,28 @@ def main():
         if clocks:
             roofline["frac_at_observed_clock"] = achieved / (fp32_peak_tflops * clocks["sm_mhz"] / sm_max)
     else:
-        hbm = peaks.get("hbm_gbs", 6650.0)
-        roofline = {"bound": "l2+fma (walk)", "achieved": None, "peak": hbm, "unit": "GB/s", "frac": None,
-                    "traffic": None, "kernel": "walk_kernel", "kernel_ms": kernel_ms,
-                    "how": "walk is latency/L2 bound; build is HBM bound (see DESIGN.md)"}
+        # one extra, untimed evaluation with counters on: accepted / visited entries per target
+        J.tree_stats(True)
+        tx = torch.from_numpy(w["x"]).cuda()
+        tm = torch.from_numpy(w["m"]).cuda()
+        J.tree_force(tx, tm, w["eps"], w["theta"], precision=w["prec"])
+        torch.cuda.synchronize()
+        st = J.tree_stats()
+        J.tree_stats(False)
+        acc_per = st["accepted"] / float(n)
+        vis_per = st["visited"] / float(n)
+        achieved = (n / world) * acc_per * FLOP_PER_INTERACTION / (kernel_ms * 1e-3) / 1e12
+        roofline = {"bound": "issue (walk); fp32_fma peak quoted", "achieved": achieved, "peak": fp32_peak_tflops,
+                    "unit": "TFLOP/s", "frac": achieved / fp32_peak_tflops, "traffic": None,
+                    "kernel": "walk_kernel", "kernel_ms": kernel_ms,
+                    "accepted_per_target": acc_per, "visited_per_target": vis_per,
+                    "tree_entries": st["entries"], "tree_cells": st["cells"], "deepest_level": st["maxlevel"],
+                    "build_ms": ms_per_step - kernel_ms,
+                    "how": "20 flop x accepted nodes (the reference's own accepted set: %.0f per target) / "
+                           "CUDA-event time of the walk kernel, against the FP32 FMA peak; ncu "
+                           "(profiles/) shows the walk is instruction-issue bound (79%% issue-active, 35 "
+                           "SASS instructions per visited entry), the build (ms_per_step - kernel_ms) is "
+                           "HBM-streaming bound" % acc_per}
 
     line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",

@@ -11,9 +11,9 @@ from .gravhopper import (Simulation, IC, GravHopperException, UninitializedSimul
                          ICException, UnknownAlgorithmException, ExternalPackageException,
                          force_centers)
 from . import jbgrav as grav
-from . import jbgrav, _jbgrav, units
+from . import jbgrav, _jbgrav, units, potentials
 
 __version__ = "0.1.0"
-__all__ = ["Simulation", "IC", "grav", "jbgrav", "_jbgrav", "units", "GravHopperException",
+__all__ = ["Simulation", "IC", "grav", "jbgrav", "_jbgrav", "units", "potentials", "GravHopperException",
            "UninitializedSimulationException", "ICException", "UnknownAlgorithmException",
            "ExternalPackageException", "force_centers"]

@@ -40,6 +40,8 @@ PROTOTYPES = {
     "gh_engine_source_stride_bytes": (C.c_int, [_eng, C.POINTER(_i64)]),
     "gh_engine_set_origin": (C.c_int, [_eng, _dp]),
     "gh_engine_prepare": (C.c_int, [_eng, C.c_double]),
+    "gh_engine_add_potential": (C.c_int, [_eng, C.c_int, _dp, C.c_int]),
+    "gh_engine_clear_potentials": (C.c_int, [_eng]),
     "gh_engine_step": (C.c_int, [_eng, C.c_double, C.c_double, C.c_double, C.c_int, _vp, C.c_int]),
     "gh_engine_run": (C.c_int, [_eng, _i64, C.c_double, C.c_double, C.c_double, C.c_int, _i64, _vp,
                                 _vp]),

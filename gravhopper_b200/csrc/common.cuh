@@ -60,6 +60,20 @@ struct DeviceBuffer {
 //            (__dmul_rn/__dadd_rn) exactly as numpy evaluates the reference expressions.
 enum { EP_ACC = 0, EP_STEP = 1 };
 
+// Device-native analytic external potentials: a tiny kernel evaluates them at
+// x_half into the step's external-acceleration buffer just before the force kernel, so a run in a
+// static background field never leaves the device (replaces the per-step Python callback of
+// gravhopper.py:462-473 for these cases; kept out of the force kernels to keep their register
+// count, and so their occupancy, unchanged).
+// Units: kpc, Msun, km/s; the returned acceleration is in km/s/Myr.
+#define GH_MAX_POTENTIALS 4
+#define GH_POT_NPARAM 8
+struct PotentialSet {
+  int n;
+  int kind[GH_MAX_POTENTIALS];
+  double prm[GH_MAX_POTENTIALS][GH_POT_NPARAM];
+};
+
 struct Epilogue {
   int mode;
   // EP_ACC
@@ -76,6 +90,54 @@ struct Epilogue {
   double dt;
   double origin[3];
 };
+
+// kinds and parameter layouts (centre always in prm[1..3], kpc):
+//  1 POINTMASS / PLUMMER: prm[0] = M [Msun], prm[4] = softening b [kpc]:  a = -G M d / (r^2+b^2)^1.5
+//  2 HERNQUIST:           prm[0] = M, prm[4] = a:                         a = -G M d / (r (r+a)^2)
+//  3 NFW:                 prm[0] = M_s = 4 pi rho0 rs^3, prm[4] = rs:     a = -G M_s (ln(1+x) - x/(1+x)) d / r^3
+//  4 LOGHALO:             prm[0] = v0 [km/s], prm[4] = rc, prm[5] = q:    a = -v0^2 (x, y, z/q^2) / (rc^2+x^2+y^2+z^2/q^2)
+//  5 MIYAMOTO-NAGAI:      prm[0] = M, prm[4] = a, prm[5] = b
+__device__ __forceinline__ void eval_potentials(const PotentialSet &ps, const double x[3], double a[3]) {
+  for (int k = 0; k < ps.n; k++) {
+    const double *q = ps.prm[k];
+    const double d0 = x[0] - q[1], d1 = x[1] - q[2], d2 = x[2] - q[3];
+    double f0 = 0.0, f1 = 0.0, f2 = 0.0;  // (km/s)^2 / kpc
+    switch (ps.kind[k]) {
+      case 1: {
+        const double s = d0 * d0 + d1 * d1 + d2 * d2 + q[4] * q[4];
+        const double w = (s > 0.0) ? -GH_G * q[0] / (s * sqrt(s)) : 0.0;
+        f0 = w * d0; f1 = w * d1; f2 = w * d2;
+      } break;
+      case 2: {
+        const double r = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+        const double w = (r > 0.0) ? -GH_G * q[0] / (r * (r + q[4]) * (r + q[4])) : 0.0;
+        f0 = w * d0; f1 = w * d1; f2 = w * d2;
+      } break;
+      case 3: {
+        const double r = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+        const double xs = r / q[4];
+        const double w = (r > 0.0) ? -GH_G * q[0] * (log1p(xs) - xs / (1.0 + xs)) / (r * r * r) : 0.0;
+        f0 = w * d0; f1 = w * d1; f2 = w * d2;
+      } break;
+      case 4: {
+        const double iq2 = 1.0 / (q[5] * q[5]);
+        const double w = -q[0] * q[0] / (q[4] * q[4] + d0 * d0 + d1 * d1 + d2 * d2 * iq2);
+        f0 = w * d0; f1 = w * d1; f2 = w * d2 * iq2;
+      } break;
+      case 5: {
+        const double zb = sqrt(d2 * d2 + q[5] * q[5]);
+        const double az = q[4] + zb;
+        const double s = d0 * d0 + d1 * d1 + az * az;
+        const double w = -GH_G * q[0] / (s * sqrt(s));
+        f0 = w * d0; f1 = w * d1; f2 = (zb > 0.0) ? w * d2 * az / zb : 0.0;
+      } break;
+      default: break;
+    }
+    a[0] += f0 * GH_KPC_PER_KMS_MYR;  // 1 (km/s)^2/kpc = K km/s/Myr
+    a[1] += f1 * GH_KPC_PER_KMS_MYR;
+    a[2] += f2 * GH_KPC_PER_KMS_MYR;
+  }
+}
 
 __device__ __forceinline__ void apply_epilogue(const Epilogue &ep, int64_t i, double ax, double ay,
                                                double az) {
@@ -132,6 +194,9 @@ int launch_pack32(const double *pos, const double *mass, int64_t n, const double
 int launch_energy(const double *x, const double *v, const double *m_tgt, int64_t ni,
                   const double *src_pos, const double *src_mass, int64_t nj, int64_t self_offset,
                   double eps, double *out2, cudaStream_t stream);
+// ext_out[i] = (ext_in ? ext_in[i] : 0) + sum of native potentials at xhalf[i]   (km/s/Myr)
+int launch_potentials(const PotentialSet &ps, const double *xhalf, int64_t n, const double *ext_in,
+                      double *ext_out, cudaStream_t stream);
 // x_half = x + ((0.5 v) dt) K   (gravhopper.py:409)
 int launch_half_drift(const double *x, const double *v, const double *mass, int64_t n, double dt,
                       double *xhalf, float4 *src32, const double origin[3], cudaStream_t stream);

@@ -66,8 +66,8 @@ __device__ __forceinline__ void store_tile32(Tile32<BLOCK> &t, int tid, float4 g
 // MODE 1: per-source scaling described above: 11 FP32 ops, but d' of a source that coincides
 //         with the target is a rounding residue instead of an exact zero -> only usable when
 //         the caller knows targets never coincide with sources (kept for measurement).
-template <int BLOCK, int KI, bool GUARD, int MODE>
-__global__ void __launch_bounds__(BLOCK)
+template <int BLOCK, int KI, bool GUARD, int MODE, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
 direct_f32_kernel(const float4 *__restrict__ src, int64_t nj, const float4 *__restrict__ tgt,
                   int64_t ni, float eps2, int64_t jchunk, double *__restrict__ partial,
                   Epilogue ep) {
@@ -367,7 +367,7 @@ static Split choose_split(int64_t ni, int64_t nj, int itile, int tj) {
   return sp;
 }
 
-template <int BLOCK, int KI>
+template <int BLOCK, int KI, int MINB = 1>
 static int run_f32(const DirectArgs &a, DeviceBuffer &ws, cudaStream_t st, cudaEvent_t *ev) {
   Split sp = choose_split(a.ni, a.nj, BLOCK * KI, BLOCK);
   double *partial = nullptr;
@@ -380,13 +380,13 @@ static int run_f32(const DirectArgs &a, DeviceBuffer &ws, cudaStream_t st, cudaE
   if (ev) GH_CUDA(cudaEventRecord(ev[0], st));
   const int mode = env_int("GH_F32_MODE", 0);
   if (a.eps == 0.0)
-    direct_f32_kernel<BLOCK, KI, true, 0><<<grid, BLOCK, 0, st>>>(a.src32, a.nj, a.tgt32, a.ni, eps2,
+    direct_f32_kernel<BLOCK, KI, true, 0, MINB><<<grid, BLOCK, 0, st>>>(a.src32, a.nj, a.tgt32, a.ni, eps2,
                                                                  sp.jchunk, partial, a.ep);
   else if (mode == 1)
-    direct_f32_kernel<BLOCK, KI, false, 1><<<grid, BLOCK, 0, st>>>(a.src32, a.nj, a.tgt32, a.ni, eps2,
+    direct_f32_kernel<BLOCK, KI, false, 1, MINB><<<grid, BLOCK, 0, st>>>(a.src32, a.nj, a.tgt32, a.ni, eps2,
                                                                   sp.jchunk, partial, a.ep);
   else
-    direct_f32_kernel<BLOCK, KI, false, 0><<<grid, BLOCK, 0, st>>>(a.src32, a.nj, a.tgt32, a.ni, eps2,
+    direct_f32_kernel<BLOCK, KI, false, 0, MINB><<<grid, BLOCK, 0, st>>>(a.src32, a.nj, a.tgt32, a.ni, eps2,
                                                                   sp.jchunk, partial, a.ep);
   GH_LAUNCH_CHECK();
   if (ev) GH_CUDA(cudaEventRecord(ev[1], st));
@@ -432,6 +432,11 @@ int launch_direct(const DirectArgs &a, DeviceBuffer &ws, cudaStream_t st, cudaEv
     // fastest shape once there are enough targets to fill the chip
     if (ki == 0) ki = (a.ni >= 131072) ? 8 : (a.ni >= 16384 ? 2 : 1);
     if (blk == 0) blk = 128;
+    const int minb = env_int("GH_F32_MINB", 1);
+    if (ki == 8 && blk == 128 && minb == 3) return run_f32<128, 8, 3>(a, ws, st, ev);
+    if (ki == 8 && blk == 128 && minb == 4) return run_f32<128, 8, 4>(a, ws, st, ev);
+    if (ki == 4 && blk == 256 && minb == 3) return run_f32<256, 4, 3>(a, ws, st, ev);
+    if (ki == 4 && blk == 128 && minb == 6) return run_f32<128, 4, 6>(a, ws, st, ev);
     switch (ki * 1000 + blk) {
       case 8128: return run_f32<128, 8>(a, ws, st, ev);
       case 8064: return run_f32<64, 8>(a, ws, st, ev);
@@ -500,6 +505,27 @@ int launch_half_drift(const double *x, const double *v, const double *mass, int6
   if (n <= 0) return GH_OK;
   half_drift_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, v, mass, n, dt, xhalf, src32,
                                                                origin[0], origin[1], origin[2]);
+  GH_LAUNCH_CHECK();
+  return GH_OK;
+}
+
+__global__ void potentials_kernel(PotentialSet ps, const double *__restrict__ xhalf, int64_t n,
+                                  const double *__restrict__ ext_in, double *__restrict__ ext_out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x[3] = {xhalf[3 * i], xhalf[3 * i + 1], xhalf[3 * i + 2]};
+  double a[3] = {0.0, 0.0, 0.0};
+  if (ext_in) { a[0] = ext_in[3 * i]; a[1] = ext_in[3 * i + 1]; a[2] = ext_in[3 * i + 2]; }
+  eval_potentials(ps, x, a);
+  ext_out[3 * i] = a[0];
+  ext_out[3 * i + 1] = a[1];
+  ext_out[3 * i + 2] = a[2];
+}
+
+int launch_potentials(const PotentialSet &ps, const double *xhalf, int64_t n, const double *ext_in,
+                      double *ext_out, cudaStream_t st) {
+  if (n <= 0) return GH_OK;
+  potentials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ps, xhalf, n, ext_in, ext_out);
   GH_LAUNCH_CHECK();
   return GH_OK;
 }

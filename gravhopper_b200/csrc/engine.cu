@@ -217,12 +217,13 @@ struct gh_engine {
   double origin[3] = {0, 0, 0};
   double dt_built = 0.0;
   bool uploaded = false, xhalf_valid = false;
-  DeviceBuffer ws, ext;
+  DeviceBuffer ws, ext, ext2;
   TreeWorkspace *tw = nullptr;
   cudaEvent_t fev[2] = {nullptr, nullptr};
   bool fev_valid = false;
   int64_t launches = 0;
   double *d_energy = nullptr;
+  PotentialSet pots;
 
   double *xhalf_own(int b) const {
     return prec == GH_PREC_F64 ? reinterpret_cast<double *>(src[b]) + 3 * ib : xh_private;
@@ -319,6 +320,7 @@ int gh_engine_create(gh_engine **out, int device, int64_t n_total, int64_t i_beg
   e->ib = i_begin;
   e->ni = i_count;
   e->prec = prec;
+  memset(&e->pots, 0, sizeof(e->pots));
   auto fail = [&](int rc) { gh_engine_destroy(e); return rc; };
 #define E_CUDA(call)                                                                   \
   do {                                                                                 \
@@ -370,6 +372,7 @@ int gh_engine_destroy(gh_engine *e) {
   cudaFree(e->d_energy);
   e->ws.release();
   e->ext.release();
+  e->ext2.release();
   tree_workspace_destroy(e->tw);
   if (e->stream) cudaStreamDestroy(e->stream);
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
@@ -381,6 +384,23 @@ int gh_engine_set_origin(gh_engine *e, const double origin[3]) {
   if (!e || !origin) return GH_EINVAL;
   for (int k = 0; k < 3; k++) e->origin[k] = origin[k];
   e->xhalf_valid = false;
+  return GH_OK;
+}
+
+int gh_engine_clear_potentials(gh_engine *e) {
+  if (!e) return GH_EINVAL;
+  memset(&e->pots, 0, sizeof(e->pots));
+  return GH_OK;
+}
+int gh_engine_add_potential(gh_engine *e, int kind, const double *params, int nparams) {
+  if (!e || !params) return GH_EINVAL;
+  if (kind < 1 || kind > 5) { set_error("unknown potential kind %d", kind); return GH_EINVAL; }
+  if (nparams < 1 || nparams > GH_POT_NPARAM) { set_error("potential takes 1..%d parameters", GH_POT_NPARAM); return GH_EINVAL; }
+  if (e->pots.n >= GH_MAX_POTENTIALS) { set_error("at most %d native potentials", GH_MAX_POTENTIALS); return GH_EINVAL; }
+  const int k = e->pots.n++;
+  e->pots.kind[k] = kind;
+  for (int j = 0; j < GH_POT_NPARAM; j++) e->pots.prm[k][j] = (j < nparams) ? params[j] : 0.0;
+  if ((kind == 4) && e->pots.prm[k][5] == 0.0) e->pots.prm[k][5] = 1.0;  // q defaults to spherical
   return GH_OK;
 }
 
@@ -450,6 +470,11 @@ static int engine_step_impl(gh_engine *e, double dt, double eps, double theta, i
   if (e->copy_pending[nxt]) {
     GH_CUDA(cudaStreamWaitEvent(e->stream, e->copied[nxt], 0));
     e->copy_pending[nxt] = false;
+  }
+  if (e->pots.n > 0) {  // native potentials -> external-acceleration buffer, on the device
+    GH_TRY(e->ext2.reserve(sizeof(double) * 3 * (size_t)e->ni));
+    GH_TRY(launch_potentials(e->pots, e->xhalf_own(e->scur), e->ni, ext_dev, e->ext2.as<double>(), e->stream));
+    ext_dev = e->ext2.as<double>();
   }
   Epilogue ep;
   memset(&ep, 0, sizeof(ep));

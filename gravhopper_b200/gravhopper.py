@@ -25,6 +25,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib, ic_raw, jbgrav
+from .potentials import NativePotential
 from .units import (u, const, has_units, to_value, LENUNIT, VELUNIT, MASSUNIT, TIMEUNIT,
                     ACCELUNIT)
 
@@ -87,6 +88,12 @@ class _Engine(object):
             self.h = None
 
     __del__ = close
+
+    def set_potentials(self, pots):
+        _lib.check(self.lib.gh_engine_clear_potentials(self.h))
+        for p in pots:
+            prm = (C.c_double * 8)(*[float(v) for v in p.params()])
+            _lib.check(self.lib.gh_engine_add_potential(self.h, p.kind, prm, 8), "gh_engine_add_potential")
 
     def upload(self, pos, vel, mass):
         pos = np.ascontiguousarray(pos, dtype=np.float64)
@@ -157,6 +164,7 @@ class Simulation(object):
         self.extra_force_functions = []
         self.extra_timedependent_force_functions = []
         self.extra_velocitydependent_force_functions = []
+        self.native_potentials = []  # analytic fields evaluated on the device (potentials.py)
         # Things can come in in various units, but use these internally (gravhopper.py:150-154)
         self.lenunit = LENUNIT
         self.velunit = VELUNIT
@@ -298,6 +306,7 @@ class Simulation(object):
         eng = self._get_engine()
         s0 = self.timestep
         eng.upload(self._pos[s0], self._vel[s0], self._mass)
+        eng.set_potentials(self.native_potentials)
         if not self._has_hooks():
             # fully fused path: nothing leaves the device except the snapshots
             eng.run(N, dt, eps, theta, alg, every, self._pos[s0 + 1:s0 + 1 + nnew],
@@ -378,6 +387,7 @@ class Simulation(object):
         eng = self._get_engine()
         s = self.timestep
         eng.upload(self._pos[s - 1], self._vel[s - 1], self._mass)
+        eng.set_potentials(self.native_potentials)
         eng.prepare(dt)
         ext = None
         if self._has_hooks():
@@ -398,13 +408,20 @@ class Simulation(object):
                 raise UnknownAlgorithmException()
         else:
             nbody_gravity = np.zeros((self.Np, 3)) * self.accelunit
-        extra_accel = self.calculate_extra_acceleration(self.current_snap()['pos'], nbody_gravity,
-                                                        time=time, vel=self.prev_snap()['vel'])
+        self._include_native_in_extra = True  # here the natives are evaluated on the host too
+        try:
+            extra_accel = self.calculate_extra_acceleration(self.current_snap()['pos'], nbody_gravity,
+                                                            time=time, vel=self.prev_snap()['vel'])
+        finally:
+            self._include_native_in_extra = False
         return nbody_gravity + extra_accel
 
     def calculate_extra_acceleration(self, pos, template_array, time=None, vel=None):
         """Acceleration due to the registered external forces only (gravhopper.py:462-473)."""
         extaccel = np.zeros_like(template_array)
+        if getattr(self, "_include_native_in_extra", False):
+            for pot in self.native_potentials:
+                extaccel += pot(pos, None)
         for fn, args in self.extra_force_functions:
             extaccel += fn(pos, args)
         for fn, args in self.extra_timedependent_force_functions:
@@ -430,6 +447,12 @@ class Simulation(object):
         if isinstance(fn, list):
             for item in fn:
                 self.add_external_force(item, args)
+            return
+        if isinstance(fn, NativePotential):
+            if len(self.native_potentials) >= 4:
+                self.extra_force_functions.append((fn, args))  # beyond 4: falls back to a callback
+            else:
+                self.native_potentials.append(fn)
             return
         if not callable(fn):
             raise ExternalPackageException("galpy/gala/agama potential objects are not supported "

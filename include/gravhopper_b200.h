@@ -140,6 +140,23 @@ int gh_engine_prepare(gh_engine *e, double dt);
 int gh_engine_step(gh_engine *e, double dt, double eps, double theta, int algorithm,
                    const double *ext_acc, int ext_mem);
 
+/* Device-native analytic external potentials, evaluated at x_half inside the step kernels
+ * (replaces the Python callbacks of gravhopper.py:462-473 for these static fields).
+ * Units kpc, Msun, km/s.  params[1..3] = centre.  Kinds:
+ *   GH_POT_POINTMASS  params[0] = M, [4] = Plummer softening b        a = -G M d / (r^2+b^2)^{3/2}
+ *   GH_POT_HERNQUIST  params[0] = M, [4] = a                          a = -G M d / (r (r+a)^2)
+ *   GH_POT_NFW        params[0] = 4 pi rho0 rs^3, [4] = rs            a = -G M_s (ln(1+x) - x/(1+x)) d / r^3
+ *   GH_POT_LOGHALO    params[0] = v0 [km/s], [4] = rc, [5] = q        a = -v0^2 (x,y,z/q^2)/(rc^2+x^2+y^2+z^2/q^2)
+ *   GH_POT_MIYAMOTO   params[0] = M, [4] = a, [5] = b
+ * At most 4 per engine. */
+#define GH_POT_POINTMASS 1
+#define GH_POT_HERNQUIST 2
+#define GH_POT_NFW 3
+#define GH_POT_LOGHALO 4
+#define GH_POT_MIYAMOTO 5
+int gh_engine_add_potential(gh_engine *e, int kind, const double *params, int nparams);
+int gh_engine_clear_potentials(gh_engine *e);
+
 /* Single-GPU convenience: run nsteps steps back to back on the device.  Every `snapshot_every`
  * steps (and always after the last one when snapshot_every > 0) the state is copied to
  * pos_hist/vel_hist (host, (nsnap, i_count, 3) float64, row k = k-th snapshot taken); the copies
