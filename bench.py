@@ -44,6 +44,19 @@ FP32_LANES_PER_SM = 128
 
 def workload(kind):
     from gravhopper_b200 import ic_raw
+    if kind == "direct4m":
+        n = 1 << 22
+        x, v, m = ic_raw.Plummer(n, 1e-3, 1e6, seed=42)
+        return dict(x=np.ascontiguousarray(x), v=np.ascontiguousarray(v), m=m, eps=5e-5, dt=0.005,
+                    theta=0.7, alg="direct", prec="fp32",
+                    name="Plummer N=4194304, direct summation fp32, 1 DKD leapfrog step (north_star: 8-GPU scaling at N=4M)")
+    if kind == "galaxy":
+        n = 10_000_000
+        x, v, m = ic_raw.galaxy_model(n)
+        return dict(x=np.ascontiguousarray(x), v=np.ascontiguousarray(v), m=m, eps=0.05, dt=1.0, theta=0.7,
+                    alg="tree", prec="fp32",
+                    name="Exponential disk (2M) + Hernquist halo (8M) N=10000000, Barnes-Hut theta=0.7 fp32 walk, "
+                         "1 DKD leapfrog step (BASELINE.json configs[4])")
     if kind == "direct":
         x, v, m = ic_raw.Plummer(N_DIRECT, 1e-3, 1e6, seed=42)
         return dict(x=np.ascontiguousarray(x), v=np.ascontiguousarray(v), m=m, eps=5e-5, dt=0.005,
@@ -193,7 +206,8 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     P = max(1, min(cores, 32))
     kind = "reference" if O.ref() is not None else "port"
-    if args.workload == "direct":
+    wl_direct = w["alg"] == "direct"
+    if wl_direct:
         per = 24  # targets per process per step: ~1.3 s of reference C, 0.8 GB scratch each
     else:
         per = 2048
@@ -205,19 +219,19 @@ def run_reference(args):
             jobs = []
             for p in range(P):
                 sel = rng.choice(n, per, replace=False)
-                jobs.append((args.workload, w["x"][sel]))
+                jobs.append(("direct" if wl_direct else "tree", w["x"][sel]))
             t0 = time.perf_counter()
             pool.map(_ref_worker, jobs)
             if s >= args.warmup:
                 times.append(time.perf_counter() - t0)
     tot = sum(times)
-    units = (per * P * n) if args.workload == "direct" else (per * P)
+    units = (per * P * n) if wl_direct else (per * P)
     value = units * args.steps / tot
-    unit = "interactions/s" if args.workload == "direct" else "particle-steps/s"
+    unit = "interactions/s" if wl_direct else "particle-steps/s"
     sample = ("%d processes x %d targets x %d sources per step (direct_summation_position)" % (P, per, n)
-              if args.workload == "direct" else
+              if wl_direct else
               "%d processes, each: tree build over %d sources + walk of %d targets per step" % (P, n, per))
-    line = {"impl": "reference", "metric": "pairwise interactions/s" if args.workload == "direct" else "particle-steps/s",
+    line = {"impl": "reference", "metric": "pairwise interactions/s" if wl_direct else "particle-steps/s",
             "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -233,7 +247,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", choices=["direct", "tree"], default="direct")
+    ap.add_argument("--workload", choices=["direct", "tree", "direct4m", "galaxy"], default="direct")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -301,7 +315,8 @@ def main():
     ms_total, kernel_ms = float(t[0]), float(t[1])
     ms_per_step = ms_total / args.steps
 
-    if args.workload == "direct":
+    is_direct = w["alg"] == "direct"
+    if is_direct:
         units_per_step = float(n) * float(n)
         metric, unit = "pairwise interactions/s", "interactions/s"
     else:
@@ -314,12 +329,12 @@ def main():
     if rank == 0:
         hx = torch.from_numpy(w["x"]).pin_memory().numpy()
         hm = torch.from_numpy(w["m"]).pin_memory().numpy()
-        if args.workload == "direct":
+        if is_direct:
             call = lambda: J.direct_summation(hx, hm, w["eps"], precision=w["prec"])  # noqa: E731
         else:
             call = lambda: J.tree_force(hx, hm, w["eps"], w["theta"], precision=w["prec"])  # noqa: E731
         call()
-        reps = 3 if args.workload == "direct" else 5
+        reps = (1 if n > (1 << 21) else 3) if is_direct else 5
         t0 = time.perf_counter()
         for _ in range(reps):
             out = call()
@@ -327,8 +342,7 @@ def main():
         e2e = {"value": units_per_step / te, "unit": unit, "h2d_bytes_per_step": int(hx.nbytes + hm.nbytes),
                "d2h_bytes_per_step": int(out.nbytes), "ms_per_call": te * 1e3, "n_gpus_used": 1,
                "call": "_jbgrav.%s(host ndarray pos, mass, eps%s) -> host ndarray" %
-                       ("direct_summation" if args.workload == "direct" else "tree_force",
-                        "" if args.workload == "direct" else ", theta")}
+                       ("direct_summation" if is_direct else "tree_force", "" if is_direct else ", theta")}
 
     if rank != 0:
         if world > 1:
@@ -339,7 +353,7 @@ def main():
     peaks = measured_peaks()
     sm_max = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
     fp32_peak_tflops = SM_COUNT * FP32_LANES_PER_SM * 2 * sm_max * 1e6 / 1e12
-    if args.workload == "direct":
+    if is_direct:
         per_rank_units = units_per_step / world
         achieved = per_rank_units * FLOP_PER_INTERACTION / (kernel_ms * 1e-3) / 1e12
         roofline = {"bound": "fp32_fma", "achieved": achieved, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
@@ -382,7 +396,7 @@ def main():
                        "l2": "256 MB flush write between steps"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
     if not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"] = cpu_baseline_direct(w) if args.workload == "direct" else cpu_baseline_tree(w)
+        line["cpu_baseline"] = cpu_baseline_direct(w) if is_direct else cpu_baseline_tree(w)
     print(json.dumps(line))
     if world > 1:
         dist.barrier()

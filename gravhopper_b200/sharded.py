@@ -36,6 +36,48 @@ def partition(n, world):
     return out
 
 
+def morton_order(pos, bits=16):
+    """Permutation that sorts particles along a 3-D Morton (Z-order) curve of their bounding box
+    (host side, numpy; used only to lay particles out so that every rank's slice is spatially
+    coherent -- the engines build their own exact keys on the device)."""
+    pos = np.asarray(pos, dtype=np.float64)
+    lo = pos.min(axis=0)
+    span = np.maximum(pos.max(axis=0) - lo, 1e-300)
+    q = np.minimum(((pos - lo) / span * (1 << bits)).astype(np.uint64), (1 << bits) - 1)
+    key = np.zeros(len(pos), dtype=np.uint64)
+    for b in range(bits):
+        for k in range(3):
+            key |= ((q[:, k] >> np.uint64(b)) & np.uint64(1)) << np.uint64(3 * b + k)
+    return np.argsort(key, kind="stable")
+
+
+def interleaved_layout(pos, world, block=2048):
+    """Global particle order for a sharded TREE run: particles are sorted along the Morton curve,
+    cut into blocks of `block`, and the blocks are dealt round-robin to the ranks; rank r's blocks
+    are then stored contiguously (so ownership stays a contiguous index range).  Every warp of the
+    walk then handles 32 spatial neighbours (coherent traversal), and every rank gets the same mix
+    of dense and sparse regions (load balance).  Returns perm with
+    new_array = old_array[perm]; the counts per rank follow `partition(n, world)`."""
+    n = len(pos)
+    order = morton_order(pos)
+    if world == 1:
+        return order
+    parts = partition(n, world)
+    nblocks = (n + block - 1) // block
+    owner_blocks = [[] for _ in range(world)]
+    for b in range(nblocks):
+        owner_blocks[b % world].append(order[b * block:(b + 1) * block])
+    dealt = [np.concatenate(bl) if bl else np.zeros(0, dtype=order.dtype) for bl in owner_blocks]
+    # round-robin dealing gives counts that can differ from partition() by up to one block:
+    # rebalance by moving the overflow of each rank to the next one
+    flat = np.concatenate(dealt)
+    out, ofs = [], 0
+    for (_, c) in parts:
+        out.append(flat[ofs:ofs + c])
+        ofs += c
+    return np.concatenate(out)
+
+
 class CudaShard(object):
     """One rank's gh_engine over torch-owned source buffers."""
 
@@ -120,7 +162,7 @@ class ShardedSimulation(object):
     (host arrays; synthetic ICs are generated identically on every rank) and keeps its slice."""
 
     def __init__(self, pos, vel, mass, dt, eps, algorithm="direct", theta=0.7, precision="fp64",
-                 rank=0, world=1, device=0, group=None, shard_factory=None):
+                 rank=0, world=1, device=0, group=None, shard_factory=None, layout=True):
         import torch.distributed as dist
         self.dist = dist
         self.rank, self.world, self.group = rank, world, group
@@ -135,9 +177,17 @@ class ShardedSimulation(object):
         factory = shard_factory or (lambda n, b, c: CudaShard(n, b, c, precision, device))
         self.shard = factory(self.n, self.begin, self.count)
         pos = np.asarray(pos, dtype=np.float64)
+        vel = np.asarray(vel, dtype=np.float64)
+        mass = np.asarray(mass, dtype=np.float64)
         origin = pos.mean(axis=0)  # identical on every rank: all ranks hold the same ICs
+        # tree: lay the particles out in Morton blocks dealt round-robin over the ranks (coherent
+        # warps + load balance); identical on every rank.  self.perm maps new index -> original.
+        self.perm = None
+        if algorithm == "tree" and layout:
+            self.perm = interleaved_layout(pos, world)
+            pos, vel, mass = pos[self.perm], vel[self.perm], mass[self.perm]
         sl = slice(self.begin, self.begin + self.count)
-        self.shard.upload(pos[sl], np.asarray(vel, dtype=np.float64)[sl], mass, origin)
+        self.shard.upload(pos[sl], vel[sl], mass, origin)
         self.shard.prepare(self.dt)
         self.steps_done = 0
 
@@ -172,9 +222,14 @@ class ShardedSimulation(object):
         """Full (pos, vel) on every rank (host arrays) -- output cadence only."""
         import torch
         pos, vel = self.shard.download()
-        if self.world == 1:
-            return pos, vel
-        objs = [None] * self.world
-        self.dist.all_gather_object(objs, (pos, vel), group=self.group)
-        return (np.concatenate([o[0] for o in objs], axis=0),
-                np.concatenate([o[1] for o in objs], axis=0))
+        if self.world > 1:
+            objs = [None] * self.world
+            self.dist.all_gather_object(objs, (pos, vel), group=self.group)
+            pos = np.concatenate([o[0] for o in objs], axis=0)
+            vel = np.concatenate([o[1] for o in objs], axis=0)
+        if self.perm is not None:  # back to the caller's particle order
+            p2, v2 = np.empty_like(pos), np.empty_like(vel)
+            p2[self.perm] = pos
+            v2[self.perm] = vel
+            pos, vel = p2, v2
+        return pos, vel
