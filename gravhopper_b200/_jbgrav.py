@@ -145,6 +145,7 @@ def tree_stats(enable=None):
     if enable is not None:
         _lib.check(L.gh_set_tree_stats(1 if enable else 0))
         return None
-    out = (C.c_int64 * 5)()
+    out = (C.c_int64 * 8)()
     _lib.check(L.gh_tree_last_stats(out))
-    return dict(entries=out[0], cells=out[1], maxlevel=out[2], accepted=out[3], visited=out[4])
+    return dict(entries=out[0], cells=out[1], maxlevel=out[2], accepted=out[3], visited=out[4],
+                warp_entries=out[5], warp_entries_max=out[6], warps=out[7])

@@ -222,6 +222,6 @@ struct TreeArgs {
 };
 int launch_tree(const TreeArgs &a, TreeWorkspace *ws, cudaStream_t stream,
                 cudaEvent_t *force_events);
-int tree_last_stats(TreeWorkspace *ws, int64_t out[5]);
+int tree_last_stats(TreeWorkspace *ws, int64_t out[8]);
 
 }  // namespace gh

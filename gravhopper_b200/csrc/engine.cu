@@ -37,7 +37,7 @@ struct Stateless {
   DeviceBuffer pos, mass, tpos, acc, src32, tgt32, ws, root, part;
   TreeWorkspace *tw = nullptr;
   cudaStream_t stream = nullptr;
-  int64_t tree_stats[5] = {0, 0, 0, 0, 0};
+  int64_t tree_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   bool want_stats = false;
 };
 static thread_local Stateless *g_sl = nullptr;
@@ -288,10 +288,10 @@ int gh_tree_force_position(int prec, const double *pos, const double *mass, int6
   if (nf == 0) return GH_OK;
   return force_common(GH_ALG_TREE, prec, pos, mass, np, force_pos, nf, eps, theta, acc_out, mem, stream);
 }
-int gh_tree_last_stats(int64_t out[5]) {
+int gh_tree_last_stats(int64_t out[8]) {
   Stateless *s = stateless();
   if (!s || !out) return GH_EINVAL;
-  for (int k = 0; k < 5; k++) out[k] = s->tree_stats[k];
+  for (int k = 0; k < 8; k++) out[k] = s->tree_stats[k];
   return GH_OK;
 }
 int gh_set_tree_stats(int enable) {
@@ -655,7 +655,7 @@ int gh_engine_last_force_ms(gh_engine *e, float *ms) {
   GH_CUDA(cudaEventElapsedTime(ms, e->fev[0], e->fev[1]));
   return GH_OK;
 }
-int gh_engine_tree_stats(gh_engine *e, int64_t out[5]) {
+int gh_engine_tree_stats(gh_engine *e, int64_t out[8]) {
   if (!e || !out) return GH_EINVAL;
   return tree_last_stats(e->tw, out);
 }

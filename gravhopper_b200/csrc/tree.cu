@@ -578,9 +578,10 @@ walk_kernel(const Node<Real> *__restrict__ nodes, const int *__restrict__ skips,
   }
   int until = valid ? 0 : INT_MAX;
   Real ax = 0, ay = 0, az = 0;
-  unsigned long long nacc = 0, nvis = 0;
+  unsigned long long nacc = 0, nvis = 0, niter = 0;
   int i = 0;
   while (i < nentries) {
+    if (STATS) niter++;
     const auto cen = nodes[i].cen;
     const auto com = nodes[i].com;
     const int sk = skips[i];
@@ -607,7 +608,12 @@ walk_kernel(const Node<Real> *__restrict__ nodes, const int *__restrict__ skips,
       nacc += __shfl_down_sync(0xffffffffu, nacc, o);
       nvis += __shfl_down_sync(0xffffffffu, nvis, o);
     }
-    if (lane == 0) { atomicAdd(&stats[0], nacc); atomicAdd(&stats[1], nvis); }
+    if (lane == 0) {
+      atomicAdd(&stats[0], nacc);
+      atomicAdd(&stats[1], nvis);
+      atomicAdd(&stats[2], niter);  // entries this warp stepped through (union over its lanes)
+      atomicMax(&stats[3], niter);
+    }
   }
 }
 
@@ -615,7 +621,7 @@ walk_kernel(const Node<Real> *__restrict__ nodes, const int *__restrict__ skips,
 struct TreeWorkspace {
   DeviceBuffer root, part, hi, lo, hi2, lo2, idx, idx2, clev, cnt, base, P, cubtmp;
   DeviceBuffer node, skip, misc, thi, tidx, thi2, tidx2, sorted, bsum;
-  int64_t last_stats[5] = {0, 0, 0, 0, 0};
+  int64_t last_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int *h_pinned = nullptr;  // [0] nentries, [1] maxlevel ; pinned for async readback
   unsigned long long *h_stats = nullptr;
 };
@@ -631,8 +637,8 @@ void tree_workspace_destroy(TreeWorkspace *w) {
   if (w->h_stats) cudaFreeHost(w->h_stats);
   delete w;
 }
-int tree_last_stats(TreeWorkspace *w, int64_t out[5]) {
-  for (int k = 0; k < 5; k++) out[k] = w->last_stats[k];
+int tree_last_stats(TreeWorkspace *w, int64_t out[8]) {
+  for (int k = 0; k < 8; k++) out[k] = w->last_stats[k];
   return GH_OK;
 }
 
@@ -647,7 +653,7 @@ static int tree_impl(const TreeArgs &a, Src src, const float4 *tgt32, TreeWorksp
   const bool deep = levels > LEVELS_HI;
   const bool rel_origin = (sizeof(Real) == 4);  // fp32 entries are stored relative to the root centre
   if (!w->h_pinned) GH_CUDA(cudaMallocHost(&w->h_pinned, 4 * sizeof(int)));
-  if (!w->h_stats) GH_CUDA(cudaMallocHost(&w->h_stats, 2 * sizeof(unsigned long long)));
+  if (!w->h_stats) GH_CUDA(cudaMallocHost(&w->h_stats, 4 * sizeof(unsigned long long)));
 
   // K3
   const int nb = (int)((n + 256 * 8 - 1) / (256 * 8) < 1024 ? (n + 256 * 8 - 1) / (256 * 8) : 1024);
@@ -786,11 +792,13 @@ static int tree_impl(const TreeArgs &a, Src src, const float4 *tgt32, TreeWorksp
   // K8
   const Real eps2 = (Real)(a.eps * a.eps);
   const int64_t nwarps = (ni + 31) / 32;
-  const unsigned blocks = (unsigned)((nwarps + 3) / 4);
+  int wb = 128;
+  if (const char *env = getenv("GH_WALK_BLOCK")) { int v = atoi(env); if (v == 32 || v == 64 || v == 128) wb = v; }
+  const unsigned blocks = (unsigned)((nwarps + wb / 32 - 1) / (wb / 32));
   if (ev) GH_CUDA(cudaEventRecord(ev[0], st));
   const bool guard = (a.eps == 0.0);
 #define GH_WALK(STATS, GUARD)                                                                      \
-  walk_kernel<Real, STATS, GUARD><<<blocks, 128, 0, st>>>(E.node, E.skip, nentries, tv, ni, root, \
+  walk_kernel<Real, STATS, GUARD><<<blocks, wb, 0, st>>>(E.node, E.skip, nentries, tv, ni, root, \
                                                          rel_origin, eps2, a.ep, dstats)
   if (a.want_stats) { if (guard) GH_WALK(true, true); else GH_WALK(true, false); }
   else { if (guard) GH_WALK(false, true); else GH_WALK(false, false); }
@@ -801,11 +809,14 @@ static int tree_impl(const TreeArgs &a, Src src, const float4 *tgt32, TreeWorksp
   w->last_stats[0] = nentries;
   w->last_stats[1] = nentries - n;
   if (a.want_stats) {
-    GH_CUDA(cudaMemcpyAsync(w->h_stats, dstats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    GH_CUDA(cudaMemcpyAsync(w->h_stats, dstats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     GH_CUDA(cudaStreamSynchronize(st));
     w->last_stats[2] = w->h_pinned[1];
     w->last_stats[3] = (int64_t)w->h_stats[0];
     w->last_stats[4] = (int64_t)w->h_stats[1];
+    w->last_stats[5] = (int64_t)w->h_stats[2];
+    w->last_stats[6] = (int64_t)w->h_stats[3];
+    w->last_stats[7] = (int64_t)((ni + 31) / 32);
   }
   return GH_OK;
 }

@@ -92,8 +92,10 @@ int gh_tree_force_position(int prec, const double *pos, const double *mass, int6
 /* Statistics of the most recent tree evaluation made by the calling thread:
  * out[0] = tree entries (cells + leaves), out[1] = cells, out[2] = deepest cell level,
  * out[3] = accepted entries summed over targets, out[4] = visited entries summed over targets
- * (out[3], out[4] only when the evaluation was made with gh_set_tree_stats(1)). */
-int gh_tree_last_stats(int64_t out[5]);
+ * out[5] = entries stepped through summed over warps (each warp scans the union of what its 32
+ * targets need), out[6] = the largest such count of any warp, out[7] = number of warps
+ * (out[3..6] only when the evaluation was made with gh_set_tree_stats(1)). */
+int gh_tree_last_stats(int64_t out[8]);
 int gh_set_tree_stats(int enable);
 
 /* ---- device-resident leapfrog engine: Simulation.run ------------------------------------- */
@@ -181,7 +183,7 @@ int gh_engine_state_ptrs(gh_engine *e, double **pos_dev, double **vel_dev);
 /* The engine's cudaStream_t (as void*), e.g. to order an NCCL all-gather against the steps. */
 int gh_engine_stream(gh_engine *e, void **stream);
 /* Tree statistics of the engine's last tree step (layout as gh_tree_last_stats). */
-int gh_engine_tree_stats(gh_engine *e, int64_t out[5]);
+int gh_engine_tree_stats(gh_engine *e, int64_t out[8]);
 /* Kernel launches issued by this engine since creation (bench.py's gpu_launches). */
 int gh_engine_launch_count(gh_engine *e, int64_t *count);
 /* Device time (ms, CUDA events on the engine's stream) of the force kernel of the last step. */

@@ -1,4 +1,4 @@
-"""Walk cost vs target subset (scratch): all targets, contiguous Morton half, alternate Morton blocks, random half."""
+"""Walk cost vs target subset and block size (scratch)."""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -12,15 +12,27 @@ order = morton_order(x)
 xs = np.ascontiguousarray(x[order]); ms = m[order]
 tx, tm = torch.from_numpy(xs).cuda(), torch.from_numpy(ms).cuda()
 blocks = np.arange(n) // 2048
-subsets = {"all_self": None, "contig_half": np.arange(n // 2), "alt_blocks": np.nonzero(blocks % 2 == 0)[0],
-           "random_half": np.sort(np.random.default_rng(0).choice(n, n // 2, replace=False)),
-           "alt_blocks_8": np.nonzero(blocks % 8 == 0)[0]}
+subsets = {"all_self": None, "alt_blocks_2": np.nonzero(blocks % 2 == 0)[0], "alt_blocks_8": np.nonzero(blocks % 8 == 0)[0]}
+J.tree_stats(True)
 for name, sel in subsets.items():
-    for rep in range(2):
-        if sel is None:
-            J.tree_force(tx, tm, 0.05, 0.7, precision="fp32")
-        else:
-            tt = torch.from_numpy(np.ascontiguousarray(xs[sel])).cuda()
-            J.tree_force_position(tx, tm, tt, 0.05, 0.7, precision="fp32")
+    if sel is None:
+        J.tree_force(tx, tm, 0.05, 0.7, precision="fp32")
+    else:
+        tt = torch.from_numpy(np.ascontiguousarray(xs[sel])).cuda()
+        J.tree_force_position(tx, tm, tt, 0.05, 0.7, precision="fp32")
     torch.cuda.synchronize()
-    print("done", name, flush=True)
+    st = J.tree_stats()
+    print("STATS", name, "warps", st["warps"], "mean warp entries %.0f" % (st["warp_entries"] / st["warps"]), "max", st["warp_entries_max"],
+          "visited/target %.0f accepted/target %.0f" % (st["visited"] / (st["warps"] * 32), st["accepted"] / (st["warps"] * 32)), flush=True)
+J.tree_stats(False)
+for wb in (128, 64, 32):
+    os.environ["GH_WALK_BLOCK"] = str(wb)
+    for name, sel in subsets.items():
+        for rep in range(2):
+            if sel is None:
+                J.tree_force(tx, tm, 0.05, 0.7, precision="fp32")
+            else:
+                tt = torch.from_numpy(np.ascontiguousarray(xs[sel])).cuda()
+                J.tree_force_position(tx, tm, tt, 0.05, 0.7, precision="fp32")
+        torch.cuda.synchronize()
+        print("done", wb, name, flush=True)
