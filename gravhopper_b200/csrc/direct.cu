@@ -274,35 +274,79 @@ direct_f64_kernel(const double *__restrict__ spos, const double *__restrict__ sm
     if (j < je) return make_double4(spos[3 * j], spos[3 * j + 1], spos[3 * j + 2], smass[j]);
     return make_double4(0.0, 0.0, 0.0, 0.0);  // zero mass: contributes exactly zero
   };
-  tile[0].s[tid] = fetch(jb + tid);
-  __syncthreads();
+  // tiles whose sources all carry the same mass m0 factor it out of the inner loop (17 -> 16 DP
+  // operations per interaction); the tile's sum is accumulated separately and scaled once
+  double m0 = (jb < je) ? smass[jb] : 0.0;
+  bool uni;
+  {
+    double4 g = fetch(jb + tid);
+    tile[0].s[tid] = g;
+    uni = __syncthreads_and(g.w == m0) != 0;
+  }
 
   for (int t = 0; t < ntiles; t++) {
     const bool more = (t + 1 < ntiles);
     double4 g = make_double4(0.0, 0.0, 0.0, 0.0);
-    if (more) g = fetch(jb + (int64_t)(t + 1) * BLOCK + tid);
+    double m0n = 0.0;
+    if (more) {
+      const int64_t jt = jb + (int64_t)(t + 1) * BLOCK;
+      g = fetch(jt + tid);
+      m0n = smass[jt];
+    }
     const Tile64<BLOCK> &T = tile[t & 1];
+    if (uni) {
+      double tx[KI], ty[KI], tz[KI];
+#pragma unroll
+      for (int k = 0; k < KI; k++) tx[k] = ty[k] = tz[k] = 0.0;
 #pragma unroll 4
-    for (int p = 0; p < BLOCK; p++) {
-      const double4 sj = T.s[p];
+      for (int p = 0; p < BLOCK; p++) {
+        const double4 sj = T.s[p];
+#pragma unroll
+        for (int k = 0; k < KI; k++) {
+          double dx = sj.x - xi[k];
+          double dy = sj.y - yi[k];
+          double dz = sj.z - zi[k];
+          double s = fma(dx, dx, eps2);
+          s = fma(dy, dy, s);
+          s = fma(dz, dz, s);
+          double y = rsqrt64(s);
+          if (GUARD) y = (s > 0.0) ? y : 0.0;
+          double w = y * y * y;
+          tx[k] = fma(w, dx, tx[k]);
+          ty[k] = fma(w, dy, ty[k]);
+          tz[k] = fma(w, dz, tz[k]);
+        }
+      }
 #pragma unroll
       for (int k = 0; k < KI; k++) {
-        double dx = sj.x - xi[k];
-        double dy = sj.y - yi[k];
-        double dz = sj.z - zi[k];
-        double s = fma(dx, dx, eps2);
-        s = fma(dy, dy, s);
-        s = fma(dz, dz, s);
-        double y = rsqrt64(s);
-        if (GUARD) y = (s > 0.0) ? y : 0.0;  // _jbgrav.c:327-328
-        double w = sj.w * (y * y * y);
-        ax[k] = fma(w, dx, ax[k]);
-        ay[k] = fma(w, dy, ay[k]);
-        az[k] = fma(w, dz, az[k]);
+        ax[k] = fma(m0, tx[k], ax[k]);
+        ay[k] = fma(m0, ty[k], ay[k]);
+        az[k] = fma(m0, tz[k], az[k]);
+      }
+    } else {
+#pragma unroll 4
+      for (int p = 0; p < BLOCK; p++) {
+        const double4 sj = T.s[p];
+#pragma unroll
+        for (int k = 0; k < KI; k++) {
+          double dx = sj.x - xi[k];
+          double dy = sj.y - yi[k];
+          double dz = sj.z - zi[k];
+          double s = fma(dx, dx, eps2);
+          s = fma(dy, dy, s);
+          s = fma(dz, dz, s);
+          double y = rsqrt64(s);
+          if (GUARD) y = (s > 0.0) ? y : 0.0;  // _jbgrav.c:327-328
+          double w = sj.w * (y * y * y);
+          ax[k] = fma(w, dx, ax[k]);
+          ay[k] = fma(w, dy, ay[k]);
+          az[k] = fma(w, dz, az[k]);
+        }
       }
     }
     if (more) tile[(t + 1) & 1].s[tid] = g;
-    __syncthreads();
+    uni = __syncthreads_and(more && g.w == m0n) != 0;
+    m0 = m0n;
   }
 
 #pragma unroll

@@ -545,7 +545,7 @@ struct TargetsView {
 // with one REDUX: the scan only touches entries some lane still needs.  Branch-free body.
 // fp32: plain fp32 accumulation (<= ~1e3 accepted terms per target; error ~1e-6, far below the
 // monopole error).
-template <class Real, bool STATS, bool GUARD>
+template <class Real, bool STATS, bool GUARD, bool PREFETCH>
 __global__ void __launch_bounds__(128, 8)
 walk_kernel(const Node<Real> *__restrict__ nodes, const int *__restrict__ skips, int nentries,
             TargetsView tv, int64_t ni, const double *__restrict__ root, bool rel_origin, Real eps2,
@@ -585,6 +585,12 @@ walk_kernel(const Node<Real> *__restrict__ nodes, const int *__restrict__ skips,
     const auto cen = nodes[i].cen;
     const auto com = nodes[i].com;
     const int sk = skips[i];
+    if (PREFETCH) {
+      // optional L2 prefetch hint of the entry after this subtree.  Measured on B200 (N = 4M):
+      // +19 % time when all 131k warps run (issue bound), -6 % with 16k warps; a register
+      // double-buffer prefetch of entry i+1 was 85 % slower.  Off by default.
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(nodes + (sk < nentries ? sk : i)));
+    }
     const Real dx = cen.x - x, dy = cen.y - y, dz = cen.z - z;
     const Real d2 = dx * dx + dy * dy + dz * dz;
     const bool active = i >= until;
@@ -797,11 +803,16 @@ static int tree_impl(const TreeArgs &a, Src src, const float4 *tgt32, TreeWorksp
   const unsigned blocks = (unsigned)((nwarps + wb / 32 - 1) / (wb / 32));
   if (ev) GH_CUDA(cudaEventRecord(ev[0], st));
   const bool guard = (a.eps == 0.0);
-#define GH_WALK(STATS, GUARD)                                                                      \
-  walk_kernel<Real, STATS, GUARD><<<blocks, wb, 0, st>>>(E.node, E.skip, nentries, tv, ni, root, \
-                                                         rel_origin, eps2, a.ep, dstats)
-  if (a.want_stats) { if (guard) GH_WALK(true, true); else GH_WALK(true, false); }
-  else { if (guard) GH_WALK(false, true); else GH_WALK(false, false); }
+  // L2 prefetch hint of each entry's skip target; GH_WALK_PREFETCH=0/1 overrides
+  bool prefetch = false;
+  if (const char *env = getenv("GH_WALK_PREFETCH")) prefetch = atoi(env) != 0;
+#define GH_WALK(STATS, GUARD, PF)                                                                      \
+  walk_kernel<Real, STATS, GUARD, PF><<<blocks, wb, 0, st>>>(E.node, E.skip, nentries, tv, ni, root, \
+                                                            rel_origin, eps2, a.ep, dstats)
+#define GH_WALK2(STATS, GUARD) do { if (prefetch) GH_WALK(STATS, GUARD, true); else GH_WALK(STATS, GUARD, false); } while (0)
+  if (a.want_stats) { if (guard) GH_WALK2(true, true); else GH_WALK2(true, false); }
+  else { if (guard) GH_WALK2(false, true); else GH_WALK2(false, false); }
+#undef GH_WALK2
 #undef GH_WALK
   GH_LAUNCH_CHECK();
   if (ev) GH_CUDA(cudaEventRecord(ev[1], st));

@@ -25,8 +25,8 @@ for name, sel in subsets.items():
     print("STATS", name, "warps", st["warps"], "mean warp entries %.0f" % (st["warp_entries"] / st["warps"]), "max", st["warp_entries_max"],
           "visited/target %.0f accepted/target %.0f" % (st["visited"] / (st["warps"] * 32), st["accepted"] / (st["warps"] * 32)), flush=True)
 J.tree_stats(False)
-for wb in (128, 64, 32):
-    os.environ["GH_WALK_BLOCK"] = str(wb)
+for wb in (0, 1):
+    os.environ["GH_WALK_PREFETCH"] = str(wb)
     for name, sel in subsets.items():
         for rep in range(2):
             if sel is None:

@@ -87,7 +87,8 @@ def test_tree_4m_hernquist_sampled(oracle, prec):
 
 
 def test_tree_galaxy_model_sampled(oracle):
-    """Config 5 analogue at 2M particles (two mass species, thin disk): fp64 tree == reference tree."""
+    """Config 5 analogue at 2M particles (two mass species, thin disk): fp64 tree == reference
+    tree; fp32 tree error against direct summation no worse than the reference tree's."""
     n = 2_000_000
     x, v, m = ic_raw.galaxy_model(n)
     x = np.ascontiguousarray(x)
@@ -95,3 +96,11 @@ def test_tree_galaxy_model_sampled(oracle):
     a = J.tree_force(x, m, 0.05, 0.7)
     reft = oracle.tree_force_position(x, m, x[sel], 0.05, 0.7, nthreads=0)
     assert relerr(a[sel], reft).max() <= 1e-12
+    refd = oracle.direct_summation_position(x, m, x[sel], 0.05, nthreads=0)
+    a32 = J.tree_force(x, m, 0.05, 0.7, precision="fp32")
+    eref, egpu = relerr(reft, refd), relerr(a32[sel], refd)
+    assert egpu.mean() <= eref.mean() * 1.02 + 1e-6
+    assert np.percentile(egpu, 99) <= np.percentile(eref, 99) * 1.05 + 1e-6
+    assert egpu.max() <= eref.max() * 1.1 + 1e-6
+    d32 = J.direct_summation_position(x, m, x[sel], 0.05, precision="fp32")  # mixed-mass tiles
+    assert relerr(d32, refd).max() <= 1e-5
