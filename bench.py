@@ -324,25 +324,43 @@ def main():
         metric, unit = "particle-steps/s", "particle-steps/s"
     value = units_per_step / (ms_per_step * 1e-3)
 
-    # ---- end to end through the reference-facing call with HOST (pinned) buffers, rank-local ----
-    e2e = None
-    if rank == 0:
-        hx = torch.from_numpy(w["x"]).pin_memory().numpy()
-        hm = torch.from_numpy(w["m"]).pin_memory().numpy()
+    # ---- end to end through the reference-facing call with HOST (pinned) buffers ----
+    # Every rank evaluates its share of the targets against all sources through the public
+    # _jbgrav call with host arrays (H2D of the sources + its targets, D2H of its accelerations
+    # inside the timed region); the job's rate is all units / the slowest rank's time.
+    hx = torch.from_numpy(w["x"]).pin_memory().numpy()
+    hm = torch.from_numpy(w["m"]).pin_memory().numpy()
+    b0, cnt = sim.begin, sim.count
+    ht = torch.from_numpy(np.ascontiguousarray(w["x"][b0:b0 + cnt])).pin_memory().numpy()
+    if world == 1:
         if is_direct:
             call = lambda: J.direct_summation(hx, hm, w["eps"], precision=w["prec"])  # noqa: E731
         else:
             call = lambda: J.tree_force(hx, hm, w["eps"], w["theta"], precision=w["prec"])  # noqa: E731
-        call()
-        reps = (1 if n > (1 << 21) else 3) if is_direct else 5
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            out = call()
-        te = (time.perf_counter() - t0) / reps
-        e2e = {"value": units_per_step / te, "unit": unit, "h2d_bytes_per_step": int(hx.nbytes + hm.nbytes),
-               "d2h_bytes_per_step": int(out.nbytes), "ms_per_call": te * 1e3, "n_gpus_used": 1,
-               "call": "_jbgrav.%s(host ndarray pos, mass, eps%s) -> host ndarray" %
-                       ("direct_summation" if is_direct else "tree_force", "" if is_direct else ", theta")}
+        name = "direct_summation" if is_direct else "tree_force"
+        h2d = int(hx.nbytes + hm.nbytes)
+    else:
+        if is_direct:
+            call = lambda: J.direct_summation_position(hx, hm, ht, w["eps"], precision=w["prec"])  # noqa: E731
+        else:
+            call = lambda: J.tree_force_position(hx, hm, ht, w["eps"], w["theta"], precision=w["prec"])  # noqa: E731
+        name = "direct_summation_position" if is_direct else "tree_force_position"
+        h2d = int(hx.nbytes + hm.nbytes + ht.nbytes)
+    out = call()
+    reps = (1 if n > (1 << 21) else 3) if is_direct else 5
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        out = call()
+    te = (time.perf_counter() - t0) / reps
+    tt = torch.tensor([te], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    te = float(tt[0])
+    e2e = {"value": units_per_step / te, "unit": unit, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": int(out.nbytes), "ms_per_call": te * 1e3, "n_gpus_used": world,
+           "call": "_jbgrav.%s(host ndarrays) -> host ndarray, one call per rank on its share of the targets"
+                   % name}
 
     if rank != 0:
         if world > 1:
@@ -356,8 +374,12 @@ def main():
     if is_direct:
         per_rank_units = units_per_step / world
         achieved = per_rank_units * FLOP_PER_INTERACTION / (kernel_ms * 1e-3) / 1e12
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at N = 2^20 on one GPU from
+        # `ncu --set full` (profiles/r01_direct_f32_N1M.txt): 25.8 MB + 79.2 MB
+        traffic = 104.9e6 if (n == N_DIRECT and world == 1) else None
         roofline = {"bound": "fp32_fma", "achieved": achieved, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
-                    "frac": achieved / fp32_peak_tflops, "traffic": None,
+                    "frac": achieved / fp32_peak_tflops, "traffic": traffic,
+                    "traffic_unit": "bytes per launch (ncu); algorithmic: 16.8 MB sources read + 24 MB x S partial sums",
                     "kernel": "direct_f32_kernel", "kernel_ms": kernel_ms,
                     "how": "20 flop/interaction x N_i x N_j per launch / CUDA-event time of the force kernel; "
                            "peak = 148 SMs x 128 FP32 lanes x 2 flop x clocks.max.sm (%.0f MHz); no measured FP32 "

@@ -66,7 +66,7 @@ __device__ __forceinline__ void store_tile32(Tile32<BLOCK> &t, int tid, float4 g
 // MODE 1: per-source scaling described above: 11 FP32 ops, but d' of a source that coincides
 //         with the target is a rounding residue instead of an exact zero -> only usable when
 //         the caller knows targets never coincide with sources (kept for measurement).
-template <int BLOCK, int KI, bool GUARD, int MODE, int MINB>
+template <int BLOCK, int KI, bool GUARD, int MODE, int MINB, int UNR>
 __global__ void __launch_bounds__(BLOCK, MINB)
 direct_f32_kernel(const float4 *__restrict__ src, int64_t nj, const float4 *__restrict__ tgt,
                   int64_t ni, float eps2, int64_t jchunk, double *__restrict__ partial,
@@ -120,7 +120,7 @@ direct_f32_kernel(const float4 *__restrict__ src, int64_t nj, const float4 *__re
     for (int k = 0; k < KI; k++) fx[k] = fy[k] = fz[k] = make_float2(0.f, 0.f);
 
     if (MODE == 0 && uni) {
-#pragma unroll 4
+#pragma unroll UNR
       for (int p = 0; p < BLOCK / 2; p++) {
         const float4 A = T.a[p];
         const float2 zj = *reinterpret_cast<const float2 *>(&T.b[p]);
@@ -411,7 +411,7 @@ static Split choose_split(int64_t ni, int64_t nj, int itile, int tj) {
   return sp;
 }
 
-template <int BLOCK, int KI, int MINB = 1>
+template <int BLOCK, int KI, int MINB = 1, int UNR = 4>
 static int run_f32(const DirectArgs &a, DeviceBuffer &ws, cudaStream_t st, cudaEvent_t *ev) {
   Split sp = choose_split(a.ni, a.nj, BLOCK * KI, BLOCK);
   double *partial = nullptr;
@@ -424,13 +424,13 @@ static int run_f32(const DirectArgs &a, DeviceBuffer &ws, cudaStream_t st, cudaE
   if (ev) GH_CUDA(cudaEventRecord(ev[0], st));
   const int mode = env_int("GH_F32_MODE", 0);
   if (a.eps == 0.0)
-    direct_f32_kernel<BLOCK, KI, true, 0, MINB><<<grid, BLOCK, 0, st>>>(a.src32, a.nj, a.tgt32, a.ni, eps2,
+    direct_f32_kernel<BLOCK, KI, true, 0, MINB, UNR><<<grid, BLOCK, 0, st>>>(a.src32, a.nj, a.tgt32, a.ni, eps2,
                                                                  sp.jchunk, partial, a.ep);
   else if (mode == 1)
-    direct_f32_kernel<BLOCK, KI, false, 1, MINB><<<grid, BLOCK, 0, st>>>(a.src32, a.nj, a.tgt32, a.ni, eps2,
+    direct_f32_kernel<BLOCK, KI, false, 1, MINB, UNR><<<grid, BLOCK, 0, st>>>(a.src32, a.nj, a.tgt32, a.ni, eps2,
                                                                   sp.jchunk, partial, a.ep);
   else
-    direct_f32_kernel<BLOCK, KI, false, 0, MINB><<<grid, BLOCK, 0, st>>>(a.src32, a.nj, a.tgt32, a.ni, eps2,
+    direct_f32_kernel<BLOCK, KI, false, 0, MINB, UNR><<<grid, BLOCK, 0, st>>>(a.src32, a.nj, a.tgt32, a.ni, eps2,
                                                                   sp.jchunk, partial, a.ep);
   GH_LAUNCH_CHECK();
   if (ev) GH_CUDA(cudaEventRecord(ev[1], st));
@@ -472,11 +472,22 @@ int launch_direct(const DirectArgs &a, DeviceBuffer &ws, cudaStream_t st, cudaEv
   if (a.prec == GH_PREC_F32) {
     int ki = env_int("GH_F32_KI", 0);
     int blk = env_int("GH_F32_BLOCK", 0);
-    // measured on B200 (profiles/r01_sweep_direct.txt): 8 targets/thread x 128 threads is the
-    // fastest shape once there are enough targets to fill the chip
-    if (ki == 0) ki = (a.ni >= 131072) ? 8 : (a.ni >= 16384 ? 2 : 1);
-    if (blk == 0) blk = 128;
+    // measured on B200 (profiles/r01_sweep_direct*.txt): 4 targets/thread x 256 threads and
+    // 8 x 128 are within 2 % of each other (76 / 74-76 % of peak); smaller shapes only pay off
+    // when there are too few targets to fill the chip
+    if (ki == 0) ki = (a.ni >= 131072) ? 4 : (a.ni >= 16384 ? 2 : 1);
+    if (blk == 0) blk = (ki == 4) ? 256 : 128;
     const int minb = env_int("GH_F32_MINB", 1);
+    const int unr = env_int("GH_F32_UNROLL", 4);
+    if (ki == 8 && blk == 128 && unr == 2) return run_f32<128, 8, 1, 2>(a, ws, st, ev);
+    if (ki == 8 && blk == 128 && unr == 1) return run_f32<128, 8, 1, 1>(a, ws, st, ev);
+    if (ki == 8 && blk == 128 && unr == 8) return run_f32<128, 8, 1, 8>(a, ws, st, ev);
+    if (ki == 4 && blk == 256 && unr == 2) return run_f32<256, 4, 1, 2>(a, ws, st, ev);
+    if (ki == 4 && blk == 256 && unr == 8) return run_f32<256, 4, 1, 8>(a, ws, st, ev);
+    if (ki == 6 && blk == 128) return run_f32<128, 6, 1, 4>(a, ws, st, ev);
+    if (ki == 6 && blk == 192) return run_f32<192, 6, 1, 4>(a, ws, st, ev);
+    if (ki == 12 && blk == 64) return run_f32<64, 12, 1, 2>(a, ws, st, ev);
+    if (ki == 16 && blk == 64) return run_f32<64, 16, 1, 2>(a, ws, st, ev);
     if (ki == 8 && blk == 128 && minb == 3) return run_f32<128, 8, 3>(a, ws, st, ev);
     if (ki == 8 && blk == 128 && minb == 4) return run_f32<128, 8, 4>(a, ws, st, ev);
     if (ki == 4 && blk == 256 && minb == 3) return run_f32<256, 4, 3>(a, ws, st, ev);
