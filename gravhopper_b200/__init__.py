@@ -11,7 +11,7 @@ from .gravhopper import (Simulation, IC, GravHopperException, UninitializedSimul
                          ICException, UnknownAlgorithmException, ExternalPackageException,
                          force_centers)
 from . import jbgrav as grav
-from . import jbgrav, _jbgrav, units, potentials
+from . import jbgrav, _jbgrav, units, potentials, ic_gpu
 
 __version__ = "0.1.0"
 __all__ = ["Simulation", "IC", "grav", "jbgrav", "_jbgrav", "units", "potentials", "GravHopperException",

@@ -201,6 +201,11 @@ int launch_potentials(const PotentialSet &ps, const double *xhalf, int64_t n, co
 int launch_half_drift(const double *x, const double *v, const double *mass, int64_t n, double dt,
                       double *xhalf, float4 *src32, const double origin[3], cudaStream_t stream);
 
+// ---- device-side IC sampling (ic.cu) -------------------------------------------------------
+int launch_ic(int kind, int64_t n, const double prm[3], const double *tx, const double *ty, int nt,
+              uint64_t seed, double *pos, double *vel, double *mass, double *scratch,
+              cudaStream_t stream);
+
 // ---- tree (tree.cu) -------------------------------------------------------------------------
 struct TreeWorkspace;
 TreeWorkspace *tree_workspace_create();

@@ -34,7 +34,7 @@ static int check_device() {
 
 // Per-thread scratch of the stateless entry points (grow-only, reused between calls).
 struct Stateless {
-  DeviceBuffer pos, mass, tpos, acc, src32, tgt32, ws, root, part;
+  DeviceBuffer pos, mass, tpos, acc, src32, tgt32, ws, root, part, ictab, icout;
   TreeWorkspace *tw = nullptr;
   cudaStream_t stream = nullptr;
   int64_t tree_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -301,6 +301,47 @@ int gh_set_tree_stats(int enable) {
   return GH_OK;
 }
 
+int gh_ic_sample(int kind, int64_t n, const double *params, int nparams, const double *table_x,
+                 const double *table_y, int ntable, uint64_t seed, double *pos, double *vel,
+                 double *mass, int mem, void *stream) {
+  if (kind < 1 || kind > 3) { set_error("unknown IC kind %d (1 Plummer, 2 Hernquist, 3 TSIS)", kind); return GH_EINVAL; }
+  if (n < 0 || !params || nparams < 2 || nparams > 3) { set_error("bad IC parameters"); return GH_EINVAL; }
+  if (kind != 3 && (!table_x || !table_y || ntable < 2)) { set_error("this IC kind needs an inverse-CDF table"); return GH_EINVAL; }
+  if (n == 0) return GH_OK;
+  if (!pos || !vel || !mass) { set_error("null output pointer"); return GH_EINVAL; }
+  GH_TRY(check_device());
+  Stateless *s = stateless();
+  if (!s) return GH_ENOMEM;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mem == GH_MEM_HOST && !st) {
+    if (!s->stream) GH_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    st = s->stream;
+  }
+  double prm[3] = {params[0], params[1], nparams > 2 ? params[2] : 0.0};
+  const int nt = (kind == 3) ? 0 : ntable;
+  GH_TRY(s->ictab.reserve(sizeof(double) * (2 * (size_t)(nt > 0 ? nt : 1) + 3 * 256)));
+  double *tx = s->ictab.as<double>(), *ty = tx + (nt > 0 ? nt : 1), *scratch = ty + (nt > 0 ? nt : 1);
+  if (nt > 0) {
+    GH_CUDA(cudaMemcpyAsync(tx, table_x, sizeof(double) * nt, cudaMemcpyHostToDevice, st));
+    GH_CUDA(cudaMemcpyAsync(ty, table_y, sizeof(double) * nt, cudaMemcpyHostToDevice, st));
+  }
+  double *dpos = pos, *dvel = vel, *dmass = mass;
+  if (mem == GH_MEM_HOST) {
+    GH_TRY(s->icout.reserve(sizeof(double) * 7 * (size_t)n));
+    dpos = s->icout.as<double>();
+    dvel = dpos + 3 * n;
+    dmass = dvel + 3 * n;
+  }
+  GH_TRY(launch_ic(kind, n, prm, tx, ty, nt, seed, dpos, dvel, dmass, scratch, st));
+  if (mem == GH_MEM_HOST) {
+    GH_CUDA(cudaMemcpyAsync(pos, dpos, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, st));
+    GH_CUDA(cudaMemcpyAsync(vel, dvel, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, st));
+    GH_CUDA(cudaMemcpyAsync(mass, dmass, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    GH_CUDA(cudaStreamSynchronize(st));
+  }
+  return GH_OK;
+}
+
 int gh_engine_create(gh_engine **out, int device, int64_t n_total, int64_t i_begin, int64_t i_count,
                      int prec) {
   if (!out) return GH_EINVAL;
@@ -412,6 +453,20 @@ int gh_engine_upload(gh_engine *e, const double *pos, const double *vel, const d
   GH_CUDA(cudaMemcpyAsync(e->x[e->cur], pos, sizeof(double) * 3 * e->ni, cudaMemcpyHostToDevice, e->stream));
   GH_CUDA(cudaMemcpyAsync(e->v[e->cur], vel, sizeof(double) * 3 * e->ni, cudaMemcpyHostToDevice, e->stream));
   GH_CUDA(cudaMemcpyAsync(e->mass, mass_all, sizeof(double) * e->n, cudaMemcpyHostToDevice, e->stream));
+  GH_CUDA(cudaStreamSynchronize(e->stream));
+  e->uploaded = true;
+  e->xhalf_valid = false;
+  return GH_OK;
+}
+
+int gh_engine_upload_device(gh_engine *e, const double *pos, const double *vel, const double *mass_all) {
+  GH_ENGINE_GUARD(e);
+  if (!pos || !vel || !mass_all) { set_error("null pointer argument"); return GH_EINVAL; }
+  GH_CUDA(cudaStreamSynchronize(e->copy_stream));
+  for (int r = 0; r < RING; r++) e->copy_pending[r] = false;
+  GH_CUDA(cudaMemcpyAsync(e->x[e->cur], pos, sizeof(double) * 3 * e->ni, cudaMemcpyDeviceToDevice, e->stream));
+  GH_CUDA(cudaMemcpyAsync(e->v[e->cur], vel, sizeof(double) * 3 * e->ni, cudaMemcpyDeviceToDevice, e->stream));
+  GH_CUDA(cudaMemcpyAsync(e->mass, mass_all, sizeof(double) * e->n, cudaMemcpyDeviceToDevice, e->stream));
   GH_CUDA(cudaStreamSynchronize(e->stream));
   e->uploaded = true;
   e->xhalf_valid = false;

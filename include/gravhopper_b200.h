@@ -98,6 +98,23 @@ int gh_tree_force_position(int prec, const double *pos, const double *mass, int6
 int gh_tree_last_stats(int64_t out[8]);
 int gh_set_tree_stats(int enable);
 
+/* ---- device-side initial conditions (inputs of the path; gravhopper.py:1327-1607) ----------- */
+
+/* Sample n particles of an equilibrium model on the GPU with a counter-based generator
+ * (Philox4x32-10, one stream per particle; NOT the numpy stream of the host generators) and
+ * centre positions and velocities on their means (force_centers, gravhopper.py:1768-1785).
+ *   GH_IC_PLUMMER   params = {b [kpc], M [Msun]};          table: cumulative q-distribution -> q
+ *   GH_IC_HERNQUIST params = {a [kpc], M [Msun], cutoff};  table: E -> cumulative f(E) (both ways)
+ *   GH_IC_TSIS      params = {maxrad [kpc], M [Msun]};     no table
+ * Tables are host pointers (a few hundred doubles, built by the caller exactly as the reference
+ * builds them).  Outputs: pos (n,3) kpc, vel (n,3) km/s, mass (n) Msun, host or device per mem. */
+#define GH_IC_PLUMMER 1
+#define GH_IC_HERNQUIST 2
+#define GH_IC_TSIS 3
+int gh_ic_sample(int kind, int64_t n, const double *params, int nparams, const double *table_x,
+                 const double *table_y, int ntable, uint64_t seed, double *pos, double *vel,
+                 double *mass, int mem, void *stream);
+
 /* ---- device-resident leapfrog engine: Simulation.run ------------------------------------- */
 
 typedef struct gh_engine gh_engine;
@@ -112,6 +129,10 @@ int gh_engine_destroy(gh_engine *e);
 /* Upload the state at a snapshot: pos/vel of the OWNED targets (i_count,3) in kpc and km/s, and
  * the masses of ALL n_total particles in Msun (gravhopper.py:338-340).  Host pointers. */
 int gh_engine_upload(gh_engine *e, const double *pos, const double *vel, const double *mass_all);
+
+/* Same from DEVICE pointers (e.g. the outputs of gh_ic_sample with GH_MEM_DEVICE). */
+int gh_engine_upload_device(gh_engine *e, const double *pos, const double *vel,
+                            const double *mass_all);
 
 /* Multi-GPU only: use two caller-owned device buffers (e.g. torch tensors) as the double-buffered
  * source array that an NCCL all-gather fills each step.  Layout per particle: 3 float64
