@@ -35,13 +35,18 @@ def test_same_distribution_as_host_generator(name, gpu, host):
     assert np.allclose(mg, mh[0]) and np.isclose(mg.sum(), mh.sum())
     assert np.abs(xg.mean(axis=0)).max() < 1e-9 * np.abs(xg).max()
     assert np.abs(vg.mean(axis=0)).max() < 1e-9 * np.abs(vg).max()
-    rg, rh = np.linalg.norm(xg, axis=1), np.linalg.norm(xh, axis=1)
-    sg, sh = np.linalg.norm(vg, axis=1), np.linalg.norm(vh, axis=1)
+    rg = np.linalg.norm(xg - np.median(xg, axis=0), axis=1)
+    rh = np.linalg.norm(xh - np.median(xh, axis=0), axis=1)
+    sg = np.linalg.norm(vg - np.median(vg, axis=0), axis=1)
+    sh = np.linalg.norm(vh - np.median(vh, axis=0), axis=1)
     assert ks(rg, rh) < KS_NOISE, (name, "radius", ks(rg, rh))
     assert ks(sg, sh) < KS_NOISE, (name, "speed", ks(sg, sh))
-    for k in range(3):  # isotropy: each Cartesian component separately
-        assert ks(xg[:, k], xh[:, k]) < KS_NOISE
-        assert ks(vg[:, k], vh[:, k]) < KS_NOISE
+    # isotropy: each Cartesian component separately.  Both generators subtract their own sample
+    # mean (force_centers), which for untruncated models is set by a few far outliers and so
+    # differs between any two samples by more than the core size: compare about the medians.
+    for k in range(3):
+        assert ks(xg[:, k] - np.median(xg[:, k]), xh[:, k] - np.median(xh[:, k])) < KS_NOISE
+        assert ks(vg[:, k] - np.median(vg[:, k]), vh[:, k] - np.median(vh[:, k])) < KS_NOISE
     # speed distribution conditional on radius (the DF): three radial bins
     qs = np.quantile(rh, [0.0, 0.33, 0.66, 1.0])
     for lo, hi in zip(qs[:-1], qs[1:]):
