@@ -36,7 +36,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 N_DIRECT = 1 << 20
-N_TREE = 1 << 22
+N_TREE = int(os.environ.get("GH_BENCH_TREE_N", 1 << 22))
 FLOP_PER_INTERACTION = 20  # north_star / GPU-Gems-3 convention
 SM_COUNT = 148
 FP32_LANES_PER_SM = 128
@@ -66,8 +66,8 @@ def workload(kind):
     x, v, m = ic_raw.Hernquist(N_TREE, 1.0, 1e10, seed=42)
     return dict(x=np.ascontiguousarray(x), v=np.ascontiguousarray(v), m=m, eps=0.05, dt=1.0, theta=0.7,
                 alg="tree", prec="fp32",
-                name="Hernquist N=4194304 a=1kpc M=1e10Msun eps=0.05kpc dt=1Myr, Barnes-Hut theta=0.7 fp32 walk, "
-                     "1 DKD leapfrog step (BASELINE.json configs[3])")
+                name="Hernquist N=%d a=1kpc M=1e10Msun eps=0.05kpc dt=1Myr, Barnes-Hut theta=0.7 fp32 walk, "
+                     "1 DKD leapfrog step (BASELINE.json configs[3])" % N_TREE)
 
 
 class ClockSampler(object):

@@ -12,7 +12,10 @@ order = morton_order(x)
 xs = np.ascontiguousarray(x[order]); ms = m[order]
 tx, tm = torch.from_numpy(xs).cuda(), torch.from_numpy(ms).cuda()
 blocks = np.arange(n) // 2048
-subsets = {"all_self": None, "alt_blocks_2": np.nonzero(blocks % 2 == 0)[0], "alt_blocks_8": np.nonzero(blocks % 8 == 0)[0]}
+subsets = {"all_self": None}
+for bs in (2048, 16384, 65536, 262144):
+    blk = np.arange(n) // bs
+    subsets["alt8_block%d" % bs] = np.nonzero(blk % 8 == 3)[0]
 J.tree_stats(True)
 for name, sel in subsets.items():
     if sel is None:
@@ -25,8 +28,7 @@ for name, sel in subsets.items():
     print("STATS", name, "warps", st["warps"], "mean warp entries %.0f" % (st["warp_entries"] / st["warps"]), "max", st["warp_entries_max"],
           "visited/target %.0f accepted/target %.0f" % (st["visited"] / (st["warps"] * 32), st["accepted"] / (st["warps"] * 32)), flush=True)
 J.tree_stats(False)
-for wb in (0, 1):
-    os.environ["GH_WALK_PREFETCH"] = str(wb)
+for wb in (0,):
     for name, sel in subsets.items():
         for rep in range(2):
             if sel is None:
