@@ -388,9 +388,19 @@ template <> struct Vec4<float> { using type = float4; };
 
 template <class Real>
 struct Node {
-  typename Vec4<Real>::type cen;  // (centre - origin, s2 = side^2 / theta^2); s2 = -1 marks a leaf
-  typename Vec4<Real>::type com;  // (COM - origin, mass)
+  // centre and centre of mass interleaved component by component, so that the fp32 walk forms
+  // (centre - x, COM - x) with ONE packed FADD2 per axis and (|.|^2, |.|^2 + eps^2) with packed
+  // FFMA2s:  a = (cx, mx, cy, my),  b = (cz, mz, s2, m)
+  // c* = cell centre - origin, m* = centre of mass - origin, s2 = side^2 / theta^2 (-1 marks a
+  // leaf), m = mass
+  typename Vec4<Real>::type a;
+  typename Vec4<Real>::type b;
 };
+template <class Real, class V4>
+__device__ __forceinline__ void pack_node(Node<Real> &nd, const V4 &cen, const V4 &com) {
+  nd.a.x = cen.x; nd.a.y = com.x; nd.a.z = cen.y; nd.a.w = com.y;
+  nd.b.x = cen.z; nd.b.y = com.z; nd.b.z = cen.w; nd.b.w = com.w;
+}
 template <class Real>
 struct Entries {
   Node<Real> *node;
@@ -472,8 +482,7 @@ __global__ void emit_kernel(const double4 *__restrict__ sp, const uint64_t *__re
         cen.z = (Real)(cc[2] - oz);
         // (size / dist) < theta  <=>  size^2 / theta^2 < dist^2   (theta = 0: inf, never accepted)
         cen.w = (Real)(__dmul_rn(__dmul_rn(size, size), inv_theta2));
-        E.node[e].cen = cen;
-        E.node[e].com = com;
+        pack_node(E.node[e], cen, com);
         E.skip[e] = base[b + 1];
         e++;
         deepest = level;
@@ -500,8 +509,7 @@ __global__ void emit_kernel(const double4 *__restrict__ sp, const uint64_t *__re
   com.w = (Real)self.w;
   cen.x = cen.y = cen.z = (Real)0;
   cen.w = (Real)-1;
-  E.node[e].cen = cen;
-  E.node[e].com = com;
+  pack_node(E.node[e], cen, com);
   E.skip[e] = e + 1;
 }
 
@@ -582,8 +590,8 @@ walk_kernel(const Node<Real> *__restrict__ nodes, const int *__restrict__ skips,
   int i = 0;
   while (i < nentries) {
     if (STATS) niter++;
-    const auto cen = nodes[i].cen;
-    const auto com = nodes[i].com;
+    const auto na = nodes[i].a;
+    const auto nb = nodes[i].b;
     const int sk = skips[i];
     if (PREFETCH) {
       // optional L2 prefetch hint of the entry after this subtree.  Measured on B200 (N = 4M):
@@ -591,15 +599,31 @@ walk_kernel(const Node<Real> *__restrict__ nodes, const int *__restrict__ skips,
       // double-buffer prefetch of entry i+1 was 85 % slower.  Off by default.
       asm volatile("prefetch.global.L2 [%0];" ::"l"(nodes + (sk < nentries ? sk : i)));
     }
-    const Real dx = cen.x - x, dy = cen.y - y, dz = cen.z - z;
-    const Real d2 = dx * dx + dy * dy + dz * dz;
     const bool active = i >= until;
-    const bool pass = cen.w < d2;
+    bool pass;
+    Real ex, ey, ez, s;
+    if (sizeof(Real) == 4) {
+      // packed: lane .x of every pair is the opening test (centre), lane .y the force (COM)
+      const float2 nx2 = make_float2(-(float)x, -(float)x), ny2 = make_float2(-(float)y, -(float)y),
+                   nz2 = make_float2(-(float)z, -(float)z);
+      const float2 dx = __fadd2_rn(make_float2((float)na.x, (float)na.y), nx2);
+      const float2 dy = __fadd2_rn(make_float2((float)na.z, (float)na.w), ny2);
+      const float2 dz = __fadd2_rn(make_float2((float)nb.x, (float)nb.y), nz2);
+      float2 q = __ffma2_rn(dx, dx, make_float2(0.f, (float)eps2));
+      q = __ffma2_rn(dy, dy, q);
+      q = __ffma2_rn(dz, dz, q);
+      pass = (float)nb.z < q.x;
+      ex = (Real)dx.y; ey = (Real)dy.y; ez = (Real)dz.y; s = (Real)q.y;
+    } else {
+      const Real dx = na.x - x, dy = na.z - y, dz = nb.x - z;
+      const Real d2 = dx * dx + dy * dy + dz * dz;
+      pass = nb.z < d2;
+      ex = na.y - x; ey = na.w - y; ez = nb.y - z;
+      s = ex * ex + ey * ey + ez * ez + eps2;
+    }
     const bool acc = active && pass;
     const bool open = active && !pass;
-    const Real ex = com.x - x, ey = com.y - y, ez = com.z - z;
-    const Real s = ex * ex + ey * ey + ez * ez + eps2;
-    const Real w = acc ? com.w * inv_cube<GUARD>(s) : (Real)0;
+    const Real w = acc ? nb.w * inv_cube<GUARD>(s) : (Real)0;
     ax += w * ex;
     ay += w * ey;
     az += w * ez;
