@@ -83,9 +83,12 @@ class _Engine(object):
         self.h = h
 
     def close(self):
-        if getattr(self, 'h', None):
-            self.lib.gh_engine_destroy(self.h)
-            self.h = None
+        h, self.h = getattr(self, 'h', None), None
+        if h:
+            try:
+                self.lib.gh_engine_destroy(h)
+            except Exception:  # interpreter shutdown: the library may already be gone
+                pass
 
     __del__ = close
 
