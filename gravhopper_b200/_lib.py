@@ -30,6 +30,7 @@ PROTOTYPES = {
     "gh_tree_force": (C.c_int, [C.c_int, _vp, _vp, _i64, C.c_double, C.c_double, _vp, C.c_int, _vp]),
     "gh_tree_force_position": (C.c_int, [C.c_int, _vp, _vp, _i64, _vp, _i64, C.c_double, C.c_double,
                                          _vp, C.c_int, _vp]),
+    "gh_release_thread_scratch": (C.c_int, []),
     "gh_tree_last_stats": (C.c_int, [C.POINTER(_i64)]),
     "gh_set_tree_stats": (C.c_int, [C.c_int]),
     "gh_ic_sample": (C.c_int, [C.c_int, _i64, _dp, C.c_int, _vp, _vp, C.c_int, C.c_uint64, _vp, _vp, _vp,

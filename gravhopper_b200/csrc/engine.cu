@@ -288,6 +288,18 @@ int gh_tree_force_position(int prec, const double *pos, const double *mass, int6
   if (nf == 0) return GH_OK;
   return force_common(GH_ALG_TREE, prec, pos, mass, np, force_pos, nf, eps, theta, acc_out, mem, stream);
 }
+int gh_release_thread_scratch(void) {
+  Stateless *s = g_sl;
+  if (!s) return GH_OK;
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  DeviceBuffer *all[] = {&s->pos, &s->mass, &s->tpos, &s->acc, &s->src32, &s->tgt32, &s->ws, &s->root,
+                         &s->part, &s->ictab, &s->icout};
+  for (auto *b : all) b->release();
+  if (s->tw) { tree_workspace_destroy(s->tw); s->tw = nullptr; }
+  if (s->stream) { cudaStreamDestroy(s->stream); s->stream = nullptr; }
+  return GH_OK;
+}
+
 int gh_tree_last_stats(int64_t out[8]) {
   Stateless *s = stateless();
   if (!s || !out) return GH_EINVAL;

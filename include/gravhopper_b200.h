@@ -89,6 +89,10 @@ int gh_tree_force_position(int prec, const double *pos, const double *mass, int6
                            const double *force_pos, int64_t nf, double eps, double theta,
                            double *acc_out, int mem, void *stream);
 
+/* The stateless entry points keep grow-only device scratch per calling thread (so repeated calls
+ * do not cudaMalloc); this frees the calling thread's scratch. */
+int gh_release_thread_scratch(void);
+
 /* Statistics of the most recent tree evaluation made by the calling thread:
  * out[0] = tree entries (cells + leaves), out[1] = cells, out[2] = deepest cell level,
  * out[3] = accepted entries summed over targets, out[4] = visited entries summed over targets
