@@ -51,7 +51,7 @@ def morton_order(pos, bits=16):
     return np.argsort(key, kind="stable")
 
 
-def interleaved_layout(pos, world, block=2048):
+def interleaved_layout(pos, world, block=None):
     """Global particle order for a sharded TREE run: particles are sorted along the Morton curve,
     cut into blocks of `block`, and the blocks are dealt round-robin to the ranks; rank r's blocks
     are then stored contiguously (so ownership stays a contiguous index range).  Every warp of the
@@ -62,6 +62,11 @@ def interleaved_layout(pos, world, block=2048):
     order = morton_order(pos)
     if world == 1:
         return order
+    if block is None:
+        # 8 blocks per rank: large enough that the warps resident on a GPU at any time work on
+        # a compact part of the tree (measured on B200, N = 4M, 1/8 of the targets: 1.57 ms with
+        # 65536-particle blocks vs 1.80 ms with 2048), small enough to mix dense and sparse regions
+        block = max(2048, (n // (world * 8)) // 32 * 32)
     parts = partition(n, world)
     nblocks = (n + block - 1) // block
     owner_blocks = [[] for _ in range(world)]
