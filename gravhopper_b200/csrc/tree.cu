@@ -233,14 +233,16 @@ __global__ void gather_sorted_kernel(Src src, const int *__restrict__ idx, int64
   out[p] = make_double4(x, y, z, src.m(j));
 }
 // Deterministic three-phase inclusive scan of the four double-double moment sequences, fused
-// (one read of the sorted double4 array per phase, fixed summation order -> bitwise reproducible
-// run to run, unlike a decoupled-look-back scan with a non-associative operator).
-//   phase 1: per-CTA totals of SCAN_CHUNK consecutive particles
-//   phase 2: one CTA scans the CTA totals (exclusive)
-//   phase 3: each CTA rescans its chunk from its offset and writes P_c[p+1], c = 0..3
+// and fully coalesced (fixed summation order -> bitwise reproducible run to run, unlike a
+// decoupled-look-back scan with a non-associative operator).  The unit of work is one warp and
+// SCAN_WARP_ELEMS = 256 consecutive particles, taken 32 at a time (lane l <-> element 32 r + l):
+//   phase 1: per-warp totals (per round a shuffle scan across the lanes, lane 31 carries)
+//   phase 2: the warp totals are scanned by the same two kernels, recursively (depth 3 at 10M)
+//   phase 3: each warp rescans its 256 particles from its offset: per round a shuffle scan across
+//            the lanes plus the running carry; writes P[p+1] as one 64-byte DD4 per particle
 static constexpr int SCAN_THREADS = 256;
-static constexpr int SCAN_PER_THREAD = 8;
-static constexpr int SCAN_CHUNK = SCAN_THREADS * SCAN_PER_THREAD;
+static constexpr int SCAN_ROUNDS = 8;
+static constexpr int SCAN_WARP_ELEMS = 32 * SCAN_ROUNDS;
 
 struct DD4 {
   DD c[4];
@@ -278,107 +280,95 @@ __device__ __forceinline__ DD4 dd4_shfl_up(const DD4 &v, int d) {
   }
   return r;
 }
-// inclusive scan of one DD4 per thread across the CTA (warp shuffles + smem for warp totals);
-// returns the inclusive value; *total (all threads) receives the CTA total
-__device__ __forceinline__ DD4 block_scan_dd4(DD4 v, DD4 *total, DD4 *sh /* SCAN_THREADS/32 + 1 */) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+__device__ __forceinline__ DD4 dd4_shfl(const DD4 &v, int src) {
+  DD4 r;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    r.c[k].h = __shfl_sync(0xffffffffu, v.c[k].h, src);
+    r.c[k].l = __shfl_sync(0xffffffffu, v.c[k].l, src);
+  }
+  return r;
+}
+// inclusive scan across the 32 lanes (fixed order: Hillis-Steele, lower lanes on the left)
+__device__ __forceinline__ DD4 warp_scan_dd4(DD4 v, int lane) {
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     DD4 o = dd4_shfl_up(v, d);
     if (lane >= d) v = dd4_add(o, v);
   }
-  if (lane == 31) sh[wid] = v;
-  __syncthreads();
-  if (wid == 0) {
-    DD4 t = (lane < SCAN_THREADS / 32) ? sh[lane] : dd4_zero();
-#pragma unroll
-    for (int d = 1; d < SCAN_THREADS / 32; d <<= 1) {
-      DD4 o = dd4_shfl_up(t, d);
-      if (lane >= d) t = dd4_add(o, t);
-    }
-    if (lane < SCAN_THREADS / 32) sh[lane] = t;  // inclusive warp totals
-  }
-  __syncthreads();
-  if (wid > 0) v = dd4_add(sh[wid - 1], v);
-  *total = sh[SCAN_THREADS / 32 - 1];
-  __syncthreads();
   return v;
 }
 
+struct InParticles {  // element q = (m, m x, m y, m z) of sorted particle q, products exact
+  const double4 *sp;
+  __device__ __forceinline__ DD4 operator()(int64_t q) const { return dd4_of(sp[q]); }
+};
+struct InDD4 {
+  const DD4 *a;
+  __device__ __forceinline__ DD4 operator()(int64_t q) const { return a[q]; }
+};
+
+template <class In>
 __global__ void __launch_bounds__(SCAN_THREADS)
-moments_phase1(const double4 *__restrict__ sp, int64_t n, DD4 *__restrict__ blocksum) {
-  __shared__ DD4 sh[SCAN_THREADS / 32 + 1];
-  const int64_t base = (int64_t)blockIdx.x * SCAN_CHUNK + (int64_t)threadIdx.x * SCAN_PER_THREAD;
+scan_phase1(In in, int64_t n, DD4 *__restrict__ warpsum) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t base = w * SCAN_WARP_ELEMS;
+  if (base >= n) return;
   DD4 acc = dd4_zero();
-#pragma unroll
-  for (int k = 0; k < SCAN_PER_THREAD; k++)
-    if (base + k < n) acc = dd4_add(acc, dd4_of(sp[base + k]));
-  DD4 total;
-  block_scan_dd4(acc, &total, sh);
-  if (threadIdx.x == 0) blocksum[blockIdx.x] = total;
+#pragma unroll 2
+  for (int r = 0; r < SCAN_ROUNDS; r++) {  // element order inside the warp: round-major
+    const int64_t q = base + r * 32 + lane;
+    DD4 v = (q < n) ? in(q) : dd4_zero();
+    v = warp_scan_dd4(v, lane);  // same association as phase 3
+    acc = dd4_add(acc, dd4_shfl(v, 31));
+  }
+  if (lane == 0) warpsum[w] = acc;
 }
+// P[q + 1] = offset of the warp + inclusive scan inside the warp; P[0] = 0.
+// warpoff == nullptr: single-warp launch over the whole (short) array.
+template <class In>
 __global__ void __launch_bounds__(SCAN_THREADS)
-moments_phase2(DD4 *__restrict__ blocksum, int nblocks) {
-  // exclusive scan of blocksum in place; one CTA, each thread owns a contiguous run
-  __shared__ DD4 sh[SCAN_THREADS / 32 + 1];
-  const int per = (nblocks + SCAN_THREADS - 1) / SCAN_THREADS;
-  const int b0 = threadIdx.x * per;
-  DD4 acc = dd4_zero();
-  for (int k = 0; k < per; k++)
-    if (b0 + k < nblocks) acc = dd4_add(acc, blocksum[b0 + k]);
-  DD4 total;
-  DD4 incl = block_scan_dd4(acc, &total, sh);
-  // exclusive prefix of this thread's run = incl - acc, recomputed by re-adding to stay exact:
-  // walk the run again starting from the previous thread's inclusive value
-  DD4 prev = dd4_zero();
-  {
-    __shared__ DD4 inc_all[SCAN_THREADS];
-    inc_all[threadIdx.x] = incl;
-    __syncthreads();
-    if (threadIdx.x > 0) prev = inc_all[threadIdx.x - 1];
-  }
-  for (int k = 0; k < per; k++) {
-    if (b0 + k < nblocks) {
-      DD4 v = blocksum[b0 + k];
-      blocksum[b0 + k] = prev;
-      prev = dd4_add(prev, v);
-    }
+scan_phase3(In in, int64_t n, const DD4 *__restrict__ warpoff, DD4 *__restrict__ P /* n + 1 */,
+            int rounds) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t base = w * SCAN_WARP_ELEMS;
+  if (base >= n) return;
+  DD4 carry = warpoff ? warpoff[w] : dd4_zero();
+  if (w == 0 && lane == 0) P[0] = dd4_zero();
+  for (int r = 0; r < rounds; r++) {
+    const int64_t q = base + r * 32 + lane;
+    DD4 v = (q < n) ? in(q) : dd4_zero();
+    v = warp_scan_dd4(v, lane);
+    const DD4 out = dd4_add(carry, v);
+    if (q < n) P[q + 1] = out;
+    carry = dd4_add(carry, dd4_shfl(v, 31));
   }
 }
-__global__ void __launch_bounds__(SCAN_THREADS)
-moments_phase3(const double4 *__restrict__ sp, int64_t n, const DD4 *__restrict__ blockoff,
-               DD *__restrict__ P0, DD *__restrict__ P1, DD *__restrict__ P2, DD *__restrict__ P3) {
-  __shared__ DD4 sh[SCAN_THREADS / 32 + 1];
-  __shared__ DD4 inc_all[SCAN_THREADS];
-  const int64_t base = (int64_t)blockIdx.x * SCAN_CHUNK + (int64_t)threadIdx.x * SCAN_PER_THREAD;
-  DD4 v[SCAN_PER_THREAD];
-  DD4 acc = dd4_zero();
-#pragma unroll
-  for (int k = 0; k < SCAN_PER_THREAD; k++) {
-    v[k] = (base + k < n) ? dd4_of(sp[base + k]) : dd4_zero();
-    acc = dd4_add(acc, v[k]);
+
+// P[0..n] = exclusive-then-inclusive prefix of in(0..n-1); recursion over 256-element warp chunks
+// (depth 3 at n = 10M).  `levels` supplies scratch for the per-level totals and their prefixes.
+template <class In>
+static int dd4_scan(In in, int64_t n, DD4 *P, DeviceBuffer *levels, int depth, cudaStream_t st) {
+  if (n <= SCAN_WARP_ELEMS) {
+    scan_phase3<In><<<1, 32, 0, st>>>(in, n, nullptr, P, SCAN_ROUNDS);
+    GH_LAUNCH_CHECK();
+    return GH_OK;
   }
-  DD4 total;
-  DD4 incl = block_scan_dd4(acc, &total, sh);
-  inc_all[threadIdx.x] = incl;
-  __syncthreads();
-  DD4 run = blockoff[blockIdx.x];
-  if (threadIdx.x > 0) run = dd4_add(run, inc_all[threadIdx.x - 1]);
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    DD z;
-    z.h = z.l = 0.0;
-    P0[0] = z; P1[0] = z; P2[0] = z; P3[0] = z;
-  }
-#pragma unroll
-  for (int k = 0; k < SCAN_PER_THREAD; k++) {
-    if (base + k < n) {
-      run = dd4_add(run, v[k]);
-      P0[base + k + 1] = run.c[0];
-      P1[base + k + 1] = run.c[1];
-      P2[base + k + 1] = run.c[2];
-      P3[base + k + 1] = run.c[3];
-    }
-  }
+  if (depth >= 3) { set_error("dd4_scan: too many levels"); return GH_EINVAL; }
+  const int64_t nw = (n + SCAN_WARP_ELEMS - 1) / SCAN_WARP_ELEMS;
+  const unsigned nsb = (unsigned)((nw * 32 + SCAN_THREADS - 1) / SCAN_THREADS);
+  // layout of this level's scratch: totals[nw] followed by prefix[nw + 1]
+  GH_TRY(levels[depth].reserve(sizeof(DD4) * (size_t)(2 * nw + 1)));
+  DD4 *totals = levels[depth].as<DD4>();
+  DD4 *prefix = totals + nw;
+  scan_phase1<In><<<nsb, SCAN_THREADS, 0, st>>>(in, n, totals);
+  GH_LAUNCH_CHECK();
+  GH_TRY(dd4_scan<InDD4>(InDD4{totals}, nw, prefix, levels, depth + 1, st));
+  scan_phase3<In><<<nsb, SCAN_THREADS, 0, st>>>(in, n, prefix, P, SCAN_ROUNDS);
+  GH_LAUNCH_CHECK();
+  return GH_OK;
 }
 
 // ---- K6b emit -----------------------------------------------------------------------------------
@@ -418,12 +408,22 @@ __device__ __forceinline__ bool same_prefix(uint64_t h, uint64_t l, uint64_t h0,
   return (l >> sh) == (l0 >> sh);
 }
 
+// every third bit of a 63-bit Morton key, compacted (the 21-bit index along one axis)
+__device__ __forceinline__ uint64_t compact3(uint64_t x) {
+  x &= 0x1249249249249249ull;
+  x = (x ^ (x >> 2)) & 0x10c30c30c30c30c3ull;
+  x = (x ^ (x >> 4)) & 0x100f00f00f00f00full;
+  x = (x ^ (x >> 8)) & 0x001f0000ff0000ffull;
+  x = (x ^ (x >> 16)) & 0x001f00000000ffffull;
+  x = (x ^ (x >> 32)) & 0x00000000001fffffull;
+  return x;
+}
+
 template <class Src, class Real>
 __global__ void emit_kernel(const double4 *__restrict__ sp, const uint64_t *__restrict__ hi,
                             const uint64_t *__restrict__ lo, const signed char *__restrict__ clev,
                             const int *__restrict__ base /* n+1, exclusive scan of cnt */,
-                            const DD *__restrict__ P0, const DD *__restrict__ P1,
-                            const DD *__restrict__ P2, const DD *__restrict__ P3, int64_t n,
+                            const DD4 *__restrict__ P, int64_t n,
                             const double *__restrict__ root, bool rel_origin, double inv_theta2,
                             Entries<Real> E, int *__restrict__ maxlevel) {
   int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -441,7 +441,21 @@ __global__ void emit_kernel(const double4 *__restrict__ sp, const uint64_t *__re
     double cc[3] = {root[0], root[1], root[2]};
     double size = root[3];
     int deepest = 0;
-    for (int level = 0; level <= c; level++) {
+    int level0 = 0;
+    if (sizeof(Real) == 4 && cprev >= 0) {
+      // fp32 mode does not need the reference's bit-exact centre chain: jump straight to the
+      // first level this particle opens with the closed form
+      //   centre_L = root - side/2 + (i_L + 1/2) side / 2^L,  i_L = top L bits of the axis index
+      level0 = cprev + 1;
+      const double sL = ldexp(size, -level0);
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const uint64_t ik = compact3(h0 >> k) >> (LEVELS_HI - level0);
+        cc[k] = root[k] - 0.5 * size + ((double)ik + 0.5) * sL;
+      }
+      size = sL;
+    }
+    for (int level = level0; level <= c; level++) {
       if (level > cprev) {
         // this cell (level, centre cc, side size) starts at p.  Galloping + binary search for the
         // last sorted particle b sharing `level` octant levels with p (p+1 does, since c >= level).
@@ -468,10 +482,9 @@ __global__ void emit_kernel(const double4 *__restrict__ sp, const uint64_t *__re
         }
         const int64_t b = lo_i;
         double mh[4], rl;
-        dd_add(P0[b + 1].h, P0[b + 1].l, -P0[p].h, -P0[p].l, mh[0], rl);
-        dd_add(P1[b + 1].h, P1[b + 1].l, -P1[p].h, -P1[p].l, mh[1], rl);
-        dd_add(P2[b + 1].h, P2[b + 1].l, -P2[p].h, -P2[p].l, mh[2], rl);
-        dd_add(P3[b + 1].h, P3[b + 1].l, -P3[p].h, -P3[p].l, mh[3], rl);
+        const DD4 pe = P[b + 1], ps = P[p];
+#pragma unroll
+        for (int k = 0; k < 4; k++) dd_add(pe.c[k].h, pe.c[k].l, -ps.c[k].h, -ps.c[k].l, mh[k], rl);
         V4 com, cen;
         com.x = (Real)(mh[1] / mh[0] - ox);  // gravoct_finalize :477-479
         com.y = (Real)(mh[2] / mh[0] - oy);
@@ -650,7 +663,7 @@ walk_kernel(const Node<Real> *__restrict__ nodes, const int *__restrict__ skips,
 // ---- workspace + orchestration --------------------------------------------------------------------
 struct TreeWorkspace {
   DeviceBuffer root, part, hi, lo, hi2, lo2, idx, idx2, clev, cnt, base, P, cubtmp;
-  DeviceBuffer node, skip, misc, thi, tidx, thi2, tidx2, sorted, bsum;
+  DeviceBuffer node, skip, misc, thi, tidx, thi2, tidx2, sorted, bsum, scanlv[3];
   int64_t last_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int *h_pinned = nullptr;  // [0] nentries, [1] maxlevel ; pinned for async readback
   unsigned long long *h_stats = nullptr;
@@ -660,7 +673,7 @@ TreeWorkspace *tree_workspace_create() { return new TreeWorkspace(); }
 void tree_workspace_destroy(TreeWorkspace *w) {
   if (!w) return;
   DeviceBuffer *all[] = {&w->root, &w->part, &w->hi, &w->lo, &w->hi2, &w->lo2, &w->idx, &w->idx2,
-                         &w->clev, &w->cnt, &w->base, &w->P, &w->cubtmp, &w->node, &w->sorted, &w->bsum,
+                         &w->clev, &w->cnt, &w->base, &w->P, &w->cubtmp, &w->node, &w->sorted, &w->bsum, &w->scanlv[0], &w->scanlv[1], &w->scanlv[2],
                          &w->skip, &w->misc, &w->thi, &w->tidx, &w->thi2, &w->tidx2};
   for (auto *b : all) b->release();
   if (w->h_pinned) cudaFreeHost(w->h_pinned);
@@ -755,19 +768,9 @@ static int tree_impl(const TreeArgs &a, Src src, const float4 *tgt32, TreeWorksp
   double4 *sp = w->sorted.as<double4>();
   gather_sorted_kernel<<<nblk(n, 256), 256, 0, st>>>(src, sidx, n, sp);
   GH_LAUNCH_CHECK();
-  GH_TRY(w->P.reserve(sizeof(DD) * 4 * (size_t)(n + 1)));
-  DD *P[4];
-  for (int c = 0; c < 4; c++) P[c] = w->P.as<DD>() + (size_t)c * (size_t)(n + 1);
-  {
-    const int nsb = (int)((n + SCAN_CHUNK - 1) / SCAN_CHUNK);
-    GH_TRY(w->bsum.reserve(sizeof(DD4) * (size_t)nsb));
-    moments_phase1<<<nsb, SCAN_THREADS, 0, st>>>(sp, n, w->bsum.as<DD4>());
-    GH_LAUNCH_CHECK();
-    moments_phase2<<<1, SCAN_THREADS, 0, st>>>(w->bsum.as<DD4>(), nsb);
-    GH_LAUNCH_CHECK();
-    moments_phase3<<<nsb, SCAN_THREADS, 0, st>>>(sp, n, w->bsum.as<DD4>(), P[0], P[1], P[2], P[3]);
-    GH_LAUNCH_CHECK();
-  }
+  GH_TRY(w->P.reserve(sizeof(DD4) * (size_t)(n + 1)));
+  DD4 *P = w->P.as<DD4>();
+  GH_TRY(dd4_scan<InParticles>(InParticles{sp}, n, P, w->scanlv, 0, st));
 
   // entries: need the count on the host to size the arrays
   GH_CUDA(cudaStreamSynchronize(st));
@@ -779,8 +782,8 @@ static int tree_impl(const TreeArgs &a, Src src, const float4 *tgt32, TreeWorksp
   int *maxlevel = w->misc.as<int>();
   unsigned long long *dstats = reinterpret_cast<unsigned long long *>(w->misc.as<char>() + 16);
   GH_CUDA(cudaMemsetAsync(w->misc.ptr, 0, 64, st));
-  emit_kernel<Src, Real><<<nblk(n, 128), 128, 0, st>>>(sp, shi, slo, clev, base, P[0], P[1], P[2],
-                                                     P[3], n, root, rel_origin, inv_theta2, E, maxlevel);
+  emit_kernel<Src, Real><<<nblk(n, 128), 128, 0, st>>>(sp, shi, slo, clev, base, P, n, root, rel_origin,
+                                                     inv_theta2, E, maxlevel);
   GH_LAUNCH_CHECK();
 
   // targets: Morton order.  Self case: the source order restricted to the owned slice is the
