@@ -557,10 +557,8 @@ static int engine_step_impl(gh_engine *e, double dt, double eps, double theta, i
   ep.dt = dt;
   for (int k = 0; k < 3; k++) ep.origin[k] = e->origin[k];
 
-  if (e->n <= 1) {
-    // gravhopper.py:449-450: a single particle feels no N-body force; run the epilogue only
-    // through the direct kernel with zero sources is not possible (nj = 1 is fine: self term 0).
-  }
+  // gravhopper.py:449-450 (Np == 1 feels no N-body force) needs no special case: the only source
+  // is the target itself and its term is exactly zero in every kernel.
   if (algorithm == GH_ALG_DIRECT) {
     DirectArgs a;
     memset(&a, 0, sizeof(a));
