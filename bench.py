@@ -35,7 +35,7 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-N_DIRECT = 1 << 20
+N_DIRECT = int(os.environ.get("GH_BENCH_DIRECT_N", 1 << 20))  # override only for tests/experiments
 N_TREE = int(os.environ.get("GH_BENCH_TREE_N", 1 << 22))
 FLOP_PER_INTERACTION = 20  # north_star / GPU-Gems-3 convention
 SM_COUNT = 148
@@ -61,8 +61,8 @@ def workload(kind):
         x, v, m = ic_raw.Plummer(N_DIRECT, 1e-3, 1e6, seed=42)
         return dict(x=np.ascontiguousarray(x), v=np.ascontiguousarray(v), m=m, eps=5e-5, dt=0.005,
                     theta=0.7, alg="direct", prec="fp32",
-                    name="Plummer N=1048576 b=1pc M=1e6Msun eps=0.05pc dt=0.005Myr, direct summation fp32, "
-                         "1 DKD leapfrog step (BASELINE.json configs[2])")
+                    name="Plummer N=%d b=1pc M=1e6Msun eps=0.05pc dt=0.005Myr, direct summation fp32, "
+                         "1 DKD leapfrog step (BASELINE.json configs[2])" % N_DIRECT)
     x, v, m = ic_raw.Hernquist(N_TREE, 1.0, 1e10, seed=42)
     return dict(x=np.ascontiguousarray(x), v=np.ascontiguousarray(v), m=m, eps=0.05, dt=1.0, theta=0.7,
                 alg="tree", prec="fp32",
@@ -375,8 +375,8 @@ def main():
         per_rank_units = units_per_step / world
         achieved = per_rank_units * FLOP_PER_INTERACTION / (kernel_ms * 1e-3) / 1e12
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at N = 2^20 on one GPU from
-        # `ncu --set full` (profiles/r01_direct_f32_N1M.txt): 25.8 MB + 79.2 MB
-        traffic = 104.9e6 if (n == N_DIRECT and world == 1) else None
+        # `ncu --set full` (profiles/r01_direct_f32_N1M.txt): 24.4 MB + 76.5 MB
+        traffic = 101.0e6 if (n == (1 << 20) and world == 1) else None
         roofline = {"bound": "fp32_fma", "achieved": achieved, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
                     "frac": achieved / fp32_peak_tflops, "traffic": traffic,
                     "traffic_unit": "bytes per launch (ncu); algorithmic: 16.8 MB sources read + 24 MB x S partial sums",
