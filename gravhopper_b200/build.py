@@ -13,8 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgravhopper_b200.so")
 SOURCES = ["direct.cu", "tree.cu", "engine.cu", "ic.cu"]
-HEADERS = [os.path.join(CSRC, "common.cuh"),
-           os.path.join(HERE, "..", "include", "gravhopper_b200.h")]
+HEADERS = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h"))] + \
+          [os.path.join(HERE, "..", "include", "gravhopper_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--use_fast_math=false"]
 

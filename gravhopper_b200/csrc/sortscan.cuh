@@ -1,0 +1,345 @@
+// sortscan.cuh -- hand-written device primitives of the tree build (sm_100a):
+//   * chunked_scan<T>: deterministic inclusive scan (P[q+1] = x_0 (+) ... (+) x_q, P[0] = identity)
+//     over 256-element warp chunks, recursive; used for the double-double moment sums (T = DD4,
+//     non-associative operator, fixed order) and for the pre-order offsets / radix digit offsets
+//     (T = int);
+//   * radix_sort_pairs: stable LSD radix sort of (uint64 key, int value) pairs, 8 bits per pass
+//     (K5 of SURVEY 2.4).  Per pass: per-CTA digit histogram (+ global digit totals) -> per-digit
+//     row scan of the (digit, CTA) table -> scatter.  In the scatter each warp ranks its 256 keys
+//     in order with MATCH.ANY ballots (stable), the CTA's 2048 keys are placed in shared memory in
+//     digit order, and written out as contiguous runs per digit (coalesced).
+#pragma once
+#include "common.cuh"
+
+namespace gh {
+
+static constexpr int SCAN_THREADS = 256;
+static constexpr int SCAN_ROUNDS = 8;
+static constexpr int SCAN_WARP_ELEMS = 32 * SCAN_ROUNDS;
+
+// ---- element types ---------------------------------------------------------------------------
+struct DD {
+  double h, l;
+};
+struct DD4 {
+  DD c[4];
+};
+__device__ __forceinline__ void dd_add(double ah, double al, double bh, double bl, double &rh,
+                                       double &rl) {
+  double s = __dadd_rn(ah, bh);
+  double bb = __dadd_rn(s, -ah);
+  double e = __dadd_rn(__dadd_rn(ah, -__dadd_rn(s, -bb)), __dadd_rn(bh, -bb));
+  e = __dadd_rn(e, __dadd_rn(al, bl));
+  rh = __dadd_rn(s, e);
+  rl = __dadd_rn(e, -__dadd_rn(rh, -s));
+}
+
+template <class T> struct ScanOps;
+template <> struct ScanOps<int> {
+  static __device__ __forceinline__ int zero() { return 0; }
+  static __device__ __forceinline__ int add(int a, int b) { return a + b; }
+  static __device__ __forceinline__ int shfl_up(int v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+  static __device__ __forceinline__ int shfl(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+};
+template <> struct ScanOps<DD4> {
+  static __device__ __forceinline__ DD4 zero() {
+    DD4 r;
+#pragma unroll
+    for (int k = 0; k < 4; k++) r.c[k].h = r.c[k].l = 0.0;
+    return r;
+  }
+  static __device__ __forceinline__ DD4 add(const DD4 &a, const DD4 &b) {
+    DD4 r;
+#pragma unroll
+    for (int k = 0; k < 4; k++) dd_add(a.c[k].h, a.c[k].l, b.c[k].h, b.c[k].l, r.c[k].h, r.c[k].l);
+    return r;
+  }
+  static __device__ __forceinline__ DD4 shfl_up(const DD4 &v, int d) {
+    DD4 r;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      r.c[k].h = __shfl_up_sync(0xffffffffu, v.c[k].h, d);
+      r.c[k].l = __shfl_up_sync(0xffffffffu, v.c[k].l, d);
+    }
+    return r;
+  }
+  static __device__ __forceinline__ DD4 shfl(const DD4 &v, int src) {
+    DD4 r;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      r.c[k].h = __shfl_sync(0xffffffffu, v.c[k].h, src);
+      r.c[k].l = __shfl_sync(0xffffffffu, v.c[k].l, src);
+    }
+    return r;
+  }
+};
+
+// inclusive scan across the 32 lanes (fixed order: Hillis-Steele, lower lanes on the left)
+template <class T>
+__device__ __forceinline__ T warp_scan(T v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    T o = ScanOps<T>::shfl_up(v, d);
+    if (lane >= d) v = ScanOps<T>::add(o, v);
+  }
+  return v;
+}
+
+template <class T>
+struct InArray {
+  const T *a;
+  __device__ __forceinline__ T operator()(int64_t q) const { return a[q]; }
+};
+
+template <class T, class In>
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_phase1(In in, int64_t n, T *__restrict__ warpsum) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t base = w * SCAN_WARP_ELEMS;
+  if (base >= n) return;
+  T acc = ScanOps<T>::zero();
+#pragma unroll 2
+  for (int r = 0; r < SCAN_ROUNDS; r++) {  // element order inside the warp: round-major
+    const int64_t q = base + r * 32 + lane;
+    T v = (q < n) ? in(q) : ScanOps<T>::zero();
+    v = warp_scan<T>(v, lane);  // same association as phase 3
+    acc = ScanOps<T>::add(acc, ScanOps<T>::shfl(v, 31));
+  }
+  if (lane == 0) warpsum[w] = acc;
+}
+// P[q + 1] = offset of the warp (+) inclusive scan inside the warp; P[0] = identity.
+// warpoff == nullptr: single-warp launch over the whole (short) array.
+template <class T, class In>
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_phase3(In in, int64_t n, const T *__restrict__ warpoff, T *__restrict__ P /* n + 1 */) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t base = w * SCAN_WARP_ELEMS;
+  if (base >= n) return;
+  T carry = warpoff ? warpoff[w] : ScanOps<T>::zero();
+  if (w == 0 && lane == 0) P[0] = ScanOps<T>::zero();
+  for (int r = 0; r < SCAN_ROUNDS; r++) {
+    const int64_t q = base + r * 32 + lane;
+    T v = (q < n) ? in(q) : ScanOps<T>::zero();
+    v = warp_scan<T>(v, lane);
+    const T out = ScanOps<T>::add(carry, v);
+    if (q < n) P[q + 1] = out;
+    carry = ScanOps<T>::add(carry, ScanOps<T>::shfl(v, 31));
+  }
+}
+
+// P[0..n]: P[0] = identity, P[q+1] = in(0) (+) ... (+) in(q).  Recursion over 256-element warp
+// chunks (depth 3 at n = 16.7M, 4 beyond); `levels` supplies scratch for the per-level totals.
+template <class T, class In>
+static int chunked_scan(In in, int64_t n, T *P, DeviceBuffer *levels, int depth, cudaStream_t st) {
+  if (n <= 0) return GH_OK;
+  if (n <= SCAN_WARP_ELEMS) {
+    scan_phase3<T, In><<<1, 32, 0, st>>>(in, n, nullptr, P);
+    GH_LAUNCH_CHECK();
+    return GH_OK;
+  }
+  if (depth >= 4) { set_error("chunked_scan: too many levels"); return GH_EINVAL; }
+  const int64_t nw = (n + SCAN_WARP_ELEMS - 1) / SCAN_WARP_ELEMS;
+  const unsigned nsb = (unsigned)((nw * 32 + SCAN_THREADS - 1) / SCAN_THREADS);
+  GH_TRY(levels[depth].reserve(sizeof(T) * (size_t)(2 * nw + 1)));  // totals[nw] + prefix[nw + 1]
+  T *totals = levels[depth].as<T>();
+  T *prefix = totals + nw;
+  scan_phase1<T, In><<<nsb, SCAN_THREADS, 0, st>>>(in, n, totals);
+  GH_LAUNCH_CHECK();
+  GH_TRY((chunked_scan<T, InArray<T>>(InArray<T>{totals}, nw, prefix, levels, depth + 1, st)));
+  scan_phase3<T, In><<<nsb, SCAN_THREADS, 0, st>>>(in, n, prefix, P);
+  GH_LAUNCH_CHECK();
+  return GH_OK;
+}
+
+// ---- radix sort ------------------------------------------------------------------------------
+static constexpr int RS_THREADS = 256;
+static constexpr int RS_WARPS = RS_THREADS / 32;
+static constexpr int RS_ROUNDS = 8;                      // keys per thread
+static constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;   // 2048 keys per CTA
+static constexpr int RS_RADIX = 256;
+
+__global__ void __launch_bounds__(RS_THREADS)
+rs_hist_kernel(const uint64_t *__restrict__ keys, int64_t n, int shift, int *__restrict__ hist,
+               int nblocks, int *__restrict__ gtot /* [256], zeroed */) {
+  __shared__ int h[RS_RADIX];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * RS_TILE;
+#pragma unroll
+  for (int k = 0; k < RS_ROUNDS; k++) {
+    const int64_t q = base + k * RS_THREADS + threadIdx.x;
+    if (q < n) atomicAdd(&h[(int)((keys[q] >> shift) & 0xff)], 1);
+  }
+  __syncthreads();
+  const int c = h[threadIdx.x];
+  hist[(int64_t)threadIdx.x * nblocks + blockIdx.x] = c;  // digit-major table
+  if (c) atomicAdd(&gtot[threadIdx.x], c);                // integer adds: order does not matter
+}
+
+// CTA d turns row d of the table (counts of digit d per CTA of the sort) into exclusive offsets
+// within the digit: offs[d][b] = sum_{b' < b} hist[d][b'].
+__global__ void __launch_bounds__(RS_THREADS)
+rs_rowscan_kernel(int *__restrict__ hist, int nblocks) {
+  __shared__ int wtot[RS_WARPS];
+  int *row = hist + (int64_t)blockIdx.x * nblocks;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int carry = 0;
+  for (int b0 = 0; b0 < nblocks; b0 += RS_THREADS) {
+    const int b = b0 + threadIdx.x;
+    const int v = (b < nblocks) ? row[b] : 0;
+    const int incl = warp_scan<int>(v, lane);
+    if (lane == 31) wtot[w] = incl;
+    __syncthreads();
+    int woff = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < RS_WARPS; k++) {
+      woff += (k < w) ? wtot[k] : 0;
+      tot += wtot[k];
+    }
+    if (b < nblocks) row[b] = carry + woff + incl - v;
+    carry += tot;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+rs_scatter_kernel(const uint64_t *__restrict__ kin, const int *__restrict__ vin,
+                  uint64_t *__restrict__ kout, int *__restrict__ vout, int64_t n, int shift,
+                  const int *__restrict__ offs /* per-digit exclusive offsets (rs_rowscan_kernel) */,
+                  const int *__restrict__ gtot /* [256] keys per digit */, int nblocks) {
+  __shared__ int whist[RS_WARPS][RS_RADIX];  // per-warp digit counts, then per-warp digit bases
+  __shared__ int dstart[RS_RADIX];           // start of digit d in the CTA-local sorted tile
+  __shared__ int gbase[RS_RADIX];            // global start of this CTA's keys of digit d
+  __shared__ int wtot[RS_WARPS];
+  __shared__ uint64_t skey[RS_TILE];
+  __shared__ int sval[RS_TILE];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int64_t tile0 = (int64_t)blockIdx.x * RS_TILE;
+  const int64_t seg0 = tile0 + (int64_t)w * (32 * RS_ROUNDS);
+#pragma unroll
+  for (int k = 0; k < RS_WARPS; k++) whist[k][tid] = 0;
+  __syncthreads();
+
+  uint64_t key[RS_ROUNDS];
+  int val[RS_ROUNDS], lrank[RS_ROUNDS];
+#pragma unroll
+  for (int r = 0; r < RS_ROUNDS; r++) {
+    const int64_t q = seg0 + r * 32 + lane;
+    const bool valid = q < n;
+    key[r] = valid ? kin[q] : 0;
+    val[r] = valid ? vin[q] : 0;
+    // invalid lanes get private pseudo-digits so that they match nobody
+    const unsigned d = valid ? (unsigned)((key[r] >> shift) & 0xff) : (0x100u + (unsigned)lane);
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    const int leader = __ffs(peers) - 1;
+    int old = 0;
+    if (lane == leader && valid) {
+      old = whist[w][d];
+      whist[w][d] = old + __popc(peers);
+    }
+    old = __shfl_sync(0xffffffffu, old, leader);
+    lrank[r] = old + __popc(peers & ((1u << lane) - 1u));
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // thread d: turn the per-warp counts of digit d into per-warp bases, get the CTA total
+  int tot = 0;
+#pragma unroll
+  for (int k = 0; k < RS_WARPS; k++) {
+    const int c = whist[k][tid];
+    whist[k][tid] = tot;
+    tot += c;
+  }
+  // exclusive scan of the 256 digit totals across the CTA
+  int incl = warp_scan<int>(tot, lane);
+  if (lane == 31) wtot[w] = incl;
+  __syncthreads();
+  int woff = 0;
+#pragma unroll
+  for (int k = 0; k < RS_WARPS; k++) woff += (k < w) ? wtot[k] : 0;
+  dstart[tid] = woff + incl - tot;
+  __syncthreads();
+  // global start of digit d = number of keys with a smaller digit (scan of gtot across the CTA)
+  {
+    const int g = gtot[tid];
+    const int gincl = warp_scan<int>(g, lane);
+    if (lane == 31) wtot[w] = gincl;
+    __syncthreads();
+    int goff = 0;
+#pragma unroll
+    for (int k = 0; k < RS_WARPS; k++) goff += (k < w) ? wtot[k] : 0;
+    gbase[tid] = goff + gincl - g + offs[(int64_t)tid * nblocks + blockIdx.x];
+  }
+  __syncthreads();
+
+#pragma unroll
+  for (int r = 0; r < RS_ROUNDS; r++) {
+    const int64_t q = seg0 + r * 32 + lane;
+    if (q < n) {
+      const int d = (int)((key[r] >> shift) & 0xff);
+      const int pos = dstart[d] + whist[w][d] + lrank[r];
+      skey[pos] = key[r];
+      sval[pos] = val[r];
+    }
+  }
+  __syncthreads();
+  const int64_t left = n - tile0;
+  const int ntile = (int)(left < RS_TILE ? left : RS_TILE);
+#pragma unroll
+  for (int k = 0; k < RS_ROUNDS; k++) {
+    const int j = k * RS_THREADS + tid;
+    if (j < ntile) {
+      const uint64_t kk = skey[j];
+      const int d = (int)((kk >> shift) & 0xff);
+      const int64_t g = (int64_t)gbase[d] + (j - dstart[d]);
+      kout[g] = kk;
+      vout[g] = sval[j];
+    }
+  }
+}
+
+struct RadixScratch {
+  DeviceBuffer hist, gtot;
+  void release() {
+    hist.release();
+    gtot.release();
+  }
+};
+
+// Stable LSD sort of (key, value) pairs on key bits [0, nbits).  Ping-pongs between (kA, vA) and
+// (kB, vB), starting from A; *result_in_B says where the sorted data ends up (both are clobbered).
+static int radix_sort_pairs(uint64_t *kA, int *vA, uint64_t *kB, int *vB, int64_t n, int nbits,
+                            RadixScratch &rs, cudaStream_t st, bool *result_in_B) {
+  *result_in_B = false;
+  if (n <= 1) return GH_OK;
+  const int nblocks = (int)((n + RS_TILE - 1) / RS_TILE);
+  const int64_t tbl = (int64_t)RS_RADIX * nblocks;
+  const int npass = (nbits + 7) / 8;
+  GH_TRY(rs.hist.reserve(sizeof(int) * (size_t)tbl));
+  GH_TRY(rs.gtot.reserve(sizeof(int) * RS_RADIX * (size_t)npass));
+  GH_CUDA(cudaMemsetAsync(rs.gtot.ptr, 0, sizeof(int) * RS_RADIX * (size_t)npass, st));
+  uint64_t *kin = kA, *kout = kB;
+  int *vin = vA, *vout = vB;
+  bool inB = false;
+  for (int pass = 0; pass < npass; pass++) {
+    const int shift = 8 * pass;
+    int *gtot = rs.gtot.as<int>() + RS_RADIX * pass;
+    rs_hist_kernel<<<nblocks, RS_THREADS, 0, st>>>(kin, n, shift, rs.hist.as<int>(), nblocks, gtot);
+    GH_LAUNCH_CHECK();
+    rs_rowscan_kernel<<<RS_RADIX, RS_THREADS, 0, st>>>(rs.hist.as<int>(), nblocks);
+    GH_LAUNCH_CHECK();
+    rs_scatter_kernel<<<nblocks, RS_THREADS, 0, st>>>(kin, vin, kout, vout, n, shift, rs.hist.as<int>(), gtot,
+                                                     nblocks);
+    GH_LAUNCH_CHECK();
+    uint64_t *tk = kin; kin = kout; kout = tk;
+    int *tv = vin; vin = vout; vout = tv;
+    inB = !inB;
+  }
+  *result_in_B = inB;
+  return GH_OK;
+}
+
+}  // namespace gh

@@ -16,8 +16,9 @@
 //                       cell centre exactly as gravoct_calc_subnode does; 3 bits per level,
 //                       z-major so that key order == the reference's branch order (:441-450);
 //                       levels 1-21 in `hi`, 22-42 in `lo`
-//   K5  sort            stable LSD radix sort of (lo, hi) with the particle index (CUB
-//                       DeviceRadixSort and one CUB int prefix sum: library plumbing)
+//   K5  sort            stable LSD radix sort of (lo, hi) with the particle index: hand-written,
+//                       8 bits per pass, MATCH.ANY ranking, shared-memory staged coalesced
+//                       scatter (sortscan.cuh); no library kernels anywhere in the build
 //   K6a common levels   c[p] = number of octant levels shared by sorted neighbours p, p+1.
 //                       A cell of level l starts at p  <=>  c[p-1] < l <= c[p]; therefore the
 //                       depth-first (pre-order) position of every cell and leaf is a prefix sum
@@ -39,8 +40,8 @@
 // leaves, which is exact for the force and cannot loop forever on coincident particles (the
 // reference segfaults there, :401-413).
 #include "common.cuh"
+#include "sortscan.cuh"
 
-#include <cub/cub.cuh>
 #include <climits>
 #include <cstdlib>
 
@@ -208,18 +209,6 @@ __global__ void levels_kernel(const uint64_t *__restrict__ hi, const uint64_t *_
 // arithmetic (hi + lo, ~106 bits), so that the moments of a cell covering sorted particles
 // [p, b] are P[b+1] - P[p] without cancellation (errors ~1e-30 of the total).  The products m x
 // are formed exactly: hi = fl(m x), lo = fma(m, x, -hi).
-struct DD {
-  double h, l;
-};
-__device__ __forceinline__ void dd_add(double ah, double al, double bh, double bl, double &rh,
-                                       double &rl) {
-  double s = __dadd_rn(ah, bh);
-  double bb = __dadd_rn(s, -ah);
-  double e = __dadd_rn(__dadd_rn(ah, -__dadd_rn(s, -bb)), __dadd_rn(bh, -bb));
-  e = __dadd_rn(e, __dadd_rn(al, bl));
-  rh = __dadd_rn(s, e);
-  rl = __dadd_rn(e, -__dadd_rn(rh, -s));
-}
 // sources gathered once into Morton order: (x, y, z, m) as double4, so that the moment scans,
 // the emit kernel and the walk's target loads are all coalesced
 template <class Src>
@@ -232,33 +221,9 @@ __global__ void gather_sorted_kernel(Src src, const int *__restrict__ idx, int64
   src.get(j, x, y, z);
   out[p] = make_double4(x, y, z, src.m(j));
 }
-// Deterministic three-phase inclusive scan of the four double-double moment sequences, fused
-// and fully coalesced (fixed summation order -> bitwise reproducible run to run, unlike a
-// decoupled-look-back scan with a non-associative operator).  The unit of work is one warp and
-// SCAN_WARP_ELEMS = 256 consecutive particles, taken 32 at a time (lane l <-> element 32 r + l):
-//   phase 1: per-warp totals (per round a shuffle scan across the lanes, lane 31 carries)
-//   phase 2: the warp totals are scanned by the same two kernels, recursively (depth 3 at 10M)
-//   phase 3: each warp rescans its 256 particles from its offset: per round a shuffle scan across
-//            the lanes plus the running carry; writes P[p+1] as one 64-byte DD4 per particle
-static constexpr int SCAN_THREADS = 256;
-static constexpr int SCAN_ROUNDS = 8;
-static constexpr int SCAN_WARP_ELEMS = 32 * SCAN_ROUNDS;
-
-struct DD4 {
-  DD c[4];
-};
-__device__ __forceinline__ DD4 dd4_zero() {
-  DD4 r;
-#pragma unroll
-  for (int k = 0; k < 4; k++) r.c[k].h = r.c[k].l = 0.0;
-  return r;
-}
-__device__ __forceinline__ DD4 dd4_add(const DD4 &a, const DD4 &b) {
-  DD4 r;
-#pragma unroll
-  for (int k = 0; k < 4; k++) dd_add(a.c[k].h, a.c[k].l, b.c[k].h, b.c[k].l, r.c[k].h, r.c[k].l);
-  return r;
-}
+// The scan itself is chunked_scan<DD4> (sortscan.cuh): deterministic, coalesced, warp-contiguous
+// (fixed summation order -> bitwise reproducible run to run, unlike a decoupled-look-back scan
+// with a non-associative operator).
 __device__ __forceinline__ DD4 dd4_of(const double4 q) {
   DD4 r;
   r.c[0].h = q.w;
@@ -271,105 +236,10 @@ __device__ __forceinline__ DD4 dd4_of(const double4 q) {
   }
   return r;
 }
-__device__ __forceinline__ DD4 dd4_shfl_up(const DD4 &v, int d) {
-  DD4 r;
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    r.c[k].h = __shfl_up_sync(0xffffffffu, v.c[k].h, d);
-    r.c[k].l = __shfl_up_sync(0xffffffffu, v.c[k].l, d);
-  }
-  return r;
-}
-__device__ __forceinline__ DD4 dd4_shfl(const DD4 &v, int src) {
-  DD4 r;
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    r.c[k].h = __shfl_sync(0xffffffffu, v.c[k].h, src);
-    r.c[k].l = __shfl_sync(0xffffffffu, v.c[k].l, src);
-  }
-  return r;
-}
-// inclusive scan across the 32 lanes (fixed order: Hillis-Steele, lower lanes on the left)
-__device__ __forceinline__ DD4 warp_scan_dd4(DD4 v, int lane) {
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    DD4 o = dd4_shfl_up(v, d);
-    if (lane >= d) v = dd4_add(o, v);
-  }
-  return v;
-}
-
 struct InParticles {  // element q = (m, m x, m y, m z) of sorted particle q, products exact
   const double4 *sp;
   __device__ __forceinline__ DD4 operator()(int64_t q) const { return dd4_of(sp[q]); }
 };
-struct InDD4 {
-  const DD4 *a;
-  __device__ __forceinline__ DD4 operator()(int64_t q) const { return a[q]; }
-};
-
-template <class In>
-__global__ void __launch_bounds__(SCAN_THREADS)
-scan_phase1(In in, int64_t n, DD4 *__restrict__ warpsum) {
-  const int lane = threadIdx.x & 31;
-  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t base = w * SCAN_WARP_ELEMS;
-  if (base >= n) return;
-  DD4 acc = dd4_zero();
-#pragma unroll 2
-  for (int r = 0; r < SCAN_ROUNDS; r++) {  // element order inside the warp: round-major
-    const int64_t q = base + r * 32 + lane;
-    DD4 v = (q < n) ? in(q) : dd4_zero();
-    v = warp_scan_dd4(v, lane);  // same association as phase 3
-    acc = dd4_add(acc, dd4_shfl(v, 31));
-  }
-  if (lane == 0) warpsum[w] = acc;
-}
-// P[q + 1] = offset of the warp + inclusive scan inside the warp; P[0] = 0.
-// warpoff == nullptr: single-warp launch over the whole (short) array.
-template <class In>
-__global__ void __launch_bounds__(SCAN_THREADS)
-scan_phase3(In in, int64_t n, const DD4 *__restrict__ warpoff, DD4 *__restrict__ P /* n + 1 */,
-            int rounds) {
-  const int lane = threadIdx.x & 31;
-  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t base = w * SCAN_WARP_ELEMS;
-  if (base >= n) return;
-  DD4 carry = warpoff ? warpoff[w] : dd4_zero();
-  if (w == 0 && lane == 0) P[0] = dd4_zero();
-  for (int r = 0; r < rounds; r++) {
-    const int64_t q = base + r * 32 + lane;
-    DD4 v = (q < n) ? in(q) : dd4_zero();
-    v = warp_scan_dd4(v, lane);
-    const DD4 out = dd4_add(carry, v);
-    if (q < n) P[q + 1] = out;
-    carry = dd4_add(carry, dd4_shfl(v, 31));
-  }
-}
-
-// P[0..n] = exclusive-then-inclusive prefix of in(0..n-1); recursion over 256-element warp chunks
-// (depth 3 at n = 10M).  `levels` supplies scratch for the per-level totals and their prefixes.
-template <class In>
-static int dd4_scan(In in, int64_t n, DD4 *P, DeviceBuffer *levels, int depth, cudaStream_t st) {
-  if (n <= SCAN_WARP_ELEMS) {
-    scan_phase3<In><<<1, 32, 0, st>>>(in, n, nullptr, P, SCAN_ROUNDS);
-    GH_LAUNCH_CHECK();
-    return GH_OK;
-  }
-  if (depth >= 3) { set_error("dd4_scan: too many levels"); return GH_EINVAL; }
-  const int64_t nw = (n + SCAN_WARP_ELEMS - 1) / SCAN_WARP_ELEMS;
-  const unsigned nsb = (unsigned)((nw * 32 + SCAN_THREADS - 1) / SCAN_THREADS);
-  // layout of this level's scratch: totals[nw] followed by prefix[nw + 1]
-  GH_TRY(levels[depth].reserve(sizeof(DD4) * (size_t)(2 * nw + 1)));
-  DD4 *totals = levels[depth].as<DD4>();
-  DD4 *prefix = totals + nw;
-  scan_phase1<In><<<nsb, SCAN_THREADS, 0, st>>>(in, n, totals);
-  GH_LAUNCH_CHECK();
-  GH_TRY(dd4_scan<InDD4>(InDD4{totals}, nw, prefix, levels, depth + 1, st));
-  scan_phase3<In><<<nsb, SCAN_THREADS, 0, st>>>(in, n, prefix, P, SCAN_ROUNDS);
-  GH_LAUNCH_CHECK();
-  return GH_OK;
-}
 
 // ---- K6b emit -----------------------------------------------------------------------------------
 template <class Real> struct Vec4;
@@ -662,8 +532,9 @@ walk_kernel(const Node<Real> *__restrict__ nodes, const int *__restrict__ skips,
 
 // ---- workspace + orchestration --------------------------------------------------------------------
 struct TreeWorkspace {
-  DeviceBuffer root, part, hi, lo, hi2, lo2, idx, idx2, clev, cnt, base, P, cubtmp;
-  DeviceBuffer node, skip, misc, thi, tidx, thi2, tidx2, sorted, bsum, scanlv[3];
+  DeviceBuffer root, part, hi, lo, hi2, lo2, lo3, idx, idx2, clev, cnt, base, P;
+  DeviceBuffer node, skip, misc, thi, tidx, thi2, tidx2, sorted, bsum, scanlv[4], cntlv[4];
+  RadixScratch rs;
   int64_t last_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int *h_pinned = nullptr;  // [0] nentries, [1] maxlevel ; pinned for async readback
   unsigned long long *h_stats = nullptr;
@@ -672,10 +543,11 @@ struct TreeWorkspace {
 TreeWorkspace *tree_workspace_create() { return new TreeWorkspace(); }
 void tree_workspace_destroy(TreeWorkspace *w) {
   if (!w) return;
-  DeviceBuffer *all[] = {&w->root, &w->part, &w->hi, &w->lo, &w->hi2, &w->lo2, &w->idx, &w->idx2,
-                         &w->clev, &w->cnt, &w->base, &w->P, &w->cubtmp, &w->node, &w->sorted, &w->bsum, &w->scanlv[0], &w->scanlv[1], &w->scanlv[2],
+  DeviceBuffer *all[] = {&w->root, &w->part, &w->hi, &w->lo, &w->hi2, &w->lo2, &w->lo3, &w->idx, &w->idx2,
+                         &w->clev, &w->cnt, &w->base, &w->P, &w->node, &w->sorted, &w->bsum, &w->scanlv[0], &w->scanlv[1], &w->scanlv[2], &w->scanlv[3], &w->cntlv[0], &w->cntlv[1], &w->cntlv[2], &w->cntlv[3],
                          &w->skip, &w->misc, &w->thi, &w->tidx, &w->thi2, &w->tidx2};
   for (auto *b : all) b->release();
+  w->rs.release();
   if (w->h_pinned) cudaFreeHost(w->h_pinned);
   if (w->h_stats) cudaFreeHost(w->h_stats);
   delete w;
@@ -724,43 +596,43 @@ static int tree_impl(const TreeArgs &a, Src src, const float4 *tgt32, TreeWorksp
   keys_kernel<<<nblk(n, 256), 256, 0, st>>>(src, n, root, levels, hi, lo, idx);
   GH_LAUNCH_CHECK();
 
-  // K5 (CUB radix sort; LSD over (lo, hi), stable)
-  size_t tmp_bytes = 0, tb;
-  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, hi, hi2, idx, idx2, (int)n, 0, 63, st);
-  tb = 0;
-  cub::DeviceScan::InclusiveSum(nullptr, tb, (int *)nullptr, (int *)nullptr, (int)n + 1, st);
-  if (tb > tmp_bytes) tmp_bytes = tb;
-  GH_TRY(w->cubtmp.reserve(tmp_bytes));
-  void *tmp = w->cubtmp.ptr;
-  size_t tmpsz = w->cubtmp.bytes;
+  // K5: stable LSD radix sort (sortscan.cuh) over (lo, hi); both ping-pong buffers are clobbered
   const uint64_t *shi, *slo = nullptr;
   const int *sidx;
+  bool inB = false;
   if (deep) {
-    // pass 1: by lo; pass 2: by hi gathered through the pass-1 order (stable)
-    GH_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmpsz, lo, lo2, idx, idx2, (int)n, 0, 63, st));
-    gather_u64<<<nblk(n, 256), 256, 0, st>>>(hi, idx2, n, hi2);
+    // pass 1: by lo; pass 2: by hi gathered through the pass-1 order (stable).  The unsorted lo
+    // keys are needed again at the end, so keep a copy.
+    GH_TRY(w->lo3.reserve(sizeof(uint64_t) * n));
+    GH_CUDA(cudaMemcpyAsync(w->lo3.ptr, lo, sizeof(uint64_t) * n, cudaMemcpyDeviceToDevice, st));
+    GH_TRY(radix_sort_pairs(lo, idx, lo2, idx2, n, 63, w->rs, st, &inB));
+    int *order1 = inB ? idx2 : idx;
+    int *other1 = inB ? idx : idx2;
+    uint64_t *hs = inB ? lo : lo2;  // free key buffer of pass 1 holds hi gathered in pass-1 order
+    gather_u64<<<nblk(n, 256), 256, 0, st>>>(hi, order1, n, hs);
     GH_LAUNCH_CHECK();
-    GH_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmpsz, hi2, hi, idx2, idx, (int)n, 0, 63, st));
-    // sorted: hi (keys), idx (order).  lo must be re-gathered from the unsorted lo... which pass 1
-    // left untouched in `lo` (SortPairs with separate in/out buffers does not modify its input).
-    gather_u64<<<nblk(n, 256), 256, 0, st>>>(lo, idx, n, lo2);
+    GH_TRY(radix_sort_pairs(hs, order1, hi2, other1, n, 63, w->rs, st, &inB));
+    shi = inB ? hi2 : hs;
+    sidx = inB ? other1 : order1;
+    uint64_t *lsorted = (shi == hi2) ? hs : hi2;  // the key buffer not holding the result
+    gather_u64<<<nblk(n, 256), 256, 0, st>>>(w->lo3.as<uint64_t>(), sidx, n, lsorted);
     GH_LAUNCH_CHECK();
-    shi = hi; slo = lo2; sidx = idx;
+    slo = lsorted;
   } else {
-    GH_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmpsz, hi, hi2, idx, idx2, (int)n, 0, 63, st));
-    shi = hi2; sidx = idx2;
+    GH_TRY(radix_sort_pairs(hi, idx, hi2, idx2, n, 63, w->rs, st, &inB));
+    shi = inB ? hi2 : hi;
+    sidx = inB ? idx2 : idx;
   }
 
-  // K6a + scan
+  // K6a + pre-order offsets: base[p] = sum_{q<p} (cells opened at q + 1), base[n] = entries
   GH_TRY(w->clev.reserve(n));
   GH_TRY(w->cnt.reserve(sizeof(int) * (n + 1)));
   GH_TRY(w->base.reserve(sizeof(int) * (n + 1)));
   signed char *clev = w->clev.as<signed char>();
   int *cnt = w->cnt.as<int>(), *base = w->base.as<int>();
-  GH_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int), st));  // cnt is shifted by one: cnt[0] = 0
-  levels_kernel<<<nblk(n, 256), 256, 0, st>>>(shi, slo, n, levels, clev, cnt + 1);
+  levels_kernel<<<nblk(n, 256), 256, 0, st>>>(shi, slo, n, levels, clev, cnt);
   GH_LAUNCH_CHECK();
-  GH_CUDA(cub::DeviceScan::InclusiveSum(tmp, tmpsz, cnt, base, (int)n + 1, st));  // base[p] = sum_{q<p}
+  GH_TRY((chunked_scan<int, InArray<int>>(InArray<int>{cnt}, n, base, w->cntlv, 0, st)));
   GH_CUDA(cudaMemcpyAsync(&w->h_pinned[0], base + n, sizeof(int), cudaMemcpyDeviceToHost, st));
 
   // K7
@@ -770,7 +642,7 @@ static int tree_impl(const TreeArgs &a, Src src, const float4 *tgt32, TreeWorksp
   GH_LAUNCH_CHECK();
   GH_TRY(w->P.reserve(sizeof(DD4) * (size_t)(n + 1)));
   DD4 *P = w->P.as<DD4>();
-  GH_TRY(dd4_scan<InParticles>(InParticles{sp}, n, P, w->scanlv, 0, st));
+  GH_TRY((chunked_scan<DD4, InParticles>(InParticles{sp}, n, P, w->scanlv, 0, st)));
 
   // entries: need the count on the host to size the arrays
   GH_CUDA(cudaStreamSynchronize(st));
@@ -802,10 +674,6 @@ static int tree_impl(const TreeArgs &a, Src src, const float4 *tgt32, TreeWorksp
     GH_TRY(w->thi2.reserve(sizeof(uint64_t) * ni));
     GH_TRY(w->tidx.reserve(sizeof(int) * ni));
     GH_TRY(w->tidx2.reserve(sizeof(int) * ni));
-    size_t need = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, need, w->thi.as<uint64_t>(), w->thi2.as<uint64_t>(),
-                                    w->tidx.as<int>(), w->tidx2.as<int>(), (int)ni, 0, 63, st);
-    GH_TRY(w->cubtmp.reserve(need > tmp_bytes ? need : tmp_bytes));
     if (tgt32) {
       Src32 ts{tgt32};
       keys_kernel<<<nblk(ni, 256), 256, 0, st>>>(ts, ni, root, LEVELS_HI, w->thi.as<uint64_t>(),
@@ -816,10 +684,10 @@ static int tree_impl(const TreeArgs &a, Src src, const float4 *tgt32, TreeWorksp
                                                 (uint64_t *)nullptr, w->tidx.as<int>());
     }
     GH_LAUNCH_CHECK();
-    GH_CUDA(cub::DeviceRadixSort::SortPairs(w->cubtmp.ptr, w->cubtmp.bytes, w->thi.as<uint64_t>(),
-                                            w->thi2.as<uint64_t>(), w->tidx.as<int>(),
-                                            w->tidx2.as<int>(), (int)ni, 0, 63, st));
-    tv.order = w->tidx2.as<int>();
+    bool tinB = false;
+    GH_TRY(radix_sort_pairs(w->thi.as<uint64_t>(), w->tidx.as<int>(), w->thi2.as<uint64_t>(),
+                            w->tidx2.as<int>(), ni, 63, w->rs, st, &tinB));
+    tv.order = tinB ? w->tidx2.as<int>() : w->tidx.as<int>();
   }
 
   // K8
