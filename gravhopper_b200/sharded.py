@@ -63,10 +63,11 @@ def interleaved_layout(pos, world, block=None):
     if world == 1:
         return order
     if block is None:
-        # 8 blocks per rank: large enough that the warps resident on a GPU at any time work on
-        # a compact part of the tree (measured on B200, N = 4M, 1/8 of the targets: 1.57 ms with
-        # 65536-particle blocks vs 1.80 ms with 2048), small enough to mix dense and sparse regions
-        block = max(2048, (n // (world * 8)) // 32 * 32)
+        # Small blocks: measured on 8 B200 (Hernquist N = 4M) the slowest rank's walk takes 1.80 ms
+        # with 2048-particle blocks and 3.42 ms with 65536-particle blocks (8 per rank): a rank that
+        # holds the few densest blocks is far slower than the others, and balance matters more
+        # than the ~10 % locality gain big blocks give a single rank.
+        block = 2048
     parts = partition(n, world)
     nblocks = (n + block - 1) // block
     owner_blocks = [[] for _ in range(world)]
