@@ -101,3 +101,22 @@ def test_partition():
     assert partition(1 << 20, 8) == [(r * (1 << 17), 1 << 17) for r in range(8)]
     with pytest.raises(ValueError):
         partition(3, 4)
+
+
+def test_morton_layout_is_a_balanced_permutation():
+    from gravhopper_b200.sharded import interleaved_layout, morton_order
+    x, v, m = ic_raw.Hernquist(50000, 1.0, 1e10, seed=3)
+    order = morton_order(x)
+    assert sorted(order.tolist()) == list(range(50000))
+    # Z-order locality: consecutive particles are close compared with the system size
+    d = np.linalg.norm(np.diff(x[order], axis=0), axis=1)
+    d_random = np.linalg.norm(np.diff(x, axis=0), axis=1)  # the generator's order is random
+    assert np.median(d) < 0.2 * np.median(d_random)
+    for world in (1, 2, 3, 8):
+        perm = interleaved_layout(x, world)
+        assert sorted(perm.tolist()) == list(range(50000))
+        parts = partition(50000, world)
+        # every rank gets a mix of inner and outer particles (load balance of the walk)
+        r = np.linalg.norm(x[perm], axis=1)
+        med = [np.median(r[b:b + c]) for b, c in parts]
+        assert max(med) < 1.5 * min(med)
