@@ -149,3 +149,16 @@ def tree_stats(enable=None):
     _lib.check(L.gh_tree_last_stats(out))
     return dict(entries=out[0], cells=out[1], maxlevel=out[2], accepted=out[3], visited=out[4],
                 warp_entries=out[5], warp_entries_max=out[6], warps=out[7])
+
+
+def tree_walk(mode=None):
+    """Select / query how fp32 tree evaluations walk the tree: ``"group"`` (default: one traversal
+    per 32 Morton-consecutive targets, conservative bounding-box form of the reference's opening
+    test) or ``"target"`` (every target applies _jbgrav.c:502 itself).  fp64 always uses "target"."""
+    L = _lib.lib()
+    if mode is not None:
+        if mode not in ("group", "target"):
+            raise ValueError("tree walk mode must be 'group' or 'target'")
+        _lib.check(L.gh_set_tree_walk(1 if mode == "group" else 0))
+        return None
+    return "group" if L.gh_get_tree_walk() == 1 else "target"

@@ -228,5 +228,7 @@ struct TreeArgs {
 int launch_tree(const TreeArgs &a, TreeWorkspace *ws, cudaStream_t stream,
                 cudaEvent_t *force_events);
 int tree_last_stats(TreeWorkspace *ws, int64_t out[8]);
+int tree_walk_mode();
+void set_tree_walk_mode(int mode);
 
 }  // namespace gh

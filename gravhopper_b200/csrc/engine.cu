@@ -313,6 +313,13 @@ int gh_set_tree_stats(int enable) {
   return GH_OK;
 }
 
+int gh_set_tree_walk(int mode) {
+  if (mode != GH_WALK_TARGET && mode != GH_WALK_GROUP) { set_error("unknown tree walk mode %d", mode); return GH_EINVAL; }
+  set_tree_walk_mode(mode);
+  return GH_OK;
+}
+int gh_get_tree_walk(void) { return tree_walk_mode(); }
+
 int gh_ic_sample(int kind, int64_t n, const double *params, int nparams, const double *table_x,
                  const double *table_y, int ntable, uint64_t seed, double *pos, double *vel,
                  double *mass, int mem, void *stream) {

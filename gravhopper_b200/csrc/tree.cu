@@ -44,6 +44,7 @@
 
 #include <climits>
 #include <cstdlib>
+#include <cstring>
 
 namespace gh {
 
@@ -436,40 +437,43 @@ struct TargetsView {
 // with one REDUX: the scan only touches entries some lane still needs.  Branch-free body.
 // fp32: plain fp32 accumulation (<= ~1e3 accepted terms per target; error ~1e-6, far below the
 // monopole error).
-template <class Real, bool STATS, bool GUARD, bool PREFETCH>
-__global__ void __launch_bounds__(128, 8)
-walk_kernel(const Node<Real> *__restrict__ nodes, const int *__restrict__ skips, int nentries,
-            TargetsView tv, int64_t ni, const double *__restrict__ root, bool rel_origin, Real eps2,
-            Epilogue ep, unsigned long long *__restrict__ stats) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t p = warp * 32 + lane;
-  const bool valid = p < ni;
-  int64_t ti = 0;
-  Real x = 0, y = 0, z = 0;
-  if (valid) {
-    ti = tv.order ? (int64_t)tv.order[p] - tv.order_offset : p;
-    const double ox = rel_origin ? root[0] : 0.0, oy = rel_origin ? root[1] : 0.0,
-                 oz = rel_origin ? root[2] : 0.0;
-    if (tv.sorted) {
-      const double4 q = tv.sorted[p];
-      x = (Real)(q.x - ox);
-      y = (Real)(q.y - oy);
-      z = (Real)(q.z - oz);
-    } else if (tv.pos64) {
-      x = (Real)(tv.pos64[3 * ti] - ox);
-      y = (Real)(tv.pos64[3 * ti + 1] - oy);
-      z = (Real)(tv.pos64[3 * ti + 2] - oz);
-    } else {
-      float4 t = tv.pos32[ti];
-      x = (Real)((double)t.x - ox);
-      y = (Real)((double)t.y - oy);
-      z = (Real)((double)t.z - oz);
-    }
+// Loads target p of the warp's 32 (relative to the fp32 origin when rel_origin).
+template <class Real>
+__device__ __forceinline__ void load_target(const TargetsView &tv, int64_t p, bool valid,
+                                            const double *__restrict__ root, bool rel_origin,
+                                            int64_t &ti, Real &x, Real &y, Real &z) {
+  ti = 0;
+  x = y = z = 0;
+  if (!valid) return;
+  ti = tv.order ? (int64_t)tv.order[p] - tv.order_offset : p;
+  const double ox = rel_origin ? root[0] : 0.0, oy = rel_origin ? root[1] : 0.0,
+               oz = rel_origin ? root[2] : 0.0;
+  if (tv.sorted) {
+    const double4 q = tv.sorted[p];
+    x = (Real)(q.x - ox);
+    y = (Real)(q.y - oy);
+    z = (Real)(q.z - oz);
+  } else if (tv.pos64) {
+    x = (Real)(tv.pos64[3 * ti] - ox);
+    y = (Real)(tv.pos64[3 * ti + 1] - oy);
+    z = (Real)(tv.pos64[3 * ti + 2] - oz);
+  } else {
+    float4 t = tv.pos32[ti];
+    x = (Real)((double)t.x - ox);
+    y = (Real)((double)t.y - oy);
+    z = (Real)((double)t.z - oz);
   }
+}
+
+// The per-target scan of one warp (see above): every lane applies the reference's own opening
+// test, so the accepted node set is the reference's.
+template <class Real, bool STATS, bool GUARD, bool PREFETCH>
+__device__ __forceinline__ void lane_scan(const Node<Real> *__restrict__ nodes,
+                                          const int *__restrict__ skips, int nentries, bool valid,
+                                          Real x, Real y, Real z, Real eps2, Real &ax, Real &ay,
+                                          Real &az, unsigned long long &nacc,
+                                          unsigned long long &nvis, unsigned long long &niter) {
   int until = valid ? 0 : INT_MAX;
-  Real ax = 0, ay = 0, az = 0;
-  unsigned long long nacc = 0, nvis = 0, niter = 0;
   int i = 0;
   while (i < nentries) {
     if (STATS) niter++;
@@ -515,6 +519,24 @@ walk_kernel(const Node<Real> *__restrict__ nodes, const int *__restrict__ skips,
     const int next = open ? i + 1 : until;
     i = __reduce_min_sync(0xffffffffu, next);
   }
+}
+
+template <class Real, bool STATS, bool GUARD, bool PREFETCH>
+__global__ void __launch_bounds__(128, 8)
+walk_kernel(const Node<Real> *__restrict__ nodes, const int *__restrict__ skips, int nentries,
+            TargetsView tv, int64_t ni, const double *__restrict__ root, bool rel_origin, Real eps2,
+            Epilogue ep, unsigned long long *__restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t p = warp * 32 + lane;
+  const bool valid = p < ni;
+  int64_t ti;
+  Real x, y, z;
+  load_target<Real>(tv, p, valid, root, rel_origin, ti, x, y, z);
+  Real ax = 0, ay = 0, az = 0;
+  unsigned long long nacc = 0, nvis = 0, niter = 0;
+  lane_scan<Real, STATS, GUARD, PREFETCH>(nodes, skips, nentries, valid, x, y, z, eps2, ax, ay, az,
+                                          nacc, nvis, niter);
   if (valid) apply_epilogue(ep, ti, (double)ax, (double)ay, (double)az);
   if (STATS) {
     for (int o = 16; o > 0; o >>= 1) {
@@ -526,6 +548,189 @@ walk_kernel(const Node<Real> *__restrict__ nodes, const int *__restrict__ skips,
       atomicAdd(&stats[1], nvis);
       atomicAdd(&stats[2], niter);  // entries this warp stepped through (union over its lanes)
       atomicMax(&stats[3], niter);
+    }
+  }
+}
+
+// ---- K8g group walk (fp32) --------------------------------------------------------------------
+// The warp walks the tree ONCE for its 32 Morton-consecutive targets instead of once per lane.
+// Traversal and force evaluation are separated:
+//   traversal   a shared-memory stack holds sibling chains (first, end) of the pre-order array.
+//               Each iteration pops up to 32 chains; lane l loads chain l's first entry, tests it
+//               against the bounding box of the 32 targets and pushes (a) the rest of the chain
+//               (skip[first], end) and (b), if the cell must be opened, the chain of its children
+//               (first+1, skip[first]).  The 32 entry loads of an iteration are independent, so
+//               the dependent-load chain of the per-target scan (one entry at a time per warp)
+//               becomes ~80 iterations of 32 parallel loads.
+//   criterion   a cell is accepted for the group only if EVERY point of the targets' bounding box
+//               passes the reference's test, s^2/theta^2 < min_{x in box} |centre - x|^2.  That is
+//               the reference's criterion made conservative: each target's accepted set is a
+//               refinement of the set the reference would accept for it (some cells the reference
+//               accepts are opened further), so the force error is never larger in the sense of
+//               the opening angle, at the price of a longer list (measured/modelled:
+//               scripts/walk_sim.c, median 2.0x the per-target count at N = 4M).
+//   evaluation  accepted entries (COM, mass) go to a shared-memory ring in the paired layout of
+//               the direct kernel; every 32 entries all lanes evaluate them for their own target
+//               with packed FADD2/FFMA2/FMUL2: 14 FP32-pipe instructions + 2 MUFU + 2 LDS.128 per
+//               PAIR of interactions (the per-target scan spends 28 instructions per entry on
+//               test + force + control).
+// Groups whose list grows beyond `list_limit` entries (bounding boxes that straddle a jump of the
+// Morton curve; ~5 % of the groups) or whose chain stack would overflow drop what they have and
+// run the per-target scan instead, which bounds the cost of any group.
+static constexpr int GROUP_STACK = 320;  // chains per warp
+static constexpr int GROUP_RING = 64;    // list entries per warp (two chunks of 32)
+
+template <bool GUARD>
+__device__ __forceinline__ void eval_chunk(const float4 *__restrict__ pairs, float2 nx2, float2 ny2,
+                                           float2 nz2, float2 e2, float2 &fx, float2 &fy, float2 &fz) {
+#pragma unroll
+  for (int q = 0; q < 16; q++) {
+    const float4 A = pairs[2 * q], B = pairs[2 * q + 1];  // (x0,x1,y0,y1), (z0,z1,m0,m1)
+    const float2 dx = __fadd2_rn(make_float2(A.x, A.y), nx2);
+    const float2 dy = __fadd2_rn(make_float2(A.z, A.w), ny2);
+    const float2 dz = __fadd2_rn(make_float2(B.x, B.y), nz2);
+    float2 s = __ffma2_rn(dx, dx, e2);
+    s = __ffma2_rn(dy, dy, s);
+    s = __ffma2_rn(dz, dz, s);
+    float2 r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(s.x));
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(s.y));
+    if (GUARD) { r.x = (s.x > 0.f) ? r.x : 0.f; r.y = (s.y > 0.f) ? r.y : 0.f; }
+    const float2 r2 = __fmul2_rn(r, r);
+    float2 w = __fmul2_rn(r2, r);
+    w = __fmul2_rn(w, make_float2(B.z, B.w));
+    fx = __ffma2_rn(w, dx, fx);
+    fy = __ffma2_rn(w, dy, fy);
+    fz = __ffma2_rn(w, dz, fz);
+  }
+}
+
+__device__ __forceinline__ float warp_min(float v) {
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+template <bool STATS, bool GUARD>
+__global__ void __launch_bounds__(128, 8)
+walk_group_kernel(const Node<float> *__restrict__ nodes, const int *__restrict__ skips, int nentries,
+                  TargetsView tv, int64_t ni, const double *__restrict__ root, float eps2,
+                  int list_limit, Epilogue ep, unsigned long long *__restrict__ stats) {
+  __shared__ int2 s_stack[4][GROUP_STACK];
+  __shared__ float4 s_ring[4][GROUP_RING / 2 * 2];
+  const int lane = threadIdx.x & 31;
+  const int wic = threadIdx.x >> 5;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t p = warp * 32 + lane;
+  const bool valid = p < ni;
+  int64_t ti;
+  float x, y, z;
+  load_target<float>(tv, p, valid, root, true, ti, x, y, z);
+
+  // bounding box of the group's targets (centre, half extent padded by a few ulps so that
+  // rounding can only make the test more conservative)
+  const float inf = __int_as_float(0x7f800000);
+  const float lx = warp_min(valid ? x : inf), hx = warp_max(valid ? x : -inf);
+  const float ly = warp_min(valid ? y : inf), hy = warp_max(valid ? y : -inf);
+  const float lz = warp_min(valid ? z : inf), hz = warp_max(valid ? z : -inf);
+  const float bcx = 0.5f * (lx + hx), bcy = 0.5f * (ly + hy), bcz = 0.5f * (lz + hz);
+  const float pad = 1.0f + 1e-6f;
+  const float bhx = (0.5f * (hx - lx)) * pad + 1e-6f * fabsf(bcx);
+  const float bhy = (0.5f * (hy - ly)) * pad + 1e-6f * fabsf(bcy);
+  const float bhz = (0.5f * (hz - lz)) * pad + 1e-6f * fabsf(bcz);
+
+  int2 *stack = s_stack[wic];
+  float4 *ring4 = s_ring[wic];
+  float *ringf = reinterpret_cast<float *>(ring4);
+  const unsigned lt = (1u << lane) - 1u;
+  const unsigned gt = ~lt & ~(1u << lane);
+  const float2 nx2 = make_float2(-x, -x), ny2 = make_float2(-y, -y), nz2 = make_float2(-z, -z);
+  const float2 e2 = make_float2(eps2, eps2);
+  float2 fx = make_float2(0.f, 0.f), fy = fx, fz = fx;
+  unsigned long long nacc = 0, nvis = 0, niter = 0;
+
+  if (lane == 0) stack[0] = make_int2(0, nentries);
+  int sp = 1;
+  int head = 0, tail = 0;  // list entries pushed / evaluated
+  bool fallback = false;
+  __syncwarp();
+  while (sp > 0) {
+    if (STATS) niter++;
+    const int take = sp < 32 ? sp : 32;
+    const bool has = lane < take;
+    int first = 0, end = 0;
+    if (has) { const int2 it = stack[sp - 1 - lane]; first = it.x; end = it.y; }
+    sp -= take;
+    __syncwarp();
+    float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nb = na;
+    int sk = 0;
+    if (has) { na = nodes[first].a; nb = nodes[first].b; sk = skips[first]; }
+    const float ddx = fmaxf(fabsf(na.x - bcx) - bhx, 0.f);
+    const float ddy = fmaxf(fabsf(na.z - bcy) - bhy, 0.f);
+    const float ddz = fmaxf(fabsf(nb.x - bcz) - bhz, 0.f);
+    const float d2 = ddx * ddx + ddy * ddy + ddz * ddz;
+    const bool acc = has && (nb.z < d2);                     // leaves carry s2 = -1
+    const bool open = has && !acc && (first + 1 < sk);
+    const bool rem = has && (sk < end);
+    // rest of each chain first, children on top (depth first); lane 0 held the top of the stack
+    const unsigned mr = __ballot_sync(0xffffffffu, rem);
+    const unsigned mo = __ballot_sync(0xffffffffu, open);
+    if (sp + __popc(mr) + __popc(mo) > GROUP_STACK) { fallback = true; break; }
+    if (rem) stack[sp + __popc(mr & gt)] = make_int2(sk, end);
+    sp += __popc(mr);
+    if (open) stack[sp + __popc(mo & gt)] = make_int2(first + 1, sk);
+    sp += __popc(mo);
+    const unsigned ma = __ballot_sync(0xffffffffu, acc);
+    if (acc) {
+      const int slot = (head + __popc(ma & lt)) & (GROUP_RING - 1);
+      float *b = ringf + (slot >> 1) * 8 + (slot & 1);
+      b[0] = na.y; b[2] = na.w; b[4] = nb.y; b[6] = nb.w;
+    }
+    head += __popc(ma);
+    if (STATS) nvis += take;
+    __syncwarp();
+    if (head - tail >= 32) {
+      eval_chunk<GUARD>(ring4 + (tail & (GROUP_RING - 1)), nx2, ny2, nz2, e2, fx, fy, fz);
+      tail += 32;
+      __syncwarp();
+      if (head > list_limit) { fallback = true; break; }
+    }
+  }
+  float ax, ay, az;
+  if (!fallback) {
+    if (head > tail) {  // pad the last chunk with massless entries at the box centre
+      for (int k = head + lane; k < tail + 32; k += 32) {
+        const int slot = k & (GROUP_RING - 1);
+        float *b = ringf + (slot >> 1) * 8 + (slot & 1);
+        b[0] = bcx; b[2] = bcy; b[4] = bcz; b[6] = 0.f;
+      }
+      __syncwarp();
+      eval_chunk<GUARD>(ring4 + (tail & (GROUP_RING - 1)), nx2, ny2, nz2, e2, fx, fy, fz);
+    }
+    ax = fx.x + fx.y; ay = fy.x + fy.y; az = fz.x + fz.y;
+    if (STATS) nacc = valid ? (unsigned long long)head : 0ull;
+    if (STATS) nvis = valid ? nvis : 0ull;
+  } else {
+    ax = ay = az = 0.f;
+    nacc = nvis = 0;
+    unsigned long long it2 = 0;
+    lane_scan<float, STATS, GUARD, false>(nodes, skips, nentries, valid, x, y, z, eps2, ax, ay, az,
+                                          nacc, nvis, it2);
+  }
+  if (valid) apply_epilogue(ep, ti, (double)ax, (double)ay, (double)az);
+  if (STATS) {
+    for (int o = 16; o > 0; o >>= 1) {
+      nacc += __shfl_down_sync(0xffffffffu, nacc, o);
+      nvis += __shfl_down_sync(0xffffffffu, nvis, o);
+    }
+    if (lane == 0) {
+      atomicAdd(&stats[0], nacc);
+      atomicAdd(&stats[1], nvis);
+      atomicAdd(&stats[2], niter);                 // traversal iterations (32 entries each)
+      atomicAdd(&stats[3], fallback ? 1ull : 0ull);  // groups that fell back to the per-target scan
     }
   }
 }
@@ -558,6 +763,47 @@ int tree_last_stats(TreeWorkspace *w, int64_t out[8]) {
 }
 
 static inline unsigned nblk(int64_t n, int b) { return (unsigned)((n + b - 1) / b); }
+
+// walk selection: GH_WALK_GROUP (default; fp32 only) or GH_WALK_TARGET (the reference's per-target
+// criterion; always used in fp64).  Process-wide; GH_TREE_WALK=target|group sets the initial value.
+static int g_walk_mode = -1;
+int tree_walk_mode() {
+  if (g_walk_mode < 0) {
+    int m = GH_WALK_GROUP;
+    if (const char *env = getenv("GH_TREE_WALK")) {
+      if (!strcmp(env, "target") || !strcmp(env, "0")) m = GH_WALK_TARGET;
+    }
+    g_walk_mode = m;
+  }
+  return g_walk_mode;
+}
+void set_tree_walk_mode(int m) { g_walk_mode = (m == GH_WALK_TARGET) ? GH_WALK_TARGET : GH_WALK_GROUP; }
+// list length beyond which a group gives up and runs the per-target scan (GH_WALK_LIST_LIMIT)
+static int group_list_limit() {
+  static int v = -1;
+  if (v < 0) {
+    v = 2400;
+    if (const char *env = getenv("GH_WALK_LIST_LIMIT")) { int t = atoi(env); if (t >= 32) v = t; }
+  }
+  return v;
+}
+
+template <class Real> struct GroupWalk {
+  static void launch(const Node<Real> *, const int *, int, const TargetsView &, int64_t, const double *, float,
+                     const Epilogue &, unsigned long long *, bool, bool, unsigned, cudaStream_t) {}
+};
+template <> struct GroupWalk<float> {
+  static void launch(const Node<float> *nodes, const int *skips, int nentries, const TargetsView &tv,
+                     int64_t ni, const double *root, float eps2, const Epilogue &ep,
+                     unsigned long long *dstats, bool stats, bool guard, unsigned blocks, cudaStream_t st) {
+    const int lim = group_list_limit();
+#define GH_GWALK(STATS, GUARD) \
+  walk_group_kernel<STATS, GUARD><<<blocks, 128, 0, st>>>(nodes, skips, nentries, tv, ni, root, eps2, lim, ep, dstats)
+    if (stats) { if (guard) GH_GWALK(true, true); else GH_GWALK(true, false); }
+    else { if (guard) GH_GWALK(false, true); else GH_GWALK(false, false); }
+#undef GH_GWALK
+  }
+};
 
 template <class Src, class Real>
 static int tree_impl(const TreeArgs &a, Src src, const float4 *tgt32, TreeWorkspace *w,
@@ -695,20 +941,27 @@ static int tree_impl(const TreeArgs &a, Src src, const float4 *tgt32, TreeWorksp
   const int64_t nwarps = (ni + 31) / 32;
   int wb = 128;
   if (const char *env = getenv("GH_WALK_BLOCK")) { int v = atoi(env); if (v == 32 || v == 64 || v == 128) wb = v; }
+  const bool group = (sizeof(Real) == 4) && tree_walk_mode() == GH_WALK_GROUP;
+  if (group) wb = 128;
   const unsigned blocks = (unsigned)((nwarps + wb / 32 - 1) / (wb / 32));
   if (ev) GH_CUDA(cudaEventRecord(ev[0], st));
   const bool guard = (a.eps == 0.0);
   // L2 prefetch hint of each entry's skip target; GH_WALK_PREFETCH=0/1 overrides
   bool prefetch = false;
   if (const char *env = getenv("GH_WALK_PREFETCH")) prefetch = atoi(env) != 0;
+  if (group) {
+    GroupWalk<Real>::launch(E.node, E.skip, nentries, tv, ni, root, (float)eps2, a.ep, dstats, a.want_stats,
+                            guard, blocks, st);
+  } else {
 #define GH_WALK(STATS, GUARD, PF)                                                                      \
   walk_kernel<Real, STATS, GUARD, PF><<<blocks, wb, 0, st>>>(E.node, E.skip, nentries, tv, ni, root, \
                                                             rel_origin, eps2, a.ep, dstats)
 #define GH_WALK2(STATS, GUARD) do { if (prefetch) GH_WALK(STATS, GUARD, true); else GH_WALK(STATS, GUARD, false); } while (0)
-  if (a.want_stats) { if (guard) GH_WALK2(true, true); else GH_WALK2(true, false); }
-  else { if (guard) GH_WALK2(false, true); else GH_WALK2(false, false); }
+    if (a.want_stats) { if (guard) GH_WALK2(true, true); else GH_WALK2(true, false); }
+    else { if (guard) GH_WALK2(false, true); else GH_WALK2(false, false); }
 #undef GH_WALK2
 #undef GH_WALK
+  }
   GH_LAUNCH_CHECK();
   if (ev) GH_CUDA(cudaEventRecord(ev[1], st));
   GH_CUDA(cudaMemcpyAsync(&w->h_pinned[1], maxlevel, sizeof(int), cudaMemcpyDeviceToHost, st));

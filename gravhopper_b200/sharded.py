@@ -67,7 +67,8 @@ def interleaved_layout(pos, world, block=None):
         # with 2048-particle blocks and 3.42 ms with 65536-particle blocks (8 per rank): a rank that
         # holds the few densest blocks is far slower than the others, and balance matters more
         # than the ~10 % locality gain big blocks give a single rank.
-        block = 2048
+        # Never fewer than ~64 blocks per rank, or the deal is too coarse to mix regions.
+        block = max(32, min(2048, (n // (world * 64)) // 32 * 32))
     parts = partition(n, world)
     nblocks = (n + block - 1) // block
     owner_blocks = [[] for _ in range(world)]

@@ -102,6 +102,23 @@ int gh_release_thread_scratch(void);
 int gh_tree_last_stats(int64_t out[8]);
 int gh_set_tree_stats(int enable);
 
+/* How GH_PREC_F32 tree evaluations walk the tree (process-wide; GH_PREC_F64 always walks per
+ * target, which reproduces _jbgrav.c:502 node for node):
+ *   GH_WALK_TARGET  every target applies the reference's opening test itself: the accepted node set
+ *                   is exactly the reference's.
+ *   GH_WALK_GROUP   (default) the 32 Morton-consecutive targets of a warp share one traversal; a
+ *                   cell is accepted only if the reference's test passes for every point of the
+ *                   targets' bounding box, so each target's accepted set is a refinement of the
+ *                   reference's (never a coarser one).  Statistics in this mode: out[3] = list
+ *                   entries evaluated summed over targets, out[4] = entries tested summed over
+ *                   targets, out[5] = traversal iterations summed over warps, out[6] = warps that
+ *                   fell back to the per-target walk.
+ * The environment variable GH_TREE_WALK=target|group sets the initial mode. */
+#define GH_WALK_TARGET 0
+#define GH_WALK_GROUP 1
+int gh_set_tree_walk(int mode);
+int gh_get_tree_walk(void);
+
 /* ---- device-side initial conditions (inputs of the path; gravhopper.py:1327-1607) ----------- */
 
 /* Sample n particles of an equilibrium model on the GPU with a counter-based generator
