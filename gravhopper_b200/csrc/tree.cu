@@ -605,22 +605,46 @@ __device__ __forceinline__ void eval_chunk(const float4 *__restrict__ pairs, flo
   }
 }
 
-__device__ __forceinline__ float warp_min(float v) {
-  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
+// float <-> int with the same ordering (involution), so REDUX.MIN/MAX can reduce floats
+__device__ __forceinline__ int f2ord(float f) {
+  const int i = __float_as_int(f);
+  return i ^ ((i >> 31) & 0x7fffffff);
 }
-__device__ __forceinline__ float warp_max(float v) {
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
+__device__ __forceinline__ float warp_min(float v) { return ord2f(__reduce_min_sync(0xffffffffu, f2ord(v))); }
+__device__ __forceinline__ float warp_max(float v) { return ord2f(__reduce_max_sync(0xffffffffu, f2ord(v))); }
+
+// centre and padded half extent of the bounding box of the lanes with in == true (the padding of a
+// few ulps makes rounding err on the conservative side)
+struct Box { float cx, cy, cz, hx, hy, hz; };
+__device__ __forceinline__ Box warp_box(bool in, float x, float y, float z) {
+  const float inf = __int_as_float(0x7f800000);
+  const float lx = warp_min(in ? x : inf), ux = warp_max(in ? x : -inf);
+  const float ly = warp_min(in ? y : inf), uy = warp_max(in ? y : -inf);
+  const float lz = warp_min(in ? z : inf), uz = warp_max(in ? z : -inf);
+  Box b;
+  b.cx = 0.5f * (lx + ux); b.cy = 0.5f * (ly + uy); b.cz = 0.5f * (lz + uz);
+  const float pad = 1.0f + 1e-6f;
+  b.hx = (0.5f * (ux - lx)) * pad + 1e-6f * fabsf(b.cx);
+  b.hy = (0.5f * (uy - ly)) * pad + 1e-6f * fabsf(b.cy);
+  b.hz = (0.5f * (uz - lz)) * pad + 1e-6f * fabsf(b.cz);
+  return b;
+}
+// squared distance from point c to the box (0 inside)
+__device__ __forceinline__ float box_dist2(const Box &b, float cx, float cy, float cz) {
+  const float dx = fmaxf(fabsf(cx - b.cx) - b.hx, 0.f);
+  const float dy = fmaxf(fabsf(cy - b.cy) - b.hy, 0.f);
+  const float dz = fmaxf(fabsf(cz - b.cz) - b.hz, 0.f);
+  return dx * dx + dy * dy + dz * dz;
 }
 
-template <bool STATS, bool GUARD>
-__global__ void __launch_bounds__(128, 8)
+template <int WPC, bool STATS, bool GUARD>
+__global__ void __launch_bounds__(32 * WPC, 32 / WPC)
 walk_group_kernel(const Node<float> *__restrict__ nodes, const int *__restrict__ skips, int nentries,
                   TargetsView tv, int64_t ni, const double *__restrict__ root, float eps2,
                   int list_limit, Epilogue ep, unsigned long long *__restrict__ stats) {
-  __shared__ int2 s_stack[4][GROUP_STACK];
-  __shared__ float4 s_ring[4][GROUP_RING / 2 * 2];
+  __shared__ int2 s_stack[WPC][GROUP_STACK];
+  __shared__ float4 s_ring[WPC][GROUP_RING];
   const int lane = threadIdx.x & 31;
   const int wic = threadIdx.x >> 5;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -630,21 +654,21 @@ walk_group_kernel(const Node<float> *__restrict__ nodes, const int *__restrict__
   float x, y, z;
   load_target<float>(tv, p, valid, root, true, ti, x, y, z);
 
-  // bounding box of the group's targets (centre, half extent padded by a few ulps so that
-  // rounding can only make the test more conservative)
-  const float inf = __int_as_float(0x7f800000);
-  const float lx = warp_min(valid ? x : inf), hx = warp_max(valid ? x : -inf);
-  const float ly = warp_min(valid ? y : inf), hy = warp_max(valid ? y : -inf);
-  const float lz = warp_min(valid ? z : inf), hz = warp_max(valid ? z : -inf);
-  const float bcx = 0.5f * (lx + hx), bcy = 0.5f * (ly + hy), bcz = 0.5f * (lz + hz);
-  const float pad = 1.0f + 1e-6f;
-  const float bhx = (0.5f * (hx - lx)) * pad + 1e-6f * fabsf(bcx);
-  const float bhy = (0.5f * (hy - ly)) * pad + 1e-6f * fabsf(bcy);
-  const float bhz = (0.5f * (hz - lz)) * pad + 1e-6f * fabsf(bcz);
+  // Two bounding boxes: the 32 targets are cut where Morton-consecutive targets are farthest
+  // apart, so a group that straddles a jump of the curve is two compact boxes instead of one
+  // huge one (scripts/walk_sim.c: list p99 4770 -> 1507 entries at N = 4M, mean 1434 -> 1133).
+  const float xn = __shfl_down_sync(0xffffffffu, x, 1), yn = __shfl_down_sync(0xffffffffu, y, 1),
+              zn = __shfl_down_sync(0xffffffffu, z, 1);
+  const bool next_valid = lane < 31 && (p + 1 < ni);
+  const float gap = next_valid ? (xn - x) * (xn - x) + (yn - y) * (yn - y) + (zn - z) * (zn - z) : -1.f;
+  const int gmax = __reduce_max_sync(0xffffffffu, f2ord(gap));
+  const int cut = __ffs(__ballot_sync(0xffffffffu, f2ord(gap) == gmax)) - 1;  // box A = lanes <= cut
+  const Box A = warp_box(valid && lane <= cut, x, y, z);
+  Box B = warp_box(valid && lane > cut, x, y, z);
+  if (!(B.hx >= 0.f)) B = A;  // no valid lane beyond the cut
 
-  int2 *stack = s_stack[wic];
-  float4 *ring4 = s_ring[wic];
-  float *ringf = reinterpret_cast<float *>(ring4);
+#define stack s_stack[wic]
+#define ring4 s_ring[wic]
   const unsigned lt = (1u << lane) - 1u;
   const unsigned gt = ~lt & ~(1u << lane);
   const float2 nx2 = make_float2(-x, -x), ny2 = make_float2(-y, -y), nz2 = make_float2(-z, -z);
@@ -664,14 +688,18 @@ walk_group_kernel(const Node<float> *__restrict__ nodes, const int *__restrict__
     int first = 0, end = 0;
     if (has) { const int2 it = stack[sp - 1 - lane]; first = it.x; end = it.y; }
     sp -= take;
-    __syncwarp();
+    // the 32 entry loads of this iteration are issued first ...
     float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nb = na;
     int sk = 0;
     if (has) { na = nodes[first].a; nb = nodes[first].b; sk = skips[first]; }
-    const float ddx = fmaxf(fabsf(na.x - bcx) - bhx, 0.f);
-    const float ddy = fmaxf(fabsf(na.z - bcy) - bhy, 0.f);
-    const float ddz = fmaxf(fabsf(nb.x - bcz) - bhz, 0.f);
-    const float d2 = ddx * ddx + ddy * ddy + ddz * ddz;
+    // ... and the 32 list entries the previous iterations completed are evaluated while they fly
+    if (head - tail >= 32) {
+      eval_chunk<GUARD>(ring4 + (tail & (GROUP_RING - 1)), nx2, ny2, nz2, e2, fx, fy, fz);
+      tail += 32;
+      if (head > list_limit) { fallback = true; break; }
+    }
+    __syncwarp();
+    const float d2 = fminf(box_dist2(A, na.x, na.z, nb.x), box_dist2(B, na.x, na.z, nb.x));
     const bool acc = has && (nb.z < d2);                     // leaves carry s2 = -1
     const bool open = has && !acc && (first + 1 < sk);
     const bool rem = has && (sk < end);
@@ -686,26 +714,25 @@ walk_group_kernel(const Node<float> *__restrict__ nodes, const int *__restrict__
     const unsigned ma = __ballot_sync(0xffffffffu, acc);
     if (acc) {
       const int slot = (head + __popc(ma & lt)) & (GROUP_RING - 1);
-      float *b = ringf + (slot >> 1) * 8 + (slot & 1);
+      float *b = &s_ring[wic][slot & ~1].x + (slot & 1);
       b[0] = na.y; b[2] = na.w; b[4] = nb.y; b[6] = nb.w;
     }
     head += __popc(ma);
     if (STATS) nvis += take;
     __syncwarp();
+  }
+  float ax, ay, az;
+  if (!fallback) {
     if (head - tail >= 32) {
       eval_chunk<GUARD>(ring4 + (tail & (GROUP_RING - 1)), nx2, ny2, nz2, e2, fx, fy, fz);
       tail += 32;
       __syncwarp();
-      if (head > list_limit) { fallback = true; break; }
     }
-  }
-  float ax, ay, az;
-  if (!fallback) {
     if (head > tail) {  // pad the last chunk with massless entries at the box centre
       for (int k = head + lane; k < tail + 32; k += 32) {
         const int slot = k & (GROUP_RING - 1);
-        float *b = ringf + (slot >> 1) * 8 + (slot & 1);
-        b[0] = bcx; b[2] = bcy; b[4] = bcz; b[6] = 0.f;
+        float *b = &s_ring[wic][slot & ~1].x + (slot & 1);
+        b[0] = A.cx; b[2] = A.cy; b[4] = A.cz; b[6] = 0.f;
       }
       __syncwarp();
       eval_chunk<GUARD>(ring4 + (tail & (GROUP_RING - 1)), nx2, ny2, nz2, e2, fx, fy, fz);
@@ -734,6 +761,8 @@ walk_group_kernel(const Node<float> *__restrict__ nodes, const int *__restrict__
     }
   }
 }
+#undef stack
+#undef ring4
 
 // ---- workspace + orchestration --------------------------------------------------------------------
 struct TreeWorkspace {
@@ -782,7 +811,7 @@ void set_tree_walk_mode(int m) { g_walk_mode = (m == GH_WALK_TARGET) ? GH_WALK_T
 static int group_list_limit() {
   static int v = -1;
   if (v < 0) {
-    v = 2400;
+    v = 3000;
     if (const char *env = getenv("GH_WALK_LIST_LIMIT")) { int t = atoi(env); if (t >= 32) v = t; }
   }
   return v;
@@ -795,12 +824,17 @@ template <class Real> struct GroupWalk {
 template <> struct GroupWalk<float> {
   static void launch(const Node<float> *nodes, const int *skips, int nentries, const TargetsView &tv,
                      int64_t ni, const double *root, float eps2, const Epilogue &ep,
-                     unsigned long long *dstats, bool stats, bool guard, unsigned blocks, cudaStream_t st) {
+                     unsigned long long *dstats, bool stats, bool guard, unsigned blocks32, cudaStream_t st) {
     const int lim = group_list_limit();
-#define GH_GWALK(STATS, GUARD) \
-  walk_group_kernel<STATS, GUARD><<<blocks, 128, 0, st>>>(nodes, skips, nentries, tv, ni, root, eps2, lim, ep, dstats)
+    int wpc = 2;  // warps per CTA (measured at N = 4M: 32/64/128 threads -> 3.21/3.14/3.15 ms); GH_WALK_BLOCK overrides
+    if (const char *env = getenv("GH_WALK_BLOCK")) { int v = atoi(env); if (v == 32 || v == 64 || v == 128) wpc = v / 32; }
+    const unsigned nb = (blocks32 + wpc - 1) / wpc;
+#define GH_GWALK1(W, STATS, GUARD) \
+  walk_group_kernel<W, STATS, GUARD><<<nb, 32 * W, 0, st>>>(nodes, skips, nentries, tv, ni, root, eps2, lim, ep, dstats)
+#define GH_GWALK(STATS, GUARD) do { if (wpc == 1) GH_GWALK1(1, STATS, GUARD); else if (wpc == 2) GH_GWALK1(2, STATS, GUARD); else GH_GWALK1(4, STATS, GUARD); } while (0)
     if (stats) { if (guard) GH_GWALK(true, true); else GH_GWALK(true, false); }
     else { if (guard) GH_GWALK(false, true); else GH_GWALK(false, false); }
+#undef GH_GWALK1
 #undef GH_GWALK
   }
 };
@@ -942,7 +976,6 @@ static int tree_impl(const TreeArgs &a, Src src, const float4 *tgt32, TreeWorksp
   int wb = 128;
   if (const char *env = getenv("GH_WALK_BLOCK")) { int v = atoi(env); if (v == 32 || v == 64 || v == 128) wb = v; }
   const bool group = (sizeof(Real) == 4) && tree_walk_mode() == GH_WALK_GROUP;
-  if (group) wb = 128;
   const unsigned blocks = (unsigned)((nwarps + wb / 32 - 1) / (wb / 32));
   if (ev) GH_CUDA(cudaEventRecord(ev[0], st));
   const bool guard = (a.eps == 0.0);
@@ -951,7 +984,7 @@ static int tree_impl(const TreeArgs &a, Src src, const float4 *tgt32, TreeWorksp
   if (const char *env = getenv("GH_WALK_PREFETCH")) prefetch = atoi(env) != 0;
   if (group) {
     GroupWalk<Real>::launch(E.node, E.skip, nentries, tv, ni, root, (float)eps2, a.ep, dstats, a.want_stats,
-                            guard, blocks, st);
+                            guard, (unsigned)nwarps, st);
   } else {
 #define GH_WALK(STATS, GUARD, PF)                                                                      \
   walk_kernel<Real, STATS, GUARD, PF><<<blocks, wb, 0, st>>>(E.node, E.skip, nentries, tv, ni, root, \

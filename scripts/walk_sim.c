@@ -130,7 +130,7 @@ int main(int argc, char **argv) {
   double sum_acc = 0, sum_union = 0, sum_win = 0, sum_list = 0, sum_win2 = 0, sum_tested = 0;
   double max_win = 0, max_list = 0, sum_it4 = 0, sum_t4 = 0, max_sp4 = 0;
   long *lists = malloc(sizeof(long) * (N / G + 1)), *its5 = malloc(sizeof(long) * (N / G + 1)), *sps5 = malloc(sizeof(long) * (N / G + 1));
-  double sum_it5 = 0, max_sp5 = 0;
+  double sum_it5 = 0, max_sp5 = 0, sum_l6 = 0, sum_it6 = 0; long *lists6 = malloc(sizeof(long) * (N / G + 1));
   float *tx = malloc(sizeof(float) * 3 * G);
   int *until = malloc(sizeof(int) * G);
   for (int g0 = 0; g0 + G <= N; g0 += G * stride) {
@@ -247,6 +247,43 @@ int main(int argc, char **argv) {
       if (lst != list) { fprintf(stderr, "mismatch5 %ld %ld\n", lst, list); }
       its5[ngroups] = iters; sps5[ngroups] = maxsp;
     }
+    // (6) two boxes: split the group at the largest distance jump between Morton-consecutive targets
+    {
+      int split = 1; float best = -1;
+      for (int t = 0; t + 1 < G; t++) {
+        float d = 0; for (int k = 0; k < 3; k++) { float q = tx[3 * (t + 1) + k] - tx[3 * t + k]; d += q * q; }
+        if (d > best) { best = d; split = t + 1; }
+      }
+      float c2[2][3], h2[2][3];
+      for (int b = 0; b < 2; b++) {
+        float mn2[3] = {1e30f, 1e30f, 1e30f}, mx2[3] = {-1e30f, -1e30f, -1e30f};
+        for (int t = (b ? split : 0); t < (b ? G : split); t++) for (int k = 0; k < 3; k++) {
+          float v = tx[3 * t + k]; if (v < mn2[k]) mn2[k] = v; if (v > mx2[k]) mx2[k] = v; }
+        for (int k = 0; k < 3; k++) { c2[b][k] = 0.5f * (mn2[k] + mx2[k]); h2[b][k] = 0.5f * (mx2[k] - mn2[k]); }
+      }
+      static int st6[1 << 16][2];
+      int sp = 0; long lst = 0, iters = 0;
+      st6[0][0] = 0; st6[0][1] = nent; sp = 1;
+      while (sp > 0) {
+        int take = sp < 32 ? sp : 32;
+        int bf[32], be[32];
+        for (int t = 0; t < take; t++) { --sp; bf[t] = st6[sp][0]; be[t] = st6[sp][1]; }
+        iters++;
+        for (int t = take - 1; t >= 0; t--) if (eskip[bf[t]] < be[t]) { st6[sp][0] = eskip[bf[t]]; st6[sp][1] = be[t]; sp++; }
+        for (int t = take - 1; t >= 0; t--) {
+          int j = bf[t];
+          float dmin = 1e30f;
+          for (int b = 0; b < 2; b++) {
+            float d2 = 0;
+            for (int k = 0; k < 3; k++) { float d = fabsf(ecen[j][k] - c2[b][k]) - h2[b][k]; if (d > 0) d2 += d * d; }
+            if (d2 < dmin) dmin = d2;
+          }
+          if (ecen[j][3] < dmin) lst++;
+          else { st6[sp][0] = j + 1; st6[sp][1] = eskip[j]; sp++; }
+        }
+      }
+      lists6[ngroups] = lst; sum_l6 += lst; sum_it6 += iters;
+    }
     lists[ngroups] = list;
     // (3) two-level: lane 0 first checks the first entry alone?  modelled as: windows in which
     // the first entry is accepted with skip beyond the window cost a "cheap" iteration
@@ -266,6 +303,12 @@ int main(int argc, char **argv) {
     printf("cost model (T=%ld): %.0f instr/group, %.2f%% aborted\n", T, c / ngroups, 100.0 * nab / ngroups);
     long big = 0; for (long a = 0; a < ngroups; a++) if (sps5[a] > 480) big++;
     printf("groups with chain stack > 480: %ld\n", big);
+  }
+  {
+    for (long a = 1; a < ngroups; a++) { long v = lists6[a]; long b = a - 1; while (b >= 0 && lists6[b] > v) { lists6[b + 1] = lists6[b]; b--; } lists6[b + 1] = v; }
+    long nab = 0; for (long a = 0; a < ngroups; a++) if (lists6[a] > 2400) nab++;
+    printf("two-box: list mean %.1f iters %.1f p10 %ld p50 %ld p90 %ld p99 %ld max %ld  >2400: %.2f%%\n", sum_l6 / ngroups, sum_it6 / ngroups,
+           lists6[ngroups / 10], lists6[ngroups / 2], lists6[ngroups * 9 / 10], lists6[ngroups * 99 / 100], lists6[ngroups - 1], 100.0 * nab / ngroups);
   }
   // percentiles of list length
   for (long a = 1; a < ngroups; a++) { long v = lists[a]; long b = a - 1; while (b >= 0 && lists[b] > v) { lists[b + 1] = lists[b]; b--; } lists[b + 1] = v; }
