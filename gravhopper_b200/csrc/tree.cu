@@ -248,19 +248,39 @@ template <> struct Vec4<double> { using type = double4; };
 template <> struct Vec4<float> { using type = float4; };
 
 template <class Real>
-struct Node {
+struct alignas(sizeof(Real) * 8) Node {
   // centre and centre of mass interleaved component by component, so that the fp32 walk forms
   // (centre - x, COM - x) with ONE packed FADD2 per axis and (|.|^2, |.|^2 + eps^2) with packed
   // FFMA2s:  a = (cx, mx, cy, my),  b = (cz, mz, s2, m)
-  // c* = cell centre - origin, m* = centre of mass - origin, s2 = side^2 / theta^2 (-1 marks a
-  // leaf), m = mass
+  // c* = cell centre - origin, m* = centre of mass - origin, m = mass.
+  // fp64: s2 = side^2 / theta^2 (-1 marks a leaf); the skip link lives in a separate int array.
+  // fp32: the s2 slot holds the bits of (level << 27 | skip) instead (level 31 marks a leaf), so
+  //       one 32-byte load (LDG.256) brings everything the walk needs about an entry;
+  //       s2 = side_root^2 / theta^2 * 4^-level is rebuilt with one multiply, bit-identically.
   typename Vec4<Real>::type a;
   typename Vec4<Real>::type b;
 };
+static constexpr int SKIP_BITS = 27;
+static constexpr int LEAF_LEVEL = 31;
 template <class Real, class V4>
 __device__ __forceinline__ void pack_node(Node<Real> &nd, const V4 &cen, const V4 &com) {
   nd.a.x = cen.x; nd.a.y = com.x; nd.a.z = cen.y; nd.a.w = com.y;
   nd.b.x = cen.z; nd.b.y = com.z; nd.b.z = cen.w; nd.b.w = com.w;
+}
+// entry i of the fp32 array: both halves with one 256-bit load
+__device__ __forceinline__ void load_node32(const Node<float> *__restrict__ nodes, int i, float4 &a,
+                                            float4 &b) {
+  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+      : "l"(nodes + i));
+}
+// (level, skip) -> s2 and skip;  pow4[l] would be a table, the exponent arithmetic is cheaper
+__device__ __forceinline__ void unpack32(float packed, float s2root, float &s2, int &sk) {
+  const unsigned u = (unsigned)__float_as_int(packed);
+  const unsigned level = u >> SKIP_BITS;
+  sk = (int)(u & ((1u << SKIP_BITS) - 1u));
+  const float scale = __int_as_float((int)((127u - 2u * level) << 23));  // 4^-level
+  s2 = (level == (unsigned)LEAF_LEVEL) ? -1.f : s2root * scale;
 }
 template <class Real>
 struct Entries {
@@ -365,9 +385,13 @@ __global__ void emit_kernel(const double4 *__restrict__ sp, const uint64_t *__re
         cen.y = (Real)(cc[1] - oy);
         cen.z = (Real)(cc[2] - oz);
         // (size / dist) < theta  <=>  size^2 / theta^2 < dist^2   (theta = 0: inf, never accepted)
-        cen.w = (Real)(__dmul_rn(__dmul_rn(size, size), inv_theta2));
+        if (sizeof(Real) == 4) {
+          cen.w = (Real)__int_as_float((int)(((unsigned)level << SKIP_BITS) | (unsigned)base[b + 1]));
+        } else {
+          cen.w = (Real)(__dmul_rn(__dmul_rn(size, size), inv_theta2));
+          E.skip[e] = base[b + 1];
+        }
         pack_node(E.node[e], cen, com);
-        E.skip[e] = base[b + 1];
         e++;
         deepest = level;
       }
@@ -392,9 +416,13 @@ __global__ void emit_kernel(const double4 *__restrict__ sp, const uint64_t *__re
   com.z = (Real)(x[2] - oz);
   com.w = (Real)self.w;
   cen.x = cen.y = cen.z = (Real)0;
-  cen.w = (Real)-1;
+  if (sizeof(Real) == 4) {
+    cen.w = (Real)__int_as_float((int)(((unsigned)LEAF_LEVEL << SKIP_BITS) | (unsigned)(e + 1)));
+  } else {
+    cen.w = (Real)-1;
+    E.skip[e] = e + 1;
+  }
   pack_node(E.node[e], cen, com);
-  E.skip[e] = e + 1;
 }
 
 // ---- K8 walk ------------------------------------------------------------------------------------
@@ -469,8 +497,8 @@ __device__ __forceinline__ void load_target(const TargetsView &tv, int64_t p, bo
 // test, so the accepted node set is the reference's.
 template <class Real, bool STATS, bool GUARD, bool PREFETCH>
 __device__ __forceinline__ void lane_scan(const Node<Real> *__restrict__ nodes,
-                                          const int *__restrict__ skips, int nentries, bool valid,
-                                          Real x, Real y, Real z, Real eps2, Real &ax, Real &ay,
+                                          const int *__restrict__ skips, Real s2root, int nentries,
+                                          bool valid, Real x, Real y, Real z, Real eps2, Real &ax, Real &ay,
                                           Real &az, unsigned long long &nacc,
                                           unsigned long long &nvis, unsigned long long &niter) {
   int until = valid ? 0 : INT_MAX;
@@ -478,8 +506,15 @@ __device__ __forceinline__ void lane_scan(const Node<Real> *__restrict__ nodes,
   while (i < nentries) {
     if (STATS) niter++;
     const auto na = nodes[i].a;
-    const auto nb = nodes[i].b;
-    const int sk = skips[i];
+    auto nb = nodes[i].b;
+    int sk;
+    if (sizeof(Real) == 4) {
+      float s2;
+      unpack32((float)nb.z, (float)s2root, s2, sk);
+      nb.z = (Real)s2;
+    } else {
+      sk = skips[i];
+    }
     if (PREFETCH) {
       // optional L2 prefetch hint of the entry after this subtree.  Measured on B200 (N = 4M):
       // +19 % time when all 131k warps run (issue bound), -6 % with 16k warps; a register
@@ -525,7 +560,7 @@ template <class Real, bool STATS, bool GUARD, bool PREFETCH>
 __global__ void __launch_bounds__(128, 8)
 walk_kernel(const Node<Real> *__restrict__ nodes, const int *__restrict__ skips, int nentries,
             TargetsView tv, int64_t ni, const double *__restrict__ root, bool rel_origin, Real eps2,
-            Epilogue ep, unsigned long long *__restrict__ stats) {
+            double inv_theta2, Epilogue ep, unsigned long long *__restrict__ stats) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t p = warp * 32 + lane;
@@ -535,8 +570,9 @@ walk_kernel(const Node<Real> *__restrict__ nodes, const int *__restrict__ skips,
   load_target<Real>(tv, p, valid, root, rel_origin, ti, x, y, z);
   Real ax = 0, ay = 0, az = 0;
   unsigned long long nacc = 0, nvis = 0, niter = 0;
-  lane_scan<Real, STATS, GUARD, PREFETCH>(nodes, skips, nentries, valid, x, y, z, eps2, ax, ay, az,
-                                          nacc, nvis, niter);
+  const Real s2root = (Real)(root[3] * root[3] * inv_theta2);
+  lane_scan<Real, STATS, GUARD, PREFETCH>(nodes, skips, s2root, nentries, valid, x, y, z, eps2, ax, ay,
+                                          az, nacc, nvis, niter);
   if (valid) apply_epilogue(ep, ti, (double)ax, (double)ay, (double)az);
   if (STATS) {
     for (int o = 16; o > 0; o >>= 1) {
@@ -585,7 +621,7 @@ __device__ __forceinline__ void eval_chunk(const float4 *__restrict__ pairs, flo
                                            float2 nz2, float2 e2, float2 &fx, float2 &fy, float2 &fz) {
 #pragma unroll
   for (int q = 0; q < 16; q++) {
-    const float4 A = pairs[2 * q], B = pairs[2 * q + 1];  // (x0,x1,y0,y1), (z0,z1,m0,m1)
+    const float4 A = pairs[q], B = pairs[16 + q];  // (x0,x1,y0,y1), (z0,z1,m0,m1)
     const float2 dx = __fadd2_rn(make_float2(A.x, A.y), nx2);
     const float2 dy = __fadd2_rn(make_float2(A.z, A.w), ny2);
     const float2 dz = __fadd2_rn(make_float2(B.x, B.y), nz2);
@@ -640,9 +676,9 @@ __device__ __forceinline__ float box_dist2(const Box &b, float cx, float cy, flo
 
 template <int WPC, bool STATS, bool GUARD>
 __global__ void __launch_bounds__(32 * WPC, 32 / WPC)
-walk_group_kernel(const Node<float> *__restrict__ nodes, const int *__restrict__ skips, int nentries,
-                  TargetsView tv, int64_t ni, const double *__restrict__ root, float eps2,
-                  int list_limit, Epilogue ep, unsigned long long *__restrict__ stats) {
+walk_group_kernel(const Node<float> *__restrict__ nodes, int nentries, TargetsView tv, int64_t ni,
+                  const double *__restrict__ root, float eps2, double inv_theta2, int list_limit,
+                  Epilogue ep, unsigned long long *__restrict__ stats) {
   __shared__ int2 s_stack[WPC][GROUP_STACK];
   __shared__ float4 s_ring[WPC][GROUP_RING];
   const int lane = threadIdx.x & 31;
@@ -675,6 +711,7 @@ walk_group_kernel(const Node<float> *__restrict__ nodes, const int *__restrict__
   const float2 e2 = make_float2(eps2, eps2);
   float2 fx = make_float2(0.f, 0.f), fy = fx, fz = fx;
   unsigned long long nacc = 0, nvis = 0, niter = 0;
+  const float s2root = (float)(root[3] * root[3] * inv_theta2);
 
   if (lane == 0) stack[0] = make_int2(0, nentries);
   int sp = 1;
@@ -690,8 +727,7 @@ walk_group_kernel(const Node<float> *__restrict__ nodes, const int *__restrict__
     sp -= take;
     // the 32 entry loads of this iteration are issued first ...
     float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nb = na;
-    int sk = 0;
-    if (has) { na = nodes[first].a; nb = nodes[first].b; sk = skips[first]; }
+    if (has) load_node32(nodes, first, na, nb);
     // ... and the 32 list entries the previous iterations completed are evaluated while they fly
     if (head - tail >= 32) {
       eval_chunk<GUARD>(ring4 + (tail & (GROUP_RING - 1)), nx2, ny2, nz2, e2, fx, fy, fz);
@@ -699,8 +735,11 @@ walk_group_kernel(const Node<float> *__restrict__ nodes, const int *__restrict__
       if (head > list_limit) { fallback = true; break; }
     }
     __syncwarp();
+    float s2;
+    int sk;
+    unpack32(nb.z, s2root, s2, sk);
     const float d2 = fminf(box_dist2(A, na.x, na.z, nb.x), box_dist2(B, na.x, na.z, nb.x));
-    const bool acc = has && (nb.z < d2);                     // leaves carry s2 = -1
+    const bool acc = has && (s2 < d2);                       // leaves: s2 = -1
     const bool open = has && !acc && (first + 1 < sk);
     const bool rem = has && (sk < end);
     // rest of each chain first, children on top (depth first); lane 0 held the top of the stack
@@ -714,8 +753,10 @@ walk_group_kernel(const Node<float> *__restrict__ nodes, const int *__restrict__
     const unsigned ma = __ballot_sync(0xffffffffu, acc);
     if (acc) {
       const int slot = (head + __popc(ma & lt)) & (GROUP_RING - 1);
-      float *b = &s_ring[wic][slot & ~1].x + (slot & 1);
-      b[0] = na.y; b[2] = na.w; b[4] = nb.y; b[6] = nb.w;
+      // chunk of 32 entries = 16 rows (x0,x1,y0,y1) then 16 rows (z0,z1,m0,m1): 2-way bank
+      // conflicts on these stores instead of 4-way with the rows interleaved
+      float *b = &s_ring[wic][(slot & 32) + ((slot & 31) >> 1)].x + (slot & 1);
+      b[0] = na.y; b[2] = na.w; b[64] = nb.y; b[66] = nb.w;
     }
     head += __popc(ma);
     if (STATS) nvis += take;
@@ -731,8 +772,8 @@ walk_group_kernel(const Node<float> *__restrict__ nodes, const int *__restrict__
     if (head > tail) {  // pad the last chunk with massless entries at the box centre
       for (int k = head + lane; k < tail + 32; k += 32) {
         const int slot = k & (GROUP_RING - 1);
-        float *b = &s_ring[wic][slot & ~1].x + (slot & 1);
-        b[0] = A.cx; b[2] = A.cy; b[4] = A.cz; b[6] = 0.f;
+        float *b = &s_ring[wic][(slot & 32) + ((slot & 31) >> 1)].x + (slot & 1);
+        b[0] = A.cx; b[2] = A.cy; b[64] = A.cz; b[66] = 0.f;
       }
       __syncwarp();
       eval_chunk<GUARD>(ring4 + (tail & (GROUP_RING - 1)), nx2, ny2, nz2, e2, fx, fy, fz);
@@ -744,8 +785,8 @@ walk_group_kernel(const Node<float> *__restrict__ nodes, const int *__restrict__
     ax = ay = az = 0.f;
     nacc = nvis = 0;
     unsigned long long it2 = 0;
-    lane_scan<float, STATS, GUARD, false>(nodes, skips, nentries, valid, x, y, z, eps2, ax, ay, az,
-                                          nacc, nvis, it2);
+    lane_scan<float, STATS, GUARD, false>(nodes, nullptr, s2root, nentries, valid, x, y, z, eps2, ax, ay,
+                                          az, nacc, nvis, it2);
   }
   if (valid) apply_epilogue(ep, ti, (double)ax, (double)ay, (double)az);
   if (STATS) {
@@ -818,19 +859,19 @@ static int group_list_limit() {
 }
 
 template <class Real> struct GroupWalk {
-  static void launch(const Node<Real> *, const int *, int, const TargetsView &, int64_t, const double *, float,
+  static void launch(const Node<Real> *, int, const TargetsView &, int64_t, const double *, float, double,
                      const Epilogue &, unsigned long long *, bool, bool, unsigned, cudaStream_t) {}
 };
 template <> struct GroupWalk<float> {
-  static void launch(const Node<float> *nodes, const int *skips, int nentries, const TargetsView &tv,
-                     int64_t ni, const double *root, float eps2, const Epilogue &ep,
+  static void launch(const Node<float> *nodes, int nentries, const TargetsView &tv, int64_t ni,
+                     const double *root, float eps2, double inv_theta2, const Epilogue &ep,
                      unsigned long long *dstats, bool stats, bool guard, unsigned blocks32, cudaStream_t st) {
     const int lim = group_list_limit();
     int wpc = 2;  // warps per CTA (measured at N = 4M: 32/64/128 threads -> 3.21/3.14/3.15 ms); GH_WALK_BLOCK overrides
     if (const char *env = getenv("GH_WALK_BLOCK")) { int v = atoi(env); if (v == 32 || v == 64 || v == 128) wpc = v / 32; }
     const unsigned nb = (blocks32 + wpc - 1) / wpc;
 #define GH_GWALK1(W, STATS, GUARD) \
-  walk_group_kernel<W, STATS, GUARD><<<nb, 32 * W, 0, st>>>(nodes, skips, nentries, tv, ni, root, eps2, lim, ep, dstats)
+  walk_group_kernel<W, STATS, GUARD><<<nb, 32 * W, 0, st>>>(nodes, nentries, tv, ni, root, eps2, inv_theta2, lim, ep, dstats)
 #define GH_GWALK(STATS, GUARD) do { if (wpc == 1) GH_GWALK1(1, STATS, GUARD); else if (wpc == 2) GH_GWALK1(2, STATS, GUARD); else GH_GWALK1(4, STATS, GUARD); } while (0)
     if (stats) { if (guard) GH_GWALK(true, true); else GH_GWALK(true, false); }
     else { if (guard) GH_GWALK(false, true); else GH_GWALK(false, false); }
@@ -928,8 +969,12 @@ static int tree_impl(const TreeArgs &a, Src src, const float4 *tgt32, TreeWorksp
   GH_CUDA(cudaStreamSynchronize(st));
   const int nentries = w->h_pinned[0];
   GH_TRY(w->node.reserve(sizeof(Node<Real>) * (size_t)nentries));
-  GH_TRY(w->skip.reserve(sizeof(int) * (size_t)nentries));
-  Entries<Real> E{w->node.as<Node<Real>>(), w->skip.as<int>()};
+  if (sizeof(Real) == 4) {
+    if (nentries >= (1 << SKIP_BITS)) { set_error("tree: %d entries exceed the fp32 node format (2^%d)", nentries, SKIP_BITS); return GH_EINVAL; }
+  } else {
+    GH_TRY(w->skip.reserve(sizeof(int) * (size_t)nentries));
+  }
+  Entries<Real> E{w->node.as<Node<Real>>(), sizeof(Real) == 4 ? nullptr : w->skip.as<int>()};
   const double inv_theta2 = 1.0 / (a.theta * a.theta);  // theta = 0 -> inf: cells are never accepted
   int *maxlevel = w->misc.as<int>();
   unsigned long long *dstats = reinterpret_cast<unsigned long long *>(w->misc.as<char>() + 16);
@@ -983,12 +1028,12 @@ static int tree_impl(const TreeArgs &a, Src src, const float4 *tgt32, TreeWorksp
   bool prefetch = false;
   if (const char *env = getenv("GH_WALK_PREFETCH")) prefetch = atoi(env) != 0;
   if (group) {
-    GroupWalk<Real>::launch(E.node, E.skip, nentries, tv, ni, root, (float)eps2, a.ep, dstats, a.want_stats,
-                            guard, (unsigned)nwarps, st);
+    GroupWalk<Real>::launch(E.node, nentries, tv, ni, root, (float)eps2, inv_theta2, a.ep, dstats,
+                            a.want_stats, guard, (unsigned)nwarps, st);
   } else {
 #define GH_WALK(STATS, GUARD, PF)                                                                      \
   walk_kernel<Real, STATS, GUARD, PF><<<blocks, wb, 0, st>>>(E.node, E.skip, nentries, tv, ni, root, \
-                                                            rel_origin, eps2, a.ep, dstats)
+                                                            rel_origin, eps2, inv_theta2, a.ep, dstats)
 #define GH_WALK2(STATS, GUARD) do { if (prefetch) GH_WALK(STATS, GUARD, true); else GH_WALK(STATS, GUARD, false); } while (0)
     if (a.want_stats) { if (guard) GH_WALK2(true, true); else GH_WALK2(true, false); }
     else { if (guard) GH_WALK2(false, true); else GH_WALK2(false, false); }
