@@ -387,28 +387,60 @@ def main():
         if clocks:
             roofline["frac_at_observed_clock"] = achieved / (fp32_peak_tflops * clocks["sm_mhz"] / sm_max)
     else:
-        # one extra, untimed evaluation with counters on: accepted / visited entries per target
+        # one extra, untimed evaluation with counters on: list entries / tested entries per target
         J.tree_stats(True)
         tx = torch.from_numpy(w["x"]).cuda()
         tm = torch.from_numpy(w["m"]).cuda()
-        J.tree_force(tx, tm, w["eps"], w["theta"], precision=w["prec"])
+        a32 = J.tree_force(tx, tm, w["eps"], w["theta"], precision=w["prec"])
         torch.cuda.synchronize()
         st = J.tree_stats()
         J.tree_stats(False)
+        mode = J.tree_walk()
         acc_per = st["accepted"] / float(n)
         vis_per = st["visited"] / float(n)
         achieved = (n / world) * acc_per * FLOP_PER_INTERACTION / (kernel_ms * 1e-3) / 1e12
-        roofline = {"bound": "issue (walk); fp32_fma peak quoted", "achieved": achieved, "peak": fp32_peak_tflops,
-                    "unit": "TFLOP/s", "frac": achieved / fp32_peak_tflops, "traffic": None,
-                    "kernel": "walk_kernel", "kernel_ms": kernel_ms,
+        # accuracy beside the rate (north_star: "reported with accuracy matching the reference"):
+        # per-particle relative acceleration error against fp64 direct summation on sampled
+        # targets, for the timed fp32 walk and for the reference's criterion (the fp64 per-target
+        # walk accepts exactly the reference's node set: tests/test_gpu_parity.py)
+        sel = torch.from_numpy(np.random.default_rng(0).choice(n, 4096, replace=False)).cuda()
+        tsel = tx[sel].contiguous()
+        d = J.direct_summation_position(tx, tm, tsel, w["eps"])
+        r64 = J.tree_force_position(tx, tm, tsel, w["eps"], w["theta"])
+        torch.cuda.synchronize()
+
+        def errs(a):
+            e = (torch.linalg.norm(a - d, dim=1) / torch.linalg.norm(d, dim=1)).cpu().numpy()
+            return {"mean": float(e.mean()), "median": float(np.median(e)), "p99": float(np.percentile(e, 99)),
+                    "max": float(e.max())}
+        accuracy = {"vs": "fp64 direct summation, 4096 sampled targets, same theta",
+                    "timed_fp32_walk": errs(a32[sel]), "reference_criterion_fp64_walk": errs(r64)}
+        if mode == "group":
+            kernel = "walk_group_kernel"
+            how = ("20 flop x interaction-list entries (%.0f per target: one warp-cooperative traversal per 32 "
+                   "Morton-consecutive targets with the bounding-box form of the reference's opening test, which "
+                   "opens every cell the reference opens and some more; the reference's own per-target set is "
+                   "~1.9x shorter) / CUDA-event time of the walk kernel, against the FP32 FMA peak; "
+                   "visited_per_target = entries tested per group / 32 targets; the build "
+                   "(ms_per_step - kernel_ms) is HBM-streaming bound" % acc_per)
+            bound = "fp32_fma (list evaluation) + issue (traversal)"
+        else:
+            kernel = "walk_kernel"
+            how = ("20 flop x accepted nodes (the reference's own accepted set: %.0f per target) / CUDA-event time "
+                   "of the walk kernel, against the FP32 FMA peak; ncu (profiles/) shows this walk is entry-load "
+                   "latency / instruction-issue bound; the build (ms_per_step - kernel_ms) is HBM-streaming bound"
+                   % acc_per)
+            bound = "issue (walk); fp32_fma peak quoted"
+        # dram__bytes_read.sum + dram__bytes_write.sum of walk_group_kernel at N = 2^22 on one GPU from
+        # `ncu --set full` (profiles/r01_walk_group_f32_N4M_v2.txt): 591.8 MB + 192.3 MB; the
+        # algorithmic bytes are 32 B x 6.2M entries read once + 64 B x N targets/epilogue = 0.47 GB
+        traffic = 784.2e6 if (mode == "group" and n == (1 << 22) and world == 1) else None
+        roofline = {"bound": bound, "achieved": achieved, "peak": fp32_peak_tflops,
+                    "unit": "TFLOP/s", "frac": achieved / fp32_peak_tflops, "traffic": traffic,
+                    "kernel": kernel, "kernel_ms": kernel_ms, "walk": mode,
                     "accepted_per_target": acc_per, "visited_per_target": vis_per,
                     "tree_entries": st["entries"], "tree_cells": st["cells"], "deepest_level": st["maxlevel"],
-                    "build_ms": ms_per_step - kernel_ms,
-                    "how": "20 flop x accepted nodes (the reference's own accepted set: %.0f per target) / "
-                           "CUDA-event time of the walk kernel, against the FP32 FMA peak; ncu "
-                           "(profiles/) shows the walk is instruction-issue bound (79%% issue-active, 35 "
-                           "SASS instructions per visited entry), the build (ms_per_step - kernel_ms) is "
-                           "HBM-streaming bound" % acc_per}
+                    "build_ms": ms_per_step - kernel_ms, "accuracy": accuracy, "how": how}
 
     line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
