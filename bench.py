@@ -421,7 +421,7 @@ def main():
                    "Morton-consecutive targets with the bounding-box form of the reference's opening test, which "
                    "opens every cell the reference opens and some more; the reference's own per-target set is "
                    "~1.9x shorter) / CUDA-event time of the walk kernel, against the FP32 FMA peak; "
-                   "visited_per_target = entries tested per group / 32 targets; the build "
+                   "visited_per_target = entries tested by the target's group (shared by its 32 targets); the build "
                    "(ms_per_step - kernel_ms) is HBM-streaming bound" % acc_per)
             bound = "fp32_fma (list evaluation) + issue (traversal)"
         else:

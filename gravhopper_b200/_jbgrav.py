@@ -16,7 +16,7 @@ import ctypes as C
 
 import numpy as np
 
-from . import _lib
+from . import _lib, _pinned
 
 __all__ = ["direct_summation", "direct_summation_position", "tree_force", "tree_force_position"]
 
@@ -97,9 +97,9 @@ def _call(fn_name, pos, mass, fpos, eps, theta, precision, self_names):
         fpos = _as_f64(fpos)
         _check_pos(fpos, "Force position")
     tgt = pos if fpos is None else fpos
-    out = np.empty_like(tgt)  # PyArray_NewLikeArray
     if tgt.shape[0] == 0:
-        return out
+        return np.empty_like(tgt)
+    out = _pinned.empty_f64(tgt.shape)  # PyArray_NewLikeArray: a NEW array (page-locked when large)
     L = _lib.lib()
     args = [prec, _ptr(pos), _ptr(mass), pos.shape[0]]
     if fpos is not None:

@@ -31,6 +31,8 @@ PROTOTYPES = {
     "gh_tree_force_position": (C.c_int, [C.c_int, _vp, _vp, _i64, _vp, _i64, C.c_double, C.c_double,
                                          _vp, C.c_int, _vp]),
     "gh_release_thread_scratch": (C.c_int, []),
+    "gh_host_alloc": (C.c_int, [C.POINTER(_vp), _i64]),
+    "gh_host_free": (C.c_int, [_vp]),
     "gh_tree_last_stats": (C.c_int, [C.POINTER(_i64)]),
     "gh_set_tree_stats": (C.c_int, [C.c_int]),
     "gh_set_tree_walk": (C.c_int, [C.c_int]),

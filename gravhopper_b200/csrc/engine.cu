@@ -300,6 +300,26 @@ int gh_release_thread_scratch(void) {
   return GH_OK;
 }
 
+int gh_host_alloc(void **ptr, int64_t bytes) {
+  if (!ptr || bytes <= 0) { set_error("gh_host_alloc: bad arguments"); return GH_EINVAL; }
+  *ptr = nullptr;
+  GH_TRY(check_device());
+  cudaError_t e = cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocPortable);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("gh_host_alloc: cudaHostAlloc(%lld bytes): %s", (long long)bytes, cudaGetErrorString(e));
+    *ptr = nullptr;
+    return GH_ENOMEM;
+  }
+  return GH_OK;
+}
+int gh_host_free(void *ptr) {
+  if (!ptr) return GH_OK;
+  cudaError_t e = cudaFreeHost(ptr);
+  if (e != cudaSuccess) { cudaGetLastError(); set_error("gh_host_free: %s", cudaGetErrorString(e)); return GH_ECUDA; }
+  return GH_OK;
+}
+
 int gh_tree_last_stats(int64_t out[8]) {
   Stateless *s = stateless();
   if (!s || !out) return GH_EINVAL;

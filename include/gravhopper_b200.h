@@ -93,6 +93,14 @@ int gh_tree_force_position(int prec, const double *pos, const double *mass, int6
  * do not cudaMalloc); this frees the calling thread's scratch. */
 int gh_release_thread_scratch(void);
 
+/* Page-locked host memory for results and inputs of the GH_MEM_HOST entry points: copies to and
+ * from such buffers are direct DMA transfers (a pageable destination costs a staged copy plus the
+ * first-touch page faults of a fresh allocation -- 3x the device time of a tree evaluation at
+ * N = 4M).  The Python binding hands out its result arrays from a recycling pool of these
+ * (the reference returns a NEW array per call, _jbgrav.c:111,267,607,700; so does the binding). */
+int gh_host_alloc(void **ptr, int64_t bytes);
+int gh_host_free(void *ptr);
+
 /* Statistics of the most recent tree evaluation made by the calling thread:
  * out[0] = tree entries (cells + leaves), out[1] = cells, out[2] = deepest cell level,
  * out[3] = accepted entries summed over targets, out[4] = visited entries summed over targets

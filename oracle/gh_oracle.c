@@ -358,6 +358,226 @@ int gho_tree_force(const double *pos, const double *mass, int64_t np, const doub
 }
 
 /* ------------------------------------------------------------------------------------------
+ * CPU MODEL OF THE PRODUCT'S GROUP WALK (walk_group_kernel, gravhopper_b200/csrc/tree.cu).
+ * This is NOT a reference function: the reference walks the tree once per target (gho_accel
+ * above).  The product's default fp32 walk shares one traversal between the 32 depth-first
+ * (Morton) consecutive targets of a warp and accepts a cell only if the reference's test
+ * (_jbgrav.c:502) holds for every point of the targets' two bounding boxes.  The model restates
+ * that criterion on the reference-shaped tree built above, so that tests can check the GPU kernel
+ * against an independent implementation of ITS OWN criterion at full size, and can measure how
+ * the criterion's error compares with the reference tree's.
+ *
+ * Decisions (cut of the group into two boxes, box extents with the kernel's padding, the
+ * acceptance test) are made in single precision on (position - root centre), like the kernel;
+ * forces are summed in double precision from the tree's double precision moments.  The traversal
+ * reproduces the kernel's chain stack (pop up to 32 sibling chains per iteration, push the rest of
+ * each chain, then the children of opened cells) so that the two give-up conditions -- list longer
+ * than list_limit when a chunk is evaluated, more than stack_limit chains -- trigger for the same
+ * groups; such groups use the per-target walk gho_accel, as the kernel does.
+ *   order_out[np]  (nullable) depth-first leaf order (sorted position -> particle)
+ *   list_out[np]   (nullable) per particle: list length of its group, -1 if the group gave up
+ * ------------------------------------------------------------------------------------------ */
+typedef struct { float cx, cy, cz, hx, hy, hz; } gho_box;
+
+static gho_box gho_box_of(const float *x, const float *y, const float *z, int a, int b)
+{
+	gho_box bx;
+	float lx = INFINITY, ux = -INFINITY, ly = INFINITY, uy = -INFINITY, lz = INFINITY, uz = -INFINITY;
+	for (int l = a; l < b; l++) {
+		lx = fminf(lx, x[l]); ux = fmaxf(ux, x[l]);
+		ly = fminf(ly, y[l]); uy = fmaxf(uy, y[l]);
+		lz = fminf(lz, z[l]); uz = fmaxf(uz, z[l]);
+	}
+	const float pad = 1.0f + 1e-6f;
+	bx.cx = 0.5f * (lx + ux); bx.cy = 0.5f * (ly + uy); bx.cz = 0.5f * (lz + uz);
+	bx.hx = (0.5f * (ux - lx)) * pad + 1e-6f * fabsf(bx.cx);
+	bx.hy = (0.5f * (uy - ly)) * pad + 1e-6f * fabsf(bx.cy);
+	bx.hz = (0.5f * (uz - lz)) * pad + 1e-6f * fabsf(bx.cz);
+	return bx;
+}
+
+static float gho_box_dist2(const gho_box *b, float cx, float cy, float cz)
+{
+	const float dx = fmaxf(fabsf(cx - b->cx) - b->hx, 0.f);
+	const float dy = fmaxf(fabsf(cy - b->cy) - b->hy, 0.f);
+	const float dz = fmaxf(fabsf(cz - b->cz) - b->hz, 0.f);
+	return dx * dx + dy * dy + dz * dz;
+}
+
+typedef struct { int64_t parent; int slot; } gho_chain; /* siblings = children of parent at slots >= slot */
+
+int gho_tree_force_group(const double *pos, const double *mass, int64_t np, double eps, double theta,
+                         int list_limit, int stack_limit, double *acc, int64_t *order_out,
+                         int32_t *list_out, int64_t *stats, int nthreads)
+{
+	double min[3], max[3], boxsize, boxcenter[3];
+	if (np < 1) return GHO_OK;
+	for (int i = 0; i < 3; i++) { min[i] = pos[i]; max[i] = min[i]; }
+	for (int64_t i = 1; i < np; i++)
+		for (int j = 0; j < 3; j++) {
+			double q = pos[3 * i + j];
+			if (q < min[j]) min[j] = q;
+			if (q > max[j]) max[j] = q;
+		}
+	boxsize = max[0] - min[0] + eps;
+	for (int i = 1; i < 3; i++)
+		if ((max[i] - min[i]) > boxsize) boxsize = max[i] - min[i] + eps;
+	for (int i = 0; i < 3; i++) boxcenter[i] = 0.5 * (min[i] + max[i]);
+
+	gho_tree t;
+	t.cap = 2 * np + 64; t.n = 0; t.pos = pos; t.mass = mass; t.err = 0; t.maxdepth = 0;
+	t.nodes = (gho_node *)malloc(sizeof(gho_node) * (size_t)t.cap);
+	if (!t.nodes) return GHO_ENOMEM;
+	int64_t root = gho_node_new(&t, boxcenter, boxsize);
+	for (int64_t i = 0; i < np && !t.err; i++) gho_add(&t, root, i, 0);
+	if (t.err) { free(t.nodes); return t.err; }
+	gho_finalize_all(&t);
+
+	/* depth-first leaf order (children in branch order) and the level of every node */
+	int64_t *order = (int64_t *)malloc(sizeof(int64_t) * (size_t)np);
+	signed char *level = (signed char *)malloc((size_t)t.n);
+	int64_t *stk = (int64_t *)malloc(sizeof(int64_t) * (size_t)(8 * (GHO_MAXDEPTH + 2)));
+	if (!order || !level || !stk) { free(order); free(level); free(stk); free(t.nodes); return GHO_ENOMEM; }
+	{
+		int64_t sp = 0, k = 0;
+		stk[sp++] = root;
+		level[root] = 0;
+		while (sp > 0) {
+			const int64_t ni = stk[--sp];
+			const gho_node *nd = &t.nodes[ni];
+			if (nd->leaf >= 0) { order[k++] = nd->leaf; continue; }
+			for (int j = 7; j >= 0; j--)
+				if (nd->branches[j] >= 0) {
+					level[nd->branches[j]] = (signed char)(level[ni] + 1);
+					stk[sp++] = nd->branches[j];
+				}
+		}
+	}
+	free(stk);
+	if (order_out) memcpy(order_out, order, sizeof(int64_t) * (size_t)np);
+
+	const double inv_theta2 = 1.0 / (theta * theta);
+	const float s2root = (float)(boxsize * boxsize * inv_theta2);
+	const double eps2 = eps * eps;
+	const int64_t ngroups = (np + 31) / 32;
+	int64_t n_list = 0, n_tested = 0, n_iter = 0, n_fallback = 0;
+	int oom = 0;
+	gho_set_threads(nthreads);
+#pragma omp parallel reduction(+ : n_list, n_tested, n_iter, n_fallback)
+	{
+		int64_t cap = 4096, *lst = (int64_t *)malloc(sizeof(int64_t) * (size_t)cap);
+		gho_chain *stack = (gho_chain *)malloc(sizeof(gho_chain) * (size_t)(stack_limit + 64));
+		if (!lst || !stack) oom = 1;
+#pragma omp for schedule(dynamic, 16)
+		for (int64_t g = 0; g < ngroups; g++) {
+			if (oom) continue;
+			const int64_t p0 = 32 * g;
+			const int nv = (int)((np - p0) < 32 ? (np - p0) : 32);
+			float x[32], y[32], z[32];
+			for (int l = 0; l < nv; l++) {
+				const double *q = &pos[3 * order[p0 + l]];
+				x[l] = (float)(q[0] - boxcenter[0]);
+				y[l] = (float)(q[1] - boxcenter[1]);
+				z[l] = (float)(q[2] - boxcenter[2]);
+			}
+			int cut = 0;
+			float gmax = -1.f;
+			for (int l = 0; l + 1 < nv; l++) {
+				const float gap = (x[l + 1] - x[l]) * (x[l + 1] - x[l]) + (y[l + 1] - y[l]) * (y[l + 1] - y[l]) +
+				                  (z[l + 1] - z[l]) * (z[l + 1] - z[l]);
+				if (gap > gmax) { gmax = gap; cut = l; }
+			}
+			const gho_box A = gho_box_of(x, y, z, 0, cut + 1);
+			const gho_box B = (cut + 1 < nv) ? gho_box_of(x, y, z, cut + 1, nv) : A;
+
+			int sp = 0, fallback = 0;
+			int64_t head = 0, tail = 0;
+			stack[sp].parent = -1; stack[sp].slot = 0; sp++;
+			while (sp > 0 && !fallback) {
+				n_iter++;
+				const int take = sp < 32 ? sp : 32;
+				gho_chain item[32];
+				for (int l = 0; l < take; l++) item[l] = stack[sp - 1 - l];
+				sp -= take;
+				if (head - tail >= 32) {
+					tail += 32;
+					if (head > list_limit) { fallback = 1; break; }
+				}
+				gho_chain rem[32], opn[32];
+				int nrem = 0, nopn = 0;
+				int64_t accn[32];
+				int nacc = 0;
+				for (int l = 0; l < take; l++) {
+					int64_t first;
+					int k = item[l].slot, more = 0;
+					if (item[l].parent < 0) {
+						first = root;
+					} else {
+						const gho_node *pn = &t.nodes[item[l].parent];
+						while (pn->branches[k] < 0) k++;
+						first = pn->branches[k];
+						for (int j = k + 1; j < 8; j++)
+							if (pn->branches[j] >= 0) { more = 1; break; }
+					}
+					const gho_node *nd = &t.nodes[first];
+					n_tested += nv;
+					int accept;
+					if (nd->leaf >= 0) {
+						accept = 1;
+					} else {
+						const float cx = (float)(nd->center[0] - boxcenter[0]);
+						const float cy = (float)(nd->center[1] - boxcenter[1]);
+						const float cz = (float)(nd->center[2] - boxcenter[2]);
+						const float s2 = s2root * ldexpf(1.0f, -2 * level[first]);
+						const float d2 = fminf(gho_box_dist2(&A, cx, cy, cz), gho_box_dist2(&B, cx, cy, cz));
+						accept = (s2 < d2);
+					}
+					if (more) { rem[nrem].parent = item[l].parent; rem[nrem].slot = k + 1; nrem++; }
+					if (accept) accn[nacc++] = first;
+					else { opn[nopn].parent = first; opn[nopn].slot = 0; nopn++; }
+				}
+				if (sp + nrem + nopn > stack_limit) { fallback = 1; break; }
+				/* lane 0 held the top of the stack and its pushes end up on top again */
+				for (int l = nrem - 1; l >= 0; l--) stack[sp++] = rem[l];
+				for (int l = nopn - 1; l >= 0; l--) stack[sp++] = opn[l];
+				if (head + nacc > cap) {
+					cap *= 2;
+					int64_t *nl = (int64_t *)realloc(lst, sizeof(int64_t) * (size_t)cap);
+					if (!nl) { oom = 1; fallback = 1; break; }
+					lst = nl;
+				}
+				for (int l = 0; l < nacc; l++) lst[head++] = accn[l];
+			}
+			for (int l = 0; l < nv; l++) {
+				const int64_t pi = order[p0 + l];
+				const double *q = &pos[3 * pi];
+				double f[3] = {0.0, 0.0, 0.0};
+				if (fallback) {
+					gho_accel(&t, root, q, eps, theta, f, NULL);
+				} else {
+					for (int64_t e = 0; e < head; e++) {
+						const gho_node *nd = &t.nodes[lst[e]];
+						const double dx = nd->COM[0] - q[0], dy = nd->COM[1] - q[1], dz = nd->COM[2] - q[2];
+						const double s = dx * dx + dy * dy + dz * dz + eps2;
+						const double w = (s == 0.0) ? 0.0 : nd->mass / s / sqrt(s);
+						f[0] += dx * w; f[1] += dy * w; f[2] += dz * w;
+					}
+				}
+				acc[3 * pi] = f[0]; acc[3 * pi + 1] = f[1]; acc[3 * pi + 2] = f[2];
+				if (list_out) list_out[pi] = fallback ? -1 : (int32_t)head;
+			}
+			if (fallback) n_fallback++;
+			else n_list += head * nv;
+		}
+		free(lst);
+		free(stack);
+	}
+	if (stats) { stats[0] = t.n; stats[1] = n_list; stats[2] = n_tested; stats[3] = n_iter; stats[4] = n_fallback; stats[5] = ngroups; }
+	free(order); free(level); free(t.nodes);
+	return oom ? GHO_ENOMEM : GHO_OK;
+}
+
+/* ------------------------------------------------------------------------------------------
  * One drift-kick-drift leapfrog step in the reference's internal units (kpc, km/s, Msun, Myr).
  * Follows Simulation.perform_timestep, gravhopper.py:405-416, with the unit handling of
  * jbgrav.py:38-48 made explicit:

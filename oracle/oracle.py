@@ -52,6 +52,8 @@ def _lib():
         lib.gho_direct_position.argtypes = [dp, dp, i64, dp, i64, C.c_double, dp, C.c_int]
         lib.gho_tree_force.argtypes = [dp, dp, i64, dp, i64, C.c_double, C.c_double, dp,
                                        C.POINTER(i64), C.c_int]
+        lib.gho_tree_force_group.argtypes = [dp, dp, i64, C.c_double, C.c_double, C.c_int, C.c_int, dp,
+                                             C.POINTER(i64), C.POINTER(C.c_int32), C.POINTER(i64), C.c_int]
         lib.gho_leapfrog_step.argtypes = [dp, dp, dp, i64, C.c_double, C.c_double, C.c_double,
                                           C.c_int, dp, dp, C.c_int]
         lib.gho_half_drift.argtypes = [dp, dp, i64, C.c_double, dp]
@@ -114,6 +116,26 @@ def tree_force_position(pos, mass, force_pos, eps, theta, nthreads=1, return_sta
 
 def tree_force(pos, mass, eps, theta, nthreads=1, return_stats=False):
     return tree_force_position(pos, mass, pos, eps, theta, nthreads, return_stats)
+
+
+def tree_force_group(pos, mass, eps, theta, list_limit=3000, stack_limit=320, nthreads=0):
+    """CPU model of the PRODUCT's fp32 group walk (walk_group_kernel), not a reference function:
+    one traversal per 32 depth-first-consecutive targets, cell accepted only if _jbgrav.c:502 holds
+    on the targets' two bounding boxes; groups that exceed ``list_limit`` / ``stack_limit`` use the
+    per-target walk.  Returns (acc, info) with info = dict(order, list_len (-1: group gave up),
+    nodes, list_sum, tested_sum, iterations, fallback_groups, groups)."""
+    pos, mass = _f64(pos), _f64(mass)
+    n = pos.shape[0]
+    acc = np.zeros_like(pos)
+    order = np.zeros(n, dtype=np.int64)
+    llen = np.zeros(n, dtype=np.int32)
+    stats = (C.c_int64 * 6)()
+    _check(_lib().gho_tree_force_group(_p(pos), _p(mass), n, float(eps), float(theta), int(list_limit),
+                                       int(stack_limit), _p(acc), order.ctypes.data_as(C.POINTER(C.c_int64)),
+                                       llen.ctypes.data_as(C.POINTER(C.c_int32)), stats, nthreads),
+           "gho_tree_force_group")
+    return acc, dict(order=order, list_len=llen, nodes=stats[0], list_sum=stats[1], tested_sum=stats[2],
+                     iterations=stats[3], fallback_groups=stats[4], groups=stats[5])
 
 
 def leapfrog_step(x, v, mass, dt, eps, algorithm="direct", theta=0.7, ext=None, nthreads=1):

@@ -144,6 +144,31 @@ def test_group_hernquist_error_distribution(modes):
     assert np.array_equal(again, r["group"])  # deterministic: no atomics on the force path
 
 
+def test_group_kernel_equals_the_cpu_model_of_its_criterion(oracle):
+    """walk_group_kernel against oracle.tree_force_group (an independent C restatement of the same
+    criterion: fp32 decisions, fp64 sums): same list and test counts, forces equal to fp32 rounding
+    except for the rare group where a borderline acceptance flips."""
+    n = 200000
+    x, v, m = ic_raw.Hernquist(n, 1.0, 1e10, seed=42)
+    x = np.ascontiguousarray(x)
+    J.tree_walk("group")
+    J.tree_stats(True)
+    try:
+        a = J.tree_force(x, m, 0.05, 0.7, precision="fp32")
+        st = J.tree_stats()
+    finally:
+        J.tree_stats(False)
+    model, info = oracle.tree_force_group(x, m, 0.05, 0.7)
+    assert info["fallback_groups"] == st["warp_entries_max"] == 0
+    assert abs(st["accepted"] - info["list_sum"]) <= 1e-4 * info["list_sum"]
+    assert abs(st["visited"] - info["tested_sum"]) <= 1e-4 * info["tested_sum"]
+    assert abs(st["warp_entries"] - info["iterations"]) <= 1e-3 * info["iterations"]
+    diff = relerr(a, model)
+    assert np.median(diff) <= 1e-5
+    assert (diff > 1e-4).mean() <= 0.005
+    assert diff.max() <= 2e-2
+
+
 _FALLBACK = r"""
 import sys
 sys.path.insert(0, %r)
@@ -161,6 +186,42 @@ t = J.tree_force(x, m, 0.01, 0.7, precision="fp32")
 err = float(np.max(np.linalg.norm(g - t, axis=1) / np.linalg.norm(t, axis=1)))
 print("RESULT", int(np.array_equal(g, t)), sg["warp_entries_max"], sg["warps"], err)
 """
+
+
+_PARTIAL = r"""
+import sys
+sys.path.insert(0, %r)
+import numpy as np
+from gravhopper_b200 import _jbgrav as J, ic_raw
+x, v, m = ic_raw.Hernquist(50000, 1.0, 1e10, seed=9)
+x = np.ascontiguousarray(x)
+J.tree_stats(True)
+J.tree_walk("group")
+g = J.tree_force(x, m, 0.05, 0.7, precision="fp32")
+sg = J.tree_stats()
+np.save(sys.argv[1], g)
+print("RESULT", sg["warp_entries_max"], sg["warps"])
+"""
+
+
+def test_partial_fallback_matches_the_model(oracle, tmp_path):
+    # a 900-entry limit makes about half of the groups give up; the model applies the same rule
+    # (limit checked when a 32-entry chunk is evaluated) and must pick the same groups
+    env = dict(os.environ, GH_WALK_LIST_LIMIT="900")
+    env.pop("GH_TREE_WALK", None)
+    f = str(tmp_path / "g.npy")
+    out = subprocess.run([sys.executable, "-c", _PARTIAL % ROOT, f], env=env, capture_output=True, text=True,
+                         timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [ln for ln in out.stdout.splitlines() if ln.startswith("RESULT")][-1].split()
+    fallbacks, warps = int(line[1]), int(line[2])
+    x, v, m = ic_raw.Hernquist(50000, 1.0, 1e10, seed=9)
+    model, info = oracle.tree_force_group(np.ascontiguousarray(x), m, 0.05, 0.7, list_limit=900)
+    assert warps == info["groups"]
+    assert 0 < info["fallback_groups"] < info["groups"]
+    assert abs(fallbacks - info["fallback_groups"]) <= max(2, 0.01 * info["fallback_groups"])
+    diff = relerr(np.load(f), model)
+    assert np.median(diff) <= 1e-5 and (diff > 1e-4).mean() <= 0.01
 
 
 def test_groups_over_the_list_limit_reproduce_the_per_target_walk():

@@ -79,11 +79,43 @@ def test_tree_4m_hernquist_sampled(oracle, prec):
     refd = oracle.direct_summation_position(x, m, x[sel], eps, nthreads=0)
     if prec == "fp64":
         assert relerr(a[sel], reft).max() <= 1e-12
-    else:
-        eref, egpu = relerr(reft, refd), relerr(a[sel], refd)
-        assert egpu.mean() <= eref.mean() * 1.02 + 1e-6
-        assert np.percentile(egpu, 99) <= np.percentile(eref, 99) * 1.05 + 1e-6
-        assert egpu.max() <= eref.max() * 1.1 + 1e-6
+        return
+    eref, egpu = relerr(reft, refd), relerr(a[sel], refd)
+    # default fp32 walk = group walk: mean / median / p99 of the per-particle error are below the
+    # reference tree's.  The extreme tail is not: the 32 targets of a group share one list, so their
+    # errors are coherent instead of centred on each target, which shows for the ~0.01 % of
+    # particles inside the softened core whose net force nearly cancels.
+    assert egpu.mean() <= eref.mean() * 1.02 + 1e-6
+    assert np.median(egpu) <= np.median(eref) * 1.02 + 1e-6
+    assert np.percentile(egpu, 99) <= np.percentile(eref, 99) * 1.05 + 1e-6
+    assert egpu.max() <= eref.max() * 2.0
+    # the per-target walk applies _jbgrav.c:502 itself: the reference's node set, max included
+    J.tree_walk("target")
+    try:
+        at = J.tree_force(x, m, eps, 0.7, precision="fp32")
+    finally:
+        J.tree_walk("group")
+    et = relerr(at[sel], refd)
+    assert et.mean() <= eref.mean() * 1.02 + 1e-6
+    assert np.percentile(et, 99) <= np.percentile(eref, 99) * 1.05 + 1e-6
+    assert et.max() <= eref.max() * 1.1 + 1e-6
+    # the kernel against the CPU model of its own criterion (oracle.tree_force_group): same lists
+    # (fp32 decisions reproduced), forces equal to fp32 rounding for all 4M particles except where a
+    # borderline acceptance flips
+    J.tree_stats(True)
+    try:
+        a = J.tree_force(x, m, eps, 0.7, precision="fp32")
+        st = J.tree_stats()
+    finally:
+        J.tree_stats(False)
+    model, info = oracle.tree_force_group(x, m, eps, 0.7)
+    assert info["fallback_groups"] == 0 and st["warp_entries_max"] == 0
+    assert abs(st["accepted"] - info["list_sum"]) <= 1e-5 * info["list_sum"]
+    assert abs(st["visited"] - info["tested_sum"]) <= 1e-5 * info["tested_sum"]
+    diff = relerr(a, model)
+    assert np.median(diff) <= 1e-5
+    assert (diff > 1e-4).mean() <= 0.005
+    assert diff.max() <= 2e-2
 
 
 def test_tree_galaxy_model_sampled(oracle):

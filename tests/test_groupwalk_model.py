@@ -38,3 +38,22 @@ def test_group_criterion_small_and_ragged(oracle):
     # theta = 0: every cell is opened, the list is all leaves
     a, nlist = group_walk(x, m, 0.05, 0.0)
     assert nlist == n * n and relerr(a, oracle.direct_summation(x, m, 0.05)).max() <= 1e-13
+
+
+def test_c_model_equals_python_model(golden, oracle):
+    """oracle.tree_force_group (C, fp32 decisions, the kernel's chain-stack traversal and give-up
+    rules) and groupwalk_model.group_walk (Python, fp64 decisions, plain recursion) are two
+    independent restatements of the criterion: same lists, same forces."""
+    x, m, eps = golden["c1_pos"], golden["c1_mass"], float(golden["c1_eps"])
+    a, nlist = group_walk(x, m, eps, 0.7)
+    c, info = oracle.tree_force_group(x, m, eps, 0.7)
+    assert info["list_sum"] == nlist and info["fallback_groups"] == 0 and info["groups"] == 63
+    assert relerr(c, a).max() <= 1e-13
+    assert sorted(info["order"]) == list(range(len(m)))
+    # give-up rules: a tiny list limit or chain stack sends every group to the per-target walk,
+    # which is the reference tree itself
+    ref = oracle.tree_force(x, m, eps, 0.7)
+    for kw in (dict(list_limit=32), dict(stack_limit=4)):
+        f, inf = oracle.tree_force_group(x, m, eps, 0.7, **kw)
+        assert inf["fallback_groups"] == inf["groups"] and (inf["list_len"] == -1).all()
+        assert np.array_equal(f, ref)

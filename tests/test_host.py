@@ -120,3 +120,55 @@ def test_morton_layout_is_a_balanced_permutation():
         r = np.linalg.norm(x[perm], axis=1)
         med = [np.median(r[b:b + c]) for b, c in parts]
         assert max(med) < 1.5 * min(med)
+
+
+def test_pinned_output_pool_recycles_blocks(monkeypatch):
+    """gravhopper_b200/_pinned.py with the page-locked allocator swapped for libc malloc: result
+    arrays are new, writable, C-contiguous; a block returns to the pool when the last view dies and
+    is handed out again; the byte caps fall back to np.empty."""
+    import ctypes
+    import gc
+    from gravhopper_b200 import _pinned
+    libc = ctypes.CDLL(None)
+    libc.malloc.restype = ctypes.c_void_p
+    libc.malloc.argtypes = [ctypes.c_size_t]
+    libc.free.argtypes = [ctypes.c_void_p]
+    live = set()
+
+    def alloc(n):
+        p = libc.malloc(n)
+        live.add(p)
+        return p
+
+    def free(p):
+        live.remove(p)
+        libc.free(p)
+    monkeypatch.setattr(_pinned, "_raw_alloc", alloc)
+    monkeypatch.setattr(_pinned, "_raw_free", free)
+    monkeypatch.setattr(_pinned, "ENABLED", True)
+    monkeypatch.setattr(_pinned, "stats", {"allocated": 0, "reused": 0, "fallback": 0})
+    shape = (100000, 3)
+    a = _pinned.empty_f64(shape)
+    assert a.shape == shape and a.dtype == np.float64 and a.flags["C_CONTIGUOUS"] and a.flags["WRITEABLE"]
+    a[:] = 1.5
+    p0 = a.ctypes.data
+    view = a[10:20]
+    b = _pinned.empty_f64(shape)
+    assert b.ctypes.data != p0 and _pinned.stats["allocated"] == 2
+    del a
+    gc.collect()
+    c = _pinned.empty_f64(shape)              # `view` still holds the first block
+    assert c.ctypes.data != p0 and _pinned.stats["allocated"] == 3
+    assert view[0, 0] == 1.5
+    del view
+    gc.collect()
+    d = _pinned.empty_f64(shape)              # now it is recycled
+    assert d.ctypes.data == p0 and _pinned.stats["reused"] == 1
+    assert _pinned.empty_f64((10, 3)).base is None        # small: plain numpy
+    monkeypatch.setattr(_pinned, "MAX_BYTES", _pinned._total)
+    e = _pinned.empty_f64((200000, 3))                    # over the cap: plain numpy
+    assert e.base is None and _pinned.stats["fallback"] == 1
+    del b, c, d, e
+    gc.collect()
+    _pinned.trim()
+    assert not live and _pinned._total == 0 and _pinned._cached == 0
