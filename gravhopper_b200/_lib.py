@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgravhopper_b200.so")
+# GH_B200_LIB: load another build of the same ABI (kernel-variant experiments, scripts/gpu_variants.sh)
+LIB_PATH = os.environ.get("GH_B200_LIB") or os.path.join(_HERE, "libgravhopper_b200.so")
 
 GH_OK, GH_EINVAL, GH_ECUDA, GH_ENOMEM, GH_ESTATE = 0, 1, 2, 3, 4
 GH_PREC_F32, GH_PREC_F64 = 32, 64

@@ -674,8 +674,13 @@ __device__ __forceinline__ float box_dist2(const Box &b, float cx, float cy, flo
   return dx * dx + dy * dy + dz * dz;
 }
 
+// Resident warps per SM the register allocation is capped for: 32 -> 64 registers per thread,
+// 24 -> 80, 20 -> 96, 16 -> 128 (scripts/gpu_variants.sh measures the alternatives).
+#ifndef GH_GW_WARPS_PER_SM
+#define GH_GW_WARPS_PER_SM 32
+#endif
 template <int WPC, bool STATS, bool GUARD>
-__global__ void __launch_bounds__(32 * WPC, 32 / WPC)
+__global__ void __launch_bounds__(32 * WPC, GH_GW_WARPS_PER_SM / WPC)
 walk_group_kernel(const Node<float> *__restrict__ nodes, int nentries, TargetsView tv, int64_t ni,
                   const double *__restrict__ root, float eps2, double inv_theta2, int list_limit,
                   Epilogue ep, unsigned long long *__restrict__ stats) {

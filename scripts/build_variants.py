@@ -1,0 +1,33 @@
+"""Build kernel variants of libgravhopper_b200.so for A/B measurements on the GPU box:
+gravhopper_b200/variants/lib_<name>.so = the normal objects with tree.cu recompiled under extra -D
+flags.  Select one at run time with GH_B200_LIB=<path>.  usage: python scripts/build_variants.py"""
+import os, subprocess, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gravhopper_b200 import build as B
+
+VARIANTS = {
+    "w24": ["-DGH_GW_WARPS_PER_SM=24"],
+    "w20": ["-DGH_GW_WARPS_PER_SM=20"],
+    "w16": ["-DGH_GW_WARPS_PER_SM=16"],
+}
+B.build()
+out = os.path.join(B.HERE, "variants")
+os.makedirs(out, exist_ok=True)
+flags = [f for f in B.NVCC_FLAGS if not f.startswith("--use_fast_math")]
+procs = []
+for name, defs in VARIANTS.items():
+    o = os.path.join(out, "tree_%s.o" % name)
+    procs.append((name, o, subprocess.Popen([B._nvcc()] + flags + defs + ["-Xptxas", "-v", "-c", os.path.join(B.CSRC, "tree.cu"), "-o", o],
+                                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+for name, o, p in procs:
+    log, _ = p.communicate()
+    if p.returncode:
+        raise SystemExit(log)
+    lines = log.splitlines()
+    for i, l in enumerate(lines):
+        if "walk_group_kernelILi2ELb0ELb0" in l:
+            print(name, lines[i + 1].strip(), "|", lines[i + 2].strip())
+    objs = [os.path.join(B.HERE, "build", s.replace(".cu", ".o")) for s in B.SOURCES if s != "tree.cu"] + [o]
+    lib = os.path.join(out, "lib_%s.so" % name)
+    subprocess.run([B._nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs, check=True)
+    print("built", lib)
