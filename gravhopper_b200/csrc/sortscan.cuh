@@ -1,8 +1,8 @@
 // sortscan.cuh -- hand-written device primitives of the tree build (sm_100a):
 //   * chunked_scan<T>: deterministic inclusive scan (P[q+1] = x_0 (+) ... (+) x_q, P[0] = identity)
-//     over 256-element warp chunks, recursive; used for the double-double moment sums (T = DD4,
-//     non-associative operator, fixed order) and for the pre-order offsets / radix digit offsets
-//     (T = int);
+//     over 256-element warp chunks, recursive; used for the moment sums (T = DD4: double-double,
+//     fp64 tree; T = D4: plain double, fp32 tree; non-associative operators, fixed order) and for
+//     the pre-order offsets / radix digit offsets (T = int);
 //   * radix_sort_pairs: stable LSD radix sort of (uint64 key, int value) pairs, 8 bits per pass
 //     (K5 of SURVEY 2.4).  Per pass: per-CTA digit histogram (+ global digit totals) -> per-digit
 //     row scan of the (digit, CTA) table -> scatter.  In the scatter each warp ranks its 256 keys
@@ -70,6 +70,38 @@ template <> struct ScanOps<DD4> {
       r.c[k].h = __shfl_sync(0xffffffffu, v.c[k].h, src);
       r.c[k].l = __shfl_sync(0xffffffffu, v.c[k].l, src);
     }
+    return r;
+  }
+};
+
+// plain double moments (m, m x, m y, m z): the fp32 tree's scan element (half the bytes of DD4, no
+// error-free transformations; see moment_diff in tree.cu for why that is enough there)
+struct D4 {
+  double c[4];
+};
+template <> struct ScanOps<D4> {
+  static __device__ __forceinline__ D4 zero() {
+    D4 r;
+#pragma unroll
+    for (int k = 0; k < 4; k++) r.c[k] = 0.0;
+    return r;
+  }
+  static __device__ __forceinline__ D4 add(const D4 &a, const D4 &b) {
+    D4 r;
+#pragma unroll
+    for (int k = 0; k < 4; k++) r.c[k] = __dadd_rn(a.c[k], b.c[k]);
+    return r;
+  }
+  static __device__ __forceinline__ D4 shfl_up(const D4 &v, int d) {
+    D4 r;
+#pragma unroll
+    for (int k = 0; k < 4; k++) r.c[k] = __shfl_up_sync(0xffffffffu, v.c[k], d);
+    return r;
+  }
+  static __device__ __forceinline__ D4 shfl(const D4 &v, int src) {
+    D4 r;
+#pragma unroll
+    for (int k = 0; k < 4; k++) r.c[k] = __shfl_sync(0xffffffffu, v.c[k], src);
     return r;
   }
 };
@@ -204,7 +236,17 @@ rs_rowscan_kernel(int *__restrict__ hist, int nblocks) {
   }
 }
 
-__global__ void __launch_bounds__(RS_THREADS)
+// GH_RS_VARIANT / GH_RS_MINBLOCKS: scatter-kernel alternatives measured with
+// scripts/build_variants.py + scripts/gpu_variants2.sh (see DESIGN 4.3 for the outcome).
+#ifndef GH_RS_VARIANT
+#define GH_RS_VARIANT 0
+#endif
+#ifdef GH_RS_MINBLOCKS
+#define GH_RS_BOUNDS __launch_bounds__(RS_THREADS, GH_RS_MINBLOCKS)
+#else
+#define GH_RS_BOUNDS __launch_bounds__(RS_THREADS)
+#endif
+__global__ void GH_RS_BOUNDS
 rs_scatter_kernel(const uint64_t *__restrict__ kin, const int *__restrict__ vin,
                   uint64_t *__restrict__ kout, int *__restrict__ vout, int64_t n, int shift,
                   const int *__restrict__ offs /* per-digit exclusive offsets (rs_rowscan_kernel) */,
@@ -224,6 +266,8 @@ rs_scatter_kernel(const uint64_t *__restrict__ kin, const int *__restrict__ vin,
 
   uint64_t key[RS_ROUNDS];
   int val[RS_ROUNDS], lrank[RS_ROUNDS];
+#if GH_RS_VARIANT == 0
+  // one loop: load, ballot, update the running per-digit count, round by round
 #pragma unroll
   for (int r = 0; r < RS_ROUNDS; r++) {
     const int64_t q = seg0 + r * 32 + lane;
@@ -243,6 +287,49 @@ rs_scatter_kernel(const uint64_t *__restrict__ kin, const int *__restrict__ vin,
     lrank[r] = old + __popc(peers & ((1u << lane) - 1u));
     __syncwarp();
   }
+#else
+  // all key loads and all MATCH.ANY ballots first: they are independent of each other, only the
+  // running per-digit counts have to be updated round by round (stability).  ncu showed the warps
+  // waiting on one MATCH / one load at a time when the loops were one.  Variant 2 loads the values
+  // only after the ranking (they are not needed before the tile is placed in shared memory).
+  unsigned peers[RS_ROUNDS];
+#pragma unroll
+  for (int r = 0; r < RS_ROUNDS; r++) {
+    const int64_t q = seg0 + r * 32 + lane;
+    key[r] = (q < n) ? kin[q] : 0;
+#if GH_RS_VARIANT == 1
+    val[r] = (q < n) ? vin[q] : 0;
+#endif
+  }
+#pragma unroll
+  for (int r = 0; r < RS_ROUNDS; r++) {
+    const bool valid = seg0 + r * 32 + lane < n;
+    // invalid lanes get private pseudo-digits so that they match nobody
+    const unsigned d = valid ? (unsigned)((key[r] >> shift) & 0xff) : (0x100u + (unsigned)lane);
+    peers[r] = __match_any_sync(0xffffffffu, d);
+  }
+#if GH_RS_VARIANT == 2
+#pragma unroll
+  for (int r = 0; r < RS_ROUNDS; r++) {
+    const int64_t q = seg0 + r * 32 + lane;
+    val[r] = (q < n) ? vin[q] : 0;
+  }
+#endif
+#pragma unroll
+  for (int r = 0; r < RS_ROUNDS; r++) {
+    const bool valid = seg0 + r * 32 + lane < n;
+    const unsigned d = (unsigned)((key[r] >> shift) & 0xff);
+    const int leader = __ffs(peers[r]) - 1;
+    int old = 0;
+    if (lane == leader && valid) {
+      old = whist[w][d];
+      whist[w][d] = old + __popc(peers[r]);
+    }
+    old = __shfl_sync(0xffffffffu, old, leader);
+    lrank[r] = old + __popc(peers[r] & ((1u << lane) - 1u));
+    __syncwarp();
+  }
+#endif
   __syncthreads();
 
   // thread d: turn the per-warp counts of digit d into per-warp bases, get the CTA total

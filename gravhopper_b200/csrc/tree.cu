@@ -241,6 +241,40 @@ struct InParticles {  // element q = (m, m x, m y, m z) of sorted particle q, pr
   const double4 *sp;
   __device__ __forceinline__ DD4 operator()(int64_t q) const { return dd4_of(sp[q]); }
 };
+// fp32 tree: plain double moments of (x - root centre).  A cell's moments are P[b+1] - P[p]; the
+// rounding error of a prefix is ~1e-16 of the running total, so the centre of mass of even a
+// two-particle cell is off by < 1e-16 N |x| m / m_cell ~ 1e-9 kpc at N = 10M -- two orders of
+// magnitude below the fp32 resolution (6e-8 |x|) the entry is stored with.  Half the scan traffic
+// of the double-double form and none of its error-free transformations (fp64 keeps DD4: there the
+// moments must reproduce the reference's to 1e-12).
+struct InParticlesRel {
+  const double4 *sp;
+  const double *root;
+  __device__ __forceinline__ D4 operator()(int64_t q) const {
+    const double4 t = sp[q];
+    D4 r;
+    r.c[0] = t.w;
+    r.c[1] = t.w * (t.x - root[0]);
+    r.c[2] = t.w * (t.y - root[1]);
+    r.c[3] = t.w * (t.z - root[2]);
+    return r;
+  }
+};
+// moments of sorted particles [p, b]: mass and first moments (fp64: absolute coordinates,
+// double-double difference; fp32: relative to the root centre, plain difference)
+__device__ __forceinline__ void moment_diff(const DD4 *__restrict__ P, int64_t p, int64_t b, double mh[4]) {
+  const DD4 pe = P[b + 1], ps = P[p];
+  double rl;
+#pragma unroll
+  for (int k = 0; k < 4; k++) dd_add(pe.c[k].h, pe.c[k].l, -ps.c[k].h, -ps.c[k].l, mh[k], rl);
+}
+__device__ __forceinline__ void moment_diff(const D4 *__restrict__ P, int64_t p, int64_t b, double mh[4]) {
+  const D4 pe = P[b + 1], ps = P[p];
+#pragma unroll
+  for (int k = 0; k < 4; k++) mh[k] = pe.c[k] - ps.c[k];
+}
+template <class Real> struct MomentOf { using type = DD4; };
+template <> struct MomentOf<float> { using type = D4; };
 
 // ---- K6b emit -----------------------------------------------------------------------------------
 template <class Real> struct Vec4;
@@ -310,11 +344,18 @@ __device__ __forceinline__ uint64_t compact3(uint64_t x) {
   return x;
 }
 
+// GH_EMIT_MINBLOCKS: resident 128-thread CTAs per SM the register allocation is capped for
+// (scripts/build_variants.py; ncu: 66 registers -> 33 % of the warp slots active, latency bound)
+#ifdef GH_EMIT_MINBLOCKS
+#define GH_EMIT_BOUNDS __launch_bounds__(128, GH_EMIT_MINBLOCKS)
+#else
+#define GH_EMIT_BOUNDS
+#endif
 template <class Src, class Real>
-__global__ void emit_kernel(const double4 *__restrict__ sp, const uint64_t *__restrict__ hi,
+__global__ void GH_EMIT_BOUNDS emit_kernel(const double4 *__restrict__ sp, const uint64_t *__restrict__ hi,
                             const uint64_t *__restrict__ lo, const signed char *__restrict__ clev,
                             const int *__restrict__ base /* n+1, exclusive scan of cnt */,
-                            const DD4 *__restrict__ P, int64_t n,
+                            const typename MomentOf<Real>::type *__restrict__ P, int64_t n,
                             const double *__restrict__ root, bool rel_origin, double inv_theta2,
                             Entries<Real> E, int *__restrict__ maxlevel) {
   int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -372,14 +413,18 @@ __global__ void emit_kernel(const double4 *__restrict__ sp, const uint64_t *__re
           else hi_i = mid - 1;
         }
         const int64_t b = lo_i;
-        double mh[4], rl;
-        const DD4 pe = P[b + 1], ps = P[p];
-#pragma unroll
-        for (int k = 0; k < 4; k++) dd_add(pe.c[k].h, pe.c[k].l, -ps.c[k].h, -ps.c[k].l, mh[k], rl);
+        double mh[4];
+        moment_diff(P, p, b, mh);
         V4 com, cen;
-        com.x = (Real)(mh[1] / mh[0] - ox);  // gravoct_finalize :477-479
-        com.y = (Real)(mh[2] / mh[0] - oy);
-        com.z = (Real)(mh[3] / mh[0] - oz);
+        if (sizeof(Real) == 4) {  // moments already relative to the root centre
+          com.x = (Real)(mh[1] / mh[0]);
+          com.y = (Real)(mh[2] / mh[0]);
+          com.z = (Real)(mh[3] / mh[0]);
+        } else {
+          com.x = (Real)(mh[1] / mh[0] - ox);  // gravoct_finalize :477-479
+          com.y = (Real)(mh[2] / mh[0] - oy);
+          com.z = (Real)(mh[3] / mh[0] - oz);
+        }
         com.w = (Real)mh[0];
         cen.x = (Real)(cc[0] - ox);
         cen.y = (Real)(cc[1] - oy);
@@ -966,9 +1011,14 @@ static int tree_impl(const TreeArgs &a, Src src, const float4 *tgt32, TreeWorksp
   double4 *sp = w->sorted.as<double4>();
   gather_sorted_kernel<<<nblk(n, 256), 256, 0, st>>>(src, sidx, n, sp);
   GH_LAUNCH_CHECK();
-  GH_TRY(w->P.reserve(sizeof(DD4) * (size_t)(n + 1)));
-  DD4 *P = w->P.as<DD4>();
-  GH_TRY((chunked_scan<DD4, InParticles>(InParticles{sp}, n, P, w->scanlv, 0, st)));
+  using Mom = typename MomentOf<Real>::type;
+  GH_TRY(w->P.reserve(sizeof(Mom) * (size_t)(n + 1)));
+  Mom *P = w->P.as<Mom>();
+  if (sizeof(Real) == 4) {
+    GH_TRY((chunked_scan<D4, InParticlesRel>(InParticlesRel{sp, root}, n, reinterpret_cast<D4 *>(P), w->scanlv, 0, st)));
+  } else {
+    GH_TRY((chunked_scan<DD4, InParticles>(InParticles{sp}, n, reinterpret_cast<DD4 *>(P), w->scanlv, 0, st)));
+  }
 
   // entries: need the count on the host to size the arrays
   GH_CUDA(cudaStreamSynchronize(st));

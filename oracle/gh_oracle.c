@@ -406,9 +406,26 @@ static float gho_box_dist2(const gho_box *b, float cx, float cy, float cz)
 
 typedef struct { int64_t parent; int slot; } gho_chain; /* siblings = children of parent at slots >= slot */
 
+int gho_tree_force_group2(const double *pos, const double *mass, int64_t np, double eps, double theta,
+                          int list_limit, int stack_limit, double *acc, int64_t *order_out,
+                          int32_t *list_out, int64_t *stats, int nthreads, const int64_t *order_in,
+                          int group_size, int two_boxes);
+
 int gho_tree_force_group(const double *pos, const double *mass, int64_t np, double eps, double theta,
                          int list_limit, int stack_limit, double *acc, int64_t *order_out,
                          int32_t *list_out, int64_t *stats, int nthreads)
+{
+	return gho_tree_force_group2(pos, mass, np, eps, theta, list_limit, stack_limit, acc, order_out,
+	                             list_out, stats, nthreads, NULL, 32, 1);
+}
+
+/* Design-study form of the model: the targets can be grouped along any given order (order_in, e.g.
+ * a Hilbert curve instead of the depth-first/Morton order), in groups of group_size <= 32, with one
+ * or two bounding boxes.  gho_tree_force_group is the kernel's configuration (NULL, 32, 1). */
+int gho_tree_force_group2(const double *pos, const double *mass, int64_t np, double eps, double theta,
+                          int list_limit, int stack_limit, double *acc, int64_t *order_out,
+                          int32_t *list_out, int64_t *stats, int nthreads, const int64_t *order_in,
+                          int group_size, int two_boxes)
 {
 	double min[3], max[3], boxsize, boxcenter[3];
 	if (np < 1) return GHO_OK;
@@ -455,11 +472,14 @@ int gho_tree_force_group(const double *pos, const double *mass, int64_t np, doub
 	}
 	free(stk);
 	if (order_out) memcpy(order_out, order, sizeof(int64_t) * (size_t)np);
+	if (order_in) memcpy(order, order_in, sizeof(int64_t) * (size_t)np);
+	if (group_size < 1 || group_size > 32) group_size = 32;
+	const int GS = group_size;
 
 	const double inv_theta2 = 1.0 / (theta * theta);
 	const float s2root = (float)(boxsize * boxsize * inv_theta2);
 	const double eps2 = eps * eps;
-	const int64_t ngroups = (np + 31) / 32;
+	const int64_t ngroups = (np + GS - 1) / GS;
 	int64_t n_list = 0, n_tested = 0, n_iter = 0, n_fallback = 0;
 	int oom = 0;
 	gho_set_threads(nthreads);
@@ -471,8 +491,8 @@ int gho_tree_force_group(const double *pos, const double *mass, int64_t np, doub
 #pragma omp for schedule(dynamic, 16)
 		for (int64_t g = 0; g < ngroups; g++) {
 			if (oom) continue;
-			const int64_t p0 = 32 * g;
-			const int nv = (int)((np - p0) < 32 ? (np - p0) : 32);
+			const int64_t p0 = (int64_t)GS * g;
+			const int nv = (int)((np - p0) < GS ? (np - p0) : GS);
 			float x[32], y[32], z[32];
 			for (int l = 0; l < nv; l++) {
 				const double *q = &pos[3 * order[p0 + l]];
@@ -487,6 +507,7 @@ int gho_tree_force_group(const double *pos, const double *mass, int64_t np, doub
 				                  (z[l + 1] - z[l]) * (z[l + 1] - z[l]);
 				if (gap > gmax) { gmax = gap; cut = l; }
 			}
+			if (!two_boxes) cut = nv - 1;
 			const gho_box A = gho_box_of(x, y, z, 0, cut + 1);
 			const gho_box B = (cut + 1 < nv) ? gho_box_of(x, y, z, cut + 1, nv) : A;
 

@@ -6,10 +6,18 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gravhopper_b200 import build as B
 
 VARIANTS = {
-    "w24": ["-DGH_GW_WARPS_PER_SM=24"],
-    "w20": ["-DGH_GW_WARPS_PER_SM=20"],
-    "w16": ["-DGH_GW_WARPS_PER_SM=16"],
+    # group walk register caps (measured: no gain, profiles/r01_walk_group_regcap_ab.txt)
+    # "w24": ["-DGH_GW_WARPS_PER_SM=24"], "w20": ["-DGH_GW_WARPS_PER_SM=20"], "w16": ["-DGH_GW_WARPS_PER_SM=16"],
+    # radix-sort scatter kernel: loop structure x register budget (measured: noise level,
+    # profiles/r01_sort_scatter_ab.txt)
+    # "rs1": ["-DGH_RS_VARIANT=1"], "rs2": ["-DGH_RS_VARIANT=2"], "rs2b3": ["-DGH_RS_VARIANT=2", "-DGH_RS_MINBLOCKS=3"],
+    # emit kernel: occupancy against registers
+    "emit8": ["-DGH_EMIT_MINBLOCKS=8"],
+    "emit10": ["-DGH_EMIT_MINBLOCKS=10"],
+    "emit12": ["-DGH_EMIT_MINBLOCKS=12"],
+    "emit16": ["-DGH_EMIT_MINBLOCKS=16"],
 }
+KERNEL = "emit_kernelINS_5Src64Ef"
 B.build()
 out = os.path.join(B.HERE, "variants")
 os.makedirs(out, exist_ok=True)
@@ -25,7 +33,7 @@ for name, o, p in procs:
         raise SystemExit(log)
     lines = log.splitlines()
     for i, l in enumerate(lines):
-        if "walk_group_kernelILi2ELb0ELb0" in l:
+        if KERNEL in l and "Compiling" in l:
             print(name, lines[i + 1].strip(), "|", lines[i + 2].strip())
     objs = [os.path.join(B.HERE, "build", s.replace(".cu", ".o")) for s in B.SOURCES if s != "tree.cu"] + [o]
     lib = os.path.join(out, "lib_%s.so" % name)
