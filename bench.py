@@ -346,7 +346,10 @@ def main():
             call = lambda: J.tree_force_position(hx, hm, ht, w["eps"], w["theta"], precision=w["prec"])  # noqa: E731
         name = "direct_summation_position" if is_direct else "tree_force_position"
         h2d = int(hx.nbytes + hm.nbytes + ht.nbytes)
-    out = call()
+    # W >= 3 untimed calls: the stateless path's device scratch and the binding's pool of page-locked
+    # result blocks (two alternate while `out` is rebound) reach steady state before the clock starts
+    for _ in range(1 if (is_direct and n > (1 << 21)) else 3):
+        out = call()
     reps = (1 if n > (1 << 21) else 3) if is_direct else 5
     barrier()
     t0 = time.perf_counter()

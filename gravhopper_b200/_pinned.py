@@ -3,7 +3,7 @@
 The reference returns a NEW ndarray per call (PyArray_NewLikeArray, _jbgrav.c:111,267,607,700) and
 so does this binding.  A fresh pageable array makes the device-to-host copy a staged transfer into
 memory whose pages are touched for the first time (measured on B200, tree N = 4M: 28.0 ms per call
-around 4.6 ms of kernels; 16.7 ms with this pool).  Large results therefore live in page-locked blocks (gh_host_alloc):
+around 4.4 ms of kernels; 8.5 ms with this pool in steady state).  Large results therefore live in page-locked blocks (gh_host_alloc):
 the copy is one DMA transfer, and a block returns to the pool when the last array viewing it is
 garbage collected, so steady-state calls neither allocate nor fault.
 
