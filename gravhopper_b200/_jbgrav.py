@@ -147,8 +147,11 @@ def tree_stats(enable=None):
         return None
     out = (C.c_int64 * 8)()
     _lib.check(L.gh_tree_last_stats(out))
+    # group walk: out[6] = groups that gave up (low 32 bits) | targets re-evaluated by the hybrid
+    # rule (high 32 bits); per-target walk: the largest per-warp entry count
     return dict(entries=out[0], cells=out[1], maxlevel=out[2], accepted=out[3], visited=out[4],
-                warp_entries=out[5], warp_entries_max=out[6], warps=out[7])
+                warp_entries=out[5], warp_entries_max=out[6] & 0xffffffff, hybrid_targets=out[6] >> 32,
+                warps=out[7])
 
 
 def tree_walk(mode=None):
@@ -162,3 +165,14 @@ def tree_walk(mode=None):
         _lib.check(L.gh_set_tree_walk(1 if mode == "group" else 0))
         return None
     return "group" if L.gh_get_tree_walk() == 1 else "target"
+
+
+def tree_walk_hybrid(kappa=None):
+    """Set / query the hybrid rule of the fp32 group walk (0 = off, the default): targets whose net
+    acceleration is below ``kappa`` times the summed magnitude of their list's contributions are
+    re-evaluated with the per-target criterion (see include/gravhopper_b200.h)."""
+    L = _lib.lib()
+    if kappa is not None:
+        _lib.check(L.gh_set_tree_walk_hybrid(float(kappa)))
+        return None
+    return float(L.gh_get_tree_walk_hybrid())

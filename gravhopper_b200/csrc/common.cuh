@@ -230,5 +230,7 @@ int launch_tree(const TreeArgs &a, TreeWorkspace *ws, cudaStream_t stream,
 int tree_last_stats(TreeWorkspace *ws, int64_t out[8]);
 int tree_walk_mode();
 void set_tree_walk_mode(int mode);
+float group_hybrid_kappa();
+void set_group_hybrid_kappa(double kappa);
 
 }  // namespace gh

@@ -340,6 +340,13 @@ int gh_set_tree_walk(int mode) {
 }
 int gh_get_tree_walk(void) { return tree_walk_mode(); }
 
+int gh_set_tree_walk_hybrid(double kappa) {
+  if (!(kappa >= 0.0) || kappa > 1.0) { set_error("gh_set_tree_walk_hybrid: kappa must be in [0, 1]"); return GH_EINVAL; }
+  set_group_hybrid_kappa(kappa);
+  return GH_OK;
+}
+double gh_get_tree_walk_hybrid(void) { return (double)group_hybrid_kappa(); }
+
 int gh_ic_sample(int kind, int64_t n, const double *params, int nparams, const double *table_x,
                  const double *table_y, int ntable, uint64_t seed, double *pos, double *vel,
                  double *mass, int mem, void *stream) {

@@ -127,6 +127,18 @@ int gh_set_tree_stats(int enable);
 int gh_set_tree_walk(int mode);
 int gh_get_tree_walk(void);
 
+/* Hybrid rule of the group walk (off by default = 0; GH_WALK_HYBRID=<kappa> sets the initial
+ * value): a target whose net acceleration is smaller than kappa times the summed magnitude of its
+ * list's contributions (estimated from a 1/16 sample) is re-evaluated with the reference's own
+ * per-target criterion.  The shared list makes the truncation errors of a group's 32 targets one
+ * coherent vector, which matters only where the net force nearly cancels (the softened core of a
+ * cusp); kappa = 0.1 re-evaluates ~0.1 % of the targets and brings the extreme tail of the
+ * relative-error distribution back to the reference tree's (CPU model: oracle.tree_force_group).
+ * In this mode out[6] of gh_tree_last_stats carries the number of re-evaluated targets in its
+ * high 32 bits. */
+int gh_set_tree_walk_hybrid(double kappa);
+double gh_get_tree_walk_hybrid(void);
+
 /* ---- device-side initial conditions (inputs of the path; gravhopper.py:1327-1607) ----------- */
 
 /* Sample n particles of an equilibrium model on the GPU with a counter-based generator

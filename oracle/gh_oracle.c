@@ -409,23 +409,28 @@ typedef struct { int64_t parent; int slot; } gho_chain; /* siblings = children o
 int gho_tree_force_group2(const double *pos, const double *mass, int64_t np, double eps, double theta,
                           int list_limit, int stack_limit, double *acc, int64_t *order_out,
                           int32_t *list_out, int64_t *stats, int nthreads, const int64_t *order_in,
-                          int group_size, int two_boxes);
+                          int group_size, int two_boxes, double *abs_out, double hybrid_kappa);
 
 int gho_tree_force_group(const double *pos, const double *mass, int64_t np, double eps, double theta,
                          int list_limit, int stack_limit, double *acc, int64_t *order_out,
                          int32_t *list_out, int64_t *stats, int nthreads)
 {
 	return gho_tree_force_group2(pos, mass, np, eps, theta, list_limit, stack_limit, acc, order_out,
-	                             list_out, stats, nthreads, NULL, 32, 1);
+	                             list_out, stats, nthreads, NULL, 32, 1, NULL, 0.0);
 }
 
 /* Design-study form of the model: the targets can be grouped along any given order (order_in, e.g.
  * a Hilbert curve instead of the depth-first/Morton order), in groups of group_size <= 32, with one
- * or two bounding boxes.  gho_tree_force_group is the kernel's configuration (NULL, 32, 1). */
+ * or two bounding boxes.  gho_tree_force_group is the kernel's configuration (NULL, 32, 1).
+ * abs_out[np] (nullable) receives S = 16 x sum of m_e / (|d_e|^2 + eps^2) over the entries at
+ * positions 0 and 1 of every 32-entry chunk of the target's list: the kernel's 1/16 sample of the
+ * summed magnitude of the contributions, against which |acc| measures how strongly they cancel.
+ * hybrid_kappa > 0: the kernel's hybrid rule -- targets with |acc| < kappa * S are re-evaluated
+ * with the per-target walk (gho_accel); stats[6] counts them. */
 int gho_tree_force_group2(const double *pos, const double *mass, int64_t np, double eps, double theta,
                           int list_limit, int stack_limit, double *acc, int64_t *order_out,
                           int32_t *list_out, int64_t *stats, int nthreads, const int64_t *order_in,
-                          int group_size, int two_boxes)
+                          int group_size, int two_boxes, double *abs_out, double hybrid_kappa)
 {
 	double min[3], max[3], boxsize, boxcenter[3];
 	if (np < 1) return GHO_OK;
@@ -480,10 +485,10 @@ int gho_tree_force_group2(const double *pos, const double *mass, int64_t np, dou
 	const float s2root = (float)(boxsize * boxsize * inv_theta2);
 	const double eps2 = eps * eps;
 	const int64_t ngroups = (np + GS - 1) / GS;
-	int64_t n_list = 0, n_tested = 0, n_iter = 0, n_fallback = 0;
+	int64_t n_list = 0, n_tested = 0, n_iter = 0, n_fallback = 0, n_redo = 0;
 	int oom = 0;
 	gho_set_threads(nthreads);
-#pragma omp parallel reduction(+ : n_list, n_tested, n_iter, n_fallback)
+#pragma omp parallel reduction(+ : n_list, n_tested, n_iter, n_fallback, n_redo)
 	{
 		int64_t cap = 4096, *lst = (int64_t *)malloc(sizeof(int64_t) * (size_t)cap);
 		gho_chain *stack = (gho_chain *)malloc(sizeof(gho_chain) * (size_t)(stack_limit + 64));
@@ -572,7 +577,7 @@ int gho_tree_force_group2(const double *pos, const double *mass, int64_t np, dou
 			for (int l = 0; l < nv; l++) {
 				const int64_t pi = order[p0 + l];
 				const double *q = &pos[3 * pi];
-				double f[3] = {0.0, 0.0, 0.0};
+				double f[3] = {0.0, 0.0, 0.0}, fabs_sum = 0.0;
 				if (fallback) {
 					gho_accel(&t, root, q, eps, theta, f, NULL);
 				} else {
@@ -582,7 +587,15 @@ int gho_tree_force_group2(const double *pos, const double *mass, int64_t np, dou
 						const double s = dx * dx + dy * dy + dz * dz + eps2;
 						const double w = (s == 0.0) ? 0.0 : nd->mass / s / sqrt(s);
 						f[0] += dx * w; f[1] += dy * w; f[2] += dz * w;
+						if ((e & 31) < 2) fabs_sum += nd->mass / s;
 					}
+				}
+				fabs_sum *= 16.0;
+				if (abs_out) abs_out[pi] = fabs_sum;
+				if (!fallback && hybrid_kappa > 0.0 &&
+				    f[0] * f[0] + f[1] * f[1] + f[2] * f[2] < hybrid_kappa * hybrid_kappa * fabs_sum * fabs_sum) {
+					gho_accel(&t, root, q, eps, theta, f, NULL);
+					n_redo++;
 				}
 				acc[3 * pi] = f[0]; acc[3 * pi + 1] = f[1]; acc[3 * pi + 2] = f[2];
 				if (list_out) list_out[pi] = fallback ? -1 : (int32_t)head;
@@ -593,7 +606,7 @@ int gho_tree_force_group2(const double *pos, const double *mass, int64_t np, dou
 		free(lst);
 		free(stack);
 	}
-	if (stats) { stats[0] = t.n; stats[1] = n_list; stats[2] = n_tested; stats[3] = n_iter; stats[4] = n_fallback; stats[5] = ngroups; }
+	if (stats) { stats[0] = t.n; stats[1] = n_list; stats[2] = n_tested; stats[3] = n_iter; stats[4] = n_fallback; stats[5] = ngroups; stats[6] = n_redo; }
 	free(order); free(level); free(t.nodes);
 	return oom ? GHO_ENOMEM : GHO_OK;
 }

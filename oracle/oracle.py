@@ -54,7 +54,8 @@ def _lib():
                                        C.POINTER(i64), C.c_int]
         lib.gho_tree_force_group.argtypes = [dp, dp, i64, C.c_double, C.c_double, C.c_int, C.c_int, dp,
                                              C.POINTER(i64), C.POINTER(C.c_int32), C.POINTER(i64), C.c_int]
-        lib.gho_tree_force_group2.argtypes = lib.gho_tree_force_group.argtypes + [C.POINTER(i64), C.c_int, C.c_int]
+        lib.gho_tree_force_group2.argtypes = lib.gho_tree_force_group.argtypes + [C.POINTER(i64), C.c_int, C.c_int, dp,
+                                                                                  C.c_double]
         lib.gho_leapfrog_step.argtypes = [dp, dp, dp, i64, C.c_double, C.c_double, C.c_double,
                                           C.c_int, dp, dp, C.c_int]
         lib.gho_half_drift.argtypes = [dp, dp, i64, C.c_double, dp]
@@ -120,17 +121,21 @@ def tree_force(pos, mass, eps, theta, nthreads=1, return_stats=False):
 
 
 def tree_force_group(pos, mass, eps, theta, list_limit=3000, stack_limit=320, nthreads=0, order=None,
-                     group_size=32, two_boxes=True):
+                     group_size=32, two_boxes=True, hybrid=0.0):
     """CPU model of the PRODUCT's fp32 group walk (walk_group_kernel), not a reference function:
     one traversal per 32 depth-first-consecutive targets, cell accepted only if _jbgrav.c:502 holds
     on the targets' two bounding boxes; groups that exceed ``list_limit`` / ``stack_limit`` use the
-    per-target walk.  Returns (acc, info) with info = dict(order, list_len (-1: group gave up),
-    nodes, list_sum, tested_sum, iterations, fallback_groups, groups)."""
+    per-target walk.  ``hybrid`` = kappa of the kernel's hybrid rule (0: off): targets with
+    |acc| < kappa * abs_sum are re-evaluated with the per-target walk.  ``order`` / ``group_size`` /
+    ``two_boxes`` are design-study knobs (the kernel: depth-first order, 32, two boxes).
+    Returns (acc, info) with info = dict(order, list_len (-1: group gave up), abs_sum, nodes,
+    list_sum, tested_sum, iterations, fallback_groups, groups, hybrid_targets)."""
     pos, mass = _f64(pos), _f64(mass)
     n = pos.shape[0]
     acc = np.zeros_like(pos)
     llen = np.zeros(n, dtype=np.int32)
-    stats = (C.c_int64 * 6)()
+    cabs = np.zeros(n)
+    stats = (C.c_int64 * 7)()
     oin = None
     if order is not None:  # design studies: another target order (default: depth-first = Morton)
         order_in = np.ascontiguousarray(order, dtype=np.int64)
@@ -140,10 +145,10 @@ def tree_force_group(pos, mass, eps, theta, list_limit=3000, stack_limit=320, nt
     _check(_lib().gho_tree_force_group2(_p(pos), _p(mass), n, float(eps), float(theta), int(list_limit),
                                         int(stack_limit), _p(acc), order.ctypes.data_as(C.POINTER(C.c_int64)),
                                         llen.ctypes.data_as(C.POINTER(C.c_int32)), stats, nthreads, oin,
-                                        int(group_size), 1 if two_boxes else 0),
+                                        int(group_size), 1 if two_boxes else 0, _p(cabs), float(hybrid)),
            "gho_tree_force_group")
-    return acc, dict(order=order, list_len=llen, nodes=stats[0], list_sum=stats[1], tested_sum=stats[2],
-                     iterations=stats[3], fallback_groups=stats[4], groups=stats[5])
+    return acc, dict(order=order, list_len=llen, abs_sum=cabs, nodes=stats[0], list_sum=stats[1], tested_sum=stats[2],
+                     iterations=stats[3], fallback_groups=stats[4], groups=stats[5], hybrid_targets=stats[6])
 
 
 def leapfrog_step(x, v, mass, dt, eps, algorithm="direct", theta=0.7, ext=None, nthreads=1):

@@ -57,3 +57,25 @@ def test_c_model_equals_python_model(golden, oracle):
         f, inf = oracle.tree_force_group(x, m, eps, 0.7, **kw)
         assert inf["fallback_groups"] == inf["groups"] and (inf["list_len"] == -1).all()
         assert np.array_equal(f, ref)
+
+
+def test_model_hybrid_rule(oracle):
+    """The hybrid rule in the model (kernel: walk_group_kernel<..., HYBRID>): targets whose net
+    acceleration is below kappa x the sampled magnitude sum get the reference tree's own value, all
+    others keep the group value; on a cuspy model that repairs the extreme tail of the relative error."""
+    from gravhopper_b200 import ic_raw
+    n = 20000
+    x, v, m = ic_raw.Hernquist(n, 1.0, 1e10, seed=42)
+    x = np.ascontiguousarray(x)
+    eps, th, kappa = 0.05, 0.7, 0.1
+    g, info = oracle.tree_force_group(x, m, eps, th)
+    h, hinfo = oracle.tree_force_group(x, m, eps, th, hybrid=kappa)
+    ref = oracle.tree_force(x, m, eps, th, nthreads=0)
+    flag = np.linalg.norm(g, axis=1) < kappa * info["abs_sum"]
+    assert hinfo["hybrid_targets"] == flag.sum() and 0 < flag.sum() < 0.03 * n  # 0.1 % at N >= 200k
+    assert np.array_equal(h[flag], ref[flag]) and np.array_equal(h[~flag], g[~flag])
+    assert np.array_equal(info["abs_sum"], hinfo["abs_sum"])
+    d = oracle.direct_summation_position(x, m, x, eps, nthreads=0)
+    eh, er = relerr(h, d), relerr(ref, d)
+    assert eh.mean() <= er.mean() and np.percentile(eh, 99) <= np.percentile(er, 99)
+    assert eh.max() <= er.max() * 1.0001
