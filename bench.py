@@ -438,12 +438,22 @@ def main():
         # `ncu --set full` (profiles/r01_walk_group_f32_N4M_v2.txt): 591.8 MB + 192.3 MB; the
         # algorithmic bytes are 32 B x 6.2M entries read once + 64 B x N targets/epilogue = 0.47 GB
         traffic = 784.2e6 if (mode == "group" and n == (1 << 22) and world == 1) else None
+        # the build (everything of the step that is not the walk kernel) against the HBM roofline:
+        # SURVEY 8d's algorithmic bytes per particle-step, 190 + 24 x radix passes (8) = 382 B
+        build_ms = ms_per_step - kernel_ms
+        hbm_peak = float(peaks.get("hbm_gbs") or 0.0) or 6650.0
+        build_gbs = 382.0 * n / (build_ms * 1e-3) / 1e9
+        build_roofline = {"bound": "hbm", "achieved": build_gbs, "peak": hbm_peak, "unit": "GB/s",
+                          "frac": build_gbs / hbm_peak, "ms": build_ms,
+                          "how": "382 B per particle (SURVEY 8d: 190 + 24 x 8 radix passes) x N / (ms_per_step - walk "
+                                 "kernel ms); peak = %s" % ("MEASURED_PEAKS.json hbm_gbs" if peaks.get("hbm_gbs")
+                                                            else "B200_PROFILING.md fallback 7.7 TB/s")}
         roofline = {"bound": bound, "achieved": achieved, "peak": fp32_peak_tflops,
                     "unit": "TFLOP/s", "frac": achieved / fp32_peak_tflops, "traffic": traffic,
                     "kernel": kernel, "kernel_ms": kernel_ms, "walk": mode,
                     "accepted_per_target": acc_per, "visited_per_target": vis_per,
                     "tree_entries": st["entries"], "tree_cells": st["cells"], "deepest_level": st["maxlevel"],
-                    "build_ms": ms_per_step - kernel_ms, "accuracy": accuracy, "how": how}
+                    "build_ms": build_ms, "build_roofline": build_roofline, "accuracy": accuracy, "how": how}
 
     line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
