@@ -446,8 +446,9 @@ def main():
         build_roofline = {"bound": "hbm", "achieved": build_gbs, "peak": hbm_peak, "unit": "GB/s",
                           "frac": build_gbs / hbm_peak, "ms": build_ms,
                           "how": "382 B per particle (SURVEY 8d: 190 + 24 x 8 radix passes) x N / (ms_per_step - walk "
-                                 "kernel ms); peak = %s" % ("MEASURED_PEAKS.json hbm_gbs" if peaks.get("hbm_gbs")
-                                                            else "B200_PROFILING.md fallback 7.7 TB/s")}
+                                 "kernel ms); peak = %s" % ("MEASURED_PEAKS.json hbm_gbs (of measured)"
+                                                            if peaks.get("hbm_gbs")
+                                                            else "6.65 TB/s (of fallback, B200_PROFILING.md)")}
         roofline = {"bound": bound, "achieved": achieved, "peak": fp32_peak_tflops,
                     "unit": "TFLOP/s", "frac": achieved / fp32_peak_tflops, "traffic": traffic,
                     "kernel": kernel, "kernel_ms": kernel_ms, "walk": mode,
