@@ -169,6 +169,51 @@ def cpu_baseline_tree(w, ntargets=16384):
                       % (len(w["m"]), ntargets, dt)}
 
 
+def tree_roofline(n, world, ms_per_step, kernel_ms, st, mode, accuracy, peaks, fp32_peak_tflops):
+    """roofline object of the tree workloads: the walk kernel against the FP32 FMA peak (20 flop x
+    list entries), the build against the HBM roofline (SURVEY 8d bytes per particle-step)."""
+    acc_per = st["accepted"] / float(n)
+    vis_per = st["visited"] / float(n)
+    achieved = (n / world) * acc_per * FLOP_PER_INTERACTION / (kernel_ms * 1e-3) / 1e12
+    if mode == "group":
+        kernel = "walk_group_kernel"
+        how = ("20 flop x interaction-list entries (%.0f per target: one warp-cooperative traversal per 32 "
+               "Morton-consecutive targets with the bounding-box form of the reference's opening test, which "
+               "opens every cell the reference opens and some more; the reference's own per-target set is "
+               "~1.9x shorter) / CUDA-event time of the walk kernel, against the FP32 FMA peak; "
+               "visited_per_target = entries tested by the target's group (shared by its 32 targets); the build "
+               "(ms_per_step - kernel_ms) is HBM-streaming bound" % acc_per)
+        bound = "fp32_fma (list evaluation) + issue (traversal)"
+    else:
+        kernel = "walk_kernel"
+        how = ("20 flop x accepted nodes (the reference's own accepted set: %.0f per target) / CUDA-event time "
+               "of the walk kernel, against the FP32 FMA peak; ncu (profiles/) shows this walk is entry-load "
+               "latency / instruction-issue bound; the build (ms_per_step - kernel_ms) is HBM-streaming bound"
+               % acc_per)
+        bound = "issue (walk); fp32_fma peak quoted"
+    # dram__bytes_read.sum + dram__bytes_write.sum of walk_group_kernel at N = 2^22 on one GPU from
+    # `ncu --set full` (profiles/r01_walk_group_f32_N4M_v2.txt): 591.8 MB + 192.3 MB; the
+    # algorithmic bytes are 32 B x 6.2M entries read once + 64 B x N targets/epilogue = 0.47 GB
+    traffic = 784.2e6 if (mode == "group" and n == (1 << 22) and world == 1) else None
+    # the build (everything of the step that is not the walk kernel) against the HBM roofline:
+    # SURVEY 8d's algorithmic bytes per particle-step, 190 + 24 x radix passes (8) = 382 B
+    build_ms = ms_per_step - kernel_ms
+    hbm_peak = float(peaks.get("hbm_gbs") or 0.0) or 6650.0
+    build_gbs = 382.0 * n / (build_ms * 1e-3) / 1e9
+    build_roofline = {"bound": "hbm", "achieved": build_gbs, "peak": hbm_peak, "unit": "GB/s",
+                      "frac": build_gbs / hbm_peak, "ms": build_ms,
+                      "how": "382 B per particle (SURVEY 8d: 190 + 24 x 8 radix passes) x N / (ms_per_step - walk "
+                             "kernel ms); peak = %s" % ("MEASURED_PEAKS.json hbm_gbs (of measured)"
+                                                        if peaks.get("hbm_gbs")
+                                                        else "6.65 TB/s (of fallback, B200_PROFILING.md)")}
+    return {"bound": bound, "achieved": achieved, "peak": fp32_peak_tflops,
+            "unit": "TFLOP/s", "frac": achieved / fp32_peak_tflops, "traffic": traffic,
+            "kernel": kernel, "kernel_ms": kernel_ms, "walk": mode,
+            "accepted_per_target": acc_per, "visited_per_target": vis_per,
+            "tree_entries": st["entries"], "tree_cells": st["cells"], "deepest_level": st["maxlevel"],
+            "build_ms": build_ms, "build_roofline": build_roofline, "accuracy": accuracy, "how": how}
+
+
 _W = None  # workload shared with forked reference workers (no per-step pickling of the sources)
 
 
@@ -399,9 +444,6 @@ def main():
         st = J.tree_stats()
         J.tree_stats(False)
         mode = J.tree_walk()
-        acc_per = st["accepted"] / float(n)
-        vis_per = st["visited"] / float(n)
-        achieved = (n / world) * acc_per * FLOP_PER_INTERACTION / (kernel_ms * 1e-3) / 1e12
         # accuracy beside the rate (north_star: "reported with accuracy matching the reference"):
         # per-particle relative acceleration error against fp64 direct summation on sampled
         # targets, for the timed fp32 walk and for the reference's criterion (the fp64 per-target
@@ -418,43 +460,7 @@ def main():
                     "max": float(e.max())}
         accuracy = {"vs": "fp64 direct summation, 4096 sampled targets, same theta",
                     "timed_fp32_walk": errs(a32[sel]), "reference_criterion_fp64_walk": errs(r64)}
-        if mode == "group":
-            kernel = "walk_group_kernel"
-            how = ("20 flop x interaction-list entries (%.0f per target: one warp-cooperative traversal per 32 "
-                   "Morton-consecutive targets with the bounding-box form of the reference's opening test, which "
-                   "opens every cell the reference opens and some more; the reference's own per-target set is "
-                   "~1.9x shorter) / CUDA-event time of the walk kernel, against the FP32 FMA peak; "
-                   "visited_per_target = entries tested by the target's group (shared by its 32 targets); the build "
-                   "(ms_per_step - kernel_ms) is HBM-streaming bound" % acc_per)
-            bound = "fp32_fma (list evaluation) + issue (traversal)"
-        else:
-            kernel = "walk_kernel"
-            how = ("20 flop x accepted nodes (the reference's own accepted set: %.0f per target) / CUDA-event time "
-                   "of the walk kernel, against the FP32 FMA peak; ncu (profiles/) shows this walk is entry-load "
-                   "latency / instruction-issue bound; the build (ms_per_step - kernel_ms) is HBM-streaming bound"
-                   % acc_per)
-            bound = "issue (walk); fp32_fma peak quoted"
-        # dram__bytes_read.sum + dram__bytes_write.sum of walk_group_kernel at N = 2^22 on one GPU from
-        # `ncu --set full` (profiles/r01_walk_group_f32_N4M_v2.txt): 591.8 MB + 192.3 MB; the
-        # algorithmic bytes are 32 B x 6.2M entries read once + 64 B x N targets/epilogue = 0.47 GB
-        traffic = 784.2e6 if (mode == "group" and n == (1 << 22) and world == 1) else None
-        # the build (everything of the step that is not the walk kernel) against the HBM roofline:
-        # SURVEY 8d's algorithmic bytes per particle-step, 190 + 24 x radix passes (8) = 382 B
-        build_ms = ms_per_step - kernel_ms
-        hbm_peak = float(peaks.get("hbm_gbs") or 0.0) or 6650.0
-        build_gbs = 382.0 * n / (build_ms * 1e-3) / 1e9
-        build_roofline = {"bound": "hbm", "achieved": build_gbs, "peak": hbm_peak, "unit": "GB/s",
-                          "frac": build_gbs / hbm_peak, "ms": build_ms,
-                          "how": "382 B per particle (SURVEY 8d: 190 + 24 x 8 radix passes) x N / (ms_per_step - walk "
-                                 "kernel ms); peak = %s" % ("MEASURED_PEAKS.json hbm_gbs (of measured)"
-                                                            if peaks.get("hbm_gbs")
-                                                            else "6.65 TB/s (of fallback, B200_PROFILING.md)")}
-        roofline = {"bound": bound, "achieved": achieved, "peak": fp32_peak_tflops,
-                    "unit": "TFLOP/s", "frac": achieved / fp32_peak_tflops, "traffic": traffic,
-                    "kernel": kernel, "kernel_ms": kernel_ms, "walk": mode,
-                    "accepted_per_target": acc_per, "visited_per_target": vis_per,
-                    "tree_entries": st["entries"], "tree_cells": st["cells"], "deepest_level": st["maxlevel"],
-                    "build_ms": build_ms, "build_roofline": build_roofline, "accuracy": accuracy, "how": how}
+        roofline = tree_roofline(n, world, ms_per_step, kernel_ms, st, mode, accuracy, peaks, fp32_peak_tflops)
 
     line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",

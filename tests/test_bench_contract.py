@@ -52,3 +52,29 @@ def test_gpu_arm_line():
     assert d["e2e"]["value"] <= d["value"] * 1.05
     if d.get("clocks"):
         assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+
+
+def test_tree_roofline_object():
+    """bench.tree_roofline assembles the tree workloads' roofline object from measured inputs; feed it
+    the numbers of the recorded N = 4M run (profiles/r01_bench_tree_N4M_1gpu.json)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    n = 1 << 22
+    st = {"accepted": int(1133.7616 * n), "visited": int(1372.0795 * n), "entries": 6214160, "cells": 2019856,
+          "maxlevel": 18}
+    acc = {"vs": "x", "timed_fp32_walk": {}, "reference_criterion_fp64_walk": {}}
+    r = bench.tree_roofline(n, 1, 4.377, 3.000, st, "group", acc, {"hbm_gbs": 6541.1}, 74.44992)
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "kernel", "build_roofline", "accuracy"):
+        assert k in r
+    assert r["kernel"] == "walk_group_kernel" and r["unit"] == "TFLOP/s"
+    assert abs(r["achieved"] - 1133.7616 * n * 20 / 3.0e-3 / 1e12) < 1e-6 and 0.40 < r["frac"] < 0.45
+    b = r["build_roofline"]
+    assert b["bound"] == "hbm" and b["unit"] == "GB/s" and b["peak"] == 6541.1
+    assert abs(b["achieved"] - 382.0 * n / 1.377e-3 / 1e9) < 1e-6 and 0.15 < b["frac"] < 0.2
+    assert "of measured" in b["how"]
+    t = bench.tree_roofline(n, 2, 4.377, 3.000, st, "target", acc, {}, 74.44992)
+    assert t["kernel"] == "walk_kernel" and t["traffic"] is None
+    assert t["build_roofline"]["peak"] == 6650.0 and "of fallback" in t["build_roofline"]["how"]
+    assert abs(t["achieved"] - r["achieved"] / 2) < 1e-9
