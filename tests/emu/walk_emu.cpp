@@ -172,4 +172,30 @@ int emu_walk_target(const float *nodes, int nentries, const double *sorted4, con
   return 0;
 }
 
+// The fp64 per-target walk (walk_kernel<double>): entries are gh::Node<double> (8 doubles, absolute
+// coordinates, s2 = side^2/theta^2, -1 for leaves) plus the skip array; targets are arbitrary
+// positions (nt,3) in the given order (order == nullptr: identity).
+int emu_walk_target64(const double *nodes, const int *skips, int nentries, const double *tpos, const int *order,
+                      int64_t ni, const double *root, double eps2, double inv_theta2, double *acc_out,
+                      unsigned long long *stats4, int flags) {
+  using namespace gh;
+  TargetsView tv;
+  tv.sorted = nullptr;
+  tv.pos64 = tpos;
+  tv.pos32 = nullptr;
+  tv.order = order;
+  tv.order_offset = 0;
+  Epilogue ep;
+  std::memset(&ep, 0, sizeof(ep));
+  ep.mode = EP_ACC;
+  ep.acc_out = acc_out;
+  const Node<double> *nd = reinterpret_cast<const Node<double> *>(nodes);
+  const int64_t nwarps = (ni + 31) / 32;
+  if (flags & 2)
+    run_warps(nwarps, [&] { walk_kernel<double, true, true, false>(nd, skips, nentries, tv, ni, root, false, eps2, inv_theta2, ep, stats4); });
+  else
+    run_warps(nwarps, [&] { walk_kernel<double, true, false, false>(nd, skips, nentries, tv, ni, root, false, eps2, inv_theta2, ep, stats4); });
+  return 0;
+}
+
 }  // extern "C"

@@ -41,6 +41,7 @@ def emu():
     lib.emu_walk_group.argtypes = [vp, C.c_int, vp, vp, i64, vp, C.c_float, C.c_double, C.c_int, C.c_float, vp,
                                    vp, C.c_int]
     lib.emu_walk_target.argtypes = [vp, C.c_int, vp, vp, i64, vp, C.c_float, C.c_double, vp, vp, C.c_int]
+    lib.emu_walk_target64.argtypes = [vp, vp, C.c_int, vp, vp, i64, vp, C.c_double, C.c_double, vp, vp, C.c_int]
     return lib
 
 
@@ -154,3 +155,53 @@ def test_hybrid_kernel_path_equals_the_model(emu, oracle, system):
     assert 0 < changed.sum() <= 1.2 * info["hybrid_targets"] + 2
     ref = oracle.tree_force(x, m, eps, 0.7)
     assert relerr(acc[changed], ref[changed]).max() <= 2e-5       # re-evaluated = the reference's value
+
+
+def build_entries64(x, m, eps, theta):
+    """fp64 entry array + skip links as emit_kernel<., double> writes them (absolute coordinates)."""
+    sys.setrecursionlimit(max(sys.getrecursionlimit(), 20000))
+    root = G.build(x, m, eps)
+    inv_theta2 = float("inf") if theta == 0 else 1.0 / (theta * theta)
+    rows, skips = [], []
+
+    def rec(nd):
+        e = len(rows)
+        rows.append(None)
+        skips.append(0)
+        if nd.count == 1:
+            p = nd.p
+            rows[e] = (0.0, x[p, 0], 0.0, x[p, 1], 0.0, x[p, 2], -1.0, m[p])
+            skips[e] = e + 1
+            return
+        for ch in nd.child:
+            if ch is not None:
+                rec(ch)
+        com = nd.mx / nd.m
+        rows[e] = (nd.c[0], com[0], nd.c[1], com[1], nd.c[2], com[2], (nd.size * nd.size) * inv_theta2, nd.m)
+        skips[e] = len(rows)
+    rec(root)
+    rootblk = np.zeros(10)
+    rootblk[:3] = root.c
+    rootblk[3] = root.size
+    return np.array(rows, dtype=np.float64), np.array(skips, dtype=np.int32), rootblk
+
+
+@pytest.mark.parametrize("theta,eps", [(0.7, 5e-5), (0.3, 5e-5), (0.5, 0.0)])
+def test_fp64_walk_kernel_source_equals_the_reference_tree(emu, oracle, golden, theta, eps):
+    """walk_kernel<double> (the default-precision tree walk) on the CPU: the reference's node set
+    (accepted / visited counts equal the oracle's exactly) and its forces to rounding, for the
+    particles themselves and for separate target positions -- the GPU parity test of
+    tests/test_gpu_parity.py, executed here on the kernel source."""
+    x, m = golden["c1_pos"][:1500], golden["c1_mass"][:1500]
+    nodes, skips, rootblk = build_entries64(x, m, eps, theta)
+    for tpos in (x, golden["c1_force_pos"]):
+        tpos = np.ascontiguousarray(tpos)
+        acc = np.zeros_like(tpos)
+        st = np.zeros(4, dtype=np.uint64)
+        emu.emu_walk_target64(nodes.ctypes.data, skips.ctypes.data, len(nodes), tpos.ctypes.data, None, len(tpos),
+                              rootblk.ctypes.data, eps * eps, 1.0 / (theta * theta), acc.ctypes.data,
+                              st.ctypes.data, 1 | (2 if eps == 0.0 else 0))
+        ref, so = oracle.tree_force_position(x, m, tpos, eps, theta, return_stats=True)
+        assert len(nodes) == so["nodes"]
+        assert int(st[0]) == so["accepted"] and int(st[1]) == so["visited"]
+        assert relerr(acc, ref).max() <= 1e-12
