@@ -161,6 +161,7 @@ scan_phase3(In in, int64_t n, const T *__restrict__ warpoff, T *__restrict__ P /
   }
 }
 
+#ifndef GH_HOST_EMU  // launch sequence: the host emulation (tests/emu) has its own
 // P[0..n]: P[0] = identity, P[q+1] = in(0) (+) ... (+) in(q).  Recursion over 256-element warp
 // chunks (depth 3 at n = 16.7M, 4 beyond); `levels` supplies scratch for the per-level totals.
 template <class T, class In>
@@ -184,6 +185,7 @@ static int chunked_scan(In in, int64_t n, T *P, DeviceBuffer *levels, int depth,
   GH_LAUNCH_CHECK();
   return GH_OK;
 }
+#endif  // GH_HOST_EMU
 
 // ---- radix sort ------------------------------------------------------------------------------
 static constexpr int RS_THREADS = 256;
@@ -388,6 +390,7 @@ rs_scatter_kernel(const uint64_t *__restrict__ kin, const int *__restrict__ vin,
   }
 }
 
+#ifndef GH_HOST_EMU  // launch sequences: the host emulation (tests/emu) has its own
 struct RadixScratch {
   DeviceBuffer hist, gtot;
   void release() {
@@ -429,4 +432,5 @@ static int radix_sort_pairs(uint64_t *kA, int *vA, uint64_t *kB, int *vB, int64_
   return GH_OK;
 }
 
+#endif  // GH_HOST_EMU
 }  // namespace gh

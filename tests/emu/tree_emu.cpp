@@ -1,0 +1,141 @@
+// tree_emu.cpp -- the tree BUILD kernels (gravhopper_b200/csrc/build.cuh, sortscan.cuh) and the walk
+// kernels (walk.cuh), compiled for the host and run through emu::launch: TEST INFRASTRUCTURE.
+// emu_tree_build mirrors the launch sequence of tree_impl (csrc/tree.cu): bbox -> keys -> stable LSD
+// radix sort -> common levels -> pre-order offsets -> gather -> moment scan -> emit; the kernels are
+// the product's own source, the sequence is restated here (tree.cu's talks to the CUDA runtime).
+#include "emu_shim.h"
+
+#include "../../gravhopper_b200/csrc/build.cuh"
+
+#include <cstdlib>
+
+namespace gh {
+void set_error(const char *, ...) {}
+int64_t &launch_counter() { static thread_local int64_t c = 0; return c; }
+}  // namespace gh
+
+using namespace gh;
+
+static inline unsigned nblk(int64_t n, int b) { return (unsigned)((n + b - 1) / b); }
+
+// chunked_scan of sortscan.cuh, launch for launch
+template <class T, class In> static void emu_scan(In in, int64_t n, T *P) {
+  if (n <= 0) return;
+  if (n <= SCAN_WARP_ELEMS) {
+    emu::launch(1, 32, [&] { scan_phase3<T, In>(in, n, nullptr, P); });
+    return;
+  }
+  const int64_t nw = (n + SCAN_WARP_ELEMS - 1) / SCAN_WARP_ELEMS;
+  const unsigned nsb = (unsigned)((nw * 32 + SCAN_THREADS - 1) / SCAN_THREADS);
+  std::vector<T> buf((size_t)(2 * nw + 1));
+  T *totals = buf.data(), *prefix = totals + nw;
+  emu::launch(nsb, SCAN_THREADS, [&] { scan_phase1<T, In>(in, n, totals); });
+  emu_scan<T, InArray<T>>(InArray<T>{totals}, nw, prefix);
+  emu::launch(nsb, SCAN_THREADS, [&] { scan_phase3<T, In>(in, n, prefix, P); });
+}
+
+// radix_sort_pairs of sortscan.cuh, launch for launch
+static bool emu_sort(uint64_t *kA, int *vA, uint64_t *kB, int *vB, int64_t n, int nbits) {
+  if (n <= 1) return false;
+  const int nblocks = (int)((n + RS_TILE - 1) / RS_TILE);
+  const int npass = (nbits + 7) / 8;
+  std::vector<int> hist((size_t)RS_RADIX * nblocks), gtot((size_t)RS_RADIX * npass, 0);
+  uint64_t *kin = kA, *kout = kB;
+  int *vin = vA, *vout = vB;
+  bool inB = false;
+  for (int pass = 0; pass < npass; pass++) {
+    const int shift = 8 * pass;
+    int *g = gtot.data() + RS_RADIX * pass;
+    emu::launch((unsigned)nblocks, RS_THREADS, [&] { rs_hist_kernel(kin, n, shift, hist.data(), nblocks, g); });
+    emu::launch(RS_RADIX, RS_THREADS, [&] { rs_rowscan_kernel(hist.data(), nblocks); });
+    emu::launch((unsigned)nblocks, RS_THREADS, [&] { rs_scatter_kernel(kin, vin, kout, vout, n, shift, hist.data(), g, nblocks); });
+    std::swap(kin, kout);
+    std::swap(vin, vout);
+    inB = !inB;
+  }
+  return inB;
+}
+
+template <class Real>
+static int build_impl(const double *pos, const double *mass, int64_t n, double eps, double theta, void *nodes_out,
+                      int *skips_out, int nodes_cap, double *sorted_out, int *order_out, double *root_out,
+                      int *info_out) {
+  using Mom = typename MomentOf<Real>::type;
+  const int levels = (sizeof(Real) == 8) ? LEVELS_MAX : LEVELS_HI;
+  const bool deep = levels > LEVELS_HI;
+  const bool rel_origin = (sizeof(Real) == 4);
+  Src64 src{pos, mass};
+  std::vector<double> root(ROOT_DOUBLES), part(6 * 1024);
+  const int nb = (int)((n + 256 * 8 - 1) / (256 * 8) < 1024 ? (n + 256 * 8 - 1) / (256 * 8) : 1024);
+  emu::launch((unsigned)nb, 256, [&] { bbox_stage1<Src64>(src, n, part.data()); });
+  emu::launch(1, 256, [&] { bbox_stage2(part.data(), nb, eps, root.data()); });
+
+  std::vector<uint64_t> hi(n), hi2(n), lo(deep ? n : 0), lo2(deep ? n : 0), lo3(deep ? n : 0);
+  std::vector<int> idx(n), idx2(n);
+  uint64_t *lop = deep ? lo.data() : nullptr;
+  emu::launch(nblk(n, 256), 256, [&] { keys_kernel<Src64>(src, n, root.data(), levels, hi.data(), lop, idx.data()); }, true);
+
+  const uint64_t *shi, *slo = nullptr;
+  const int *sidx;
+  if (deep) {
+    lo3 = lo;
+    bool inB = emu_sort(lo.data(), idx.data(), lo2.data(), idx2.data(), n, 63);
+    int *order1 = inB ? idx2.data() : idx.data();
+    int *other1 = inB ? idx.data() : idx2.data();
+    uint64_t *hs = inB ? lo.data() : lo2.data();
+    emu::launch(nblk(n, 256), 256, [&] { gather_u64(hi.data(), order1, n, hs); }, true);
+    inB = emu_sort(hs, order1, hi2.data(), other1, n, 63);
+    shi = inB ? hi2.data() : hs;
+    sidx = inB ? other1 : order1;
+    uint64_t *lsorted = (shi == hi2.data()) ? hs : hi2.data();
+    emu::launch(nblk(n, 256), 256, [&] { gather_u64(lo3.data(), sidx, n, lsorted); }, true);
+    slo = lsorted;
+  } else {
+    const bool inB = emu_sort(hi.data(), idx.data(), hi2.data(), idx2.data(), n, 63);
+    shi = inB ? hi2.data() : hi.data();
+    sidx = inB ? idx2.data() : idx.data();
+  }
+
+  std::vector<signed char> clev(n);
+  std::vector<int> cnt(n + 1), base(n + 1);
+  emu::launch(nblk(n, 256), 256, [&] { levels_kernel(shi, slo, n, levels, clev.data(), cnt.data()); }, true);
+  emu_scan<int, InArray<int>>(InArray<int>{cnt.data()}, n, base.data());
+
+  std::vector<double4> sp(n);
+  emu::launch(nblk(n, 256), 256, [&] { gather_sorted_kernel<Src64>(src, sidx, n, sp.data()); }, true);
+  std::vector<Mom> P(n + 1);
+  if (sizeof(Real) == 4)
+    emu_scan<D4, InParticlesRel>(InParticlesRel{sp.data(), root.data()}, n, reinterpret_cast<D4 *>(P.data()));
+  else
+    emu_scan<DD4, InParticles>(InParticles{sp.data()}, n, reinterpret_cast<DD4 *>(P.data()));
+
+  const int nentries = base[n];
+  info_out[0] = nentries;
+  if (nentries > nodes_cap) return 1;
+  Entries<Real> E{reinterpret_cast<Node<Real> *>(nodes_out), sizeof(Real) == 4 ? nullptr : skips_out};
+  const double inv_theta2 = 1.0 / (theta * theta);
+  int maxlevel = 0;
+  emu::launch(nblk(n, 128), 128, [&] {
+    emit_kernel<Src64, Real>(sp.data(), shi, slo, clev.data(), base.data(), P.data(), n, root.data(), rel_origin,
+                             inv_theta2, E, &maxlevel);
+  }, true);
+  info_out[1] = maxlevel;
+  std::memcpy(sorted_out, sp.data(), sizeof(double4) * (size_t)n);
+  std::memcpy(order_out, sidx, sizeof(int) * (size_t)n);
+  std::memcpy(root_out, root.data(), sizeof(double) * ROOT_DOUBLES);
+  return 0;
+}
+
+extern "C" {
+// prec 32: Node<float> entries (8 floats each) into nodes_out; prec 64: Node<double> + skips_out.
+// info_out = {entries, deepest cell level}.  Returns 1 if nodes_cap is too small (info_out[0] = need).
+int emu_tree_build(int prec, const double *pos, const double *mass, int64_t n, double eps, double theta,
+                   void *nodes_out, int *skips_out, int nodes_cap, double *sorted_out, int *order_out,
+                   double *root_out, int *info_out) {
+  if (prec == 32)
+    return build_impl<float>(pos, mass, n, eps, theta, nodes_out, skips_out, nodes_cap, sorted_out, order_out,
+                             root_out, info_out);
+  return build_impl<double>(pos, mass, n, eps, theta, nodes_out, skips_out, nodes_cap, sorted_out, order_out,
+                            root_out, info_out);
+}
+}

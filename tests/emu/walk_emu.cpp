@@ -4,85 +4,7 @@
 // values through a barrier, __shared__ arrays become statics shared by the 32 threads, and the
 // three inline-PTX spots are replaced under GH_HOST_EMU.  One warp (= one CTA, WPC = 1) runs at a
 // time.  Built by tests/test_walk_emu.py:  g++ -O1 -std=c++20 -shared -fPIC -pthread.
-#include <atomic>
-#include <barrier>
-#include <cmath>
-#include <cstdint>
-#include <cstring>
-#include <thread>
-#include <vector>
-
-#define GH_HOST_EMU 1
-#define __launch_bounds__(...)
-#include <cuda_runtime.h>
-
-// ---- per-thread CUDA builtins ---------------------------------------------------------------------
-struct EmuDim3 { unsigned x = 0, y = 0, z = 0; };
-static thread_local EmuDim3 threadIdx, blockIdx, blockDim, gridDim;
-
-struct EmuWarp {
-  std::barrier<> bar{32};
-  uint64_t slot[32];
-};
-static EmuWarp *g_warp = nullptr;
-static thread_local int t_lane = 0;
-
-template <class T> static inline uint64_t emu_bits(T v) { uint64_t b = 0; std::memcpy(&b, &v, sizeof(T)); return b; }
-template <class T> static inline T emu_from(uint64_t b) { T v; std::memcpy(&v, &b, sizeof(T)); return v; }
-
-static inline void __syncwarp(unsigned = 0xffffffffu) { g_warp->bar.arrive_and_wait(); }
-template <class T> static inline T __shfl_down_sync(unsigned, T v, int delta) {
-  g_warp->slot[t_lane] = emu_bits(v);
-  g_warp->bar.arrive_and_wait();
-  const int src = t_lane + delta;
-  const T r = (src < 32) ? emu_from<T>(g_warp->slot[src]) : v;
-  g_warp->bar.arrive_and_wait();
-  return r;
-}
-static inline unsigned __ballot_sync(unsigned, bool pred) {
-  g_warp->slot[t_lane] = pred ? 1u : 0u;
-  g_warp->bar.arrive_and_wait();
-  unsigned m = 0;
-  for (int l = 0; l < 32; l++) m |= (unsigned)(g_warp->slot[l] & 1u) << l;
-  g_warp->bar.arrive_and_wait();
-  return m;
-}
-static inline bool __any_sync(unsigned mask, bool pred) { return __ballot_sync(mask, pred) != 0u; }
-static inline int __reduce_min_sync(unsigned, int v) {
-  g_warp->slot[t_lane] = emu_bits(v);
-  g_warp->bar.arrive_and_wait();
-  int r = emu_from<int>(g_warp->slot[0]);
-  for (int l = 1; l < 32; l++) { const int o = emu_from<int>(g_warp->slot[l]); r = o < r ? o : r; }
-  g_warp->bar.arrive_and_wait();
-  return r;
-}
-static inline int __reduce_max_sync(unsigned, int v) {
-  g_warp->slot[t_lane] = emu_bits(v);
-  g_warp->bar.arrive_and_wait();
-  int r = emu_from<int>(g_warp->slot[0]);
-  for (int l = 1; l < 32; l++) { const int o = emu_from<int>(g_warp->slot[l]); r = o > r ? o : r; }
-  g_warp->bar.arrive_and_wait();
-  return r;
-}
-static inline int __popc(unsigned v) { return __builtin_popcount(v); }
-static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
-static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
-static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
-static inline float2 __fadd2_rn(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-static inline float2 __fmul2_rn(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
-static inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
-static inline double __dmul_rn(double a, double b) { return a * b; }
-static inline double __dadd_rn(double a, double b) { return a + b; }
-static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) {
-  return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
-}
-static inline unsigned long long atomicMax(unsigned long long *p, unsigned long long v) {
-  unsigned long long old = __atomic_load_n(p, __ATOMIC_RELAXED);
-  while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
-  return old;
-}
-#undef __shared__
-#define __shared__ static
+#include "emu_shim.h"
 
 #include "../../gravhopper_b200/csrc/walk.cuh"
 
@@ -92,25 +14,7 @@ void set_error(const char *, ...) {}
 }
 
 // ---- driver ---------------------------------------------------------------------------------------
-template <class F> static void run_warps(int64_t nwarps, F body) {
-  for (int64_t w = 0; w < nwarps; w++) {
-    EmuWarp warp;
-    g_warp = &warp;
-    std::vector<std::thread> th;
-    th.reserve(32);
-    for (int l = 0; l < 32; l++)
-      th.emplace_back([&, l, w] {
-        t_lane = l;
-        threadIdx.x = (unsigned)l;
-        blockIdx.x = (unsigned)w;
-        blockDim.x = 32;
-        gridDim.x = (unsigned)nwarps;
-        body();
-      });
-    for (auto &t : th) t.join();
-  }
-  g_warp = nullptr;
-}
+template <class F> static void run_warps(int64_t nwarps, F body) { emu::launch((unsigned)nwarps, 32, body); }
 
 extern "C" {
 
