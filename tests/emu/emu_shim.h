@@ -32,15 +32,26 @@ struct Warp {
 static thread_local Warp *t_warp = nullptr;
 static thread_local std::barrier<> *t_block = nullptr;
 static thread_local int t_lane = 0;
+static unsigned g_block_y = 0, g_grid_y = 1;  // row of a 2-D grid being run
+static int g_and_flag = 1;                     // __syncthreads_and accumulator
 
 template <class T> static inline uint64_t bits(T v) { static_assert(sizeof(T) <= 8, ""); uint64_t b = 0; std::memcpy(&b, &v, sizeof(T)); return b; }
 template <class T> static inline T from(uint64_t b) { T v; std::memcpy(&v, &b, sizeof(T)); return v; }
 
-template <class F> static void launch(unsigned grid, unsigned block, F body, bool serial = false) {
+template <class F> static void launch(unsigned grid, unsigned block, F body, bool serial = false, unsigned grid_y = 1) {
+  if (grid_y > 1) {  // 2-D grid: rows one after another
+    for (unsigned y = 0; y < grid_y; y++) {
+      g_block_y = y; g_grid_y = grid_y;
+      launch(grid, block, body, serial, 1);
+    }
+    g_block_y = 0; g_grid_y = 1;
+    return;
+  }
   if (serial) {  // kernels without collectives or barriers: plain loops
     for (unsigned b = 0; b < grid; b++)
       for (unsigned t = 0; t < block; t++) {
         threadIdx.x = t; blockIdx.x = b; blockDim.x = block; gridDim.x = grid;
+        blockIdx.y = g_block_y; gridDim.y = g_grid_y;
         t_lane = (int)(t & 31);
         body();
       }
@@ -57,6 +68,7 @@ template <class F> static void launch(unsigned grid, unsigned block, F body, boo
   for (unsigned t = 0; t < block; t++)
     th.emplace_back([&, t] {
       threadIdx.x = t; blockDim.x = block; gridDim.x = grid;
+      blockIdx.y = g_block_y; gridDim.y = g_grid_y;
       t_lane = (int)(t & 31);
       t_warp = warps[t >> 5].get();
       t_block = &blockbar;
@@ -71,6 +83,15 @@ template <class F> static void launch(unsigned grid, unsigned block, F body, boo
 }  // namespace emu
 
 static inline void __syncthreads() { emu::t_block->arrive_and_wait(); }
+static inline int __syncthreads_and(int pred) {
+  if (!pred) __atomic_store_n(&emu::g_and_flag, 0, __ATOMIC_RELAXED);
+  emu::t_block->arrive_and_wait();
+  const int r = __atomic_load_n(&emu::g_and_flag, __ATOMIC_RELAXED);
+  emu::t_block->arrive_and_wait();
+  if (threadIdx.x == 0) __atomic_store_n(&emu::g_and_flag, 1, __ATOMIC_RELAXED);
+  emu::t_block->arrive_and_wait();
+  return r;
+}
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu::t_warp->bar.arrive_and_wait(); }
 template <class T> static inline T emu_exchange(T v, int src) {  // value of lane src (own if out of range)
   emu::t_warp->slot[emu::t_lane] = emu::bits(v);
@@ -123,6 +144,7 @@ static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); ret
 static inline float2 __fadd2_rn(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 static inline float2 __fmul2_rn(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
 static inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
