@@ -1,0 +1,92 @@
+"""The device-side IC sampler's real source (csrc/ic.cuh: Philox4x32-10 streams, inverse-CDF tables,
+ic_kernel, centring kernels) run on the CPU (tests/emu/ic_emu.cpp) against the host generators that
+follow the reference's sampling maths -- tests/test_gpu_ic.py without a GPU, at a smaller N.  The
+tables are the ones gravhopper_b200/ic_gpu.py uploads."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from gravhopper_b200 import ic_gpu, ic_raw
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "emu", "ic_emu.cpp")
+LIB = os.path.join(ROOT, "tests", "emu", "libic_emu.so")
+N = 60000
+
+
+@pytest.fixture(scope="module")
+def iemu():
+    csrc = os.path.join(ROOT, "gravhopper_b200", "csrc")
+    deps = [SRC, os.path.join(ROOT, "tests", "emu", "emu_shim.h"), os.path.join(csrc, "ic.cuh"),
+            os.path.join(csrc, "common.cuh")]
+    if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
+        cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+        out = subprocess.run(["g++", "-O1", "-std=c++20", "-shared", "-fPIC", "-pthread", "-I" + cuda_inc,
+                              "-o", LIB, SRC], capture_output=True, text=True)
+        if out.returncode != 0:
+            pytest.skip("host build of the IC kernels failed: " + out.stderr[-400:])
+    lib = C.CDLL(LIB)
+    vp = C.c_void_p
+    lib.emu_ic_sample.argtypes = [C.c_int, C.c_int64, vp, vp, vp, C.c_int, C.c_uint64, vp, vp, vp]
+    return lib
+
+
+def sample(lib, kind, n, params, table, seed):
+    prm = np.array(list(params) + [0.0] * (3 - len(params)), dtype=np.float64)
+    tx, ty = (None, None) if table is None else table
+    pos, vel, mass = np.zeros((n, 3)), np.zeros((n, 3)), np.zeros(n)
+    lib.emu_ic_sample(kind, n, prm.ctypes.data, None if tx is None else tx.ctypes.data,
+                      None if ty is None else ty.ctypes.data, 0 if tx is None else len(tx), seed,
+                      pos.ctypes.data, vel.ctypes.data, mass.ctypes.data)
+    return pos, vel, mass
+
+
+def ks(a, b):
+    a, b = np.sort(a), np.sort(b)
+    allv = np.concatenate((a, b))
+    ca = np.searchsorted(a, allv, side="right") / len(a)
+    cb = np.searchsorted(b, allv, side="right") / len(b)
+    return np.abs(ca - cb).max()
+
+
+KS_NOISE = 1.63 * np.sqrt(2.0 / N)  # 1 % critical value of the two-sample KS statistic
+
+
+@pytest.mark.parametrize("name", ["plummer", "hernquist", "tsis"])
+def test_sampler_source_matches_host_generators(iemu, name):
+    if name == "plummer":
+        xg, vg, mg = sample(iemu, ic_gpu.PLUMMER, N, (1e-3, 1e6), ic_gpu._plummer_table(), 11)
+        xh, vh, mh = ic_raw.Plummer(N, 1e-3, 1e6, seed=12)
+    elif name == "hernquist":
+        xg, vg, mg = sample(iemu, ic_gpu.HERNQUIST, N, (1.0, 1e10, 10.0), ic_gpu._hernquist_table(10.0), 11)
+        xh, vh, mh = ic_raw.Hernquist(N, 1.0, 1e10, seed=12)
+    else:
+        xg, vg, mg = sample(iemu, ic_gpu.TSIS_KIND, N, (100.0, 1e11), None, 11)
+        xh, vh, mh = ic_raw.TSIS(N, 100.0, 1e11, seed=12)
+    assert np.isfinite(xg).all() and np.isfinite(vg).all()
+    assert np.allclose(mg, mh[0]) and np.isclose(mg.sum(), mh.sum())
+    assert np.abs(xg.mean(axis=0)).max() < 1e-9 * np.abs(xg).max()
+    assert np.abs(vg.mean(axis=0)).max() < 1e-9 * np.abs(vg).max()
+    rg = np.linalg.norm(xg - np.median(xg, axis=0), axis=1)
+    rh = np.linalg.norm(xh - np.median(xh, axis=0), axis=1)
+    sg = np.linalg.norm(vg - np.median(vg, axis=0), axis=1)
+    sh = np.linalg.norm(vh - np.median(vh, axis=0), axis=1)
+    assert ks(rg, rh) < KS_NOISE, (name, "radius", ks(rg, rh))
+    assert ks(sg, sh) < KS_NOISE, (name, "speed", ks(sg, sh))
+    for k in range(3):
+        assert ks(xg[:, k] - np.median(xg[:, k]), xh[:, k] - np.median(xh[:, k])) < KS_NOISE
+        assert ks(vg[:, k] - np.median(vg[:, k]), vh[:, k] - np.median(vh[:, k])) < KS_NOISE
+    qs = np.quantile(rh, [0.0, 0.33, 0.66, 1.0])
+    for lo, hi in zip(qs[:-1], qs[1:]):
+        a, b = sg[(rg >= lo) & (rg < hi)], sh[(rh >= lo) & (rh < hi)]
+        assert ks(a, b) < 1.63 * np.sqrt(1.0 / len(a) + 1.0 / len(b)), (name, lo, hi)
+
+
+def test_sampler_is_deterministic_in_the_seed(iemu):
+    a = sample(iemu, ic_gpu.PLUMMER, 3000, (1e-3, 1e6), ic_gpu._plummer_table(), 5)
+    b = sample(iemu, ic_gpu.PLUMMER, 3000, (1e-3, 1e6), ic_gpu._plummer_table(), 5)
+    c = sample(iemu, ic_gpu.PLUMMER, 3000, (1e-3, 1e6), ic_gpu._plummer_table(), 6)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and not np.array_equal(a[0], c[0])
