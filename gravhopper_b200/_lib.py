@@ -42,6 +42,8 @@ PROTOTYPES = {
     "gh_get_tree_walk_hybrid": (C.c_double, []),
     "gh_ic_sample": (C.c_int, [C.c_int, _i64, _dp, C.c_int, _vp, _vp, C.c_int, C.c_uint64, _vp, _vp, _vp,
                                C.c_int, _vp]),
+    "gh_ic_sample_expdisk": (C.c_int, [_i64, _dp, _vp, _vp, _vp, _vp, C.c_int, C.c_uint64, _vp, _vp, _vp, C.c_int,
+                                       _vp]),
     "gh_engine_upload_device": (C.c_int, [_eng, _vp, _vp, _vp]),
     "gh_engine_create": (C.c_int, [C.POINTER(_eng), C.c_int, _i64, _i64, _i64, C.c_int]),
     "gh_engine_destroy": (C.c_int, [_eng]),

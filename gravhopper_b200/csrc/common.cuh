@@ -206,6 +206,10 @@ int launch_ic(int kind, int64_t n, const double prm[3], const double *tx, const 
               uint64_t seed, double *pos, double *vel, double *mass, double *scratch,
               cudaStream_t stream);
 
+int launch_ic_expdisk(int64_t n, const double prm[4], const double *tR, const double *tcum,
+                      const double *tvphi, const double *tratio, int nt, uint64_t seed, double *pos,
+                      double *vel, double *mass, double *scratch, cudaStream_t stream);
+
 // ---- tree (tree.cu) -------------------------------------------------------------------------
 struct TreeWorkspace;
 TreeWorkspace *tree_workspace_create();

@@ -388,6 +388,46 @@ int gh_ic_sample(int kind, int64_t n, const double *params, int nparams, const d
   return GH_OK;
 }
 
+int gh_ic_sample_expdisk(int64_t n, const double *params4, const double *table_R, const double *table_cum,
+                         const double *table_vphi, const double *table_ratio, int ntable, uint64_t seed,
+                         double *pos, double *vel, double *mass, int mem, void *stream) {
+  if (n < 0 || !params4) { set_error("bad IC parameters"); return GH_EINVAL; }
+  if (!table_R || !table_cum || !table_vphi || !table_ratio || ntable < 2) { set_error("expdisk needs its four radial tables"); return GH_EINVAL; }
+  if (!(params4[1] > 0.0) || !(params4[2] > 0.0)) { set_error("expdisk: Rd and z0 must be positive"); return GH_EINVAL; }
+  if (n == 0) return GH_OK;
+  if (!pos || !vel || !mass) { set_error("null output pointer"); return GH_EINVAL; }
+  GH_TRY(check_device());
+  Stateless *s = stateless();
+  if (!s) return GH_ENOMEM;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mem == GH_MEM_HOST && !st) {
+    if (!s->stream) GH_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    st = s->stream;
+  }
+  const size_t nt = (size_t)ntable;
+  GH_TRY(s->ictab.reserve(sizeof(double) * (4 * nt + 3 * 256)));
+  double *tR = s->ictab.as<double>(), *tcum = tR + nt, *tvphi = tcum + nt, *tratio = tvphi + nt, *scratch = tratio + nt;
+  GH_CUDA(cudaMemcpyAsync(tR, table_R, sizeof(double) * nt, cudaMemcpyHostToDevice, st));
+  GH_CUDA(cudaMemcpyAsync(tcum, table_cum, sizeof(double) * nt, cudaMemcpyHostToDevice, st));
+  GH_CUDA(cudaMemcpyAsync(tvphi, table_vphi, sizeof(double) * nt, cudaMemcpyHostToDevice, st));
+  GH_CUDA(cudaMemcpyAsync(tratio, table_ratio, sizeof(double) * nt, cudaMemcpyHostToDevice, st));
+  double *dpos = pos, *dvel = vel, *dmass = mass;
+  if (mem == GH_MEM_HOST) {
+    GH_TRY(s->icout.reserve(sizeof(double) * 7 * (size_t)n));
+    dpos = s->icout.as<double>();
+    dvel = dpos + 3 * n;
+    dmass = dvel + 3 * n;
+  }
+  GH_TRY(launch_ic_expdisk(n, params4, tR, tcum, tvphi, tratio, ntable, seed, dpos, dvel, dmass, scratch, st));
+  if (mem == GH_MEM_HOST) {
+    GH_CUDA(cudaMemcpyAsync(pos, dpos, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, st));
+    GH_CUDA(cudaMemcpyAsync(vel, dvel, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, st));
+    GH_CUDA(cudaMemcpyAsync(mass, dmass, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    GH_CUDA(cudaStreamSynchronize(st));
+  }
+  return GH_OK;
+}
+
 int gh_engine_create(gh_engine **out, int device, int64_t n_total, int64_t i_begin, int64_t i_count,
                      int prec) {
   if (!out) return GH_EINVAL;

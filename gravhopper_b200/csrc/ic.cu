@@ -28,4 +28,22 @@ int launch_ic(int kind, int64_t n, const double prm[3], const double *tx, const 
   return GH_OK;
 }
 
+int launch_ic_expdisk(int64_t n, const double prm[4], const double *tR, const double *tcum,
+                      const double *tvphi, const double *tratio, int nt, uint64_t seed, double *pos,
+                      double *vel, double *mass, double *scratch /* 3*256 */, cudaStream_t st) {
+  if (n <= 0) return GH_OK;
+  ic_expdisk_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, prm[0], prm[1], prm[2], prm[3], tR, tcum, tvphi,
+                                                               tratio, nt, seed, pos, vel, mass);
+  GH_LAUNCH_CHECK();
+  int nb = (int)((n + 4095) / 4096);
+  if (nb > 256) nb = 256;
+  for (double *arr : {pos, vel}) {
+    mean_stage1<<<nb, 256, 0, st>>>(arr, n, scratch);
+    GH_LAUNCH_CHECK();
+    mean_stage2_shift<<<nb, 256, 0, st>>>(arr, n, scratch, nb);
+    GH_LAUNCH_CHECK();
+  }
+  return GH_OK;
+}
+
 }  // namespace gh

@@ -120,6 +120,49 @@ __global__ void ic_kernel(int kind, int64_t n, double p0, double p1, double p2, 
   mass[i] = M / (double)n;
 }
 
+// Exponential disk (gravhopper.py:1669-1733): R from the tabulated cumulative mass profile, azimuth
+// uniform, z = 2 z0 atanh(u) with a random sign; velocities: mean rotation R Omega(R), dispersions
+// sigma_R = sigmaR(Rd) exp((1 - R/Rd) / 4), sigma_phi^2 = sigma_R^2 4 Omega^2 / kappa^2, sigma_z^2 =
+// pi G z0 Sigma(R) / 2: exactly the expressions of the reference and of the host generator
+// (ic_raw.expdisk), with the two functions that need Bessel functions and the caller's rotation
+// curve tabulated by the host on the radial grid tR:  tvphi = R sqrt(Omega^2),
+// tratio = 4 Omega^2 / kappa^2 (both smooth and bounded, unlike Omega^2 itself at R -> 0).
+// prm = {sigma0 [Msun/kpc^2], Rd [kpc], z0 [kpc], sigmaR(Rd) [km/s]}.
+__global__ void ic_expdisk_kernel(int64_t n, double sigma0, double Rd, double z0, double sigR_Rd,
+                                  const double *tR, const double *tcum, const double *tvphi,
+                                  const double *tratio, int nt, uint64_t seed, double *__restrict__ pos,
+                                  double *__restrict__ vel, double *__restrict__ mass) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Draws d(seed, (uint64_t)i);
+  const double R = fmax(interp(tcum, tR, nt, d.u[0]), 1e-6 * Rd);
+  double sp, cp;
+  sincos(6.283185307179586 * d.u[1], &sp, &cp);
+  const double zu = fmin(d.u[2], 1.0 - 1e-16);
+  const double z = 2.0 * z0 * atanh(zu) * (d.u[3] < 0.5 ? 1.0 : -1.0);
+  const double vphi_mean = interp(tR, tvphi, nt, R);
+  const double ratio = interp(tR, tratio, nt, R);
+  const double sigma_R = sigR_Rd * exp(0.25 * (1.0 - R / Rd));
+  const double sigma2_phi = sigma_R * sigma_R * ratio;
+  const double sigma2_z = 3.141592653589793 * GH_G * z0 * sigma0 * 0.5 * exp(-R / Rd);
+  // Box-Muller: three normals from four uniforms
+  const double r1 = sqrt(-2.0 * log(fmax(d.u[4], 1e-300))), r2 = sqrt(-2.0 * log(fmax(d.u[6], 1e-300)));
+  double s1, c1, s2, c2;
+  sincos(6.283185307179586 * d.u[5], &s1, &c1);
+  sincos(6.283185307179586 * d.u[7], &s2, &c2);
+  (void)s2;
+  const double vphi = sqrt(fmax(sigma2_phi, 0.0)) * (r1 * c1) + vphi_mean;
+  const double vR = sigma_R * (r1 * s1);
+  const double vz = sqrt(sigma2_z) * (r2 * c2);
+  pos[3 * i + 0] = R * cp;
+  pos[3 * i + 1] = R * sp;
+  pos[3 * i + 2] = z;
+  vel[3 * i + 0] = -vphi * sp + vR * cp;
+  vel[3 * i + 1] = vphi * cp + vR * sp;
+  vel[3 * i + 2] = vz;
+  mass[i] = 3.141592653589793 * Rd * Rd * sigma0 / (double)n;
+}
+
 // force_centers (gravhopper.py:1768-1785): subtract the unweighted mean (deterministic 2-stage sum)
 __global__ void mean_stage1(const double *__restrict__ a, int64_t n, double *__restrict__ part) {
   __shared__ double sh[3][256];

@@ -139,7 +139,7 @@ int gh_get_tree_walk(void);
 int gh_set_tree_walk_hybrid(double kappa);
 double gh_get_tree_walk_hybrid(void);
 
-/* ---- device-side initial conditions (inputs of the path; gravhopper.py:1327-1607) ----------- */
+/* ---- device-side initial conditions (inputs of the path; gravhopper.py:1327-1734) ----------- */
 
 /* Sample n particles of an equilibrium model on the GPU with a counter-based generator
  * (Philox4x32-10, one stream per particle; NOT the numpy stream of the host generators) and
@@ -155,6 +155,17 @@ double gh_get_tree_walk_hybrid(void);
 int gh_ic_sample(int kind, int64_t n, const double *params, int nparams, const double *table_x,
                  const double *table_y, int ntable, uint64_t seed, double *pos, double *vel,
                  double *mass, int mem, void *stream);
+
+/* Exponential disk (IC.expdisk, gravhopper.py:1611-1734) sampled on the GPU the same way.
+ *   params4 = {sigma0 [Msun/kpc^2], Rd [kpc], z0 [kpc], sigma_R(Rd) [km/s]}
+ * Four host tables of ntable entries on one radial grid table_R [kpc] (first entry 0): the cumulative
+ * mass fraction table_cum (gravhopper.py:1675-1677), the mean rotation table_vphi = R Omega(R) [km/s]
+ * and table_ratio = 4 Omega^2 / kappa^2, built by the caller from the disk's own Bessel-function
+ * rotation curve plus any external one (:1700-1714); gravhopper_b200/ic_gpu.py builds them. */
+int gh_ic_sample_expdisk(int64_t n, const double *params4, const double *table_R,
+                         const double *table_cum, const double *table_vphi,
+                         const double *table_ratio, int ntable, uint64_t seed, double *pos,
+                         double *vel, double *mass, int mem, void *stream);
 
 /* ---- device-resident leapfrog engine: Simulation.run ------------------------------------- */
 

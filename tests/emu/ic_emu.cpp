@@ -25,3 +25,18 @@ extern "C" int emu_ic_sample(int kind, int64_t n, const double *prm3, const doub
   }
   return 0;
 }
+
+extern "C" int emu_ic_sample_expdisk(int64_t n, const double *prm4, const double *tR, const double *tcum,
+                                     const double *tvphi, const double *tratio, int nt, uint64_t seed, double *pos,
+                                     double *vel, double *mass) {
+  if (n <= 0) return 0;
+  emu::launch((unsigned)((n + 255) / 256), 256, [&] { ic_expdisk_kernel(n, prm4[0], prm4[1], prm4[2], prm4[3], tR, tcum, tvphi, tratio, nt, seed, pos, vel, mass); }, true);
+  int nb = (int)((n + 4095) / 4096);
+  if (nb > 256) nb = 256;
+  std::vector<double> scratch(3 * 256);
+  for (double *arr : {pos, vel}) {
+    emu::launch((unsigned)nb, 256, [&] { mean_stage1(arr, n, scratch.data()); });
+    emu::launch((unsigned)nb, 256, [&] { mean_stage2_shift(arr, n, scratch.data(), nb); });
+  }
+  return 0;
+}

@@ -31,6 +31,7 @@ def iemu():
     lib = C.CDLL(LIB)
     vp = C.c_void_p
     lib.emu_ic_sample.argtypes = [C.c_int, C.c_int64, vp, vp, vp, C.c_int, C.c_uint64, vp, vp, vp]
+    lib.emu_ic_sample_expdisk.argtypes = [C.c_int64, vp, vp, vp, vp, vp, C.c_int, C.c_uint64, vp, vp, vp]
     return lib
 
 
@@ -90,3 +91,38 @@ def test_sampler_is_deterministic_in_the_seed(iemu):
     b = sample(iemu, ic_gpu.PLUMMER, 3000, (1e-3, 1e6), ic_gpu._plummer_table(), 5)
     c = sample(iemu, ic_gpu.PLUMMER, 3000, (1e-3, 1e6), ic_gpu._plummer_table(), 6)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and not np.array_equal(a[0], c[0])
+
+
+def test_expdisk_sampler_source_matches_the_host_generator(iemu):
+    """ic_expdisk_kernel (device-side IC.expdisk; compiled, not yet run on a GPU) on the CPU, in the
+    rotation curve of a Hernquist halo -- the disk of the N = 10M galaxy model -- against
+    ic_raw.expdisk: cylindrical radius, height, azimuthal / radial / vertical velocity
+    distributions overall and in radial bins."""
+    n = N
+    sigma0, Rd, z0, sigR = 200.0 * 1e6, 2.0, 0.2, 20.0
+    rot = ic_raw.hernquist_vcirc(20.0, 4e11)
+    tR, tcum, tvphi, tratio = ic_gpu.expdisk_tables(sigma0, Rd, rot)
+    assert tR[0] == 0.0 and tcum[0] == 0.0 and np.all(np.diff(tcum) >= 0) and np.isclose(tcum[-1], 1.0)
+    assert np.all(np.isfinite(tvphi)) and np.all(tratio > 0.5) and np.all(tratio < 4.5)
+    prm = np.array([sigma0, Rd, z0, sigR])
+    xg, vg, mg = np.zeros((n, 3)), np.zeros((n, 3)), np.zeros(n)
+    iemu.emu_ic_sample_expdisk(n, prm.ctypes.data, tR.ctypes.data, tcum.ctypes.data, tvphi.ctypes.data,
+                               tratio.ctypes.data, len(tR), 21, xg.ctypes.data, vg.ctypes.data, mg.ctypes.data)
+    xh, vh, mh = ic_raw.expdisk(n, sigma0, Rd, z0, sigR, external_rotcurve=rot, seed=22)
+    assert np.isfinite(xg).all() and np.isfinite(vg).all()
+    assert np.allclose(mg, mh[0]) and np.isclose(mg.sum(), np.pi * Rd ** 2 * sigma0)
+    assert np.abs(xg.mean(axis=0)).max() < 1e-9 * np.abs(xg).max()
+
+    def cyl(x, v):
+        R = np.hypot(x[:, 0], x[:, 1])
+        c, s_ = x[:, 0] / R, x[:, 1] / R
+        return R, x[:, 2], -v[:, 0] * s_ + v[:, 1] * c, v[:, 0] * c + v[:, 1] * s_, v[:, 2]
+    g, h = cyl(xg, vg), cyl(xh, vh)
+    for k, name in enumerate(("R", "z", "vphi", "vR", "vz")):
+        assert ks(g[k], h[k]) < KS_NOISE, (name, ks(g[k], h[k]))
+    qs = np.quantile(h[0], [0.0, 0.25, 0.5, 0.75, 1.0])
+    for lo, hi in zip(qs[:-1], qs[1:]):
+        a, b = (g[0] >= lo) & (g[0] < hi), (h[0] >= lo) & (h[0] < hi)
+        for k in (2, 3, 4):
+            # twelve binned comparisons: the 0.1 % critical value (1.95) instead of the 1 % one
+            assert ks(g[k][a], h[k][b]) < 1.95 * np.sqrt(1.0 / a.sum() + 1.0 / b.sum()), (k, lo, hi)
