@@ -54,6 +54,12 @@ def test_argument_validation_without_gpu():
     assert lib.gh_tree_force(64, None, None, 4, 0.1, -1.0, None, 0, None) == _lib.GH_EINVAL
     h = ctypes.c_void_p()
     assert lib.gh_engine_create(ctypes.byref(h), 0, 10, 5, 6, 64) == _lib.GH_EINVAL
+    assert lib.gh_set_tree_walk_hybrid(-0.5) == _lib.GH_EINVAL and lib.gh_set_tree_walk_hybrid(2.0) == _lib.GH_EINVAL
+    assert lib.gh_get_tree_walk_hybrid() == 0.0          # the hybrid rule is off unless asked for
+    prm = (ctypes.c_double * 4)(1.0, 2.0, 0.2, 20.0)
+    assert lib.gh_ic_sample_expdisk(10, prm, None, None, None, None, 0, 1, None, None, None, 0, None) == _lib.GH_EINVAL
+    p = ctypes.c_void_p()
+    assert lib.gh_host_alloc(ctypes.byref(p), 0) == _lib.GH_EINVAL and lib.gh_host_free(None) == _lib.GH_OK
 
 
 def test_reference_error_messages():
