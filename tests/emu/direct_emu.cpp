@@ -79,3 +79,23 @@ int emu_direct(int prec, const void *src, const double *mass, int64_t nj, const 
   }
 }
 }
+
+// Device-native analytic potentials: gh::eval_potentials (common.cuh) is what potentials_kernel
+// (csrc/direct.cu) calls per particle; out (n,3) in km/s/Myr.  kinds[k] with 8 doubles prm8[k].
+extern "C" int emu_potentials(int npot, const int *kinds, const double *prm8, const double *xhalf, int64_t n,
+                              double *out) {
+  PotentialSet ps;
+  std::memset(&ps, 0, sizeof(ps));
+  if (npot > GH_MAX_POTENTIALS) return 1;
+  ps.n = npot;
+  for (int k = 0; k < npot; k++) {
+    ps.kind[k] = kinds[k];
+    for (int j = 0; j < GH_POT_NPARAM; j++) ps.prm[k][j] = prm8[k * GH_POT_NPARAM + j];
+  }
+  for (int64_t i = 0; i < n; i++) {
+    double a[3] = {0.0, 0.0, 0.0};
+    eval_potentials(ps, xhalf + 3 * i, a);
+    out[3 * i] = a[0]; out[3 * i + 1] = a[1]; out[3 * i + 2] = a[2];
+  }
+  return 0;
+}

@@ -35,6 +35,7 @@ def demu():
     vp = C.c_void_p
     lib.emu_direct.argtypes = [C.c_int, vp, vp, C.c_int64, vp, C.c_int64, C.c_double, C.c_int, C.c_int, vp, vp, vp,
                                C.c_double, vp, vp, vp, vp]
+    lib.emu_potentials.argtypes = [C.c_int, vp, vp, vp, C.c_int64, vp]
     return lib
 
 
@@ -137,3 +138,31 @@ def test_ten_fused_steps_follow_the_reference_trajectory(demu, golden, oracle, m
         assert np.abs(x[keep] - golden["c1_direct_traj_x"][step]).max() <= 1e-12 * sx
         assert np.abs(v[keep] - golden["c1_direct_traj_v"][step]).max() <= 1e-12 * sv
     assert np.abs(x - golden["c1_direct_x10"]).max() <= 1e-12 * np.abs(golden["c1_direct_x10"]).max()
+
+
+def test_native_potentials_source_equals_the_host_formulas(demu):
+    """gh::eval_potentials (what the engine's potentials kernel evaluates at x_half on the device,
+    SURVEY 8f rank 1) against the host-side formulas of gravhopper_b200/potentials.py, which double
+    as reference-style callbacks: all five kinds, off-centre, summed."""
+    from gravhopper_b200 import potentials as P
+    rng = np.random.default_rng(8)
+    x = rng.normal(size=(500, 3)) * 5.0
+    x[0] = [0.3, -0.2, 0.1]
+    pots = [P.PointMass(1e9, center=[0.3, -0.2, 0.1], softening=0.05), P.Hernquist(1e11, 8.0, center=[1.0, 0.0, -0.5]),
+            P.NFW(3e11, 15.0), P.LogHalo(180.0, rc=2.0, q=0.8), P.MiyamotoNagai(5e10, 3.0, 0.3, center=[0.0, 0.5, 0.0])]
+    for group in ([p] for p in pots):
+        _check_pots(demu, group, x)
+    _check_pots(demu, pots[:4], x)          # GH_MAX_POTENTIALS = 4 at once
+
+
+def _check_pots(demu, group, x):
+    kinds = np.array([p.kind for p in group], dtype=np.int32)
+    prm = np.ascontiguousarray(np.array([p.params() for p in group], dtype=np.float64))
+    out = np.zeros_like(x)
+    xx = np.ascontiguousarray(x)
+    assert demu.emu_potentials(len(group), kinds.ctypes.data, prm.ctypes.data, xx.ctypes.data, len(x),
+                               out.ctypes.data) == 0
+    want = sum(p.acceleration(x) for p in group)
+    assert np.isfinite(out).all()
+    scale = np.linalg.norm(want, axis=1).max()
+    assert np.abs(out - want).max() <= 1e-12 * scale
