@@ -1,18 +1,28 @@
 #!/usr/bin/env python
-"""bench.py -- the hot path's headline number on B200, one JSON line on stdout.
+"""bench.py -- the hot path's headline numbers on B200, one JSON line on stdout.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload direct|tree] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload direct|tree|direct4m|galaxy]
+                    [--impl reference] [--no-extras] [--no-cpu-baseline]
 
-Default workload (BASELINE.json configs[2], the configuration the metric and the north_star
-target are quoted on): Plummer sphere N = 1,048,576, direct summation, fp32 pair arithmetic,
-one full DKD leapfrog step per "step" (force on all N particles from all N + kick + drift, state
-resident in HBM).  metric = pairwise interactions/s = N^2 per step.  With --gpus N > 1 (launched
-by torchrun, one rank per GPU) the targets are sharded N/P per rank and each step all-gathers the
-half-drifted positions (strong scaling: the total work is fixed).
+BASELINE.json's metric has two halves: pairwise interactions/s (direct summation) and
+particle-steps/s (Barnes-Hut tree), both at 1/2/4/8 B200.  The default run measures BOTH at every
+--gpus N:
 
---workload tree: BASELINE.json configs[3]: Hernquist N = 4,194,304, Barnes-Hut theta = 0.7, fp32
-walk; metric = particle-steps/s.
+  headline   BASELINE.json configs[2]: Plummer sphere N = 1,048,576, direct summation, fp32 pair
+             arithmetic, one full DKD leapfrog step per "step" (force on all N particles from all N
+             + kick + drift, state resident in HBM); metric = pairwise interactions/s = N^2 / step.
+  "tree"     BASELINE.json configs[3]: Hernquist sphere N = 4,194,304, Barnes-Hut theta = 0.7, fp32
+             walk, one DKD step per "step"; particle-steps/s, with its own e2e (pinned and
+             pageable host buffers), roofline (walk against the FP32 FMA peak, build against the
+             measured HBM peak), accuracy, parity_check and cpu_baseline.
+  "fp64"     configs[2]'s fp64 arm: the same Plummer N = 2^20 through the fp64 direct kernel.
 
+With --gpus N > 1 (launched by torchrun, one rank per GPU) the targets are sharded N/P per rank and
+each step all-gathers the half-drifted positions over NCCL (strong scaling: total work fixed).
+Before anything is timed every rank checks 256 of its own targets against the oracle
+("parity_check": the CPU restatement of the reference, used here only as the checker).
+
+--workload tree|galaxy|direct4m makes that workload the headline instead (no extra blocks).
 --impl reference: times the reference's own CPU implementation of the same path
 (oracle/_ref = the unmodified /root/reference/gravhopper/_jbgrav.c compiled by oracle/Makefile;
 falls back to the oracle port) on the host cores, on a bounded sample of the workload.
@@ -40,6 +50,9 @@ N_TREE = int(os.environ.get("GH_BENCH_TREE_N", 1 << 22))
 FLOP_PER_INTERACTION = 20  # north_star / GPU-Gems-3 convention
 SM_COUNT = 148
 FP32_LANES_PER_SM = 128
+FP64_LANES_PER_SM = 64
+PARITY_TARGETS = 256
+C_ACC = 4.398600412921223e-09  # jbgrav.py:48
 
 
 def workload(kind):
@@ -57,12 +70,13 @@ def workload(kind):
                     alg="tree", prec="fp32",
                     name="Exponential disk (2M) + Hernquist halo (8M) N=10000000, Barnes-Hut theta=0.7 fp32 walk, "
                          "1 DKD leapfrog step (BASELINE.json configs[4])")
-    if kind == "direct":
+    if kind in ("direct", "direct64"):
         x, v, m = ic_raw.Plummer(N_DIRECT, 1e-3, 1e6, seed=42)
+        prec = "fp32" if kind == "direct" else "fp64"
         return dict(x=np.ascontiguousarray(x), v=np.ascontiguousarray(v), m=m, eps=5e-5, dt=0.005,
-                    theta=0.7, alg="direct", prec="fp32",
-                    name="Plummer N=%d b=1pc M=1e6Msun eps=0.05pc dt=0.005Myr, direct summation fp32, "
-                         "1 DKD leapfrog step (BASELINE.json configs[2])" % N_DIRECT)
+                    theta=0.7, alg="direct", prec=prec,
+                    name="Plummer N=%d b=1pc M=1e6Msun eps=0.05pc dt=0.005Myr, direct summation %s, "
+                         "1 DKD leapfrog step (BASELINE.json configs[2])" % (N_DIRECT, prec))
     x, v, m = ic_raw.Hernquist(N_TREE, 1.0, 1e10, seed=42)
     return dict(x=np.ascontiguousarray(x), v=np.ascontiguousarray(v), m=m, eps=0.05, dt=1.0, theta=0.7,
                 alg="tree", prec="fp32",
@@ -118,6 +132,17 @@ class ClockSampler(object):
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def merge_clocks(a, b):
+    """Clock records of two timed regions -> one (the line's `clocks` covers everything timed)."""
+    if not a or not b:
+        return a or b
+    na, nb = a["samples"], b["samples"]
+    return {"sm_mhz": (a["sm_mhz"] * na + b["sm_mhz"] * nb) / (na + nb),
+            "sm_max_mhz": max(a["sm_max_mhz"], b["sm_max_mhz"]),
+            "power_w_max": max(a["power_w_max"], b["power_w_max"]), "samples": na + nb,
+            "reasons": sorted(set(a["reasons"]) | set(b["reasons"]))}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -154,7 +179,7 @@ def cpu_baseline_direct(w, seconds_target=12.0):
 def cpu_baseline_tree(w, ntargets=16384):
     from oracle import oracle as O
     ref = O.ref()
-    sel = np.random.default_rng(0).choice(len(w["m"]), ntargets, replace=False)
+    sel = np.random.default_rng(0).choice(len(w["m"]), min(ntargets, len(w["m"])), replace=False)
     t0 = time.perf_counter()
     if ref is not None:
         ref.tree_force_position(w["x"], w["m"], w["x"][sel], w["eps"], w["theta"])
@@ -164,12 +189,13 @@ def cpu_baseline_tree(w, ntargets=16384):
         kind = "port"
     dt = time.perf_counter() - t0
     # one evaluation = build (all N) + walk (sampled targets); extrapolate the walk to all N targets
-    return {"value": ntargets / dt, "unit": "particle-steps/s", "cores": 1, "kind": kind,
+    return {"value": len(sel) / dt, "unit": "particle-steps/s", "cores": 1, "kind": kind,
             "sample": "tree build over %d sources + walk of %d targets, %.1f s (build included once)"
-                      % (len(w["m"]), ntargets, dt)}
+                      % (len(w["m"]), len(sel), dt)}
 
 
-def tree_roofline(n, world, ms_per_step, kernel_ms, st, mode, accuracy, peaks, fp32_peak_tflops):
+def tree_roofline(n, world, ms_per_step, kernel_ms, st, mode, accuracy, peaks, fp32_peak_tflops, phases=None,
+                  peak_how=None):
     """roofline object of the tree workloads: the walk kernel against the FP32 FMA peak (20 flop x
     list entries), the build against the HBM roofline (SURVEY 8d bytes per particle-step)."""
     acc_per = st["accepted"] / float(n)
@@ -180,17 +206,19 @@ def tree_roofline(n, world, ms_per_step, kernel_ms, st, mode, accuracy, peaks, f
         how = ("20 flop x interaction-list entries (%.0f per target: one warp-cooperative traversal per 32 "
                "Morton-consecutive targets with the bounding-box form of the reference's opening test, which "
                "opens every cell the reference opens and some more; the reference's own per-target set is "
-               "~1.9x shorter) / CUDA-event time of the walk kernel, against the FP32 FMA peak; "
-               "visited_per_target = entries tested by the target's group (shared by its 32 targets); the build "
-               "(ms_per_step - kernel_ms) is HBM-streaming bound" % acc_per)
+               "~1.9x shorter) / mean CUDA-event time of the walk kernel over the timed steps, against the FP32 "
+               "FMA peak; visited_per_target = entries tested by the target's group (shared by its 32 targets); "
+               "the build (ms_per_step - kernel_ms) is HBM-streaming bound" % acc_per)
         bound = "fp32_fma (list evaluation) + issue (traversal)"
     else:
         kernel = "walk_kernel"
-        how = ("20 flop x accepted nodes (the reference's own accepted set: %.0f per target) / CUDA-event time "
-               "of the walk kernel, against the FP32 FMA peak; ncu (profiles/) shows this walk is entry-load "
+        how = ("20 flop x accepted nodes (the reference's own accepted set: %.0f per target) / mean CUDA-event "
+               "time of the walk kernel, against the FP32 FMA peak; ncu (profiles/) shows this walk is entry-load "
                "latency / instruction-issue bound; the build (ms_per_step - kernel_ms) is HBM-streaming bound"
                % acc_per)
         bound = "issue (walk); fp32_fma peak quoted"
+    if peak_how:
+        how += "; peak: " + peak_how
     # dram__bytes_read.sum + dram__bytes_write.sum of walk_group_kernel at N = 2^22 on one GPU from
     # `ncu --set full` (profiles/r01_walk_group_f32_N4M_v2.txt): 591.8 MB + 192.3 MB; the
     # algorithmic bytes are 32 B x 6.2M entries read once + 64 B x N targets/epilogue = 0.47 GB
@@ -203,15 +231,18 @@ def tree_roofline(n, world, ms_per_step, kernel_ms, st, mode, accuracy, peaks, f
     build_roofline = {"bound": "hbm", "achieved": build_gbs, "peak": hbm_peak, "unit": "GB/s",
                       "frac": build_gbs / hbm_peak, "ms": build_ms,
                       "how": "382 B per particle (SURVEY 8d: 190 + 24 x 8 radix passes) x N / (ms_per_step - walk "
-                             "kernel ms); peak = %s" % ("MEASURED_PEAKS.json hbm_gbs (of measured)"
-                                                        if peaks.get("hbm_gbs")
-                                                        else "6.65 TB/s (of fallback, B200_PROFILING.md)")}
-    return {"bound": bound, "achieved": achieved, "peak": fp32_peak_tflops,
-            "unit": "TFLOP/s", "frac": achieved / fp32_peak_tflops, "traffic": traffic,
-            "kernel": kernel, "kernel_ms": kernel_ms, "walk": mode,
-            "accepted_per_target": acc_per, "visited_per_target": vis_per,
-            "tree_entries": st["entries"], "tree_cells": st["cells"], "deepest_level": st["maxlevel"],
-            "build_ms": build_ms, "build_roofline": build_roofline, "accuracy": accuracy, "how": how}
+                             "kernel ms; with --gpus N > 1 this includes the NCCL exchanges); peak = %s"
+                             % ("MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks.get("hbm_gbs")
+                                else "6.65 TB/s (of fallback, B200_PROFILING.md)")}
+    r = {"bound": bound, "achieved": achieved, "peak": fp32_peak_tflops,
+         "unit": "TFLOP/s", "frac": achieved / fp32_peak_tflops, "traffic": traffic,
+         "kernel": kernel, "kernel_ms": kernel_ms, "walk": mode,
+         "accepted_per_target": acc_per, "visited_per_target": vis_per,
+         "tree_entries": st["entries"], "tree_cells": st["cells"], "deepest_level": st["maxlevel"],
+         "build_ms": build_ms, "build_roofline": build_roofline, "accuracy": accuracy, "how": how}
+    if phases:
+        r["phases_ms"] = phases
+    return r
 
 
 _W = None  # workload shared with forked reference workers (no per-step pickling of the sources)
@@ -263,102 +294,190 @@ def run_reference(args):
         for s in range(args.warmup + args.steps):
             jobs = []
             for p in range(P):
-                sel = rng.choice(n, per, replace=False)
+                sel = rng.choice(n, min(per, n), replace=False)
                 jobs.append(("direct" if wl_direct else "tree", w["x"][sel]))
             t0 = time.perf_counter()
             pool.map(_ref_worker, jobs)
             if s >= args.warmup:
                 times.append(time.perf_counter() - t0)
     tot = sum(times)
-    units = (per * P * n) if wl_direct else (per * P)
+    units = (min(per, n) * P * n) if wl_direct else (min(per, n) * P)
     value = units * args.steps / tot
     unit = "interactions/s" if wl_direct else "particle-steps/s"
     sample = ("%d processes x %d targets x %d sources per step (direct_summation_position)" % (P, per, n)
               if wl_direct else
               "%d processes, each: tree build over %d sources + walk of %d targets per step" % (P, n, per))
+    # the reference computes in IEEE fp64 whatever the GPU arm's pair arithmetic is: same particles,
+    # same N, same step; `precision` names the arithmetic of THIS arm
+    name = w["name"].replace(" fp32", "").replace(" fp64", "")
     line = {"impl": "reference", "metric": "pairwise interactions/s" if wl_direct else "particle-steps/s",
             "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": w["name"]},
+            "config": {"workload": name, "n_particles": n, "precision": "fp64",
+                       "parallelism": "%d host processes, targets sharded (the reference is single threaded)" % P},
             "cpu_baseline": {"value": value, "unit": unit, "cores": P, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", choices=["direct", "tree", "direct4m", "galaxy"], default="direct")
-    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-    if args.warmup < 3:
-        args.warmup = 3
-    if args.impl == "reference":
-        run_reference(args)
-        return
+class Ctx(object):
+    """Process-wide state of one bench run (rank, world, torch handles, peaks)."""
 
-    import torch
-    import torch.distributed as dist
-    from gravhopper_b200 import _jbgrav as J, _lib
-    from gravhopper_b200.sharded import ShardedSimulation
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        from gravhopper_b200 import _jbgrav as J, _lib, _pinned
+        self.torch, self.dist, self.J, self._lib, self._pinned = torch, dist, J, _lib, _pinned
+        self.args = args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus and self.world == 1 and args.gpus > 1:
             raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
-    torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    _lib.require_gpu()
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        _lib.require_gpu()
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+        self.peaks = measured_peaks()
+        self.fp32_peak = None
 
-    w = workload(args.workload)
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def allmax(self, vals):
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+    def allsum(self, vals):
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return [float(v) for v in t]
+
+    def close(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def fp32_peak(ctx, sm_max):
+    """FP32 FMA peak: measured by the library's FFMA-only probe kernel (gh_fp32_fma_probe: 8
+    independent FFMA chains per thread, every SM full, no memory traffic) when the library has
+    it, else the nominal lane count x clock."""
+    nominal = SM_COUNT * FP32_LANES_PER_SM * 2 * sm_max * 1e6 / 1e12
+    if ctx.fp32_peak is None:
+        ctx.fp32_peak = (nominal, "nominal: 148 SMs x 128 FP32 lanes x 2 flop x clocks.max.sm (%.0f MHz); "
+                                  "MEASURED_PEAKS.json holds HBM GB/s and bf16 TF/s only" % sm_max)
+        fn = getattr(ctx._lib.lib(), "gh_fp32_fma_probe", None)
+        if fn is not None:
+            import ctypes as C
+            tf = C.c_double()
+            fn.restype, fn.argtypes = C.c_int, [C.c_int, C.POINTER(C.c_double)]
+            if fn(5, C.byref(tf)) == 0 and tf.value > 0:
+                ctx.fp32_peak = (tf.value, "measured in this process: gh_fp32_fma_probe (FFMA-only kernel, 8 "
+                                           "independent chains per thread, best of 5) = %.2f TFLOP/s; nominal 148 x "
+                                           "128 x 2 x %.0f MHz = %.2f" % (tf.value, sm_max, nominal))
+    return ctx.fp32_peak
+
+
+def parity_check(ctx, w, sim, pos_l, vel_l, mass_l):
+    """Before timing: ONE step of the sharded engine from the initial state, then every rank
+    recovers the accelerations of 256 of its own targets from the kick (a = (v1 - v0)/dt/C_ACC,
+    exact to ~1e-14 here) and compares them with the oracle evaluated at the same half-drifted
+    positions (direct_summation_position; for the tree also the oracle's reference tree,
+    _jbgrav.c:487-541, on rank 0).  This exercises the path that is timed: all-gather, force
+    kernel(s), fused kick/drift epilogue."""
+    from oracle import oracle as O
+    torch = ctx.torch
+    b, c = sim.begin, sim.count
+    nthreads = max(1, (os.cpu_count() or 1) // max(1, ctx.world))
+    xh_all = O.half_drift(pos_l, vel_l, w["dt"])
+    sel = np.sort(np.random.default_rng(100 + ctx.rank).choice(c, min(PARITY_TARGETS, c), replace=False))
+    sim.step()
+    _, v1 = sim.local_state()
+    a_gpu = (v1[sel] - vel_l[b:b + c][sel]) / w["dt"] / C_ACC
+    tgt = np.ascontiguousarray(xh_all[b:b + c][sel])
+    truth = O.direct_summation_position(xh_all, mass_l, tgt, w["eps"], nthreads=nthreads)
+    e = np.linalg.norm(a_gpu - truth, axis=1) / np.linalg.norm(truth, axis=1)
+    if w["alg"] == "direct":
+        tol = 1e-5 if w["prec"] == "fp32" else 1e-12
+        mx, = ctx.allmax([float(e.max())])
+        return {"max_rel_err": mx, "tol": tol, "ok": bool(mx <= tol), "targets_per_rank": len(sel),
+                "vs": "oracle direct_summation_position (reference _jbgrav.c:299-353 restated) at the same x_half, "
+                      "through one step of the sharded engine"}
+    # tree: the contract is statistical (north_star: error against direct summation no worse than
+    # the reference tree's); every rank contributes its targets' errors, rank 0 evaluates the
+    # reference tree on its own targets for the bar
+    s_mean, cnt = ctx.allsum([float(e.sum()), float(len(e))])
+    mx, = ctx.allmax([float(e.max())])
+    ref_mean = ref_max = 0.0
+    if ctx.rank == 0:
+        rt = O.tree_force_position(xh_all, mass_l, tgt, w["eps"], w["theta"], nthreads=nthreads)
+        er = np.linalg.norm(rt - truth, axis=1) / np.linalg.norm(truth, axis=1)
+        ref_mean, ref_max = float(er.mean()), float(er.max())
+    ref_mean, ref_max = ctx.allmax([ref_mean, ref_max])
+    mean = s_mean / cnt
+    tol_mean, tol_max = 1.05 * ref_mean, 1.5 * ref_max
+    return {"mean_rel_err": mean, "max_rel_err": mx, "reference_tree_mean_rel_err": ref_mean,
+            "reference_tree_max_rel_err": ref_max, "tol": {"mean": tol_mean, "max": tol_max},
+            "ok": bool(mean <= tol_mean and mx <= tol_max), "targets_per_rank": len(sel),
+            "vs": "error against the oracle's direct summation at the same x_half (all ranks' targets), bar = the "
+                  "oracle's reference tree (theta = %.2f) on rank 0's targets: mean <= 1.05 x, max <= 1.5 x (samples "
+                  "of 256: the full-distribution tail checks are in tests/test_gpu_scale.py)" % w["theta"]}
+
+
+def run_block(ctx, kind, steps, warmup, with_cpu_baseline, with_e2e=True, with_parity=True):
+    """One workload through the sharded engine: parity check, timed steps, e2e, roofline."""
+    torch, dist, J = ctx.torch, ctx.dist, ctx.J
+    from gravhopper_b200.sharded import ShardedSimulation
+    rank, world, local = ctx.rank, ctx.world, ctx.local
+    w = workload(kind)
     n = len(w["m"])
     sim = ShardedSimulation(w["x"], w["v"], w["m"], w["dt"], w["eps"], algorithm=w["alg"], theta=w["theta"],
                             precision=w["prec"], rank=rank, world=world, device=local)
     shard = sim.shard
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    if sim.perm is not None:
+        pos_l, vel_l, mass_l = w["x"][sim.perm], w["v"][sim.perm], w["m"][sim.perm]
+    else:
+        pos_l, vel_l, mass_l = w["x"], w["v"], w["m"]
+    parity = parity_check(ctx, w, sim, pos_l, vel_l, mass_l) if with_parity else None
+    del pos_l, vel_l, mass_l
 
     def one_step():
         with shard.stream_context():
-            flush.zero_()  # evict L2 between steps (the 16-24 MB source array would otherwise stay hot)
+            ctx.flush.zero_()  # evict L2 between steps (the 16-24 MB source array would otherwise stay hot)
         sim.step()
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         one_step()
-    barrier()
+    ctx.barrier()
     launches0 = shard.launches()
     sampler = ClockSampler(local) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with shard.stream_context():
         ev0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         one_step()
     with shard.stream_context():
         ev1.record()
-    barrier()
+    ctx.barrier()
     ms_total = ev0.elapsed_time(ev1)
     launches = shard.launches() - launches0
     clocks = sampler.stop() if sampler else None
-    # per-kernel time of the dominant (force) kernel: events the engine records around it, last step
-    kernel_ms = shard.last_force_ms()
-    t = torch.tensor([ms_total, kernel_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, kernel_ms = float(t[0]), float(t[1])
-    ms_per_step = ms_total / args.steps
+    # per-kernel time of the dominant (force) kernel: events the engine records around it, MEAN over
+    # the timed steps (the last 64 at most)
+    kernel_ms = shard.force_ms_mean(steps)
+    phases = sim.phase_ms() if hasattr(sim, "phase_ms") else None
+    ms_total, kernel_ms = ctx.allmax([ms_total, kernel_ms])
+    ms_per_step = ms_total / steps
 
     is_direct = w["alg"] == "direct"
     if is_direct:
@@ -369,112 +488,185 @@ def main():
         metric, unit = "particle-steps/s", "particle-steps/s"
     value = units_per_step / (ms_per_step * 1e-3)
 
-    # ---- end to end through the reference-facing call with HOST (pinned) buffers ----
+    # ---- end to end through the reference-facing call with HOST buffers ----
     # Every rank evaluates its share of the targets against all sources through the public
     # _jbgrav call with host arrays (H2D of the sources + its targets, D2H of its accelerations
     # inside the timed region); the job's rate is all units / the slowest rank's time.
-    hx = torch.from_numpy(w["x"]).pin_memory().numpy()
-    hm = torch.from_numpy(w["m"]).pin_memory().numpy()
-    b0, cnt = sim.begin, sim.count
-    ht = torch.from_numpy(np.ascontiguousarray(w["x"][b0:b0 + cnt])).pin_memory().numpy()
-    if world == 1:
-        if is_direct:
-            call = lambda: J.direct_summation(hx, hm, w["eps"], precision=w["prec"])  # noqa: E731
-        else:
-            call = lambda: J.tree_force(hx, hm, w["eps"], w["theta"], precision=w["prec"])  # noqa: E731
-        name = "direct_summation" if is_direct else "tree_force"
-        h2d = int(hx.nbytes + hm.nbytes)
-    else:
-        if is_direct:
-            call = lambda: J.direct_summation_position(hx, hm, ht, w["eps"], precision=w["prec"])  # noqa: E731
-        else:
-            call = lambda: J.tree_force_position(hx, hm, ht, w["eps"], w["theta"], precision=w["prec"])  # noqa: E731
-        name = "direct_summation_position" if is_direct else "tree_force_position"
-        h2d = int(hx.nbytes + hm.nbytes + ht.nbytes)
-    # W >= 3 untimed calls: the stateless path's device scratch and the binding's pool of page-locked
-    # result blocks (two alternate while `out` is rebound) reach steady state before the clock starts
-    for _ in range(1 if (is_direct and n > (1 << 21)) else 3):
-        out = call()
-    reps = (1 if n > (1 << 21) else 3) if is_direct else 5
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        out = call()
-    te = (time.perf_counter() - t0) / reps
-    tt = torch.tensor([te], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    te = float(tt[0])
-    e2e = {"value": units_per_step / te, "unit": unit, "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": int(out.nbytes), "ms_per_call": te * 1e3, "n_gpus_used": world,
-           "call": "_jbgrav.%s(host ndarrays) -> host ndarray, one call per rank on its share of the targets"
-                   % name}
+    e2e = None
+    if with_e2e:
+        b0, cnt = sim.begin, sim.count
 
-    if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
+        def make_call(hx, hm, ht):
+            if world == 1:
+                if is_direct:
+                    return lambda: J.direct_summation(hx, hm, w["eps"], precision=w["prec"])
+                return lambda: J.tree_force(hx, hm, w["eps"], w["theta"], precision=w["prec"])
+            if is_direct:
+                return lambda: J.direct_summation_position(hx, hm, ht, w["eps"], precision=w["prec"])
+            return lambda: J.tree_force_position(hx, hm, ht, w["eps"], w["theta"], precision=w["prec"])
+
+        def time_calls(call, nwarm, reps):
+            # untimed calls first: the stateless path's device scratch and the binding's pool of page-locked
+            # result blocks (two alternate while `out` is rebound) reach steady state before the clock starts
+            out = None
+            for _ in range(nwarm):
+                out = call()
+            ctx.barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                out = call()
+            te = (time.perf_counter() - t0) / reps
+            te, = ctx.allmax([te])
+            return te, out
+
+        big = is_direct and n > (1 << 21)
+        slow = is_direct and w["prec"] == "fp64"
+        nwarm = 1 if (big or slow) else 3
+        reps = (1 if (big or slow) else 3) if is_direct else 5
+        hx = torch.from_numpy(w["x"]).pin_memory().numpy()
+        hm = torch.from_numpy(w["m"]).pin_memory().numpy()
+        tgt = np.ascontiguousarray(w["x"][b0:b0 + cnt])
+        ht = torch.from_numpy(tgt).pin_memory().numpy()
+        te, out = time_calls(make_call(hx, hm, ht), nwarm, reps)
+        name = ("direct_summation" if is_direct else "tree_force") + ("" if world == 1 else "_position")
+        h2d = int(hx.nbytes + hm.nbytes + (ht.nbytes if world > 1 else 0))
+        e2e = {"value": units_per_step / te, "unit": unit, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": int(out.nbytes), "ms_per_call": te * 1e3, "n_gpus_used": world,
+               "host_buffers": "page-locked inputs (torch pin_memory) and page-locked results (the binding's pool)",
+               "call": "_jbgrav.%s(host ndarrays) -> host ndarray, one call per rank on its share of the targets"
+                       % name}
+        if not is_direct:
+            # what a user's plain ndarrays pay: pageable inputs, a fresh pageable result per call
+            del out
+            ctx._pinned.ENABLED = False
+            try:
+                tp, out = time_calls(make_call(w["x"], w["m"], tgt), 2, 3)
+            finally:
+                ctx._pinned.ENABLED = True
+            e2e["pageable"] = {"value": units_per_step / tp, "unit": unit, "ms_per_call": tp * 1e3,
+                               "host_buffers": "plain (pageable) ndarrays in, a fresh pageable ndarray out"}
+        del hx, hm, ht, out
+
+    block = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": steps, "warmup": warmup,
+             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+             "dtype": "f32" if w["prec"] == "fp32" else "f64", "data": "synthetic",
+             "config": {"workload": w["name"], "n_particles": n, "precision": w["prec"],
+                        "parallelism": sim.describe() if hasattr(sim, "describe") else
+                        "targets sharded over %d rank(s), NCCL all-gather of x_half per step" % world,
+                        "l2": "256 MB flush write between steps"},
+             "gpu_launches": int(launches), "clocks": clocks}
+    if e2e:
+        block["e2e"] = e2e
+    if parity:
+        block["parity_check"] = parity
+
+    if rank == 0:
+        peaks = ctx.peaks
+        sm_max = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
+        if is_direct and w["prec"] == "fp32":
+            peak, peak_how = fp32_peak(ctx, sm_max)
+            per_rank_units = units_per_step / world
+            achieved = per_rank_units * FLOP_PER_INTERACTION / (kernel_ms * 1e-3) / 1e12
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at N = 2^20 on one GPU from
+            # `ncu --set full` (profiles/r01_direct_f32_N1M.txt): 24.4 MB + 76.5 MB
+            traffic = 101.0e6 if (n == (1 << 20) and world == 1) else None
+            nominal = SM_COUNT * FP32_LANES_PER_SM * 2 * sm_max * 1e6 / 1e12
+            roofline = {"bound": "fp32_fma", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                        "frac": achieved / peak, "traffic": traffic,
+                        "traffic_unit": "bytes per launch (ncu); algorithmic: 16.8 MB sources read + 24 MB x S partial sums",
+                        "kernel": "direct_f32_kernel", "kernel_ms": kernel_ms,
+                        "peak_nominal": nominal, "frac_of_nominal": achieved / nominal,
+                        "how": "20 flop/interaction x N_i x N_j per launch / mean CUDA-event time of the force kernel "
+                               "over the timed steps; peak: " + peak_how}
+            if clocks:
+                roofline["frac_at_observed_clock"] = achieved / (peak * clocks["sm_mhz"] / sm_max)
+            block["roofline"] = roofline
+        elif is_direct:
+            dfma_peak = SM_COUNT * FP64_LANES_PER_SM * 2 * sm_max * 1e6 / 1e12
+            achieved = (units_per_step / world) * FLOP_PER_INTERACTION / (kernel_ms * 1e-3) / 1e12
+            block["roofline"] = {"bound": "fp64_fma", "achieved": achieved, "peak": dfma_peak, "unit": "TFLOP/s",
+                                 "frac": achieved / dfma_peak, "traffic": None, "kernel": "direct_f64_kernel",
+                                 "kernel_ms": kernel_ms,
+                                 "how": "20 flop/interaction convention against 148 SMs x 64 DFMA lanes x 2 x clocks.max.sm "
+                                        "(nominal); the kernel executes 16-17 DP operations + 1 MUFU per interaction "
+                                        "(DESIGN 4.2), i.e. 32-34 flop-equivalents"}
+        else:
+            peak, peak_how = fp32_peak(ctx, sm_max)
+            # one extra, untimed evaluation with counters on: list entries / tested entries per target
+            J.tree_stats(True)
+            tx = torch.from_numpy(w["x"]).cuda()
+            tm = torch.from_numpy(w["m"]).cuda()
+            a32 = J.tree_force(tx, tm, w["eps"], w["theta"], precision=w["prec"])
+            torch.cuda.synchronize()
+            st = J.tree_stats()
+            J.tree_stats(False)
+            mode = J.tree_walk()
+            # accuracy beside the rate (north_star: "reported with accuracy matching the reference"):
+            # per-particle relative acceleration error against fp64 direct summation on sampled
+            # targets, for the timed fp32 walk and for the reference's criterion (the fp64 per-target
+            # walk accepts exactly the reference's node set: tests/test_gpu_parity.py)
+            sel = torch.from_numpy(np.random.default_rng(0).choice(n, min(4096, n), replace=False)).cuda()
+            tsel = tx[sel].contiguous()
+            d = J.direct_summation_position(tx, tm, tsel, w["eps"])
+            r64 = J.tree_force_position(tx, tm, tsel, w["eps"], w["theta"])
+            torch.cuda.synchronize()
+
+            def errs(a):
+                e = (torch.linalg.norm(a - d, dim=1) / torch.linalg.norm(d, dim=1)).cpu().numpy()
+                return {"mean": float(e.mean()), "median": float(np.median(e)), "p99": float(np.percentile(e, 99)),
+                        "max": float(e.max())}
+            accuracy = {"vs": "fp64 direct summation, 4096 sampled targets, same theta",
+                        "timed_fp32_walk": errs(a32[sel]), "reference_criterion_fp64_walk": errs(r64),
+                        "hybrid_kappa": J.tree_walk_hybrid(),
+                        "hybrid_targets_fraction": st.get("hybrid_targets", 0) / float(n)}
+            del tx, tm, a32, d, r64
+            block["roofline"] = tree_roofline(n, world, ms_per_step, kernel_ms, st, mode, accuracy, peaks, peak,
+                                              phases, peak_how)
+        if with_cpu_baseline and world == 1:
+            block["cpu_baseline"] = cpu_baseline_direct(w) if is_direct else cpu_baseline_tree(w)
+    sim.close() if hasattr(sim, "close") else None
+    del sim, shard
+    torch.cuda.empty_cache()
+    return block
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", choices=["direct", "tree", "direct4m", "galaxy", "direct64"], default="direct")
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline workload only (no tree / fp64 blocks)")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
         return
 
-    peaks = measured_peaks()
-    sm_max = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
-    fp32_peak_tflops = SM_COUNT * FP32_LANES_PER_SM * 2 * sm_max * 1e6 / 1e12
-    if is_direct:
-        per_rank_units = units_per_step / world
-        achieved = per_rank_units * FLOP_PER_INTERACTION / (kernel_ms * 1e-3) / 1e12
-        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at N = 2^20 on one GPU from
-        # `ncu --set full` (profiles/r01_direct_f32_N1M.txt): 24.4 MB + 76.5 MB
-        traffic = 101.0e6 if (n == (1 << 20) and world == 1) else None
-        roofline = {"bound": "fp32_fma", "achieved": achieved, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
-                    "frac": achieved / fp32_peak_tflops, "traffic": traffic,
-                    "traffic_unit": "bytes per launch (ncu); algorithmic: 16.8 MB sources read + 24 MB x S partial sums",
-                    "kernel": "direct_f32_kernel", "kernel_ms": kernel_ms,
-                    "how": "20 flop/interaction x N_i x N_j per launch / CUDA-event time of the force kernel; "
-                           "peak = 148 SMs x 128 FP32 lanes x 2 flop x clocks.max.sm (%.0f MHz); no measured FP32 "
-                           "figure exists in MEASURED_PEAKS.json (it holds HBM GB/s and bf16 TF/s)" % sm_max}
-        if clocks:
-            roofline["frac_at_observed_clock"] = achieved / (fp32_peak_tflops * clocks["sm_mhz"] / sm_max)
-    else:
-        # one extra, untimed evaluation with counters on: list entries / tested entries per target
-        J.tree_stats(True)
-        tx = torch.from_numpy(w["x"]).cuda()
-        tm = torch.from_numpy(w["m"]).cuda()
-        a32 = J.tree_force(tx, tm, w["eps"], w["theta"], precision=w["prec"])
-        torch.cuda.synchronize()
-        st = J.tree_stats()
-        J.tree_stats(False)
-        mode = J.tree_walk()
-        # accuracy beside the rate (north_star: "reported with accuracy matching the reference"):
-        # per-particle relative acceleration error against fp64 direct summation on sampled
-        # targets, for the timed fp32 walk and for the reference's criterion (the fp64 per-target
-        # walk accepts exactly the reference's node set: tests/test_gpu_parity.py)
-        sel = torch.from_numpy(np.random.default_rng(0).choice(n, 4096, replace=False)).cuda()
-        tsel = tx[sel].contiguous()
-        d = J.direct_summation_position(tx, tm, tsel, w["eps"])
-        r64 = J.tree_force_position(tx, tm, tsel, w["eps"], w["theta"])
-        torch.cuda.synchronize()
-
-        def errs(a):
-            e = (torch.linalg.norm(a - d, dim=1) / torch.linalg.norm(d, dim=1)).cpu().numpy()
-            return {"mean": float(e.mean()), "median": float(np.median(e)), "p99": float(np.percentile(e, 99)),
-                    "max": float(e.max())}
-        accuracy = {"vs": "fp64 direct summation, 4096 sampled targets, same theta",
-                    "timed_fp32_walk": errs(a32[sel]), "reference_criterion_fp64_walk": errs(r64)}
-        roofline = tree_roofline(n, world, ms_per_step, kernel_ms, st, mode, accuracy, peaks, fp32_peak_tflops)
-
-    line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["name"], "n_particles": n, "precision": w["prec"],
-                       "parallelism": "targets sharded over %d rank(s), NCCL all-gather of x_half per step" % world,
-                       "l2": "256 MB flush write between steps"},
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
-    if not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"] = cpu_baseline_direct(w) if is_direct else cpu_baseline_tree(w)
-    print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    ctx = Ctx(args)
+    cpu = not args.no_cpu_baseline
+    line = run_block(ctx, args.workload, args.steps, args.warmup, cpu)
+    if args.workload == "direct" and not args.no_extras:
+        # the other half of BASELINE.json's metric, at the same --gpus N: particle-steps/s of the tree
+        tree = run_block(ctx, "tree", max(args.steps, 10), args.warmup, cpu)
+        # configs[2]'s fp64 arm: ~1.07 s per step on one B200, so few steps
+        f64 = run_block(ctx, "direct64", 2, 3, False, with_e2e=False)
+        if ctx.rank == 0:
+            line["clocks"] = merge_clocks(merge_clocks(line.get("clocks"), tree.pop("clocks", None)),
+                                          f64.pop("clocks", None))
+            line["gpu_launches"] = int(line["gpu_launches"]) + int(tree["gpu_launches"]) + int(f64["gpu_launches"])
+            line["tree"] = tree
+            r = f64.get("roofline", {})
+            line["fp64"] = {"metric": f64["metric"], "value": f64["value"], "unit": f64["unit"],
+                            "ms_per_step": f64["ms_per_step"], "steps": f64["steps"], "warmup": f64["warmup"],
+                            "frac_of_dfma_peak": r.get("frac"), "roofline": r, "config": f64["config"],
+                            "parity_check": f64.get("parity_check")}
+    if ctx.rank == 0:
+        print(json.dumps(line))
+    ctx.close()
 
 
 if __name__ == "__main__":

@@ -25,6 +25,7 @@ PROTOTYPES = {
     "gh_last_error": (C.c_char_p, []),
     "gh_version": (C.c_int, []),
     "gh_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "gh_fp32_fma_probe": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "gh_direct_summation": (C.c_int, [C.c_int, _vp, _vp, _i64, C.c_double, _vp, C.c_int, _vp]),
     "gh_direct_summation_position": (C.c_int, [C.c_int, _vp, _vp, _i64, _vp, _i64, C.c_double, _vp,
                                                C.c_int, _vp]),
@@ -68,7 +69,24 @@ PROTOTYPES = {
     "gh_engine_tree_stats": (C.c_int, [_eng, C.POINTER(_i64)]),
     "gh_engine_launch_count": (C.c_int, [_eng, C.POINTER(_i64)]),
     "gh_engine_last_force_ms": (C.c_int, [_eng, C.POINTER(C.c_float)]),
+    "gh_engine_force_ms_mean": (C.c_int, [_eng, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
 }
+
+_grp = C.c_void_p
+PROTOTYPES.update({
+    "gh_nccl_version": (C.c_int, [C.POINTER(C.c_int)]),
+    "gh_group_create_local": (C.c_int, [C.POINTER(_grp), C.c_int, C.POINTER(C.c_int), _i64, C.c_int]),
+    "gh_group_unique_id": (C.c_int, [_vp]),
+    "gh_group_create_rank": (C.c_int, [C.POINTER(_grp), _vp, C.c_int, C.c_int, C.c_int, _i64, C.c_int]),
+    "gh_group_destroy": (C.c_int, [_grp]),
+    "gh_group_size": (C.c_int, [_grp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "gh_group_engine": (C.c_int, [_grp, C.c_int, C.POINTER(_eng), C.POINTER(_i64), C.POINTER(_i64)]),
+    "gh_group_prepare": (C.c_int, [_grp, C.c_double]),
+    "gh_group_step": (C.c_int, [_grp, _i64, C.c_double, C.c_double, C.c_double, C.c_int]),
+    "gh_group_synchronize": (C.c_int, [_grp]),
+    "gh_group_set_tree_distributed": (C.c_int, [_grp, C.c_int]),
+    "gh_group_phase_ms": (C.c_int, [_grp, C.POINTER(C.c_float)]),
+})
 
 _lib = None
 
@@ -81,9 +99,19 @@ def lib():
     """Load (building first if necessary) the C-ABI library.  Raises if that is impossible."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        if "GH_B200_LIB" not in os.environ:
+            # (re)build when the library is missing or older than any of its sources; a box without
+            # nvcc (or a read-only tree) keeps a library that exists -- and says so if it is stale
             from . import build as _build
-            _build.build()
+            if not os.path.exists(LIB_PATH):
+                _build.build()
+            elif _build.stale():
+                try:
+                    _build.build()
+                except (RuntimeError, OSError) as exc:
+                    import warnings
+                    warnings.warn("libgravhopper_b200.so is older than its sources and could not be rebuilt: %s"
+                                  % (str(exc).splitlines() or [""])[0])
         handle = C.CDLL(LIB_PATH)
         for name, (res, args) in PROTOTYPES.items():
             fn = getattr(handle, name)  # AttributeError if the .so lacks a declared symbol

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgravhopper_b200.so")
-SOURCES = ["direct.cu", "tree.cu", "engine.cu", "ic.cu"]
+SOURCES = ["direct.cu", "tree.cu", "engine.cu", "ic.cu", "probe.cu", "group.cu"]
 HEADERS = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h"))] + \
           [os.path.join(HERE, "..", "include", "gravhopper_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -31,6 +31,11 @@ def _stale(target, deps):
         return True
     t = os.path.getmtime(target)
     return any(os.path.getmtime(d) > t for d in deps)
+
+
+def stale():
+    """True when the built library is missing or older than any source or header it is made from."""
+    return _stale(LIB, [os.path.join(CSRC, f) for f in SOURCES] + HEADERS)
 
 
 def build(force=False, verbose=False):
@@ -58,7 +63,7 @@ def build(force=False, verbose=False):
         if verbose and out.strip():
             print(out)
     if force or procs or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-ldl"]
         out = subprocess.run(cmd, capture_output=True, text=True)
         if out.returncode != 0:
             raise RuntimeError("link failed:\n" + out.stdout + out.stderr)

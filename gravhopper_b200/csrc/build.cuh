@@ -143,6 +143,192 @@ __global__ void gather_u64(const uint64_t *__restrict__ in, const int *__restric
   if (i < n) out[i] = in[idx[i]];
 }
 
+// ---- distributed build (fp32 tree) -----------------------------------------------------
+// With P ranks the Morton key space is cut into P ranges by splitters; rank r sorts, scans and emits
+// only the particles whose keys fall into [split[r], split[r+1]).  The global pre-order entry array
+// is the concatenation of the ranks' segments, rank r's at [r * stride, r * stride + count_r):
+// indices are "virtual" (gaps between segments are never visited: every skip link that leaves a
+// segment points at the start of the next non-empty one), so no rank needs another rank's entry
+// count.  A cell is emitted by the rank that holds its FIRST particle; the few cells that continue
+// beyond that rank's range (at most one per level and rank boundary) take their end -- skip link
+// and moment prefix -- from a small table every rank publishes about the cells that contain ITS
+// first particle (RankRec2::tab).  Two small all-gathers carry the boundary keys (RankRec1) and
+// the tables, totals and key samples (RankRec2); one large all-gather carries the entries.
+static constexpr int DIST_SAMPLES = 64;
+static constexpr int DIST_MAX_RANKS = 64;
+struct RankRec1 {
+  uint64_t kfirst, klast;  // smallest / largest key of the rank's range (valid when n > 0)
+  int n;                   // particles in the rank's range
+  int pad[3];
+};
+struct CellEnd {
+  int bend;  // local index one past the last particle of the level-l cell containing local particle 0
+  int base;  // base_local[bend]  (pre-order offset inside the rank's segment)
+  D4 P;      // P_local[bend]     (moment prefix inside the rank)
+};
+struct RankRec2 {
+  D4 Mtot;        // P_local[n]
+  int nentries;   // base_local[n]
+  int pad;
+  CellEnd tab[LEVELS_HI + 1];
+  uint64_t samples[DIST_SAMPLES];  // sorted local keys at (j + 1/2) n / 64: next step's splitters
+};
+// per-workspace control block on the device (also used with one rank: rank 0 of 1)
+struct BuildCtl {
+  int n_local;   // particles in this rank's range (== n with one rank)
+  int rank, world;
+  int seg;       // first pre-order index of this rank's segment (rank * stride)
+  int seg_next;  // first index of the next non-empty rank's segment, or `end`
+  int stride;    // entries a segment can hold
+  int end;       // world * stride: the index every chain of the walk ends at
+  int cprev;     // octant levels shared with the previous non-empty rank's last key (-1: none)
+  int cnext;     // ... with the next non-empty rank's first key (-1: none)
+  int overflow;  // set by emit_kernel when a segment would overflow; the walk then does nothing
+  int first;     // pre-order index of the root entry: the first non-empty rank's segment start
+                 // (overflow, first) are what the walk kernels read: `walkctl`
+  int nentries;  // entries of this rank's segment (base_local[n_local])
+  int maxent;    // largest segment fill over all ranks (identical on every rank: from the gathered records)
+  int pad;
+  D4 gP;         // moment prefix of all earlier ranks
+  int xskip[LEVELS_HI + 1];   // cells of level l that start here and continue beyond this rank:
+  D4 xP[LEVELS_HI + 1];       //   their skip link and the moment prefix at their end
+  uint64_t split[DIST_MAX_RANKS + 1];       // key ranges of this step
+  uint64_t split_next[DIST_MAX_RANKS + 1];  // key ranges of the next step (from the gathered samples)
+};
+
+// one rank: the whole array is one segment of `cap` entries (virtual end = cap)
+__global__ void ctl_init_single(BuildCtl *ctl, int n, int cap) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  ctl->n_local = n; ctl->rank = 0; ctl->world = 1;
+  ctl->seg = 0; ctl->seg_next = cap; ctl->stride = cap; ctl->end = cap;
+  ctl->cprev = -1; ctl->cnext = -1; ctl->overflow = 0; ctl->first = 0; ctl->nentries = 0; ctl->maxent = 0;
+  for (int k = 0; k < 4; k++) ctl->gP.c[k] = 0.0;
+}
+
+// distributed: rank / world / stride; the splitters stay (tree_splitters sets them)
+__global__ void ctl_init_dist(BuildCtl *ctl, int rank, int world, int stride) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  ctl->n_local = 0; ctl->rank = rank; ctl->world = world;
+  ctl->seg = rank * stride; ctl->seg_next = world * stride; ctl->stride = stride; ctl->end = world * stride;
+  ctl->cprev = -1; ctl->cnext = -1; ctl->overflow = 0; ctl->first = 0; ctl->nentries = 0; ctl->maxent = 0;
+  for (int k = 0; k < 4; k++) ctl->gP.c[k] = 0.0;
+}
+__global__ void iota_kernel(int *__restrict__ v, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = (int)i;
+}
+// bootstrap of the distributed build: equal-count key ranges from fully sorted keys
+__global__ void splitters_from_sorted_kernel(const uint64_t *__restrict__ shi, int64_t n, int world,
+                                             BuildCtl *ctl) {
+  const int k = threadIdx.x;
+  if (blockIdx.x != 0 || k > world || k > DIST_MAX_RANKS) return;
+  uint64_t v = (k == 0) ? 0ull : (k == world ? ~0ull : shi[(n * k) / world]);
+  ctl->split_next[k] = v;
+  ctl->split[k] = v;
+}
+
+// ---- select: keys of this rank's range, in source order (stable) ------------------------------------
+static constexpr int SEL_THREADS = 256;
+static constexpr int SEL_ROUNDS = 8;
+static constexpr int SEL_TILE = SEL_THREADS * SEL_ROUNDS;
+// counts per tile of 2048 keys; the tile offsets are chunked_scan<int> of them
+__global__ void __launch_bounds__(SEL_THREADS)
+select_count_kernel(const uint64_t *__restrict__ keys, int64_t n, const BuildCtl *__restrict__ ctl,
+                    int *__restrict__ tilecnt) {
+  __shared__ int wsum[SEL_THREADS / 32];
+  const uint64_t lo = ctl->split[ctl->rank], hi = ctl->split[ctl->rank + 1];
+  const bool last = ctl->rank == ctl->world - 1;
+  const int64_t base = (int64_t)blockIdx.x * SEL_TILE;
+  int c = 0;
+#pragma unroll
+  for (int r = 0; r < SEL_ROUNDS; r++) {
+    const int64_t q = base + r * SEL_THREADS + threadIdx.x;
+    if (q < n) { const uint64_t k = keys[q]; c += (k >= lo && (last || k < hi)) ? 1 : 0; }
+  }
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int k = 0; k < SEL_THREADS / 32; k++) t += wsum[k];
+    tilecnt[blockIdx.x] = t;
+  }
+}
+// element order inside a tile: warp w owns 256 consecutive keys (8 rounds of 32), so the compaction
+// keeps the source order
+__global__ void __launch_bounds__(SEL_THREADS)
+select_compact_kernel(const uint64_t *__restrict__ keys, int64_t n, BuildCtl *__restrict__ ctl,
+                      const int *__restrict__ tileoff /* exclusive scan of tilecnt, ntiles + 1 */, int ntiles,
+                      uint64_t *__restrict__ kout, int *__restrict__ vout) {
+  __shared__ int wcnt[SEL_THREADS / 32];
+  const uint64_t lo = ctl->split[ctl->rank], hi = ctl->split[ctl->rank + 1];
+  const bool last = ctl->rank == ctl->world - 1;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t seg0 = (int64_t)blockIdx.x * SEL_TILE + (int64_t)w * (32 * SEL_ROUNDS);
+  uint64_t k[SEL_ROUNDS];
+  unsigned m[SEL_ROUNDS];
+  int c = 0;
+#pragma unroll
+  for (int r = 0; r < SEL_ROUNDS; r++) {
+    const int64_t q = seg0 + r * 32 + lane;
+    k[r] = (q < n) ? keys[q] : 0;
+    const bool in = (q < n) && k[r] >= lo && (last || k[r] < hi);
+    m[r] = __ballot_sync(0xffffffffu, in);
+    c += __popc(m[r]);
+  }
+  if (lane == 0) wcnt[w] = c;
+  __syncthreads();
+  int off = tileoff[blockIdx.x];
+  for (int j = 0; j < w; j++) off += wcnt[j];
+#pragma unroll
+  for (int r = 0; r < SEL_ROUNDS; r++) {
+    const int64_t q = seg0 + r * 32 + lane;
+    if (m[r] & (1u << lane)) {
+      const int dst = off + __popc(m[r] & ((1u << lane) - 1u));
+      kout[dst] = k[r];
+      vout[dst] = (int)q;
+    }
+    off += __popc(m[r]);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) ctl->n_local = tileoff[ntiles];
+}
+
+// boundary keys of this rank's sorted range -> its slot of the gathered RankRec1 array
+__global__ void rec1_kernel(const uint64_t *__restrict__ shi, const BuildCtl *__restrict__ ctl,
+                            RankRec1 *__restrict__ all) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  RankRec1 r;
+  r.n = ctl->n_local;
+  r.kfirst = r.n > 0 ? shi[0] : 0;
+  r.klast = r.n > 0 ? shi[r.n - 1] : 0;
+  r.pad[0] = r.pad[1] = r.pad[2] = 0;
+  all[ctl->rank] = r;
+}
+
+__device__ __forceinline__ int common_levels_hi(uint64_t a, uint64_t b) {
+  const uint64_t x = a ^ b;
+  return x ? __clzll((long long)(x << 1)) / 3 : LEVELS_HI;
+}
+// after the RankRec1 all-gather: octant levels shared with the neighbouring non-empty ranks
+__global__ void neighbours_kernel(const RankRec1 *__restrict__ all, BuildCtl *__restrict__ ctl) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int r = ctl->rank, P = ctl->world;
+  int cprev = -1, cnext = -1, seg_next = ctl->end;
+  if (all[r].n > 0) {
+    for (int q = r - 1; q >= 0; q--)
+      if (all[q].n > 0) { cprev = common_levels_hi(all[q].klast, all[r].kfirst); break; }
+    for (int q = r + 1; q < P; q++)
+      if (all[q].n > 0) { cnext = common_levels_hi(all[r].klast, all[q].kfirst); seg_next = q * ctl->stride; break; }
+  }
+  ctl->cprev = cprev;
+  ctl->cnext = cnext;
+  ctl->seg_next = seg_next;
+  int first = ctl->end;  // the root entry is the first entry of the first non-empty rank
+  for (int q = 0; q < P; q++)
+    if (all[q].n > 0) { first = q * ctl->stride; break; }
+  ctl->first = first;
+}
+
 // ---- K6a common levels --------------------------------------------------------------------------
 __device__ __forceinline__ int common_levels(uint64_t h0, uint64_t l0, uint64_t h1, uint64_t l1,
                                              int levels) {
@@ -155,12 +341,14 @@ __device__ __forceinline__ int common_levels(uint64_t h0, uint64_t l0, uint64_t 
 }
 
 // cnt[p] = (cells opened at sorted position p) + 1 leaf;  clev[p] = c[p] (c[n-1] = -1)
+// ctl (nullable): this rank's particle count and the levels shared across its range boundaries
 __global__ void levels_kernel(const uint64_t *__restrict__ hi, const uint64_t *__restrict__ lo,
                               int64_t n, int levels, signed char *__restrict__ clev,
-                              int *__restrict__ cnt) {
+                              int *__restrict__ cnt, const BuildCtl *__restrict__ ctl = nullptr) {
   int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ctl) n = ctl->n_local;
   if (p >= n) return;
-  int cprev = -1, c = -1;
+  int cprev = ctl ? ctl->cprev : -1, c = ctl ? ctl->cnext : -1;
   if (p > 0) cprev = common_levels(hi[p - 1], lo ? lo[p - 1] : 0, hi[p], lo ? lo[p] : 0, levels);
   if (p + 1 < n) c = common_levels(hi[p], lo ? lo[p] : 0, hi[p + 1], lo ? lo[p + 1] : 0, levels);
   clev[p] = (signed char)c;
@@ -177,8 +365,9 @@ __global__ void levels_kernel(const uint64_t *__restrict__ hi, const uint64_t *_
 // the emit kernel and the walk's target loads are all coalesced
 template <class Src>
 __global__ void gather_sorted_kernel(Src src, const int *__restrict__ idx, int64_t n,
-                                     double4 *__restrict__ out) {
+                                     double4 *__restrict__ out, const BuildCtl *__restrict__ ctl = nullptr) {
   int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ctl) n = ctl->n_local;
   if (p >= n) return;
   const int64_t j = idx[p];
   double x, y, z;
@@ -236,6 +425,17 @@ __device__ __forceinline__ void moment_diff(const D4 *__restrict__ P, int64_t p,
 #pragma unroll
   for (int k = 0; k < 4; k++) mh[k] = pe.c[k] - ps.c[k];
 }
+// a cell that starts at local particle p and continues beyond this rank's range (fp32 tree only):
+// global prefix at its end (stitch_kernel) minus the global prefix at p
+__device__ __forceinline__ void moment_diff_beyond(const D4 *__restrict__ P, int64_t p, const BuildCtl *ctl,
+                                                   int level, double mh[4]) {
+  const D4 pe = ctl->xP[level], ps = P[p], g = ctl->gP;
+#pragma unroll
+  for (int k = 0; k < 4; k++) mh[k] = pe.c[k] - __dadd_rn(g.c[k], ps.c[k]);
+}
+__device__ __forceinline__ void moment_diff_beyond(const DD4 *, int64_t, const BuildCtl *, int, double mh[4]) {
+  mh[0] = mh[1] = mh[2] = mh[3] = 0.0;  // the fp64 tree is never distributed (cnext is always -1)
+}
 template <class Real> struct MomentOf { using type = DD4; };
 template <> struct MomentOf<float> { using type = D4; };
 
@@ -268,6 +468,120 @@ __device__ __forceinline__ uint64_t compact3(uint64_t x) {
   return x;
 }
 
+// ---- distributed build: what a rank publishes about its range, and the stitch --------------------
+// One warp.  Lane l: the level-l cell that contains local particle 0 ends at local index bend (one
+// past its last particle; n when the whole range shares the prefix) -- binary search over the
+// sorted keys.  Lanes also take the key samples; lane 0 the totals.
+__global__ void rec2_kernel(const uint64_t *__restrict__ shi, const int *__restrict__ base,
+                            const D4 *__restrict__ P, const BuildCtl *__restrict__ ctl,
+                            RankRec2 *__restrict__ all) {
+  const int lane = threadIdx.x;
+  if (blockIdx.x != 0 || lane >= 32) return;
+  const int n = ctl->n_local;
+  RankRec2 *rec = &all[ctl->rank];
+  if (lane <= LEVELS_HI) {
+    int bend = 0;
+    if (n > 0) {
+      const uint64_t h0 = shi[0];
+      int lo_i = 1, hi_i = n;  // first index in [1, n] whose key leaves the prefix (n: none)
+      while (lo_i < hi_i) {
+        const int mid = (lo_i + hi_i) >> 1;
+        if (same_prefix(shi[mid], 0, h0, 0, lane)) lo_i = mid + 1; else hi_i = mid;
+      }
+      bend = lo_i;
+    }
+    rec->tab[lane].bend = bend;
+    rec->tab[lane].base = base[bend];
+    rec->tab[lane].P = P[bend];
+  }
+  for (int j = lane; j < DIST_SAMPLES; j += 32) {
+    int q = (int)(((int64_t)(2 * j + 1) * n) / (2 * DIST_SAMPLES));
+    if (q > n - 1) q = n - 1;
+    rec->samples[j] = n > 0 ? shi[q] : 0;
+  }
+  if (lane == 0) {
+    rec->Mtot = P[n];
+    rec->nentries = base[n];
+    rec->pad = 0;
+  }
+}
+
+__device__ __forceinline__ D4 d4_add(const D4 &a, const D4 &b) {
+  D4 r;
+#pragma unroll
+  for (int k = 0; k < 4; k++) r.c[k] = __dadd_rn(a.c[k], b.c[k]);
+  return r;
+}
+// After the RankRec2 all-gather (one thread; P <= 64 ranks, <= 22 levels): moment prefix of the
+// earlier ranks, the ends of the cells that leave this rank's range, and the next step's splitters.
+__global__ void stitch_kernel(const RankRec1 *__restrict__ r1, const RankRec2 *__restrict__ r2,
+                              BuildCtl *__restrict__ ctl, int64_t n_total) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int r = ctl->rank, P = ctl->world, stride = ctl->stride;
+  D4 g;
+  for (int k = 0; k < 4; k++) g.c[k] = 0.0;
+  for (int q = 0; q < r; q++) g = d4_add(g, r2[q].Mtot);
+  ctl->gP = g;
+  ctl->nentries = r2[r].nentries;
+  // a segment that does not fit anywhere stops the walk on EVERY rank (all see the same records)
+  int maxent = 0;
+  for (int q = 0; q < P; q++) maxent = r2[q].nentries > maxent ? r2[q].nentries : maxent;
+  ctl->maxent = maxent;
+  if (maxent > stride) ctl->overflow = 1;
+  // cells of level l <= cnext that contain my last particle continue into the next non-empty rank
+  for (int l = 0; l <= ctl->cnext && l <= LEVELS_HI; l++) {
+    D4 gq = d4_add(g, r2[r].Mtot);  // moment prefix at the start of rank q
+    int q = r + 1;
+    while (q < P && r1[q].n == 0) q++;
+    int skip = ctl->end;
+    D4 pend = gq;
+    while (q < P) {
+      const CellEnd t = r2[q].tab[l];
+      if (t.bend < r1[q].n) {  // the cell ends inside rank q
+        skip = q * stride + t.base;
+        pend = d4_add(gq, t.P);
+        break;
+      }
+      // the cell covers all of rank q: does it continue into the following non-empty rank?
+      int q2 = q + 1;
+      while (q2 < P && r1[q2].n == 0) q2++;
+      const D4 gq2 = d4_add(gq, r2[q].Mtot);
+      if (q2 < P && common_levels_hi(r1[q].klast, r1[q2].kfirst) >= l) { q = q2; gq = gq2; continue; }
+      skip = (q2 < P) ? q2 * stride : ctl->end;
+      pend = gq2;
+      break;
+    }
+    ctl->xskip[l] = skip;
+    ctl->xP[l] = pend;
+  }
+  // next step's key ranges: equal counts, from the ranks' key samples (sample j of rank q sits at
+  // global sorted position G_q + (j + 1/2) n_q / 64)
+  ctl->split_next[0] = 0;
+  ctl->split_next[P] = ~0ull;
+  int64_t G[DIST_MAX_RANKS + 1];
+  G[0] = 0;
+  for (int q = 0; q < P; q++) G[q + 1] = G[q] + r1[q].n;
+  for (int k = 1; k < P; k++) {
+    const int64_t t = (n_total * k) / P;
+    int q = 0;
+    while (q < P - 1 && (G[q + 1] <= t || r1[q].n == 0)) q++;
+    uint64_t sk = ctl->split[k];
+    if (r1[q].n > 0) {
+      int64_t j = ((t - G[q]) * DIST_SAMPLES) / r1[q].n;
+      if (j < 0) j = 0;
+      if (j > DIST_SAMPLES - 1) j = DIST_SAMPLES - 1;
+      sk = r2[q].samples[j];
+    }
+    if (sk < ctl->split_next[k - 1]) sk = ctl->split_next[k - 1];
+    ctl->split_next[k] = sk;
+  }
+}
+// adopt the splitters the previous step computed (start of a step)
+__global__ void splitters_advance_kernel(BuildCtl *ctl, int world) {
+  const int k = threadIdx.x;
+  if (blockIdx.x == 0 && k <= world && k <= DIST_MAX_RANKS) ctl->split[k] = ctl->split_next[k];
+}
+
 // GH_EMIT_MINBLOCKS: resident 128-thread CTAs per SM the register allocation is capped for
 // (scripts/build_variants.py; ncu: 66 registers -> 33 % of the warp slots active, latency bound)
 #ifdef GH_EMIT_MINBLOCKS
@@ -275,23 +589,28 @@ __device__ __forceinline__ uint64_t compact3(uint64_t x) {
 #else
 #define GH_EMIT_BOUNDS
 #endif
+// ctl: segment placement (seg, seg_next, stride), the cross-rank cell ends and, with `dist`, the
+// particle count of this rank.  Every skip link that would leave the segment is seg_next.
 template <class Src, class Real>
 __global__ void GH_EMIT_BOUNDS emit_kernel(const double4 *__restrict__ sp, const uint64_t *__restrict__ hi,
                             const uint64_t *__restrict__ lo, const signed char *__restrict__ clev,
                             const int *__restrict__ base /* n+1, exclusive scan of cnt */,
                             const typename MomentOf<Real>::type *__restrict__ P, int64_t n,
                             const double *__restrict__ root, bool rel_origin, double inv_theta2,
-                            Entries<Real> E, int *__restrict__ maxlevel) {
+                            Entries<Real> E, int *__restrict__ maxlevel, BuildCtl *__restrict__ ctl,
+                            bool dist) {
   int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (dist) n = ctl->n_local;
   if (p >= n) return;
   using V4 = typename Vec4<Real>::type;
+  const int seg = ctl->seg, seg_next = ctl->seg_next, seg_cap = ctl->seg + ctl->stride;
   const double ox = rel_origin ? root[0] : 0.0, oy = rel_origin ? root[1] : 0.0,
                oz = rel_origin ? root[2] : 0.0;
   const int c = clev[p];
-  const int cprev = (p > 0) ? clev[p - 1] : -1;
+  const int cprev = (p > 0) ? clev[p - 1] : ctl->cprev;
   const double4 self = sp[p];
   const double x[3] = {self.x, self.y, self.z};
-  int e = base[p];
+  int e = seg + base[p];
   if (c > cprev) {
     const uint64_t h0 = hi[p], l0 = lo ? lo[p] : 0;
     double cc[3] = {root[0], root[1], root[2]};
@@ -337,8 +656,18 @@ __global__ void GH_EMIT_BOUNDS emit_kernel(const double4 *__restrict__ sp, const
           else hi_i = mid - 1;
         }
         const int64_t b = lo_i;
+        // a cell that holds this rank's last particle and whose prefix the next rank's first key
+        // shares continues beyond the range: its end comes from the stitched table
+        const bool beyond = (b == n - 1) && (ctl->cnext >= level);
         double mh[4];
-        moment_diff(P, p, b, mh);
+        int skipidx;
+        if (beyond) {
+          moment_diff_beyond(P, p, ctl, level, mh);
+          skipidx = ctl->xskip[level];
+        } else {
+          moment_diff(P, p, b, mh);
+          skipidx = (b + 1 < n) ? seg + base[b + 1] : seg_next;
+        }
         V4 com, cen;
         if (sizeof(Real) == 4) {  // moments already relative to the root centre
           com.x = (Real)(mh[1] / mh[0]);
@@ -353,14 +682,18 @@ __global__ void GH_EMIT_BOUNDS emit_kernel(const double4 *__restrict__ sp, const
         cen.x = (Real)(cc[0] - ox);
         cen.y = (Real)(cc[1] - oy);
         cen.z = (Real)(cc[2] - oz);
-        // (size / dist) < theta  <=>  size^2 / theta^2 < dist^2   (theta = 0: inf, never accepted)
-        if (sizeof(Real) == 4) {
-          cen.w = (Real)__int_as_float((int)(((unsigned)level << SKIP_BITS) | (unsigned)base[b + 1]));
+        if (e < seg_cap) {
+          // (size / dist) < theta  <=>  size^2 / theta^2 < dist^2   (theta = 0: inf, never accepted)
+          if (sizeof(Real) == 4) {
+            cen.w = (Real)__int_as_float((int)(((unsigned)level << SKIP_BITS) | (unsigned)skipidx));
+          } else {
+            cen.w = (Real)(__dmul_rn(__dmul_rn(size, size), inv_theta2));
+            E.skip[e] = skipidx;
+          }
+          pack_node(E.node[e], cen, com);
         } else {
-          cen.w = (Real)(__dmul_rn(__dmul_rn(size, size), inv_theta2));
-          E.skip[e] = base[b + 1];
+          ctl->overflow = 1;
         }
-        pack_node(E.node[e], cen, com);
         e++;
         deepest = level;
       }
@@ -385,11 +718,13 @@ __global__ void GH_EMIT_BOUNDS emit_kernel(const double4 *__restrict__ sp, const
   com.z = (Real)(x[2] - oz);
   com.w = (Real)self.w;
   cen.x = cen.y = cen.z = (Real)0;
+  const int after = (p + 1 < n) ? e + 1 : seg_next;
+  if (e >= seg_cap) { ctl->overflow = 1; return; }
   if (sizeof(Real) == 4) {
-    cen.w = (Real)__int_as_float((int)(((unsigned)LEAF_LEVEL << SKIP_BITS) | (unsigned)(e + 1)));
+    cen.w = (Real)__int_as_float((int)(((unsigned)LEAF_LEVEL << SKIP_BITS) | (unsigned)after));
   } else {
     cen.w = (Real)-1;
-    E.skip[e] = e + 1;
+    E.skip[e] = after;
   }
   pack_node(E.node[e], cen, com);
 }

@@ -31,6 +31,10 @@ int64_t &launch_counter();  // per-thread count of kernel launches (bench.py gpu
     GH_CUDA(cudaGetLastError());     \
   } while (0)
 
+// fp32 kernels: eps^2 below this (kpc^2) is treated as 0 with the zero-distance guard (an fp32
+// self term m * rsqrt(eps^2)^3 * 0 would otherwise be inf * 0 = NaN; fp64 and the reference stay finite)
+#define GH_F32_MIN_EPS2 1e-16f
+
 // Grow-only device scratch buffer.
 struct DeviceBuffer {
   void *ptr = nullptr;
@@ -228,9 +232,25 @@ struct TreeArgs {
   double eps, theta;
   Epilogue ep;
   bool want_stats;
+  bool sync_check;  // the caller synchronises anyway: check (and repair) an entry-array overflow
 };
+// One evaluation never needs the host to learn a count from the device: the entry array has a
+// capacity, the walk ends its chains at the capacity, an overflow raises a device flag.
 int launch_tree(const TreeArgs &a, TreeWorkspace *ws, cudaStream_t stream,
                 cudaEvent_t *force_events);
+// Distributed build (fp32): this rank sorts / scans / emits only the particles of its key range
+// into segment [rank * stride, (rank + 1) * stride) of the global entry array.  The caller runs
+// phase 0, all-gathers exchange buffer 1, phase 1, all-gathers buffer 2, phase 2, all-gathers
+// buffer 3 (the entries), phase 3 (walk).  See build.cuh.
+struct TreeDist {
+  int rank, world;
+  int64_t stride;
+};
+int launch_tree_phase(const TreeArgs &a, TreeWorkspace *ws, cudaStream_t stream, cudaEvent_t *force_events,
+                      const TreeDist *dist, int phase);
+int tree_exchange_buffer(TreeWorkspace *ws, int which, void **ptr, int64_t *bytes_per_rank);
+int tree_splitters(TreeWorkspace *ws, int world, cudaStream_t stream);
+int tree_poll_overflow(TreeWorkspace *ws, int64_t *entries);
 int tree_last_stats(TreeWorkspace *ws, int64_t out[8]);
 int tree_walk_mode();
 void set_tree_walk_mode(int mode);

@@ -39,9 +39,14 @@ static int run_f32(const DirectArgs &a, DeviceBuffer &ws, cudaStream_t st, cudaE
   }
   dim3 grid(sp.itiles, sp.S);
   float eps2 = (float)(a.eps * a.eps);
+  // fp32: a softening whose square is below ~1e-16 kpc^2 cannot regularise anything at fp32
+  // resolution, and m * rsqrt(eps^2)^3 of the self term would overflow to inf (inf * 0 = NaN):
+  // treat it as eps = 0 with the zero-distance guard, like the reference's _position guard
+  const bool tiny_eps = !(eps2 >= GH_F32_MIN_EPS2);
+  if (tiny_eps) eps2 = 0.f;
   if (ev) GH_CUDA(cudaEventRecord(ev[0], st));
   const int mode = env_int("GH_F32_MODE", 0);
-  if (a.eps == 0.0)
+  if (tiny_eps)
     direct_f32_kernel<BLOCK, KI, true, 0, MINB, UNR><<<grid, BLOCK, 0, st>>>(a.src32, a.nj, a.tgt32, a.ni, eps2,
                                                                  sp.jchunk, partial, a.ep);
   else if (mode == 1)

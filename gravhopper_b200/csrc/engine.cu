@@ -1,6 +1,7 @@
 // engine.cu -- the C ABI of libgravhopper_b200.so (include/gravhopper_b200.h): the four
 // stateless force entry points and the device-resident leapfrog engine.
 #include "common.cuh"
+#include "engine.cuh"
 
 #include <cstdarg>
 #include <cstdio>
@@ -32,18 +33,44 @@ static int check_device() {
   return GH_OK;
 }
 
-// Per-thread scratch of the stateless entry points (grow-only, reused between calls).
+// Per-thread, PER-DEVICE scratch of the stateless entry points (grow-only, reused between calls).
+// Keyed by the current device: a call with tensors on another GPU gets that GPU's own buffers.
+// Calls on different streams of one device share the scratch, so every call first makes its stream
+// wait for the event the previous call recorded on its own stream (no two calls ever touch the
+// scratch concurrently; calls on one stream are ordered anyway).
 struct Stateless {
   DeviceBuffer pos, mass, tpos, acc, src32, tgt32, ws, root, part, ictab, icout;
   TreeWorkspace *tw = nullptr;
   cudaStream_t stream = nullptr;
+  cudaEvent_t last_done = nullptr;   // recorded at the end of the previous call ...
+  cudaStream_t last_stream = nullptr;  // ... on this stream
+  bool last_valid = false;
+};
+static constexpr int GH_MAX_DEVICES = 64;
+struct ThreadState {
+  Stateless *dev[GH_MAX_DEVICES] = {};
   int64_t tree_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   bool want_stats = false;
 };
-static thread_local Stateless *g_sl = nullptr;
+static thread_local ThreadState g_ts;
 static Stateless *stateless() {
-  if (!g_sl) g_sl = new (std::nothrow) Stateless();
-  return g_sl;
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); d = 0; }
+  if (d < 0 || d >= GH_MAX_DEVICES) return nullptr;
+  if (!g_ts.dev[d]) g_ts.dev[d] = new (std::nothrow) Stateless();
+  return g_ts.dev[d];
+}
+// order this call after the previous one that used the scratch (see above)
+static int scratch_acquire(Stateless *s, cudaStream_t st) {
+  if (s->last_valid && s->last_stream != st) GH_CUDA(cudaStreamWaitEvent(st, s->last_done, 0));
+  return GH_OK;
+}
+static int scratch_release(Stateless *s, cudaStream_t st) {
+  if (!s->last_done) GH_CUDA(cudaEventCreateWithFlags(&s->last_done, cudaEventDisableTiming));
+  GH_CUDA(cudaEventRecord(s->last_done, st));
+  s->last_stream = st;
+  s->last_valid = true;
+  return GH_OK;
 }
 
 // mean position -> origin[3] on the device (for the f32 packing).  The mean, not the bbox
@@ -101,6 +128,7 @@ static int force_common(int alg, int prec, const double *pos, const double *mass
     if (!s->stream) GH_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     st = s->stream;
   }
+  GH_TRY(scratch_acquire(s, st));
   const double *dpos = pos, *dmass = mass, *dt = fpos;
   double *dacc = acc_out;
   if (mem == GH_MEM_HOST) {
@@ -179,14 +207,16 @@ static int force_common(int alg, int prec, const double *pos, const double *mass
     a.eps = eps;
     a.theta = theta;
     a.ep = ep;
-    a.want_stats = s->want_stats;
+    a.want_stats = g_ts.want_stats;
+    a.sync_check = true;  // one synchronisation at the END of the call (none inside the evaluation)
     GH_TRY(launch_tree(a, s->tw, st, nullptr));
-    tree_last_stats(s->tw, s->tree_stats);
+    tree_last_stats(s->tw, g_ts.tree_stats);
   }
   if (mem == GH_MEM_HOST) {
     GH_CUDA(cudaMemcpyAsync(acc_out, dacc, sizeof(double) * 3 * nf, cudaMemcpyDeviceToHost, st));
     GH_CUDA(cudaStreamSynchronize(st));
   }
+  GH_TRY(scratch_release(s, st));
   return GH_OK;
 }
 
@@ -197,55 +227,6 @@ using namespace gh;
 // ---------------------------------------------------------------------------------------------
 // engine
 // ---------------------------------------------------------------------------------------------
-static constexpr int RING = 3;
-
-struct gh_engine {
-  int device = 0;
-  int64_t n = 0, ib = 0, ni = 0;
-  int prec = GH_PREC_F64;
-  cudaStream_t stream = nullptr, copy_stream = nullptr;
-  double *mass = nullptr;             // (n)
-  double *x[RING] = {nullptr}, *v[RING] = {nullptr};
-  int cur = 0;
-  cudaEvent_t copied[RING] = {nullptr};
-  bool copy_pending[RING] = {false};
-  cudaEvent_t step_done = nullptr;
-  bool external_src = false;
-  void *src[2] = {nullptr, nullptr};  // f64: double (n,3); f32: float4 (n)
-  int scur = 0;
-  double *xh_private = nullptr;       // f32: (ni,3) own x_half in float64
-  double origin[3] = {0, 0, 0};
-  double dt_built = 0.0;
-  bool uploaded = false, xhalf_valid = false;
-  DeviceBuffer ws, ext, ext2;
-  TreeWorkspace *tw = nullptr;
-  cudaEvent_t fev[2] = {nullptr, nullptr};
-  bool fev_valid = false;
-  int64_t launches = 0;
-  double *d_energy = nullptr;
-  PotentialSet pots;
-
-  double *xhalf_own(int b) const {
-    return prec == GH_PREC_F64 ? reinterpret_cast<double *>(src[b]) + 3 * ib : xh_private;
-  }
-  float4 *src32_own(int b) const {
-    return prec == GH_PREC_F32 ? reinterpret_cast<float4 *>(src[b]) + ib : nullptr;
-  }
-  size_t src_stride() const { return prec == GH_PREC_F64 ? 3 * sizeof(double) : sizeof(float4); }
-};
-
-struct LaunchScope {  // attribute this thread's kernel launches to the engine
-  gh_engine *e;
-  int64_t before;
-  explicit LaunchScope(gh_engine *e_) : e(e_), before(launch_counter()) {}
-  ~LaunchScope() { e->launches += launch_counter() - before; }
-};
-
-#define GH_ENGINE_GUARD(e)                                          \
-  if (!(e)) { set_error("null engine"); return GH_EINVAL; }         \
-  GH_CUDA(cudaSetDevice((e)->device));                              \
-  LaunchScope scope_(e)
-
 extern "C" {
 
 const char *gh_last_error(void) { return g_err; }
@@ -289,14 +270,26 @@ int gh_tree_force_position(int prec, const double *pos, const double *mass, int6
   return force_common(GH_ALG_TREE, prec, pos, mass, np, force_pos, nf, eps, theta, acc_out, mem, stream);
 }
 int gh_release_thread_scratch(void) {
-  Stateless *s = g_sl;
-  if (!s) return GH_OK;
-  if (s->stream) cudaStreamSynchronize(s->stream);
-  DeviceBuffer *all[] = {&s->pos, &s->mass, &s->tpos, &s->acc, &s->src32, &s->tgt32, &s->ws, &s->root,
-                         &s->part, &s->ictab, &s->icout};
-  for (auto *b : all) b->release();
-  if (s->tw) { tree_workspace_destroy(s->tw); s->tw = nullptr; }
-  if (s->stream) { cudaStreamDestroy(s->stream); s->stream = nullptr; }
+  int cur = 0;
+  const bool have_cur = cudaGetDevice(&cur) == cudaSuccess;
+  cudaGetLastError();
+  for (int d = 0; d < GH_MAX_DEVICES; d++) {
+    Stateless *s = g_ts.dev[d];
+    if (!s) continue;
+    cudaSetDevice(d);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->last_valid) cudaEventSynchronize(s->last_done);
+    DeviceBuffer *all[] = {&s->pos, &s->mass, &s->tpos, &s->acc, &s->src32, &s->tgt32, &s->ws, &s->root,
+                           &s->part, &s->ictab, &s->icout};
+    for (auto *b : all) b->release();
+    if (s->tw) { tree_workspace_destroy(s->tw); s->tw = nullptr; }
+    if (s->stream) { cudaStreamDestroy(s->stream); s->stream = nullptr; }
+    if (s->last_done) { cudaEventDestroy(s->last_done); s->last_done = nullptr; }
+    delete s;
+    g_ts.dev[d] = nullptr;
+  }
+  if (have_cur) cudaSetDevice(cur);
+  cudaGetLastError();
   return GH_OK;
 }
 
@@ -321,15 +314,12 @@ int gh_host_free(void *ptr) {
 }
 
 int gh_tree_last_stats(int64_t out[8]) {
-  Stateless *s = stateless();
-  if (!s || !out) return GH_EINVAL;
-  for (int k = 0; k < 8; k++) out[k] = s->tree_stats[k];
+  if (!out) return GH_EINVAL;
+  for (int k = 0; k < 8; k++) out[k] = g_ts.tree_stats[k];
   return GH_OK;
 }
 int gh_set_tree_stats(int enable) {
-  Stateless *s = stateless();
-  if (!s) return GH_ENOMEM;
-  s->want_stats = enable != 0;
+  g_ts.want_stats = enable != 0;
   return GH_OK;
 }
 
@@ -363,6 +353,7 @@ int gh_ic_sample(int kind, int64_t n, const double *params, int nparams, const d
     if (!s->stream) GH_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     st = s->stream;
   }
+  GH_TRY(scratch_acquire(s, st));
   double prm[3] = {params[0], params[1], nparams > 2 ? params[2] : 0.0};
   const int nt = (kind == 3) ? 0 : ntable;
   GH_TRY(s->ictab.reserve(sizeof(double) * (2 * (size_t)(nt > 0 ? nt : 1) + 3 * 256)));
@@ -385,6 +376,7 @@ int gh_ic_sample(int kind, int64_t n, const double *params, int nparams, const d
     GH_CUDA(cudaMemcpyAsync(mass, dmass, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
     GH_CUDA(cudaStreamSynchronize(st));
   }
+  GH_TRY(scratch_release(s, st));
   return GH_OK;
 }
 
@@ -404,6 +396,7 @@ int gh_ic_sample_expdisk(int64_t n, const double *params4, const double *table_R
     if (!s->stream) GH_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     st = s->stream;
   }
+  GH_TRY(scratch_acquire(s, st));
   const size_t nt = (size_t)ntable;
   GH_TRY(s->ictab.reserve(sizeof(double) * (4 * nt + 3 * 256)));
   double *tR = s->ictab.as<double>(), *tcum = tR + nt, *tvphi = tcum + nt, *tratio = tvphi + nt, *scratch = tratio + nt;
@@ -425,6 +418,7 @@ int gh_ic_sample_expdisk(int64_t n, const double *params4, const double *table_R
     GH_CUDA(cudaMemcpyAsync(mass, dmass, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
     GH_CUDA(cudaStreamSynchronize(st));
   }
+  GH_TRY(scratch_release(s, st));
   return GH_OK;
 }
 
@@ -460,20 +454,27 @@ int gh_engine_create(gh_engine **out, int device, int64_t n_total, int64_t i_beg
   E_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   E_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
   E_CUDA(cudaMalloc(&e->mass, sizeof(double) * n_total));
-  for (int r = 0; r < RING; r++) {
+  for (int r = 0; r < GH_RING; r++) {
     E_CUDA(cudaMalloc(&e->x[r], sizeof(double) * 3 * i_count));
     E_CUDA(cudaMalloc(&e->v[r], sizeof(double) * 3 * i_count));
     E_CUDA(cudaEventCreateWithFlags(&e->copied[r], cudaEventDisableTiming));
   }
   E_CUDA(cudaEventCreateWithFlags(&e->step_done, cudaEventDisableTiming));
-  E_CUDA(cudaEventCreate(&e->fev[0]));
-  E_CUDA(cudaEventCreate(&e->fev[1]));
+  for (int r = 0; r < gh_engine::FEV_RING; r++) {
+    E_CUDA(cudaEventCreate(&e->fev[r][0]));
+    E_CUDA(cudaEventCreate(&e->fev[r][1]));
+  }
   for (int b = 0; b < 2; b++) {
     E_CUDA(cudaMalloc(&e->src[b], e->src_stride() * n_total));
     E_CUDA(cudaMemset(e->src[b], 0, e->src_stride() * n_total));
   }
   if (prec == GH_PREC_F32) E_CUDA(cudaMalloc(&e->xh_private, sizeof(double) * 3 * i_count));
   E_CUDA(cudaMalloc(&e->d_energy, sizeof(double) * 2));
+  E_CUDA(cudaMallocHost(&e->h_maxent, sizeof(int) * gh_engine::MAXENT_RING));
+  for (int r = 0; r < gh_engine::MAXENT_RING; r++) {
+    e->h_maxent[r] = 0;
+    E_CUDA(cudaEventCreateWithFlags(&e->maxent_ev[r], cudaEventDisableTiming));
+  }
 #undef E_CUDA
   e->tw = tree_workspace_create();
   *out = e;
@@ -486,17 +487,22 @@ int gh_engine_destroy(gh_engine *e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
   cudaFree(e->mass);
-  for (int r = 0; r < RING; r++) {
+  for (int r = 0; r < GH_RING; r++) {
     cudaFree(e->x[r]);
     cudaFree(e->v[r]);
     if (e->copied[r]) cudaEventDestroy(e->copied[r]);
   }
   if (e->step_done) cudaEventDestroy(e->step_done);
-  if (e->fev[0]) cudaEventDestroy(e->fev[0]);
-  if (e->fev[1]) cudaEventDestroy(e->fev[1]);
+  for (int r = 0; r < gh_engine::FEV_RING; r++) {
+    if (e->fev[r][0]) cudaEventDestroy(e->fev[r][0]);
+    if (e->fev[r][1]) cudaEventDestroy(e->fev[r][1]);
+  }
   if (!e->external_src) { cudaFree(e->src[0]); cudaFree(e->src[1]); }
   cudaFree(e->xh_private);
   cudaFree(e->d_energy);
+  if (e->h_maxent) cudaFreeHost(e->h_maxent);
+  for (int r = 0; r < gh_engine::MAXENT_RING; r++)
+    if (e->maxent_ev[r]) cudaEventDestroy(e->maxent_ev[r]);
   e->ws.release();
   e->ext.release();
   e->ext2.release();
@@ -535,13 +541,14 @@ int gh_engine_upload(gh_engine *e, const double *pos, const double *vel, const d
   GH_ENGINE_GUARD(e);
   if (!pos || !vel || !mass_all) { set_error("null pointer argument"); return GH_EINVAL; }
   GH_CUDA(cudaStreamSynchronize(e->copy_stream));
-  for (int r = 0; r < RING; r++) e->copy_pending[r] = false;
+  for (int r = 0; r < GH_RING; r++) e->copy_pending[r] = false;
   GH_CUDA(cudaMemcpyAsync(e->x[e->cur], pos, sizeof(double) * 3 * e->ni, cudaMemcpyHostToDevice, e->stream));
   GH_CUDA(cudaMemcpyAsync(e->v[e->cur], vel, sizeof(double) * 3 * e->ni, cudaMemcpyHostToDevice, e->stream));
   GH_CUDA(cudaMemcpyAsync(e->mass, mass_all, sizeof(double) * e->n, cudaMemcpyHostToDevice, e->stream));
   GH_CUDA(cudaStreamSynchronize(e->stream));
   e->uploaded = true;
   e->xhalf_valid = false;
+  e->dist_ready = false;
   return GH_OK;
 }
 
@@ -549,7 +556,7 @@ int gh_engine_upload_device(gh_engine *e, const double *pos, const double *vel, 
   GH_ENGINE_GUARD(e);
   if (!pos || !vel || !mass_all) { set_error("null pointer argument"); return GH_EINVAL; }
   GH_CUDA(cudaStreamSynchronize(e->copy_stream));
-  for (int r = 0; r < RING; r++) e->copy_pending[r] = false;
+  for (int r = 0; r < GH_RING; r++) e->copy_pending[r] = false;
   GH_CUDA(cudaMemcpyAsync(e->x[e->cur], pos, sizeof(double) * 3 * e->ni, cudaMemcpyDeviceToDevice, e->stream));
   GH_CUDA(cudaMemcpyAsync(e->v[e->cur], vel, sizeof(double) * 3 * e->ni, cudaMemcpyDeviceToDevice, e->stream));
   GH_CUDA(cudaMemcpyAsync(e->mass, mass_all, sizeof(double) * e->n, cudaMemcpyDeviceToDevice, e->stream));
@@ -595,8 +602,11 @@ int gh_engine_prepare(gh_engine *e, double dt) {
 
 int gh_engine_set_dt(gh_engine *e, double dt) { return gh_engine_prepare(e, dt); }
 
-static int engine_step_impl(gh_engine *e, double dt, double eps, double theta, int algorithm,
-                            const double *ext_dev) {
+}  // extern "C"
+
+namespace gh {
+int engine_step_args(gh_engine *e, double dt, double eps, double theta, int algorithm, const double *ext_dev,
+                     StepArgs *out) {
   if (!e->uploaded) { set_error("engine has no state: call gh_engine_upload first"); return GH_ESTATE; }
   if (algorithm != GH_ALG_DIRECT && algorithm != GH_ALG_TREE) { set_error("unknown algorithm %d", algorithm); return GH_EINVAL; }
   if (!e->xhalf_valid || dt != e->dt_built) {
@@ -607,7 +617,7 @@ static int engine_step_impl(gh_engine *e, double dt, double eps, double theta, i
     }
     GH_TRY(gh_engine_prepare(e, dt));
   }
-  const int nxt = (e->cur + 1) % RING;
+  const int nxt = (e->cur + 1) % GH_RING;
   if (e->copy_pending[nxt]) {
     GH_CUDA(cudaStreamWaitEvent(e->stream, e->copied[nxt], 0));
     e->copy_pending[nxt] = false;
@@ -633,9 +643,10 @@ static int engine_step_impl(gh_engine *e, double dt, double eps, double theta, i
 
   // gravhopper.py:449-450 (Np == 1 feels no N-body force) needs no special case: the only source
   // is the target itself and its term is exactly zero in every kernel.
+  memset(out, 0, sizeof(*out));
+  out->algorithm = algorithm;
   if (algorithm == GH_ALG_DIRECT) {
-    DirectArgs a;
-    memset(&a, 0, sizeof(a));
+    DirectArgs &a = out->direct;
     a.prec = e->prec;
     a.nj = e->n;
     a.ni = e->ni;
@@ -649,10 +660,8 @@ static int engine_step_impl(gh_engine *e, double dt, double eps, double theta, i
       a.src32 = reinterpret_cast<const float4 *>(e->src[e->scur]);
       a.tgt32 = a.src32 + e->ib;
     }
-    GH_TRY(launch_direct(a, e->ws, e->stream, e->fev));
   } else {
-    TreeArgs a;
-    memset(&a, 0, sizeof(a));
+    TreeArgs &a = out->tree;
     a.prec = e->prec;
     a.nj = e->n;
     a.ni = e->ni;
@@ -669,13 +678,40 @@ static int engine_step_impl(gh_engine *e, double dt, double eps, double theta, i
       a.src32 = reinterpret_cast<const float4 *>(e->src[e->scur]);
       a.tgt32 = a.src32 + e->ib;
     }
-    GH_TRY(launch_tree(a, e->tw, e->stream, e->fev));
   }
-  e->fev_valid = true;
-  e->cur = nxt;
-  e->scur ^= 1;
   return GH_OK;
 }
+
+void engine_step_done(gh_engine *e) {
+  e->fev_count++;
+  e->cur = (e->cur + 1) % GH_RING;
+  e->scur ^= 1;
+}
+
+int engine_step_impl(gh_engine *e, double dt, double eps, double theta, int algorithm, const double *ext_dev) {
+  StepArgs sa;
+  GH_TRY(engine_step_args(e, dt, eps, theta, algorithm, ext_dev, &sa));
+  cudaEvent_t *ev = e->fev[e->fev_count % gh_engine::FEV_RING];
+  if (algorithm == GH_ALG_DIRECT) GH_TRY(launch_direct(sa.direct, e->ws, e->stream, ev));
+  else GH_TRY(launch_tree(sa.tree, e->tw, e->stream, ev));
+  engine_step_done(e);
+  return GH_OK;
+}
+
+// The engine never synchronises inside a tree step, so an entry-array overflow (the walk then
+// leaves the state untouched) can only be reported when the host next waits for the stream.
+int engine_check_tree(gh_engine *e) {
+  int64_t entries = 0;
+  if (e->tw && tree_poll_overflow(e->tw, &entries) < 0) {
+    set_error("tree: the entry array overflowed during a step (%lld entries needed); the state stopped advancing "
+              "there -- upload it again and rerun (capacity grows with the largest count seen)", (long long)entries);
+    return GH_ESTATE;
+  }
+  return GH_OK;
+}
+}  // namespace gh
+
+extern "C" {
 
 int gh_engine_step(gh_engine *e, double dt, double eps, double theta, int algorithm,
                    const double *ext_acc, int ext_mem) {
@@ -722,13 +758,14 @@ int gh_engine_run(gh_engine *e, int64_t nsteps, double dt, double eps, double th
   }
   cudaError_t c1 = cudaStreamSynchronize(e->stream);
   cudaError_t c2 = cudaStreamSynchronize(e->copy_stream);
-  for (int r = 0; r < RING; r++) e->copy_pending[r] = false;
+  for (int r = 0; r < GH_RING; r++) e->copy_pending[r] = false;
   if (reg_p) cudaHostUnregister(pos_hist);
   if (reg_v) cudaHostUnregister(vel_hist);
   if (rc == GH_OK && (c1 != cudaSuccess || c2 != cudaSuccess)) {
     set_error("gh_engine_run: %s", cudaGetErrorString(c1 != cudaSuccess ? c1 : c2));
     rc = GH_ECUDA;
   }
+  if (rc == GH_OK && algorithm == GH_ALG_TREE) rc = engine_check_tree(e);
   return rc;
 }
 
@@ -738,7 +775,7 @@ int gh_engine_download(gh_engine *e, double *pos, double *vel) {
   if (pos) GH_CUDA(cudaMemcpyAsync(pos, e->x[e->cur], sizeof(double) * 3 * e->ni, cudaMemcpyDeviceToHost, e->stream));
   if (vel) GH_CUDA(cudaMemcpyAsync(vel, e->v[e->cur], sizeof(double) * 3 * e->ni, cudaMemcpyDeviceToHost, e->stream));
   GH_CUDA(cudaStreamSynchronize(e->stream));
-  return GH_OK;
+  return engine_check_tree(e);
 }
 
 int gh_engine_download_xhalf(gh_engine *e, double *xhalf) {
@@ -767,7 +804,7 @@ int gh_engine_synchronize(gh_engine *e) {
   GH_ENGINE_GUARD(e);
   GH_CUDA(cudaStreamSynchronize(e->stream));
   GH_CUDA(cudaStreamSynchronize(e->copy_stream));
-  return GH_OK;
+  return engine_check_tree(e);
 }
 
 int gh_engine_state_ptrs(gh_engine *e, double **pos_dev, double **vel_dev) {
@@ -789,9 +826,29 @@ int gh_engine_launch_count(gh_engine *e, int64_t *count) {
 int gh_engine_last_force_ms(gh_engine *e, float *ms) {
   GH_ENGINE_GUARD(e);
   if (!ms) return GH_EINVAL;
-  if (!e->fev_valid) { set_error("no step has run"); return GH_ESTATE; }
-  GH_CUDA(cudaEventSynchronize(e->fev[1]));
-  GH_CUDA(cudaEventElapsedTime(ms, e->fev[0], e->fev[1]));
+  if (e->fev_count <= 0) { set_error("no step has run"); return GH_ESTATE; }
+  cudaEvent_t *ev = e->fev[(e->fev_count - 1) % gh_engine::FEV_RING];
+  GH_CUDA(cudaEventSynchronize(ev[1]));
+  GH_CUDA(cudaEventElapsedTime(ms, ev[0], ev[1]));
+  return GH_OK;
+}
+int gh_engine_force_ms_mean(gh_engine *e, int last_k, float *mean_ms, int *count) {
+  GH_ENGINE_GUARD(e);
+  if (!mean_ms || last_k <= 0) { set_error("gh_engine_force_ms_mean: bad arguments"); return GH_EINVAL; }
+  if (e->fev_count <= 0) { set_error("no step has run"); return GH_ESTATE; }
+  int64_t k = last_k;
+  if (k > e->fev_count) k = e->fev_count;
+  if (k > gh_engine::FEV_RING) k = gh_engine::FEV_RING;
+  double sum = 0.0;
+  for (int64_t j = 0; j < k; j++) {
+    cudaEvent_t *ev = e->fev[(e->fev_count - 1 - j) % gh_engine::FEV_RING];
+    float ms = 0.f;
+    GH_CUDA(cudaEventSynchronize(ev[1]));
+    GH_CUDA(cudaEventElapsedTime(&ms, ev[0], ev[1]));
+    sum += ms;
+  }
+  *mean_ms = (float)(sum / (double)k);
+  if (count) *count = (int)k;
   return GH_OK;
 }
 int gh_engine_tree_stats(gh_engine *e, int64_t out[8]) {

@@ -123,13 +123,20 @@ struct InArray {
   __device__ __forceinline__ T operator()(int64_t q) const { return a[q]; }
 };
 
+// `ndev` (nullable): the element count lives on the device (distributed tree build: a rank does not
+// know on the host how many particles fall into its key range); `n` is then the capacity the
+// launch was sized for, and chunks beyond the real count contribute zeros.
 template <class T, class In>
 __global__ void __launch_bounds__(SCAN_THREADS)
-scan_phase1(In in, int64_t n, T *__restrict__ warpsum) {
+scan_phase1(In in, int64_t n, T *__restrict__ warpsum, const int *__restrict__ ndev = nullptr) {
   const int lane = threadIdx.x & 31;
   const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t base = w * SCAN_WARP_ELEMS;
   if (base >= n) return;
+  if (ndev) {
+    n = *ndev;
+    if (base >= n) { if (lane == 0) warpsum[w] = ScanOps<T>::zero(); return; }
+  }
   T acc = ScanOps<T>::zero();
 #pragma unroll 2
   for (int r = 0; r < SCAN_ROUNDS; r++) {  // element order inside the warp: round-major
@@ -144,13 +151,15 @@ scan_phase1(In in, int64_t n, T *__restrict__ warpsum) {
 // warpoff == nullptr: single-warp launch over the whole (short) array.
 template <class T, class In>
 __global__ void __launch_bounds__(SCAN_THREADS)
-scan_phase3(In in, int64_t n, const T *__restrict__ warpoff, T *__restrict__ P /* n + 1 */) {
+scan_phase3(In in, int64_t n, const T *__restrict__ warpoff, T *__restrict__ P /* n + 1 */,
+            const int *__restrict__ ndev = nullptr) {
   const int lane = threadIdx.x & 31;
   const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t base = w * SCAN_WARP_ELEMS;
+  if (w == 0 && lane == 0) P[0] = ScanOps<T>::zero();
+  if (ndev) n = *ndev;
   if (base >= n) return;
   T carry = warpoff ? warpoff[w] : ScanOps<T>::zero();
-  if (w == 0 && lane == 0) P[0] = ScanOps<T>::zero();
   for (int r = 0; r < SCAN_ROUNDS; r++) {
     const int64_t q = base + r * 32 + lane;
     T v = (q < n) ? in(q) : ScanOps<T>::zero();
@@ -164,11 +173,13 @@ scan_phase3(In in, int64_t n, const T *__restrict__ warpoff, T *__restrict__ P /
 #ifndef GH_HOST_EMU  // launch sequence: the host emulation (tests/emu) has its own
 // P[0..n]: P[0] = identity, P[q+1] = in(0) (+) ... (+) in(q).  Recursion over 256-element warp
 // chunks (depth 3 at n = 16.7M, 4 beyond); `levels` supplies scratch for the per-level totals.
+// `ndev` (nullable): real element count on the device, n = capacity (see scan_phase1).
 template <class T, class In>
-static int chunked_scan(In in, int64_t n, T *P, DeviceBuffer *levels, int depth, cudaStream_t st) {
+static int chunked_scan(In in, int64_t n, T *P, DeviceBuffer *levels, int depth, cudaStream_t st,
+                        const int *ndev = nullptr) {
   if (n <= 0) return GH_OK;
   if (n <= SCAN_WARP_ELEMS) {
-    scan_phase3<T, In><<<1, 32, 0, st>>>(in, n, nullptr, P);
+    scan_phase3<T, In><<<1, 32, 0, st>>>(in, n, nullptr, P, ndev);
     GH_LAUNCH_CHECK();
     return GH_OK;
   }
@@ -178,10 +189,10 @@ static int chunked_scan(In in, int64_t n, T *P, DeviceBuffer *levels, int depth,
   GH_TRY(levels[depth].reserve(sizeof(T) * (size_t)(2 * nw + 1)));  // totals[nw] + prefix[nw + 1]
   T *totals = levels[depth].as<T>();
   T *prefix = totals + nw;
-  scan_phase1<T, In><<<nsb, SCAN_THREADS, 0, st>>>(in, n, totals);
+  scan_phase1<T, In><<<nsb, SCAN_THREADS, 0, st>>>(in, n, totals, ndev);
   GH_LAUNCH_CHECK();
   GH_TRY((chunked_scan<T, InArray<T>>(InArray<T>{totals}, nw, prefix, levels, depth + 1, st)));
-  scan_phase3<T, In><<<nsb, SCAN_THREADS, 0, st>>>(in, n, prefix, P);
+  scan_phase3<T, In><<<nsb, SCAN_THREADS, 0, st>>>(in, n, prefix, P, ndev);
   GH_LAUNCH_CHECK();
   return GH_OK;
 }
@@ -196,8 +207,9 @@ static constexpr int RS_RADIX = 256;
 
 __global__ void __launch_bounds__(RS_THREADS)
 rs_hist_kernel(const uint64_t *__restrict__ keys, int64_t n, int shift, int *__restrict__ hist,
-               int nblocks, int *__restrict__ gtot /* [256], zeroed */) {
+               int nblocks, int *__restrict__ gtot /* [256], zeroed */, const int *__restrict__ ndev = nullptr) {
   __shared__ int h[RS_RADIX];
+  if (ndev) n = *ndev;  // real count on the device; the grid covers the capacity
   h[threadIdx.x] = 0;
   __syncthreads();
   const int64_t base = (int64_t)blockIdx.x * RS_TILE;
@@ -252,7 +264,8 @@ __global__ void GH_RS_BOUNDS
 rs_scatter_kernel(const uint64_t *__restrict__ kin, const int *__restrict__ vin,
                   uint64_t *__restrict__ kout, int *__restrict__ vout, int64_t n, int shift,
                   const int *__restrict__ offs /* per-digit exclusive offsets (rs_rowscan_kernel) */,
-                  const int *__restrict__ gtot /* [256] keys per digit */, int nblocks) {
+                  const int *__restrict__ gtot /* [256] keys per digit */, int nblocks,
+                  const int *__restrict__ ndev = nullptr) {
   __shared__ int whist[RS_WARPS][RS_RADIX];  // per-warp digit counts, then per-warp digit bases
   __shared__ int dstart[RS_RADIX];           // start of digit d in the CTA-local sorted tile
   __shared__ int gbase[RS_RADIX];            // global start of this CTA's keys of digit d
@@ -262,6 +275,8 @@ rs_scatter_kernel(const uint64_t *__restrict__ kin, const int *__restrict__ vin,
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int64_t tile0 = (int64_t)blockIdx.x * RS_TILE;
   const int64_t seg0 = tile0 + (int64_t)w * (32 * RS_ROUNDS);
+  if (ndev) n = *ndev;
+  if (tile0 >= n) return;  // whole CTA (capacity-sized grid)
 #pragma unroll
   for (int k = 0; k < RS_WARPS; k++) whist[k][tid] = 0;
   __syncthreads();
@@ -401,8 +416,9 @@ struct RadixScratch {
 
 // Stable LSD sort of (key, value) pairs on key bits [0, nbits).  Ping-pongs between (kA, vA) and
 // (kB, vB), starting from A; *result_in_B says where the sorted data ends up (both are clobbered).
+// `ndev` (nullable): real pair count on the device, n = capacity the grids are sized for.
 static int radix_sort_pairs(uint64_t *kA, int *vA, uint64_t *kB, int *vB, int64_t n, int nbits,
-                            RadixScratch &rs, cudaStream_t st, bool *result_in_B) {
+                            RadixScratch &rs, cudaStream_t st, bool *result_in_B, const int *ndev = nullptr) {
   *result_in_B = false;
   if (n <= 1) return GH_OK;
   const int nblocks = (int)((n + RS_TILE - 1) / RS_TILE);
@@ -417,12 +433,12 @@ static int radix_sort_pairs(uint64_t *kA, int *vA, uint64_t *kB, int *vB, int64_
   for (int pass = 0; pass < npass; pass++) {
     const int shift = 8 * pass;
     int *gtot = rs.gtot.as<int>() + RS_RADIX * pass;
-    rs_hist_kernel<<<nblocks, RS_THREADS, 0, st>>>(kin, n, shift, rs.hist.as<int>(), nblocks, gtot);
+    rs_hist_kernel<<<nblocks, RS_THREADS, 0, st>>>(kin, n, shift, rs.hist.as<int>(), nblocks, gtot, ndev);
     GH_LAUNCH_CHECK();
     rs_rowscan_kernel<<<RS_RADIX, RS_THREADS, 0, st>>>(rs.hist.as<int>(), nblocks);
     GH_LAUNCH_CHECK();
     rs_scatter_kernel<<<nblocks, RS_THREADS, 0, st>>>(kin, vin, kout, vout, n, shift, rs.hist.as<int>(), gtot,
-                                                     nblocks);
+                                                     nblocks, ndev);
     GH_LAUNCH_CHECK();
     uint64_t *tk = kin; kin = kout; kout = tk;
     int *tv = vin; vin = vout; vout = tv;

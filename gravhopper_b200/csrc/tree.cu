@@ -51,13 +51,32 @@
 namespace gh {
 
 // ---- workspace + orchestration --------------------------------------------------------------------
+// What one evaluation leaves behind for its later phases (the distributed build interleaves the
+// phases with collectives the caller issues; a single-rank evaluation runs them back to back).
+struct TreePhaseState {
+  int64_t n = 0;            // sources (capacity of the sorted arrays)
+  const uint64_t *shi = nullptr, *slo = nullptr;
+  const int *sidx = nullptr;
+  const int *ndev = nullptr;  // &ctl->n_local when the count lives on the device
+  int levels = 0;
+  bool deep = false, dist = false;
+  int rank = 0, world = 1;
+  int64_t ecap = 0;         // entries per segment (stride)
+  int end = 0;              // world * stride
+};
 struct TreeWorkspace {
   DeviceBuffer root, part, hi, lo, hi2, lo2, lo3, idx, idx2, clev, cnt, base, P;
   DeviceBuffer node, skip, misc, thi, tidx, thi2, tidx2, sorted, bsum, scanlv[4], cntlv[4];
+  DeviceBuffer ctl, rec1, rec2, keys_all, tilecnt, tileoff, tilelv[4];
   RadixScratch rs;
+  TreePhaseState ph;
+  int64_t ecap = 0;          // entries the node buffer holds per segment (grow-only)
+  int64_t node_slots = 0;    // entries allocated in `node`
   int64_t last_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  int *h_pinned = nullptr;  // [0] nentries, [1] maxlevel ; pinned for async readback
+  int *h_pinned = nullptr;  // [0] entries of the last build, [1] maxlevel, [2] overflow flag ; async readback
   unsigned long long *h_stats = nullptr;
+  cudaEvent_t readback = nullptr;  // recorded after the async readback of the last evaluation
+  bool readback_valid = false;
 };
 
 TreeWorkspace *tree_workspace_create() { return new TreeWorkspace(); }
@@ -65,11 +84,13 @@ void tree_workspace_destroy(TreeWorkspace *w) {
   if (!w) return;
   DeviceBuffer *all[] = {&w->root, &w->part, &w->hi, &w->lo, &w->hi2, &w->lo2, &w->lo3, &w->idx, &w->idx2,
                          &w->clev, &w->cnt, &w->base, &w->P, &w->node, &w->sorted, &w->bsum, &w->scanlv[0], &w->scanlv[1], &w->scanlv[2], &w->scanlv[3], &w->cntlv[0], &w->cntlv[1], &w->cntlv[2], &w->cntlv[3],
-                         &w->skip, &w->misc, &w->thi, &w->tidx, &w->thi2, &w->tidx2};
+                         &w->skip, &w->misc, &w->thi, &w->tidx, &w->thi2, &w->tidx2, &w->ctl, &w->rec1, &w->rec2,
+                         &w->keys_all, &w->tilecnt, &w->tileoff, &w->tilelv[0], &w->tilelv[1], &w->tilelv[2], &w->tilelv[3]};
   for (auto *b : all) b->release();
   w->rs.release();
   if (w->h_pinned) cudaFreeHost(w->h_pinned);
   if (w->h_stats) cudaFreeHost(w->h_stats);
+  if (w->readback) cudaEventDestroy(w->readback);
   delete w;
 }
 int tree_last_stats(TreeWorkspace *w, int64_t out[8]) {
@@ -118,12 +139,13 @@ void set_group_hybrid_kappa(double k) { g_hybrid_kappa = (k > 0.0 && k <= 1.0) ?
 
 template <class Real> struct GroupWalk {
   static void launch(const Node<Real> *, int, const TargetsView &, int64_t, const double *, float, double,
-                     const Epilogue &, unsigned long long *, bool, bool, unsigned, cudaStream_t) {}
+                     const Epilogue &, unsigned long long *, bool, bool, unsigned, cudaStream_t, const int *) {}
 };
 template <> struct GroupWalk<float> {
   static void launch(const Node<float> *nodes, int nentries, const TargetsView &tv, int64_t ni,
                      const double *root, float eps2, double inv_theta2, const Epilogue &ep,
-                     unsigned long long *dstats, bool stats, bool guard, unsigned blocks32, cudaStream_t st) {
+                     unsigned long long *dstats, bool stats, bool guard, unsigned blocks32, cudaStream_t st,
+                     const int *ovf) {
     const int lim = group_list_limit();
     int wpc = 2;  // warps per CTA (measured at N = 4M: 32/64/128 threads -> 3.21/3.14/3.15 ms); GH_WALK_BLOCK overrides
     if (const char *env = getenv("GH_WALK_BLOCK")) { int v = atoi(env); if (v == 32 || v == 64 || v == 128) wpc = v / 32; }
@@ -135,7 +157,7 @@ template <> struct GroupWalk<float> {
       cudaMemcpyToSymbolAsync(c_hybrid_kappa2, &k2, sizeof(float), 0, cudaMemcpyHostToDevice, st);
     }
 #define GH_GWALK0(W, STATS, GUARD, HYB) \
-  walk_group_kernel<W, STATS, GUARD, HYB><<<nb, 32 * W, 0, st>>>(nodes, nentries, tv, ni, root, eps2, inv_theta2, lim, ep, dstats)
+  walk_group_kernel<W, STATS, GUARD, HYB><<<nb, 32 * W, 0, st>>>(nodes, nentries, tv, ni, root, eps2, inv_theta2, lim, ep, dstats, ovf)
 #define GH_GWALK1(W, STATS, GUARD) do { if (hyb) GH_GWALK0(W, STATS, GUARD, true); else GH_GWALK0(W, STATS, GUARD, false); } while (0)
 #define GH_GWALK(STATS, GUARD) do { if (wpc == 1) GH_GWALK1(1, STATS, GUARD); else if (wpc == 2) GH_GWALK1(2, STATS, GUARD); else GH_GWALK1(4, STATS, GUARD); } while (0)
     if (stats) { if (guard) GH_GWALK(true, true); else GH_GWALK(true, false); }
@@ -146,204 +168,398 @@ template <> struct GroupWalk<float> {
   }
 };
 
+// entries a segment must be able to hold.  Single rank: grow-only, at least 2 n (the reference
+// octree has ~1.5 entries per particle; chains of single-child cells above tight pairs add to
+// that), raised ahead of time when the last completed build came within 80 % of it.  The count is
+// never needed on the host during an evaluation: the walk ends its chains at the CAPACITY, emit
+// guards its writes, and an overflow is a flag the host looks at when it next synchronises.
+static int64_t entry_capacity(TreeWorkspace *w, int64_t n, bool fp32) {
+  int64_t want = 2 * n + 1024;
+  if (w->ecap > want) want = w->ecap;
+  const int64_t seen = w->h_pinned ? (int64_t)w->h_pinned[0] : 0;  // possibly one evaluation stale
+  if (seen > 0 && 10 * seen > 8 * want) want = seen + seen / 2;
+  if (fp32 && want >= (1 << SKIP_BITS)) want = (1 << SKIP_BITS) - 1;
+  return want;
+}
+
 template <class Src, class Real>
-static int tree_impl(const TreeArgs &a, Src src, const float4 *tgt32, TreeWorkspace *w,
-                     cudaStream_t st, cudaEvent_t *ev) {
-  const int64_t n = a.nj, ni = a.ni;
-  if (n > (int64_t)INT_MAX / 48) { set_error("tree: too many particles (%lld)", (long long)n); return GH_EINVAL; }
-  const int levels = (sizeof(Real) == 8) ? LEVELS_MAX : LEVELS_HI;
-  const bool deep = levels > LEVELS_HI;
-  const bool rel_origin = (sizeof(Real) == 4);  // fp32 entries are stored relative to the root centre
-  if (!w->h_pinned) GH_CUDA(cudaMallocHost(&w->h_pinned, 4 * sizeof(int)));
-  if (!w->h_stats) GH_CUDA(cudaMallocHost(&w->h_stats, 4 * sizeof(unsigned long long)));
-
-  // K3
-  const int nb = (int)((n + 256 * 8 - 1) / (256 * 8) < 1024 ? (n + 256 * 8 - 1) / (256 * 8) : 1024);
-  GH_TRY(w->root.reserve(sizeof(double) * ROOT_DOUBLES));
-  GH_TRY(w->part.reserve(sizeof(double) * 6 * 1024));
-  GH_TRY(w->misc.reserve(64));
-  double *root = w->root.as<double>();
-  bbox_stage1<<<nb, 256, 0, st>>>(src, n, w->part.as<double>());
-  GH_LAUNCH_CHECK();
-  bbox_stage2<<<1, 256, 0, st>>>(w->part.as<double>(), nb, a.eps, root);
-  GH_LAUNCH_CHECK();
-
-  // K4
-  GH_TRY(w->hi.reserve(sizeof(uint64_t) * n));
-  GH_TRY(w->hi2.reserve(sizeof(uint64_t) * n));
-  GH_TRY(w->idx.reserve(sizeof(int) * n));
-  GH_TRY(w->idx2.reserve(sizeof(int) * n));
-  if (deep) {
-    GH_TRY(w->lo.reserve(sizeof(uint64_t) * n));
-    GH_TRY(w->lo2.reserve(sizeof(uint64_t) * n));
-  }
-  uint64_t *hi = w->hi.as<uint64_t>(), *hi2 = w->hi2.as<uint64_t>();
-  uint64_t *lo = deep ? w->lo.as<uint64_t>() : nullptr, *lo2 = deep ? w->lo2.as<uint64_t>() : nullptr;
-  int *idx = w->idx.as<int>(), *idx2 = w->idx2.as<int>();
-  keys_kernel<<<nblk(n, 256), 256, 0, st>>>(src, n, root, levels, hi, lo, idx);
-  GH_LAUNCH_CHECK();
-
-  // K5: stable LSD radix sort (sortscan.cuh) over (lo, hi); both ping-pong buffers are clobbered
-  const uint64_t *shi, *slo = nullptr;
-  const int *sidx;
-  bool inB = false;
-  if (deep) {
-    // pass 1: by lo; pass 2: by hi gathered through the pass-1 order (stable).  The unsorted lo
-    // keys are needed again at the end, so keep a copy.
-    GH_TRY(w->lo3.reserve(sizeof(uint64_t) * n));
-    GH_CUDA(cudaMemcpyAsync(w->lo3.ptr, lo, sizeof(uint64_t) * n, cudaMemcpyDeviceToDevice, st));
-    GH_TRY(radix_sort_pairs(lo, idx, lo2, idx2, n, 63, w->rs, st, &inB));
-    int *order1 = inB ? idx2 : idx;
-    int *other1 = inB ? idx : idx2;
-    uint64_t *hs = inB ? lo : lo2;  // free key buffer of pass 1 holds hi gathered in pass-1 order
-    gather_u64<<<nblk(n, 256), 256, 0, st>>>(hi, order1, n, hs);
-    GH_LAUNCH_CHECK();
-    GH_TRY(radix_sort_pairs(hs, order1, hi2, other1, n, 63, w->rs, st, &inB));
-    shi = inB ? hi2 : hs;
-    sidx = inB ? other1 : order1;
-    uint64_t *lsorted = (shi == hi2) ? hs : hi2;  // the key buffer not holding the result
-    gather_u64<<<nblk(n, 256), 256, 0, st>>>(w->lo3.as<uint64_t>(), sidx, n, lsorted);
-    GH_LAUNCH_CHECK();
-    slo = lsorted;
-  } else {
-    GH_TRY(radix_sort_pairs(hi, idx, hi2, idx2, n, 63, w->rs, st, &inB));
-    shi = inB ? hi2 : hi;
-    sidx = inB ? idx2 : idx;
-  }
-
-  // K6a + pre-order offsets: base[p] = sum_{q<p} (cells opened at q + 1), base[n] = entries
-  GH_TRY(w->clev.reserve(n));
-  GH_TRY(w->cnt.reserve(sizeof(int) * (n + 1)));
-  GH_TRY(w->base.reserve(sizeof(int) * (n + 1)));
-  signed char *clev = w->clev.as<signed char>();
-  int *cnt = w->cnt.as<int>(), *base = w->base.as<int>();
-  levels_kernel<<<nblk(n, 256), 256, 0, st>>>(shi, slo, n, levels, clev, cnt);
-  GH_LAUNCH_CHECK();
-  GH_TRY((chunked_scan<int, InArray<int>>(InArray<int>{cnt}, n, base, w->cntlv, 0, st)));
-  GH_CUDA(cudaMemcpyAsync(&w->h_pinned[0], base + n, sizeof(int), cudaMemcpyDeviceToHost, st));
-
-  // K7
-  GH_TRY(w->sorted.reserve(sizeof(double4) * (size_t)n));
-  double4 *sp = w->sorted.as<double4>();
-  gather_sorted_kernel<<<nblk(n, 256), 256, 0, st>>>(src, sidx, n, sp);
-  GH_LAUNCH_CHECK();
+struct TreeRun {
   using Mom = typename MomentOf<Real>::type;
-  GH_TRY(w->P.reserve(sizeof(Mom) * (size_t)(n + 1)));
-  Mom *P = w->P.as<Mom>();
-  if (sizeof(Real) == 4) {
-    GH_TRY((chunked_scan<D4, InParticlesRel>(InParticlesRel{sp, root}, n, reinterpret_cast<D4 *>(P), w->scanlv, 0, st)));
-  } else {
-    GH_TRY((chunked_scan<DD4, InParticles>(InParticles{sp}, n, reinterpret_cast<DD4 *>(P), w->scanlv, 0, st)));
-  }
 
-  // entries: need the count on the host to size the arrays
-  GH_CUDA(cudaStreamSynchronize(st));
-  const int nentries = w->h_pinned[0];
-  GH_TRY(w->node.reserve(sizeof(Node<Real>) * (size_t)nentries));
-  if (sizeof(Real) == 4) {
-    if (nentries >= (1 << SKIP_BITS)) { set_error("tree: %d entries exceed the fp32 node format (2^%d)", nentries, SKIP_BITS); return GH_EINVAL; }
-  } else {
-    GH_TRY(w->skip.reserve(sizeof(int) * (size_t)nentries));
-  }
-  Entries<Real> E{w->node.as<Node<Real>>(), sizeof(Real) == 4 ? nullptr : w->skip.as<int>()};
-  const double inv_theta2 = 1.0 / (a.theta * a.theta);  // theta = 0 -> inf: cells are never accepted
-  int *maxlevel = w->misc.as<int>();
-  unsigned long long *dstats = reinterpret_cast<unsigned long long *>(w->misc.as<char>() + 16);
-  GH_CUDA(cudaMemsetAsync(w->misc.ptr, 0, 64, st));
-  emit_kernel<Src, Real><<<nblk(n, 128), 128, 0, st>>>(sp, shi, slo, clev, base, P, n, root, rel_origin,
-                                                     inv_theta2, E, maxlevel);
-  GH_LAUNCH_CHECK();
-
-  // targets: Morton order.  Self case: the source order restricted to the owned slice is the
-  // sorted order itself when the slice is everything; otherwise sort the targets' own keys.
-  TargetsView tv;
-  tv.sorted = nullptr;
-  tv.pos64 = tgt32 ? nullptr : a.tgt_pos;
-  tv.pos32 = tgt32;
-  tv.order = nullptr;
-  tv.order_offset = 0;
-  if (a.targets_are_sources && ni == n) {
-    tv.order = sidx;
-    tv.sorted = sp;
-  } else if (ni > 32) {
-    GH_TRY(w->thi.reserve(sizeof(uint64_t) * ni));
-    GH_TRY(w->thi2.reserve(sizeof(uint64_t) * ni));
-    GH_TRY(w->tidx.reserve(sizeof(int) * ni));
-    GH_TRY(w->tidx2.reserve(sizeof(int) * ni));
-    if (tgt32) {
-      Src32 ts{tgt32};
-      keys_kernel<<<nblk(ni, 256), 256, 0, st>>>(ts, ni, root, LEVELS_HI, w->thi.as<uint64_t>(),
-                                                (uint64_t *)nullptr, w->tidx.as<int>());
-    } else {
-      Src64 ts{a.tgt_pos, nullptr};
-      keys_kernel<<<nblk(ni, 256), 256, 0, st>>>(ts, ni, root, LEVELS_HI, w->thi.as<uint64_t>(),
-                                                (uint64_t *)nullptr, w->tidx.as<int>());
+  // ---- phase A: bbox, keys, (select,) sort, (boundary keys) ---------------------------------------
+  static int phase_a(const TreeArgs &a, Src src, TreeWorkspace *w, cudaStream_t st, const TreeDist *d) {
+    const int64_t n = a.nj;
+    if (n > (int64_t)INT_MAX / 48) { set_error("tree: too many particles (%lld)", (long long)n); return GH_EINVAL; }
+    TreePhaseState &ph = w->ph;
+    ph = TreePhaseState();
+    ph.n = n;
+    ph.levels = (sizeof(Real) == 8) ? LEVELS_MAX : LEVELS_HI;
+    ph.deep = ph.levels > LEVELS_HI;
+    ph.dist = d != nullptr && d->world > 1;
+    if (ph.dist && ph.deep) { set_error("the distributed tree build is fp32 only"); return GH_EINVAL; }
+    if (ph.dist && d->world > DIST_MAX_RANKS) { set_error("at most %d ranks", DIST_MAX_RANKS); return GH_EINVAL; }
+    ph.rank = ph.dist ? d->rank : 0;
+    ph.world = ph.dist ? d->world : 1;
+    if (!w->h_pinned) {
+      GH_CUDA(cudaMallocHost(&w->h_pinned, 4 * sizeof(int)));
+      w->h_pinned[0] = w->h_pinned[1] = w->h_pinned[2] = w->h_pinned[3] = 0;
     }
+    if (!w->h_stats) GH_CUDA(cudaMallocHost(&w->h_stats, 4 * sizeof(unsigned long long)));
+    if (!w->readback) GH_CUDA(cudaEventCreateWithFlags(&w->readback, cudaEventDisableTiming));
+    const bool deep = ph.deep;
+
+    // entry array: capacity known before anything runs (no host round trip inside an evaluation)
+    const bool fp32 = sizeof(Real) == 4;
+    int64_t ecap = ph.dist ? (int64_t)d->stride : entry_capacity(w, n, fp32);
+    if (fp32 && ecap * ph.world >= (1 << SKIP_BITS)) {
+      if (!ph.dist && n + 1 < (1 << SKIP_BITS)) ecap = (1 << SKIP_BITS) - 1;
+      else { set_error("tree: %lld entries exceed the fp32 node format (2^%d)", (long long)(ecap * ph.world), SKIP_BITS); return GH_EINVAL; }
+    }
+    ph.ecap = ecap;
+    ph.end = (int)(ecap * ph.world);
+    w->ecap = ph.dist ? w->ecap : ecap;
+    GH_TRY(w->node.reserve(sizeof(Node<Real>) * (size_t)ph.end));
+    if (!fp32) GH_TRY(w->skip.reserve(sizeof(int) * (size_t)ph.end));
+
+    GH_TRY(w->root.reserve(sizeof(double) * ROOT_DOUBLES));
+    GH_TRY(w->part.reserve(sizeof(double) * 6 * 1024));
+    GH_TRY(w->misc.reserve(64));
+    GH_TRY(w->ctl.reserve(sizeof(BuildCtl)));
+    BuildCtl *ctl = w->ctl.as<BuildCtl>();
+
+    // K3
+    const int nb = (int)((n + 256 * 8 - 1) / (256 * 8) < 1024 ? (n + 256 * 8 - 1) / (256 * 8) : 1024);
+    double *root = w->root.as<double>();
+    bbox_stage1<<<nb, 256, 0, st>>>(src, n, w->part.as<double>());
     GH_LAUNCH_CHECK();
-    bool tinB = false;
-    GH_TRY(radix_sort_pairs(w->thi.as<uint64_t>(), w->tidx.as<int>(), w->thi2.as<uint64_t>(),
-                            w->tidx2.as<int>(), ni, 63, w->rs, st, &tinB));
-    tv.order = tinB ? w->tidx2.as<int>() : w->tidx.as<int>();
+    bbox_stage2<<<1, 256, 0, st>>>(w->part.as<double>(), nb, a.eps, root);
+    GH_LAUNCH_CHECK();
+
+    // K4
+    GH_TRY(w->hi.reserve(sizeof(uint64_t) * n));
+    GH_TRY(w->hi2.reserve(sizeof(uint64_t) * n));
+    GH_TRY(w->idx.reserve(sizeof(int) * n));
+    GH_TRY(w->idx2.reserve(sizeof(int) * n));
+    if (deep) {
+      GH_TRY(w->lo.reserve(sizeof(uint64_t) * n));
+      GH_TRY(w->lo2.reserve(sizeof(uint64_t) * n));
+    }
+    uint64_t *hi = w->hi.as<uint64_t>(), *hi2 = w->hi2.as<uint64_t>();
+    uint64_t *lo = deep ? w->lo.as<uint64_t>() : nullptr, *lo2 = deep ? w->lo2.as<uint64_t>() : nullptr;
+    int *idx = w->idx.as<int>(), *idx2 = w->idx2.as<int>();
+    if (ph.dist) {
+      // keys of ALL sources (the rank's own targets are among them), then the stable selection of
+      // the keys in this rank's range
+      GH_TRY(w->keys_all.reserve(sizeof(uint64_t) * n));
+      uint64_t *kall = w->keys_all.as<uint64_t>();
+      keys_kernel<<<nblk(n, 256), 256, 0, st>>>(src, n, root, ph.levels, kall, (uint64_t *)nullptr, idx2);
+      GH_LAUNCH_CHECK();
+      const int ntiles = (int)((n + SEL_TILE - 1) / SEL_TILE);
+      GH_TRY(w->tilecnt.reserve(sizeof(int) * (size_t)(ntiles + 1)));
+      GH_TRY(w->tileoff.reserve(sizeof(int) * (size_t)(ntiles + 1)));
+      ctl_init_dist<<<1, 1, 0, st>>>(ctl, ph.rank, ph.world, (int)ecap);
+      GH_LAUNCH_CHECK();
+      // key ranges of this step = what the previous step derived from the gathered key samples
+      // (or the bootstrap's, tree_splitters)
+      splitters_advance_kernel<<<1, DIST_MAX_RANKS + 1, 0, st>>>(ctl, ph.world);
+      GH_LAUNCH_CHECK();
+      select_count_kernel<<<ntiles, SEL_THREADS, 0, st>>>(kall, n, ctl, w->tilecnt.as<int>());
+      GH_LAUNCH_CHECK();
+      GH_TRY((chunked_scan<int, InArray<int>>(InArray<int>{w->tilecnt.as<int>()}, ntiles, w->tileoff.as<int>(),
+                                               w->tilelv, 0, st)));
+      select_compact_kernel<<<ntiles, SEL_THREADS, 0, st>>>(kall, n, ctl, w->tileoff.as<int>(), ntiles, hi, idx);
+      GH_LAUNCH_CHECK();
+      ph.ndev = &ctl->n_local;
+    } else {
+      keys_kernel<<<nblk(n, 256), 256, 0, st>>>(src, n, root, ph.levels, hi, lo, idx);
+      GH_LAUNCH_CHECK();
+      ctl_init_single<<<1, 1, 0, st>>>(ctl, (int)n, (int)ecap);
+      GH_LAUNCH_CHECK();
+    }
+
+    // K5: stable LSD radix sort (sortscan.cuh) over (lo, hi); both ping-pong buffers are clobbered
+    bool inB = false;
+    if (deep) {
+      // pass 1: by lo; pass 2: by hi gathered through the pass-1 order (stable).  The unsorted lo
+      // keys are needed again at the end, so keep a copy.
+      GH_TRY(w->lo3.reserve(sizeof(uint64_t) * n));
+      GH_CUDA(cudaMemcpyAsync(w->lo3.ptr, lo, sizeof(uint64_t) * n, cudaMemcpyDeviceToDevice, st));
+      GH_TRY(radix_sort_pairs(lo, idx, lo2, idx2, n, 63, w->rs, st, &inB));
+      int *order1 = inB ? idx2 : idx;
+      int *other1 = inB ? idx : idx2;
+      uint64_t *hs = inB ? lo : lo2;  // free key buffer of pass 1 holds hi gathered in pass-1 order
+      gather_u64<<<nblk(n, 256), 256, 0, st>>>(hi, order1, n, hs);
+      GH_LAUNCH_CHECK();
+      GH_TRY(radix_sort_pairs(hs, order1, hi2, other1, n, 63, w->rs, st, &inB));
+      ph.shi = inB ? hi2 : hs;
+      ph.sidx = inB ? other1 : order1;
+      uint64_t *lsorted = (ph.shi == hi2) ? hs : hi2;  // the key buffer not holding the result
+      gather_u64<<<nblk(n, 256), 256, 0, st>>>(w->lo3.as<uint64_t>(), ph.sidx, n, lsorted);
+      GH_LAUNCH_CHECK();
+      ph.slo = lsorted;
+    } else {
+      GH_TRY(radix_sort_pairs(hi, idx, hi2, idx2, n, 63, w->rs, st, &inB, ph.ndev));
+      ph.shi = inB ? hi2 : hi;
+      ph.sidx = inB ? idx2 : idx;
+    }
+    if (ph.dist) {
+      GH_TRY(w->rec1.reserve(sizeof(RankRec1) * (size_t)ph.world));
+      GH_TRY(w->rec2.reserve(sizeof(RankRec2) * (size_t)ph.world));
+      rec1_kernel<<<1, 1, 0, st>>>(ph.shi, ctl, w->rec1.as<RankRec1>());
+      GH_LAUNCH_CHECK();
+    }
+    return GH_OK;
   }
 
-  // K8
-  const Real eps2 = (Real)(a.eps * a.eps);
-  const int64_t nwarps = (ni + 31) / 32;
-  int wb = 128;
-  if (const char *env = getenv("GH_WALK_BLOCK")) { int v = atoi(env); if (v == 32 || v == 64 || v == 128) wb = v; }
-  const bool group = (sizeof(Real) == 4) && tree_walk_mode() == GH_WALK_GROUP;
-  const unsigned blocks = (unsigned)((nwarps + wb / 32 - 1) / (wb / 32));
-  if (ev) GH_CUDA(cudaEventRecord(ev[0], st));
-  const bool guard = (a.eps == 0.0);
-  // L2 prefetch hint of each entry's skip target; GH_WALK_PREFETCH=0/1 overrides
-  bool prefetch = false;
-  if (const char *env = getenv("GH_WALK_PREFETCH")) prefetch = atoi(env) != 0;
-  if (group) {
-    GroupWalk<Real>::launch(E.node, nentries, tv, ni, root, (float)eps2, inv_theta2, a.ep, dstats,
-                            a.want_stats, guard, (unsigned)nwarps, st);
-  } else {
+  // ---- phase B: common levels, pre-order offsets, Morton gather, moments, (cell-end table) ----------
+  static int phase_b(const TreeArgs &a, Src src, TreeWorkspace *w, cudaStream_t st) {
+    TreePhaseState &ph = w->ph;
+    const int64_t n = ph.n;
+    BuildCtl *ctl = w->ctl.as<BuildCtl>();
+    const BuildCtl *cd = ph.dist ? ctl : nullptr;
+    if (ph.dist) {
+      neighbours_kernel<<<1, 1, 0, st>>>(w->rec1.as<RankRec1>(), ctl);
+      GH_LAUNCH_CHECK();
+    }
+    // K6a + pre-order offsets: base[p] = sum_{q<p} (cells opened at q + 1), base[n] = entries
+    GH_TRY(w->clev.reserve(n));
+    GH_TRY(w->cnt.reserve(sizeof(int) * (n + 1)));
+    GH_TRY(w->base.reserve(sizeof(int) * (n + 1)));
+    signed char *clev = w->clev.as<signed char>();
+    int *cnt = w->cnt.as<int>(), *base = w->base.as<int>();
+    levels_kernel<<<nblk(n, 256), 256, 0, st>>>(ph.shi, ph.slo, n, ph.levels, clev, cnt, cd);
+    GH_LAUNCH_CHECK();
+    GH_TRY((chunked_scan<int, InArray<int>>(InArray<int>{cnt}, n, base, w->cntlv, 0, st, ph.ndev)));
+    if (!ph.dist) GH_CUDA(cudaMemcpyAsync(&w->h_pinned[0], base + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+
+    // K7
+    GH_TRY(w->sorted.reserve(sizeof(double4) * (size_t)n));
+    double4 *sp = w->sorted.as<double4>();
+    gather_sorted_kernel<<<nblk(n, 256), 256, 0, st>>>(src, ph.sidx, n, sp, cd);
+    GH_LAUNCH_CHECK();
+    GH_TRY(w->P.reserve(sizeof(Mom) * (size_t)(n + 1)));
+    Mom *P = w->P.as<Mom>();
+    double *root = w->root.as<double>();
+    if (sizeof(Real) == 4) {
+      GH_TRY((chunked_scan<D4, InParticlesRel>(InParticlesRel{sp, root}, n, reinterpret_cast<D4 *>(P), w->scanlv, 0, st, ph.ndev)));
+    } else {
+      GH_TRY((chunked_scan<DD4, InParticles>(InParticles{sp}, n, reinterpret_cast<DD4 *>(P), w->scanlv, 0, st)));
+    }
+    if (ph.dist) {
+      rec2_kernel<<<1, 32, 0, st>>>(ph.shi, base, reinterpret_cast<const D4 *>(P), ctl, w->rec2.as<RankRec2>());
+      GH_LAUNCH_CHECK();
+    }
+    return GH_OK;
+  }
+
+  // ---- phase C: (stitch,) emit ------------------------------------------------------------------------
+  static int phase_c(const TreeArgs &a, Src src, TreeWorkspace *w, cudaStream_t st) {
+    TreePhaseState &ph = w->ph;
+    const int64_t n = ph.n;
+    BuildCtl *ctl = w->ctl.as<BuildCtl>();
+    if (ph.dist) {
+      stitch_kernel<<<1, 1, 0, st>>>(w->rec1.as<RankRec1>(), w->rec2.as<RankRec2>(), ctl, n);
+      GH_LAUNCH_CHECK();
+    }
+    const bool rel_origin = (sizeof(Real) == 4);  // fp32 entries are stored relative to the root centre
+    Entries<Real> E{w->node.as<Node<Real>>(), sizeof(Real) == 4 ? nullptr : w->skip.as<int>()};
+    const double inv_theta2 = 1.0 / (a.theta * a.theta);  // theta = 0 -> inf: cells are never accepted
+    int *maxlevel = w->misc.as<int>();
+    GH_CUDA(cudaMemsetAsync(w->misc.ptr, 0, 64, st));
+    emit_kernel<Src, Real><<<nblk(n, 128), 128, 0, st>>>(w->sorted.as<double4>(), ph.shi, ph.slo,
+                                                       w->clev.as<signed char>(), w->base.as<int>(),
+                                                       w->P.as<Mom>(), n, w->root.as<double>(), rel_origin,
+                                                       inv_theta2, E, maxlevel, ctl, ph.dist);
+    GH_LAUNCH_CHECK();
+    return GH_OK;
+  }
+
+  // ---- phase D: targets in Morton order, walk, epilogue ----------------------------------------------
+  static int phase_d(const TreeArgs &a, Src src, const float4 *tgt32, TreeWorkspace *w, cudaStream_t st,
+                     cudaEvent_t *ev) {
+    TreePhaseState &ph = w->ph;
+    const int64_t n = ph.n, ni = a.ni;
+    BuildCtl *ctl = w->ctl.as<BuildCtl>();
+    double *root = w->root.as<double>();
+    const bool rel_origin = (sizeof(Real) == 4);
+    Entries<Real> E{w->node.as<Node<Real>>(), sizeof(Real) == 4 ? nullptr : w->skip.as<int>()};
+    const double inv_theta2 = 1.0 / (a.theta * a.theta);
+    int *maxlevel = w->misc.as<int>();
+    unsigned long long *dstats = reinterpret_cast<unsigned long long *>(w->misc.as<char>() + 16);
+    const int nentries = ph.end;  // where every chain ends (capacity, see entry_capacity)
+
+    // targets: Morton order.  Self case: the source order restricted to the owned slice is the
+    // sorted order itself when the slice is everything; otherwise sort the targets' own keys.
+    TargetsView tv;
+    tv.sorted = nullptr;
+    tv.pos64 = tgt32 ? nullptr : a.tgt_pos;
+    tv.pos32 = tgt32;
+    tv.order = nullptr;
+    tv.order_offset = 0;
+    if (!ph.dist && a.targets_are_sources && ni == n) {
+      tv.order = ph.sidx;
+      tv.sorted = w->sorted.as<double4>();
+    } else if (ni > 32) {
+      GH_TRY(w->thi.reserve(sizeof(uint64_t) * ni));
+      GH_TRY(w->thi2.reserve(sizeof(uint64_t) * ni));
+      GH_TRY(w->tidx.reserve(sizeof(int) * ni));
+      GH_TRY(w->tidx2.reserve(sizeof(int) * ni));
+      if (ph.dist && a.targets_are_sources) {
+        // the owned targets are sources [tgt_offset, tgt_offset + ni): their keys exist already
+        GH_CUDA(cudaMemcpyAsync(w->thi.ptr, w->keys_all.as<uint64_t>() + a.tgt_offset, sizeof(uint64_t) * ni,
+                                cudaMemcpyDeviceToDevice, st));
+        launch_counter()++;
+        iota_kernel<<<nblk(ni, 256), 256, 0, st>>>(w->tidx.as<int>(), ni);
+      } else if (tgt32) {
+        Src32 ts{tgt32};
+        keys_kernel<<<nblk(ni, 256), 256, 0, st>>>(ts, ni, root, LEVELS_HI, w->thi.as<uint64_t>(),
+                                                  (uint64_t *)nullptr, w->tidx.as<int>());
+      } else {
+        Src64 ts{a.tgt_pos, nullptr};
+        keys_kernel<<<nblk(ni, 256), 256, 0, st>>>(ts, ni, root, LEVELS_HI, w->thi.as<uint64_t>(),
+                                                  (uint64_t *)nullptr, w->tidx.as<int>());
+      }
+      GH_LAUNCH_CHECK();
+      bool tinB = false;
+      GH_TRY(radix_sort_pairs(w->thi.as<uint64_t>(), w->tidx.as<int>(), w->thi2.as<uint64_t>(),
+                              w->tidx2.as<int>(), ni, 63, w->rs, st, &tinB));
+      tv.order = tinB ? w->tidx2.as<int>() : w->tidx.as<int>();
+    }
+
+    // K8
+    Real eps2 = (Real)(a.eps * a.eps);
+    // fp32: see GH_F32_MIN_EPS2 (common.cuh)
+    const bool tiny_eps = (sizeof(Real) == 4) ? !((float)eps2 >= GH_F32_MIN_EPS2) : (a.eps == 0.0);
+    if (tiny_eps) eps2 = (Real)0;
+    const int64_t nwarps = (ni + 31) / 32;
+    int wb = 128;
+    if (const char *env = getenv("GH_WALK_BLOCK")) { int v = atoi(env); if (v == 32 || v == 64 || v == 128) wb = v; }
+    const bool group = (sizeof(Real) == 4) && tree_walk_mode() == GH_WALK_GROUP;
+    const unsigned blocks = (unsigned)((nwarps + wb / 32 - 1) / (wb / 32));
+    if (ev) GH_CUDA(cudaEventRecord(ev[0], st));
+    const bool guard = tiny_eps;
+    const int *ovf = &ctl->overflow;  // (overflow, first): the walk kernels' `walkctl`
+    // L2 prefetch hint of each entry's skip target; GH_WALK_PREFETCH=0/1 overrides
+    bool prefetch = false;
+    if (const char *env = getenv("GH_WALK_PREFETCH")) prefetch = atoi(env) != 0;
+    if (group) {
+      GroupWalk<Real>::launch(E.node, nentries, tv, ni, root, (float)eps2, inv_theta2, a.ep, dstats,
+                              a.want_stats, guard, (unsigned)nwarps, st, ovf);
+    } else {
 #define GH_WALK(STATS, GUARD, PF)                                                                      \
   walk_kernel<Real, STATS, GUARD, PF><<<blocks, wb, 0, st>>>(E.node, E.skip, nentries, tv, ni, root, \
-                                                            rel_origin, eps2, inv_theta2, a.ep, dstats)
+                                                            rel_origin, eps2, inv_theta2, a.ep, dstats, ovf)
 #define GH_WALK2(STATS, GUARD) do { if (prefetch) GH_WALK(STATS, GUARD, true); else GH_WALK(STATS, GUARD, false); } while (0)
-    if (a.want_stats) { if (guard) GH_WALK2(true, true); else GH_WALK2(true, false); }
-    else { if (guard) GH_WALK2(false, true); else GH_WALK2(false, false); }
+      if (a.want_stats) { if (guard) GH_WALK2(true, true); else GH_WALK2(true, false); }
+      else { if (guard) GH_WALK2(false, true); else GH_WALK2(false, false); }
 #undef GH_WALK2
 #undef GH_WALK
+    }
+    GH_LAUNCH_CHECK();
+    if (ev) GH_CUDA(cudaEventRecord(ev[1], st));
+    // async readback: deepest level, overflow flag, (distributed: this rank's entry count)
+    GH_CUDA(cudaMemcpyAsync(&w->h_pinned[1], maxlevel, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GH_CUDA(cudaMemcpyAsync(&w->h_pinned[2], &ctl->overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (ph.dist) GH_CUDA(cudaMemcpyAsync(&w->h_pinned[0], &ctl->nentries, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GH_CUDA(cudaEventRecord(w->readback, st));
+    w->readback_valid = true;
+    if (a.want_stats) {
+      GH_CUDA(cudaMemcpyAsync(w->h_stats, dstats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+      GH_CUDA(cudaStreamSynchronize(st));
+      w->last_stats[0] = w->h_pinned[0];
+      w->last_stats[1] = w->h_pinned[0] - n;
+      w->last_stats[2] = w->h_pinned[1];
+      w->last_stats[3] = (int64_t)w->h_stats[0];
+      w->last_stats[4] = (int64_t)w->h_stats[1];
+      w->last_stats[5] = (int64_t)w->h_stats[2];
+      w->last_stats[6] = (int64_t)w->h_stats[3];
+      w->last_stats[7] = (int64_t)((ni + 31) / 32);
+    }
+    return GH_OK;
   }
-  GH_LAUNCH_CHECK();
-  if (ev) GH_CUDA(cudaEventRecord(ev[1], st));
-  GH_CUDA(cudaMemcpyAsync(&w->h_pinned[1], maxlevel, sizeof(int), cudaMemcpyDeviceToHost, st));
-  w->last_stats[0] = nentries;
-  w->last_stats[1] = nentries - n;
-  if (a.want_stats) {
-    GH_CUDA(cudaMemcpyAsync(w->h_stats, dstats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    GH_CUDA(cudaStreamSynchronize(st));
-    w->last_stats[2] = w->h_pinned[1];
-    w->last_stats[3] = (int64_t)w->h_stats[0];
-    w->last_stats[4] = (int64_t)w->h_stats[1];
-    w->last_stats[5] = (int64_t)w->h_stats[2];
-    w->last_stats[6] = (int64_t)w->h_stats[3];
-    w->last_stats[7] = (int64_t)((ni + 31) / 32);
+};
+
+// phase: 0 = A, 1 = B, 2 = C, 3 = D, -1 = all (single rank)
+static int tree_dispatch(const TreeArgs &a, TreeWorkspace *w, cudaStream_t st, cudaEvent_t *ev,
+                         const TreeDist *d, int phase) {
+#define GH_TREE_PHASES(SRC, REAL, src, tgt)                                                    \
+  do {                                                                                         \
+    if (phase == 0 || phase < 0) GH_TRY((TreeRun<SRC, REAL>::phase_a(a, src, w, st, d)));      \
+    if (phase == 1 || phase < 0) GH_TRY((TreeRun<SRC, REAL>::phase_b(a, src, w, st)));         \
+    if (phase == 2 || phase < 0) GH_TRY((TreeRun<SRC, REAL>::phase_c(a, src, w, st)));         \
+    if (phase == 3 || phase < 0) GH_TRY((TreeRun<SRC, REAL>::phase_d(a, src, tgt, w, st, ev))); \
+    return GH_OK;                                                                              \
+  } while (0)
+  if (a.prec == GH_PREC_F64) {
+    Src64 s{a.src_pos, a.src_mass};
+    GH_TREE_PHASES(Src64, double, s, nullptr);
+  } else if (a.prec == GH_PREC_F32) {
+    if (a.src32) {  // f32 engine: sources and targets are float4 (x - origin, m)
+      Src32 s{a.src32};
+      GH_TREE_PHASES(Src32, float, s, a.tgt32);
+    }
+    Src64 s{a.src_pos, a.src_mass};
+    GH_TREE_PHASES(Src64, float, s, nullptr);
   }
-  return GH_OK;
+#undef GH_TREE_PHASES
+  set_error("launch_tree: bad precision %d", a.prec);
+  return GH_EINVAL;
 }
 
 int launch_tree(const TreeArgs &a, TreeWorkspace *w, cudaStream_t st, cudaEvent_t *ev) {
   if (a.ni <= 0 || a.nj <= 0) return GH_OK;
-  if (a.prec == GH_PREC_F64) {
-    Src64 s{a.src_pos, a.src_mass};
-    return tree_impl<Src64, double>(a, s, nullptr, w, st, ev);
-  } else if (a.prec == GH_PREC_F32) {
-    if (a.src32) {  // f32 engine: sources and targets are float4 (x - origin, m)
-      Src32 s{a.src32};
-      return tree_impl<Src32, float>(a, s, a.tgt32, w, st, ev);
+  GH_TRY(tree_dispatch(a, w, st, ev, nullptr, -1));
+  if (a.sync_check) {
+    // callers that synchronise anyway (the stateless entry points): an overflow of the entry
+    // array is repaired here by growing it to the exact need and evaluating again
+    GH_CUDA(cudaStreamSynchronize(st));
+    if (w->h_pinned[2]) {
+      w->ecap = (int64_t)w->h_pinned[0] + (int64_t)w->h_pinned[0] / 8 + 1024;
+      GH_TRY(tree_dispatch(a, w, st, ev, nullptr, -1));
+      GH_CUDA(cudaStreamSynchronize(st));
+      if (w->h_pinned[2]) { set_error("tree: entry array overflow (%d entries)", w->h_pinned[0]); return GH_ENOMEM; }
     }
-    Src64 s{a.src_pos, a.src_mass};
-    return tree_impl<Src64, float>(a, s, nullptr, w, st, ev);
+    if (!a.want_stats) { w->last_stats[0] = w->h_pinned[0]; w->last_stats[1] = w->h_pinned[0] - a.nj; w->last_stats[2] = w->h_pinned[1]; }
   }
-  set_error("launch_tree: bad precision %d", a.prec);
-  return GH_EINVAL;
+  return GH_OK;
+}
+
+int launch_tree_phase(const TreeArgs &a, TreeWorkspace *w, cudaStream_t st, cudaEvent_t *ev,
+                      const TreeDist *d, int phase) {
+  if (a.ni <= 0 || a.nj <= 0) return GH_OK;
+  return tree_dispatch(a, w, st, ev, d, phase);
+}
+
+// 0: no evaluation finished yet / still running; 1: finished without overflow; -1: overflowed.
+// Never blocks.  *entries (nullable) = the entry count of that evaluation.
+int tree_poll_overflow(TreeWorkspace *w, int64_t *entries) {
+  if (!w || !w->readback_valid) return 0;
+  if (cudaEventQuery(w->readback) != cudaSuccess) { cudaGetLastError(); return 0; }
+  if (entries) *entries = w->h_pinned[0];
+  return w->h_pinned[2] ? -1 : 1;
+}
+
+const int *tree_maxent_ptr(TreeWorkspace *w) { return &w->ctl.as<BuildCtl>()->maxent; }
+
+int tree_exchange_buffer(TreeWorkspace *w, int which, void **ptr, int64_t *bytes_per_rank) {
+  if (!w || !ptr || !bytes_per_rank) return GH_EINVAL;
+  switch (which) {
+    case 1: *ptr = w->rec1.ptr; *bytes_per_rank = sizeof(RankRec1); return GH_OK;
+    case 2: *ptr = w->rec2.ptr; *bytes_per_rank = sizeof(RankRec2); return GH_OK;
+    case 3: *ptr = w->node.ptr; *bytes_per_rank = (int64_t)sizeof(Node<float>) * w->ph.ecap; return GH_OK;
+    default: return GH_EINVAL;
+  }
+}
+
+// Bootstrap of the distributed build: equal-count key ranges from the fully sorted keys of the
+// single-rank build that just ran in this workspace (every later step derives the next step's
+// ranges from the gathered key samples, stitch_kernel).
+int tree_splitters(TreeWorkspace *w, int world, cudaStream_t st) {
+  if (!w || !w->ctl.ptr || !w->ph.shi || w->ph.dist) { set_error("tree_splitters: needs a finished single-rank build"); return GH_ESTATE; }
+  if (world < 1 || world > DIST_MAX_RANKS) { set_error("tree_splitters: 1..%d ranks", DIST_MAX_RANKS); return GH_EINVAL; }
+  splitters_from_sorted_kernel<<<1, DIST_MAX_RANKS + 1, 0, st>>>(w->ph.shi, w->ph.n, world, w->ctl.as<BuildCtl>());
+  GH_LAUNCH_CHECK();
+  return GH_OK;
 }
 
 }  // namespace gh

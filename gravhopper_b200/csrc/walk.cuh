@@ -137,9 +137,10 @@ __device__ __forceinline__ void lane_scan(const Node<Real> *__restrict__ nodes,
                                           const int *__restrict__ skips, Real s2root, int nentries,
                                           bool valid, Real x, Real y, Real z, Real eps2, Real &ax, Real &ay,
                                           Real &az, unsigned long long &nacc,
-                                          unsigned long long &nvis, unsigned long long &niter) {
+                                          unsigned long long &nvis, unsigned long long &niter,
+                                          int first_entry = 0) {
   int until = valid ? 0 : INT_MAX;
-  int i = 0;
+  int i = first_entry;
   while (i < nentries) {
     if (STATS) niter++;
     const auto na = nodes[i].a;
@@ -199,7 +200,15 @@ template <class Real, bool STATS, bool GUARD, bool PREFETCH>
 __global__ void __launch_bounds__(128, 8)
 walk_kernel(const Node<Real> *__restrict__ nodes, const int *__restrict__ skips, int nentries,
             TargetsView tv, int64_t ni, const double *__restrict__ root, bool rel_origin, Real eps2,
-            double inv_theta2, Epilogue ep, unsigned long long *__restrict__ stats) {
+            double inv_theta2, Epilogue ep, unsigned long long *__restrict__ stats,
+            const int *__restrict__ walkctl = nullptr) {
+  // `nentries` is the index every chain ends at (the capacity of the entry array, not its fill:
+  // the build never tells the host how many entries it wrote).  walkctl (BuildCtl::overflow,
+  // ::first): a build whose entries did not fit sets [0]; the walk then leaves the state alone and
+  // the host reports it at its next sync.  [1] is the index of the root entry (the first
+  // non-empty rank's segment start in a distributed build; 0 otherwise).
+  if (walkctl && walkctl[0]) return;
+  const int first_entry = walkctl ? walkctl[1] : 0;
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t p = warp * 32 + lane;
@@ -211,7 +220,7 @@ walk_kernel(const Node<Real> *__restrict__ nodes, const int *__restrict__ skips,
   unsigned long long nacc = 0, nvis = 0, niter = 0;
   const Real s2root = (Real)(root[3] * root[3] * inv_theta2);
   lane_scan<Real, STATS, GUARD, PREFETCH>(nodes, skips, s2root, nentries, valid, x, y, z, eps2, ax, ay,
-                                          az, nacc, nvis, niter);
+                                          az, nacc, nvis, niter, first_entry);
   if (valid) apply_epilogue(ep, ti, (double)ax, (double)ay, (double)az);
   if (STATS) {
     for (int o = 16; o > 0; o >>= 1) {
@@ -341,9 +350,12 @@ template <int WPC, bool STATS, bool GUARD, bool HYBRID = false>
 __global__ void __launch_bounds__(32 * WPC, GH_GW_WARPS_PER_SM / WPC)
 walk_group_kernel(const Node<float> *__restrict__ nodes, int nentries, TargetsView tv, int64_t ni,
                   const double *__restrict__ root, float eps2, double inv_theta2, int list_limit,
-                  Epilogue ep, unsigned long long *__restrict__ stats) {
+                  Epilogue ep, unsigned long long *__restrict__ stats,
+                  const int *__restrict__ walkctl = nullptr) {
   __shared__ int2 s_stack[WPC][GROUP_STACK];
   __shared__ float4 s_ring[WPC][GROUP_RING];
+  if (walkctl && walkctl[0]) return;  // see walk_kernel
+  const int first_entry = walkctl ? walkctl[1] : 0;
   const int lane = threadIdx.x & 31;
   const int wic = threadIdx.x >> 5;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -352,6 +364,9 @@ walk_group_kernel(const Node<float> *__restrict__ nodes, int nentries, TargetsVi
   int64_t ti;
   float x, y, z;
   load_target<float>(tv, p, valid, root, true, ti, x, y, z);
+  // a warp without any target (tail of the last CTA when WPC > 1) has nothing to do; without this
+  // its NaN boxes would open every cell until the list limit sends it to the per-target scan
+  if (__ballot_sync(0xffffffffu, valid) == 0u) return;
 
   // Two bounding boxes: the 32 targets are cut where Morton-consecutive targets are farthest
   // apart, so a group that straddles a jump of the curve is two compact boxes instead of one
@@ -377,7 +392,7 @@ walk_group_kernel(const Node<float> *__restrict__ nodes, int nentries, TargetsVi
   unsigned long long nacc = 0, nvis = 0, niter = 0, nredo = 0;
   const float s2root = (float)(root[3] * root[3] * inv_theta2);
 
-  if (lane == 0) stack[0] = make_int2(0, nentries);
+  if (lane == 0) stack[0] = make_int2(first_entry, nentries);
   int sp = 1;
   int head = 0, tail = 0;  // list entries pushed / evaluated
   bool fallback = false;
@@ -452,7 +467,7 @@ walk_group_kernel(const Node<float> *__restrict__ nodes, int nentries, TargetsVi
         float bx = 0.f, by = 0.f, bz = 0.f;
         unsigned long long c0 = 0, c1 = 0, c2 = 0;
         lane_scan<float, false, GUARD, false>(nodes, nullptr, s2root, nentries, redo, x, y, z, eps2, bx, by, bz,
-                                              c0, c1, c2);
+                                              c0, c1, c2, first_entry);
         if (redo) { ax = bx; ay = by; az = bz; }
         if (STATS) nredo = redo ? 1ull : 0ull;
       }
@@ -462,7 +477,7 @@ walk_group_kernel(const Node<float> *__restrict__ nodes, int nentries, TargetsVi
     nacc = nvis = 0;
     unsigned long long it2 = 0;
     lane_scan<float, STATS, GUARD, false>(nodes, nullptr, s2root, nentries, valid, x, y, z, eps2, ax, ay,
-                                          az, nacc, nvis, it2);
+                                          az, nacc, nvis, it2, first_entry);
   }
   if (valid) apply_epilogue(ep, ti, (double)ax, (double)ay, (double)az);
   if (STATS) {

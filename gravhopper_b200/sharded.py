@@ -163,6 +163,11 @@ class CudaShard(object):
         _lib.check(self.lib.gh_engine_last_force_ms(self.h, C.byref(ms)))
         return ms.value
 
+    def force_ms_mean(self, last_k):
+        ms, cnt = C.c_float(), C.c_int()
+        _lib.check(self.lib.gh_engine_force_ms_mean(self.h, int(last_k), C.byref(ms), C.byref(cnt)))
+        return ms.value
+
     def stream_context(self):
         return self.torch.cuda.stream(self.stream)
 
@@ -227,6 +232,11 @@ class ShardedSimulation(object):
 
     def local_state(self):
         return self.shard.download()
+
+    def close(self):
+        """Release the rank's engine (device memory) now instead of at garbage collection."""
+        if hasattr(self.shard, "close"):
+            self.shard.close()
 
     def gather_state(self):
         """Full (pos, vel) on every rank (host arrays) -- output cadence only."""

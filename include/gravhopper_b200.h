@@ -67,6 +67,10 @@ const char *gh_last_error(void);
 int gh_version(void);
 /* number of CUDA devices visible; *n = 0 and GH_ECUDA when there is none */
 int gh_device_count(int *n);
+/* Measurement aid (bench.py's roofline denominator, not on the hot path): FP32 FMA throughput of
+ * the current device measured with an FFMA-only kernel (8 independent chains per thread, every SM
+ * full, no memory traffic), best of `repeats` launches, in TFLOP/s (2 flop per FFMA). */
+int gh_fp32_fma_probe(int repeats, double *tflops);
 
 /* ---- stateless force evaluation: the four _jbgrav entry points ---------------------------- */
 
@@ -261,6 +265,42 @@ int gh_engine_tree_stats(gh_engine *e, int64_t out[8]);
 int gh_engine_launch_count(gh_engine *e, int64_t *count);
 /* Device time (ms, CUDA events on the engine's stream) of the force kernel of the last step. */
 int gh_engine_last_force_ms(gh_engine *e, float *ms);
+/* Mean device time (ms) of the force kernel over the last `last_k` steps (at most 64 are kept);
+ * *count (nullable) = the number of steps averaged. */
+int gh_engine_force_ms_mean(gh_engine *e, int last_k, float *mean_ms, int *count);
+
+/* ---- engine groups: one system on several GPUs -------------------------------------
+ * Replaces nothing in the reference (it is single threaded); this is the multi-GPU form of
+ * Simulation.run (gravhopper.py:293-320, :405-416).  Targets are sharded evenly over `world` ranks
+ * (rank r owns particles [begin_r, begin_r + count_r), the first n % world ranks one more); each
+ * step all-gathers the half-drifted positions over NCCL; direct summation tiles all sources per
+ * rank; the fp32 tree is built DISTRIBUTED (every rank sorts and emits one Morton key range, the
+ * entry segments are all-gathered) and walked per rank; the fp64 tree is built redundantly.
+ * NCCL is loaded at run time (libnccl.so.2, or $GH_NCCL_LIB).  A group is driven by one thread. */
+typedef struct gh_group gh_group;
+int gh_nccl_version(int *version);
+/* All GPUs of one process: engines on `devices[0..ndev)` (NULL = 0..ndev-1), ncclCommInitAll. */
+int gh_group_create_local(gh_group **g, int ndev, const int *devices, int64_t n_total, int prec);
+/* One rank of a multi-process job: rank 0 calls gh_group_unique_id and hands the 128 bytes to
+ * every rank (e.g. with torch.distributed / MPI); every rank then calls gh_group_create_rank. */
+int gh_group_unique_id(void *id128);
+int gh_group_create_rank(gh_group **g, const void *id128, int rank, int world, int device,
+                         int64_t n_total, int prec);
+int gh_group_destroy(gh_group *g);
+int gh_group_size(gh_group *g, int *nlocal, int *world, int *rank0);
+/* Local engine k (rank rank0 + k) and its particle range: upload / download / potentials go
+ * through the gh_engine_* calls on it; stepping goes through the group. */
+int gh_group_engine(gh_group *g, int k, gh_engine **e, int64_t *begin, int64_t *count);
+int gh_group_prepare(gh_group *g, double dt);
+/* nsteps DKD steps of the whole system (collectives included), asynchronous. */
+int gh_group_step(gh_group *g, int64_t nsteps, double dt, double eps, double theta, int algorithm);
+int gh_group_synchronize(gh_group *g);
+/* 0: build the fp32 tree redundantly on every rank instead of distributed (default 1; GH_TREE_DIST). */
+int gh_group_set_tree_distributed(gh_group *g, int enable);
+/* Device time (ms) of the phases of the last step on local engine 0: [0] source all-gather,
+ * [1] bbox + keys + select + sort, [2] boundary-key exchange, [3] levels + scans + moments,
+ * [4] table exchange, [5] stitch + emit, [6] entry all-gather, [7] target sort + walk, [8] step. */
+int gh_group_phase_ms(gh_group *g, float out[9]);
 
 #ifdef __cplusplus
 }

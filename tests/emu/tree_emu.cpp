@@ -19,23 +19,23 @@ using namespace gh;
 static inline unsigned nblk(int64_t n, int b) { return (unsigned)((n + b - 1) / b); }
 
 // chunked_scan of sortscan.cuh, launch for launch
-template <class T, class In> static void emu_scan(In in, int64_t n, T *P) {
+template <class T, class In> static void emu_scan(In in, int64_t n, T *P, const int *ndev = nullptr) {
   if (n <= 0) return;
   if (n <= SCAN_WARP_ELEMS) {
-    emu::launch(1, 32, [&] { scan_phase3<T, In>(in, n, nullptr, P); });
+    emu::launch(1, 32, [&] { scan_phase3<T, In>(in, n, nullptr, P, ndev); });
     return;
   }
   const int64_t nw = (n + SCAN_WARP_ELEMS - 1) / SCAN_WARP_ELEMS;
   const unsigned nsb = (unsigned)((nw * 32 + SCAN_THREADS - 1) / SCAN_THREADS);
   std::vector<T> buf((size_t)(2 * nw + 1));
   T *totals = buf.data(), *prefix = totals + nw;
-  emu::launch(nsb, SCAN_THREADS, [&] { scan_phase1<T, In>(in, n, totals); });
+  emu::launch(nsb, SCAN_THREADS, [&] { scan_phase1<T, In>(in, n, totals, ndev); });
   emu_scan<T, InArray<T>>(InArray<T>{totals}, nw, prefix);
-  emu::launch(nsb, SCAN_THREADS, [&] { scan_phase3<T, In>(in, n, prefix, P); });
+  emu::launch(nsb, SCAN_THREADS, [&] { scan_phase3<T, In>(in, n, prefix, P, ndev); });
 }
 
 // radix_sort_pairs of sortscan.cuh, launch for launch
-static bool emu_sort(uint64_t *kA, int *vA, uint64_t *kB, int *vB, int64_t n, int nbits) {
+static bool emu_sort(uint64_t *kA, int *vA, uint64_t *kB, int *vB, int64_t n, int nbits, const int *ndev = nullptr) {
   if (n <= 1) return false;
   const int nblocks = (int)((n + RS_TILE - 1) / RS_TILE);
   const int npass = (nbits + 7) / 8;
@@ -46,9 +46,9 @@ static bool emu_sort(uint64_t *kA, int *vA, uint64_t *kB, int *vB, int64_t n, in
   for (int pass = 0; pass < npass; pass++) {
     const int shift = 8 * pass;
     int *g = gtot.data() + RS_RADIX * pass;
-    emu::launch((unsigned)nblocks, RS_THREADS, [&] { rs_hist_kernel(kin, n, shift, hist.data(), nblocks, g); });
+    emu::launch((unsigned)nblocks, RS_THREADS, [&] { rs_hist_kernel(kin, n, shift, hist.data(), nblocks, g, ndev); });
     emu::launch(RS_RADIX, RS_THREADS, [&] { rs_rowscan_kernel(hist.data(), nblocks); });
-    emu::launch((unsigned)nblocks, RS_THREADS, [&] { rs_scatter_kernel(kin, vin, kout, vout, n, shift, hist.data(), g, nblocks); });
+    emu::launch((unsigned)nblocks, RS_THREADS, [&] { rs_scatter_kernel(kin, vin, kout, vout, n, shift, hist.data(), g, nblocks, ndev); });
     std::swap(kin, kout);
     std::swap(vin, vout);
     inB = !inB;
@@ -59,7 +59,7 @@ static bool emu_sort(uint64_t *kA, int *vA, uint64_t *kB, int *vB, int64_t n, in
 template <class Real>
 static int build_impl(const double *pos, const double *mass, int64_t n, double eps, double theta, void *nodes_out,
                       int *skips_out, int nodes_cap, double *sorted_out, int *order_out, double *root_out,
-                      int *info_out) {
+                      int *info_out, uint64_t *keys_out, int seg_cap) {
   using Mom = typename MomentOf<Real>::type;
   const int levels = (sizeof(Real) == 8) ? LEVELS_MAX : LEVELS_HI;
   const bool deep = levels > LEVELS_HI;
@@ -115,11 +115,18 @@ static int build_impl(const double *pos, const double *mass, int64_t n, double e
   Entries<Real> E{reinterpret_cast<Node<Real> *>(nodes_out), sizeof(Real) == 4 ? nullptr : skips_out};
   const double inv_theta2 = 1.0 / (theta * theta);
   int maxlevel = 0;
+  // one segment whose capacity is the entry count itself, so that the chain end == entry count
+  // (the product sizes the segment generously and ends the chains at the capacity)
+  BuildCtl ctl;
+  std::memset(&ctl, 0, sizeof(ctl));
+  emu::launch(1, 1, [&] { ctl_init_single(&ctl, (int)n, seg_cap > 0 ? seg_cap : nentries); }, true);
   emu::launch(nblk(n, 128), 128, [&] {
     emit_kernel<Src64, Real>(sp.data(), shi, slo, clev.data(), base.data(), P.data(), n, root.data(), rel_origin,
-                             inv_theta2, E, &maxlevel);
+                             inv_theta2, E, &maxlevel, &ctl, false);
   }, true);
   info_out[1] = maxlevel;
+  info_out[2] = ctl.overflow;
+  if (keys_out) std::memcpy(keys_out, shi, sizeof(uint64_t) * (size_t)n);
   std::memcpy(sorted_out, sp.data(), sizeof(double4) * (size_t)n);
   std::memcpy(order_out, sidx, sizeof(int) * (size_t)n);
   std::memcpy(root_out, root.data(), sizeof(double) * ROOT_DOUBLES);
@@ -129,13 +136,105 @@ static int build_impl(const double *pos, const double *mass, int64_t n, double e
 extern "C" {
 // prec 32: Node<float> entries (8 floats each) into nodes_out; prec 64: Node<double> + skips_out.
 // info_out = {entries, deepest cell level}.  Returns 1 if nodes_cap is too small (info_out[0] = need).
+// info_out = {entries, deepest cell level, overflow flag}; keys_out (nullable): the sorted `hi` keys;
+// seg_cap > 0: capacity of the segment (chains end there; entries beyond it raise the overflow flag).
 int emu_tree_build(int prec, const double *pos, const double *mass, int64_t n, double eps, double theta,
                    void *nodes_out, int *skips_out, int nodes_cap, double *sorted_out, int *order_out,
-                   double *root_out, int *info_out) {
+                   double *root_out, int *info_out, uint64_t *keys_out, int seg_cap) {
   if (prec == 32)
     return build_impl<float>(pos, mass, n, eps, theta, nodes_out, skips_out, nodes_cap, sorted_out, order_out,
-                             root_out, info_out);
+                             root_out, info_out, keys_out, seg_cap);
   return build_impl<double>(pos, mass, n, eps, theta, nodes_out, skips_out, nodes_cap, sorted_out, order_out,
-                            root_out, info_out);
+                            root_out, info_out, keys_out, seg_cap);
+}
+
+// The DISTRIBUTED fp32 build (tree.cu phases A-C with TreeDist) for `world` ranks run one after the
+// other on the host; the three all-gathers are shared arrays every rank's kernels write their slot
+// of.  split[world+1]: the key ranges (split[0] = 0; the last rank is unbounded above).
+// nodes_out: (world * stride, 8) floats, the global virtual-index entry array.
+// counts_out[2*world]: {n_local, entries} per rank; split_next_out[world+1]: the next step's
+// ranges as rank 0's stitch derived them; sorted_out / order_out: the ranks' sorted particles
+// concatenated.  Returns 0, or 2 when a rank raised the overflow flag.
+int emu_tree_build_dist(int world, const uint64_t *split, const double *pos, const double *mass, int64_t n,
+                        double eps, double theta, float *nodes_out, int stride, double *sorted_out, int *order_out,
+                        double *root_out, int *counts_out, uint64_t *split_next_out, int *maxlevel_out) {
+  const int levels = LEVELS_HI;
+  Src64 src{pos, mass};
+  std::vector<double> root(ROOT_DOUBLES), part(6 * 1024);
+  const int nb = (int)((n + 256 * 8 - 1) / (256 * 8) < 1024 ? (n + 256 * 8 - 1) / (256 * 8) : 1024);
+  emu::launch((unsigned)nb, 256, [&] { bbox_stage1<Src64>(src, n, part.data()); });
+  emu::launch(1, 256, [&] { bbox_stage2(part.data(), nb, eps, root.data()); });
+  std::vector<uint64_t> kall(n);
+  std::vector<int> dummy(n);
+  emu::launch(nblk(n, 256), 256, [&] { keys_kernel<Src64>(src, n, root.data(), levels, kall.data(), (uint64_t *)nullptr, dummy.data()); }, true);
+
+  struct Rank {
+    BuildCtl ctl;
+    std::vector<uint64_t> hi, hi2;
+    std::vector<int> idx, idx2, cnt, base;
+    std::vector<signed char> clev;
+    std::vector<double4> sp;
+    std::vector<D4> P;
+    const uint64_t *shi;
+    const int *sidx;
+  };
+  std::vector<Rank> R(world);
+  std::vector<RankRec1> rec1(world);
+  std::vector<RankRec2> rec2(world);
+  const int ntiles = (int)((n + SEL_TILE - 1) / SEL_TILE);
+  // phase A
+  for (int r = 0; r < world; r++) {
+    Rank &k = R[r];
+    std::memset(&k.ctl, 0, sizeof(k.ctl));
+    for (int j = 0; j <= world; j++) k.ctl.split_next[j] = split[j];
+    k.hi.assign(n, 0); k.hi2.assign(n, 0); k.idx.assign(n, 0); k.idx2.assign(n, 0);
+    emu::launch(1, 1, [&] { ctl_init_dist(&k.ctl, r, world, stride); }, true);
+    emu::launch(1, DIST_MAX_RANKS + 1, [&] { splitters_advance_kernel(&k.ctl, world); }, true);
+    std::vector<int> tilecnt(ntiles + 1), tileoff(ntiles + 2);
+    emu::launch((unsigned)ntiles, SEL_THREADS, [&] { select_count_kernel(kall.data(), n, &k.ctl, tilecnt.data()); });
+    emu_scan<int, InArray<int>>(InArray<int>{tilecnt.data()}, ntiles, tileoff.data());
+    emu::launch((unsigned)ntiles, SEL_THREADS, [&] { select_compact_kernel(kall.data(), n, &k.ctl, tileoff.data(), ntiles, k.hi.data(), k.idx.data()); });
+    const bool inB = emu_sort(k.hi.data(), k.idx.data(), k.hi2.data(), k.idx2.data(), n, 63, &k.ctl.n_local);
+    k.shi = inB ? k.hi2.data() : k.hi.data();
+    k.sidx = inB ? k.idx2.data() : k.idx.data();
+    emu::launch(1, 1, [&] { rec1_kernel(k.shi, &k.ctl, rec1.data()); }, true);
+  }
+  // phase B (after the all-gather of rec1)
+  for (int r = 0; r < world; r++) {
+    Rank &k = R[r];
+    emu::launch(1, 1, [&] { neighbours_kernel(rec1.data(), &k.ctl); }, true);
+    k.clev.assign(n, 0); k.cnt.assign(n + 1, 0); k.base.assign(n + 1, 0);
+    emu::launch(nblk(n, 256), 256, [&] { levels_kernel(k.shi, nullptr, n, levels, k.clev.data(), k.cnt.data(), &k.ctl); }, true);
+    emu_scan<int, InArray<int>>(InArray<int>{k.cnt.data()}, n, k.base.data(), &k.ctl.n_local);
+    k.sp.assign(n, double4{0, 0, 0, 0});
+    emu::launch(nblk(n, 256), 256, [&] { gather_sorted_kernel<Src64>(src, k.sidx, n, k.sp.data(), &k.ctl); }, true);
+    k.P.assign(n + 1, D4{{0, 0, 0, 0}});
+    emu_scan<D4, InParticlesRel>(InParticlesRel{k.sp.data(), root.data()}, n, k.P.data(), &k.ctl.n_local);
+    emu::launch(1, 32, [&] { rec2_kernel(k.shi, k.base.data(), k.P.data(), &k.ctl, rec2.data()); });
+  }
+  // phase C (after the all-gather of rec2): stitch + emit into the rank's segment
+  const double inv_theta2 = 1.0 / (theta * theta);
+  int maxlevel = 0, rc = 0;
+  int64_t ofs = 0;
+  Entries<float> E{reinterpret_cast<Node<float> *>(nodes_out), nullptr};
+  for (int r = 0; r < world; r++) {
+    Rank &k = R[r];
+    emu::launch(1, 1, [&] { stitch_kernel(rec1.data(), rec2.data(), &k.ctl, n); }, true);
+    emu::launch(nblk(n, 128), 128, [&] {
+      emit_kernel<Src64, float>(k.sp.data(), k.shi, nullptr, k.clev.data(), k.base.data(), k.P.data(), n, root.data(),
+                                true, inv_theta2, E, &maxlevel, &k.ctl, true);
+    }, true);
+    if (k.ctl.overflow) rc = 2;
+    counts_out[2 * r] = k.ctl.n_local;
+    counts_out[2 * r + 1] = k.ctl.nentries;
+    std::memcpy(sorted_out + 4 * ofs, k.sp.data(), sizeof(double4) * (size_t)k.ctl.n_local);
+    std::memcpy(order_out + ofs, k.sidx, sizeof(int) * (size_t)k.ctl.n_local);
+    ofs += k.ctl.n_local;
+  }
+  for (int j = 0; j <= world; j++) split_next_out[j] = R[0].ctl.split_next[j];
+  std::memcpy(root_out, root.data(), sizeof(double) * ROOT_DOUBLES);
+  maxlevel_out[0] = maxlevel;
+  maxlevel_out[1] = R[0].ctl.first;  // index of the root entry (first non-empty rank's segment)
+  return ofs == n ? rc : 3;
 }
 }

@@ -22,7 +22,8 @@ extern "C" {
 // the sorted sources themselves.  flags: bit 0 STATS, bit 1 GUARD (eps == 0), bit 2 HYBRID.
 int emu_walk_group(const float *nodes, int nentries, const double *sorted4, const int *order, int64_t ni,
                    const double *root, float eps2, double inv_theta2, int list_limit, float kappa,
-                   double *acc_out, unsigned long long *stats4, int flags) {
+                   double *acc_out, unsigned long long *stats4, int flags, const int *walkctl) {
+  // walkctl (nullable): {overflow flag, index of the root entry}, see walk_kernel
   using namespace gh;
   TargetsView tv;
   tv.sorted = reinterpret_cast<const double4 *>(sorted4);
@@ -37,7 +38,7 @@ int emu_walk_group(const float *nodes, int nentries, const double *sorted4, cons
   c_hybrid_kappa2 = kappa * kappa;
   const Node<float> *nd = reinterpret_cast<const Node<float> *>(nodes);
   const int64_t nwarps = (ni + 31) / 32;
-#define EMU_GW(S, G, H) run_warps(nwarps, [&] { walk_group_kernel<1, S, G, H>(nd, nentries, tv, ni, root, eps2, inv_theta2, list_limit, ep, stats4); })
+#define EMU_GW(S, G, H) run_warps(nwarps, [&] { walk_group_kernel<1, S, G, H>(nd, nentries, tv, ni, root, eps2, inv_theta2, list_limit, ep, stats4, walkctl); })
   switch (flags & 7) {
     case 0: EMU_GW(false, false, false); break;
     case 1: EMU_GW(true, false, false); break;

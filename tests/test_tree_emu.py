@@ -37,11 +37,13 @@ def temu():
     lib = C.CDLL(LIB)
     vp = C.c_void_p
     lib.emu_tree_build.argtypes = [C.c_int, vp, vp, C.c_int64, C.c_double, C.c_double, vp, vp, C.c_int, vp, vp,
-                                   vp, vp]
+                                   vp, vp, vp, C.c_int]
+    lib.emu_tree_build_dist.argtypes = [C.c_int, vp, vp, vp, C.c_int64, C.c_double, C.c_double, vp, C.c_int, vp, vp,
+                                        vp, vp, vp, vp]
     return lib
 
 
-def emu_build(lib, prec, x, m, eps, theta):
+def emu_build(lib, prec, x, m, eps, theta, want_keys=False, seg_cap=0):
     n = len(m)
     x, m = np.ascontiguousarray(x, dtype=np.float64), np.ascontiguousarray(m, dtype=np.float64)
     cap = 44 * n + 64  # chains of single-child cells included (<= levels per particle)
@@ -50,12 +52,17 @@ def emu_build(lib, prec, x, m, eps, theta):
     sorted4 = np.zeros((n, 4))
     order = np.zeros(n, dtype=np.int32)
     root = np.zeros(10)
-    info = np.zeros(2, dtype=np.int32)
+    info = np.zeros(3, dtype=np.int32)
+    keys = np.zeros(n, dtype=np.uint64)
     rc = lib.emu_tree_build(prec, x.ctypes.data, m.ctypes.data, n, eps, theta, nodes.ctypes.data, skips.ctypes.data,
-                            cap, sorted4.ctypes.data, order.ctypes.data, root.ctypes.data, info.ctypes.data)
+                            cap, sorted4.ctypes.data, order.ctypes.data, root.ctypes.data, info.ctypes.data,
+                            keys.ctypes.data, seg_cap)
     assert rc == 0
     ne = int(info[0])
-    return np.ascontiguousarray(nodes[:ne]), np.ascontiguousarray(skips[:ne]), sorted4, order, root, int(info[1])
+    out = (np.ascontiguousarray(nodes[:ne]), np.ascontiguousarray(skips[:ne]), sorted4, order, root, int(info[1]))
+    if seg_cap:
+        return out + (int(info[2]),)
+    return out + (keys,) if want_keys else out
 
 
 def test_fp64_build_is_the_reference_octree_and_walks_to_the_oracle(temu, emu, oracle, golden):
@@ -122,3 +129,110 @@ def test_coincident_particles_do_not_break_the_build(temu, emu, oracle, prec):
     else:
         acc, st = run_group(emu, nodes, sorted4, order, root, eps, 0.0)
         assert relerr(acc, d).max() <= 1e-5
+
+
+# ---- distributed build: P ranks, each sorting / scanning / emitting its key range --------
+def emu_build_dist(lib, world, split, x, m, eps, theta, stride):
+    n = len(m)
+    x, m = np.ascontiguousarray(x, dtype=np.float64), np.ascontiguousarray(m, dtype=np.float64)
+    split = np.ascontiguousarray(split, dtype=np.uint64)
+    assert len(split) == world + 1
+    nodes = np.zeros((world * stride, 8), dtype=np.float32)
+    sorted4 = np.zeros((n, 4))
+    order = np.zeros(n, dtype=np.int32)
+    root = np.zeros(10)
+    counts = np.zeros(2 * world, dtype=np.int32)
+    split_next = np.zeros(world + 1, dtype=np.uint64)
+    maxlevel = np.zeros(2, dtype=np.int32)
+    rc = lib.emu_tree_build_dist(world, split.ctypes.data, x.ctypes.data, m.ctypes.data, n, eps, theta,
+                                 nodes.ctypes.data, stride, sorted4.ctypes.data, order.ctypes.data, root.ctypes.data,
+                                 counts.ctypes.data, split_next.ctypes.data, maxlevel.ctypes.data)
+    return rc, nodes, sorted4, order, root, counts.reshape(world, 2), split_next, (int(maxlevel[0]), int(maxlevel[1]))
+
+
+def compact_segments(nodes, counts, stride):
+    """Global virtual-index array (rank r's entries at [r*stride, r*stride + count_r)) -> the contiguous
+    pre-order array a single rank would have written, skip links remapped."""
+    world = len(counts)
+    ne = counts[:, 1].astype(np.int64)
+    start = np.concatenate([[0], np.cumsum(ne)])
+    parts = [nodes[r * stride:r * stride + ne[r]] for r in range(world)]
+    out = np.ascontiguousarray(np.vstack(parts))
+    bits = out.view(np.uint32)
+    packed = bits[:, 6].astype(np.int64)
+    skip = packed & ((1 << 27) - 1)
+    rank = np.minimum(skip // stride, world)          # skip == world*stride: the end
+    local = skip - rank * stride
+    assert np.all((local == 0) | (rank < world)) and np.all(local <= np.append(ne, 0)[rank])
+    bits[:, 6] = ((packed >> 27) << 27 | (start[rank] + local)).astype(np.uint32)
+    return out
+
+
+@pytest.mark.parametrize("world,how", [(2, "equal"), (3, "equal"), (8, "equal"), (4, "random"), (4, "empty"),
+                                       (5, "tiny")])
+def test_distributed_build_is_the_single_rank_tree(temu, emu, world, how):
+    from gravhopper_b200 import ic_raw
+    n = 2500
+    x, v, m = ic_raw.Hernquist(n, 1.0, 1e10, seed=5)
+    x = np.ascontiguousarray(x)
+    eps, theta = 0.05, 0.7
+    nodes1, _, sorted1, order1, root1, maxlevel1, keys = emu_build(temu, 32, x, m, eps, theta, want_keys=True)
+    rng = np.random.default_rng(world)
+    split = np.zeros(world + 1, dtype=np.uint64)
+    split[world] = np.uint64(2 ** 64 - 1)
+    if how == "equal":
+        split[1:world] = keys[(n * np.arange(1, world)) // world]
+    elif how == "random":       # uneven ranges, cut inside deep cells
+        split[1:world] = np.sort(keys[rng.choice(n, world - 1, replace=False)] + np.uint64(1))
+    elif how == "empty":        # two ranks own nothing (equal splitters; a range below every key)
+        split[1] = keys[0]
+        split[2] = keys[n // 2]
+        split[3] = keys[n // 2]
+    else:                       # ranks of one and two particles
+        split[1] = keys[1]
+        split[2] = keys[3]
+        split[3] = keys[n - 2]
+        split[4] = keys[n - 1]
+    stride = int(len(nodes1) * 1.2) if how in ("random", "empty", "tiny") else int(len(nodes1) / world * 1.3) + 64
+    rc, nodes, sorted4, order, root, counts, split_next, (maxlevel, first) = emu_build_dist(temu, world, split, x, m,
+                                                                                          eps, theta, stride)
+    assert rc == 0
+    assert first == stride * int(np.argmax(counts[:, 0] > 0))   # the root entry: first non-empty rank's segment
+    assert counts[:, 0].sum() == n and counts[:, 1].sum() == len(nodes1)
+    if how == "equal":
+        assert abs(counts[:, 0] - n / world).max() <= 1
+    if how == "empty":
+        assert (counts[:, 0] == 0).sum() == 2
+    assert np.array_equal(order, order1) and np.array_equal(sorted4, sorted1) and np.array_equal(root, root1)
+    assert maxlevel == maxlevel1
+    flat = compact_segments(nodes, counts, stride)
+    assert np.array_equal(flat.view(np.uint32)[:, 6], nodes1.view(np.uint32)[:, 6])   # levels and skip links
+    assert np.array_equal(flat[:, [0, 2, 4]], nodes1[:, [0, 2, 4]])                   # cell centres
+    assert np.allclose(flat[:, [1, 3, 5, 7]], nodes1[:, [1, 3, 5, 7]], rtol=2e-6, atol=2e-6 * root[3])
+    # the walk runs on the virtual-index array as it is (chains end at world * stride)
+    acc1, st1 = run_group(emu, nodes1, sorted1, order1, root1, eps, theta)
+    acc, st = run_group(emu, nodes, sorted4, order, root, eps, theta, walkctl=[0, first])
+    assert st["accepted"] == st1["accepted"] and st["visited"] == st1["visited"]
+    assert relerr(acc, acc1).max() <= 2e-6
+    # next step's key ranges: equal counts to the sampling granularity (1/64 of a rank's particles)
+    if how in ("equal", "random"):
+        cnt = np.diff(np.searchsorted(keys, split_next[1:world], side="left"), prepend=0, append=n)
+        assert abs(cnt - n / world).max() <= max(counts[:, 0].max() / 64 + 2, 3)
+
+
+def test_segment_overflow_raises_the_flag_and_the_walk_stands_still(temu, emu):
+    from gravhopper_b200 import ic_raw
+    x, v, m = ic_raw.Hernquist(2000, 1.0, 1e10, seed=6)
+    x = np.ascontiguousarray(x)
+    nodes, _, sorted4, order, root, maxlevel, overflow = emu_build(temu, 32, x, m, 0.05, 0.7, seg_cap=2500)
+    assert overflow == 1 and len(nodes) > 2500
+    nodes, _, sorted4, order, root, maxlevel, overflow = emu_build(temu, 32, x, m, 0.05, 0.7, seg_cap=len(nodes) + 7)
+    assert overflow == 0
+    # a generous capacity: every chain ends at the capacity, entries beyond the fill are never read
+    cap = len(nodes) + 7
+    padded = np.full((cap, 8), np.nan, dtype=np.float32)
+    padded[:len(nodes)] = nodes
+    tight = emu_build(temu, 32, x, m, 0.05, 0.7)
+    acc1, st1 = run_group(emu, tight[0], tight[2], tight[3], tight[4], 0.05, 0.7)
+    acc, st = run_group(emu, padded, sorted4, order, root, 0.05, 0.7)
+    assert st["accepted"] == st1["accepted"] and np.array_equal(acc, acc1)

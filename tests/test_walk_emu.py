@@ -39,7 +39,7 @@ def emu():
     lib = C.CDLL(LIB)
     vp, i64 = C.c_void_p, C.c_int64
     lib.emu_walk_group.argtypes = [vp, C.c_int, vp, vp, i64, vp, C.c_float, C.c_double, C.c_int, C.c_float, vp,
-                                   vp, C.c_int]
+                                   vp, C.c_int, vp]
     lib.emu_walk_target.argtypes = [vp, C.c_int, vp, vp, i64, vp, C.c_float, C.c_double, vp, vp, C.c_int]
     lib.emu_walk_target64.argtypes = [vp, vp, C.c_int, vp, vp, i64, vp, C.c_double, C.c_double, vp, vp, C.c_int]
     return lib
@@ -85,7 +85,7 @@ def build_entries(x, m, eps):
     return nodes, sorted4, order, rootblk
 
 
-def run_group(lib, nodes, sorted4, order, rootblk, eps, theta, list_limit=3000, kappa=0.0, stats=True):
+def run_group(lib, nodes, sorted4, order, rootblk, eps, theta, list_limit=3000, kappa=0.0, stats=True, walkctl=None):
     ni = len(order)
     acc = np.zeros((ni, 3))
     st = np.zeros(4, dtype=np.uint64)
@@ -93,7 +93,8 @@ def run_group(lib, nodes, sorted4, order, rootblk, eps, theta, list_limit=3000, 
     inv_theta2 = float("inf") if theta == 0 else 1.0 / theta ** 2
     lib.emu_walk_group(nodes.ctypes.data, len(nodes), sorted4.ctypes.data, order.ctypes.data, ni,
                        rootblk.ctypes.data, np.float32(eps * eps), inv_theta2, list_limit, np.float32(kappa),
-                       acc.ctypes.data, st.ctypes.data, flags)
+                       acc.ctypes.data, st.ctypes.data, flags,
+                       None if walkctl is None else np.ascontiguousarray(walkctl, dtype=np.int32).ctypes.data)
     return acc, dict(accepted=int(st[0]), visited=int(st[1]), iterations=int(st[2]),
                      fallback=int(st[3]) & 0xffffffff, hybrid_targets=int(st[3]) >> 32)
 
