@@ -185,6 +185,10 @@ struct DirectArgs {
   int64_t ni;
   double eps;
   Epilogue ep;
+  // 1: the sources are known to carry different masses (the uniform-mass tile fast path will not
+  // trigger): the fp32 launch then uses 128 threads x 8 targets, measured 71.0 % of the FP32 peak
+  // against 68.8 % for the default 256 x 4 at N = 2^20 (profiles/r01_sweep_direct.txt)
+  int mixed_mass;
 };
 // Launches the force kernel (and a finalize kernel when the source range is split).  `ws` is
 // scratch for the per-split partial sums.  force_ms_events (nullable): two events recorded

@@ -98,7 +98,7 @@ int launch_direct(const DirectArgs &a, DeviceBuffer &ws, cudaStream_t st, cudaEv
     // measured on B200 (profiles/r01_sweep_direct*.txt): 4 targets/thread x 256 threads and
     // 8 x 128 are within 2 % of each other (76 / 74-76 % of peak); smaller shapes only pay off
     // when there are too few targets to fill the chip
-    if (ki == 0) ki = (a.ni >= 131072) ? 4 : (a.ni >= 16384 ? 2 : 1);
+    if (ki == 0) ki = (a.ni >= 131072) ? (a.mixed_mass ? 8 : 4) : (a.ni >= 16384 ? 2 : 1);
     if (blk == 0) blk = (ki == 4) ? 256 : 128;
     const int minb = env_int("GH_F32_MINB", 1);
     const int unr = env_int("GH_F32_UNROLL", 4);

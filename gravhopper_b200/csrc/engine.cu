@@ -73,6 +73,12 @@ static int scratch_release(Stateless *s, cudaStream_t st) {
   return GH_OK;
 }
 
+static bool masses_differ(const double *m, int64_t n) {
+  for (int64_t i = 1; i < n; i++)
+    if (m[i] != m[0]) return true;
+  return false;
+}
+
 // mean position -> origin[3] on the device (for the f32 packing).  The mean, not the bbox
 // midpoint: centrally concentrated systems have outliers at 10^3 scale radii (untruncated
 // Plummer), and an origin far from the core costs fp32 digits exactly where pairs are closest.
@@ -163,6 +169,7 @@ static int force_common(int alg, int prec, const double *pos, const double *mass
     a.ni = nf;
     a.eps = eps;
     a.ep = ep;
+    a.mixed_mass = (mem == GH_MEM_HOST && prec == GH_PREC_F32 && nf >= 131072) ? masses_differ(mass, np) : 0;
     if (prec == GH_PREC_F64) {
       a.src_pos = dpos;
       a.src_mass = dmass;
@@ -545,6 +552,7 @@ int gh_engine_upload(gh_engine *e, const double *pos, const double *vel, const d
   GH_CUDA(cudaMemcpyAsync(e->x[e->cur], pos, sizeof(double) * 3 * e->ni, cudaMemcpyHostToDevice, e->stream));
   GH_CUDA(cudaMemcpyAsync(e->v[e->cur], vel, sizeof(double) * 3 * e->ni, cudaMemcpyHostToDevice, e->stream));
   GH_CUDA(cudaMemcpyAsync(e->mass, mass_all, sizeof(double) * e->n, cudaMemcpyHostToDevice, e->stream));
+  e->mixed_mass = masses_differ(mass_all, e->n);
   GH_CUDA(cudaStreamSynchronize(e->stream));
   e->uploaded = true;
   e->xhalf_valid = false;
@@ -652,6 +660,7 @@ int engine_step_args(gh_engine *e, double dt, double eps, double theta, int algo
     a.ni = e->ni;
     a.eps = eps;
     a.ep = ep;
+    a.mixed_mass = e->mixed_mass ? 1 : 0;
     if (e->prec == GH_PREC_F64) {
       a.src_pos = reinterpret_cast<const double *>(e->src[e->scur]);
       a.src_mass = e->mass;

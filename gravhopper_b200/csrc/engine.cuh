@@ -39,6 +39,7 @@ struct gh_engine {
   int64_t launches = 0;
   double *d_energy = nullptr;
   PotentialSet pots;
+  bool mixed_mass = false;  // the uploaded masses are not all equal (launch-shape hint, direct fp32)
   // distributed tree build (group.cu): bootstrapped by one redundant single-rank build, then
   // every rank builds its key range; stride = entries a rank's segment holds
   bool dist_ready = false;

@@ -331,20 +331,79 @@ __device__ __forceinline__ float box_dist2(const Box &b, float cx, float cy, flo
   return dx * dx + dy * dy + dz * dz;
 }
 
+// The reference's per-target walk (_jbgrav.c:487-541) for ONE target, executed by the whole warp:
+// the group walk's chain-stack traversal with the point itself as the "box" (so the opening test
+// is the reference's own, side^2/theta^2 < |centre - x|^2), every lane tests one entry per
+// iteration and adds the monopole of the entry it accepted to its private partial sum; the 32
+// partial sums are added at the end (fixed order).  ~35 iterations instead of the ~1240 dependent
+// steps of lane_scan with one active lane: this is what the hybrid rule re-evaluates with.
+// Returns false (sums unusable) if the chain stack would overflow.
+template <bool GUARD>
+__device__ __forceinline__ bool point_walk(const Node<float> *__restrict__ nodes, int first_entry, int nentries,
+                                           float s2root, float px, float py, float pz, float eps2, int2 *stack,
+                                           int lane, float &ox, float &oy, float &oz) {
+  const unsigned gt = ~((1u << lane) - 1u) & ~(1u << lane);
+  float fx = 0.f, fy = 0.f, fz = 0.f;
+  __syncwarp();
+  if (lane == 0) stack[0] = make_int2(first_entry, nentries);
+  int sp = 1;
+  bool ok = true;
+  __syncwarp();
+  while (sp > 0) {
+    const int take = sp < 32 ? sp : 32;
+    const bool has = lane < take;
+    int first = 0, end = 0;
+    if (has) { const int2 it = stack[sp - 1 - lane]; first = it.x; end = it.y; }
+    sp -= take;
+    float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nb = na;
+    if (has) load_node32(nodes, first, na, nb);
+    __syncwarp();
+    float s2;
+    int sk;
+    unpack32(nb.z, s2root, s2, sk);
+    const float cx = na.x - px, cy = na.z - py, cz = nb.x - pz;
+    const float d2 = cx * cx + cy * cy + cz * cz;
+    const bool acc = has && (s2 < d2);  // leaves: s2 = -1
+    const bool open = has && !acc && (first + 1 < sk);
+    const bool rem = has && (sk < end);
+    const unsigned mr = __ballot_sync(0xffffffffu, rem);
+    const unsigned mo = __ballot_sync(0xffffffffu, open);
+    if (sp + __popc(mr) + __popc(mo) > GROUP_STACK) { ok = false; break; }
+    if (rem) stack[sp + __popc(mr & gt)] = make_int2(sk, end);
+    sp += __popc(mr);
+    if (open) stack[sp + __popc(mo & gt)] = make_int2(first + 1, sk);
+    sp += __popc(mo);
+    if (acc) {
+      const float ex = na.y - px, ey = na.w - py, ez = nb.y - pz;
+      const float w = nb.w * inv_cube<GUARD>(ex * ex + ey * ey + ez * ez + eps2);
+      fx += w * ex; fy += w * ey; fz += w * ez;
+    }
+    __syncwarp();
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    fx += __shfl_xor_sync(0xffffffffu, fx, o);
+    fy += __shfl_xor_sync(0xffffffffu, fy, o);
+    fz += __shfl_xor_sync(0xffffffffu, fz, o);
+  }
+  ox = fx; oy = fy; oz = fz;
+  return ok;
+}
+
 // Resident warps per SM the register allocation is capped for: 32 -> 64 registers per thread,
 // 24 -> 80, 20 -> 96, 16 -> 128 (scripts/gpu_variants.sh measures the alternatives).
 #ifndef GH_GW_WARPS_PER_SM
 #define GH_GW_WARPS_PER_SM 32
 #endif
-// HYBRID (off by default; GH_WALK_HYBRID=<kappa> turns it on): the 32 targets of a group share one
+// HYBRID (the default, kappa = 0.15; GH_WALK_HYBRID=0 turns it off): the 32 targets of a group share one
 // list, so their truncation errors are one coherent vector; where a target's net force nearly
 // cancels (|a| << sum of |contributions|: the softened core of a cusp) that vector does not
 // average out the way the per-target walk's errors do, and the relative error of ~0.01 % of the
 // particles exceeds the reference tree's.  With HYBRID each lane compares |a| with a 1/16 sample
 // of sum m/(d^2+eps^2) over its list; lanes with |a| < kappa * sum repeat the evaluation with the
-// reference's own per-target criterion (lane_scan).  CPU model of this rule (test infrastructure):
-// kappa = 0.1 flags 0.1 % of the particles (0.2-0.3 % of the groups) at N = 200k...4M and brings
-// p99.99 and max of the error distribution back to the reference tree's.
+// reference's own per-target criterion (point_walk: the whole warp on one flagged target at a
+// time).  Measured on B200 over all particles of the N = 4M Hernquist sphere
+// (profiles/r02_hybrid_sweep_N4M.json): kappa = 0.1 re-evaluates 0.10 % of the targets (p99.99 of
+// the error 1.015x the reference tree's, max equal), 0.15 0.30 % (1.002x), 0.2 1.3 % (1.000x).
 __constant__ float c_hybrid_kappa2;
 template <int WPC, bool STATS, bool GUARD, bool HYBRID = false>
 __global__ void __launch_bounds__(32 * WPC, GH_GW_WARPS_PER_SM / WPC)
@@ -355,7 +414,9 @@ walk_group_kernel(const Node<float> *__restrict__ nodes, int nentries, TargetsVi
   __shared__ int2 s_stack[WPC][GROUP_STACK];
   __shared__ float4 s_ring[WPC][GROUP_RING];
   if (walkctl && walkctl[0]) return;  // see walk_kernel
-  const int first_entry = walkctl ? walkctl[1] : 0;
+  // index of the root entry: re-read where it is needed (start, rare re-evaluations) rather than
+  // kept in a register for the whole walk
+#define GH_FIRST_ENTRY (walkctl ? walkctl[1] : 0)
   const int lane = threadIdx.x & 31;
   const int wic = threadIdx.x >> 5;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -392,7 +453,7 @@ walk_group_kernel(const Node<float> *__restrict__ nodes, int nentries, TargetsVi
   unsigned long long nacc = 0, nvis = 0, niter = 0, nredo = 0;
   const float s2root = (float)(root[3] * root[3] * inv_theta2);
 
-  if (lane == 0) stack[0] = make_int2(first_entry, nentries);
+  if (lane == 0) stack[0] = make_int2(GH_FIRST_ENTRY, nentries);
   int sp = 1;
   int head = 0, tail = 0;  // list entries pushed / evaluated
   bool fallback = false;
@@ -463,13 +524,24 @@ walk_group_kernel(const Node<float> *__restrict__ nodes, int nentries, TargetsVi
     if (HYBRID) {
       const float S = 16.f * (sabs.x + sabs.y);
       const bool redo = valid && (ax * ax + ay * ay + az * az < c_hybrid_kappa2 * S * S);
-      if (__any_sync(0xffffffffu, redo)) {
+      unsigned todo = __ballot_sync(0xffffffffu, redo);
+      if (STATS) nredo = redo ? 1ull : 0ull;
+      while (todo) {  // one flagged target at a time, the whole warp on it (point_walk)
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1u;
+        const float px = __shfl_sync(0xffffffffu, x, src), py = __shfl_sync(0xffffffffu, y, src),
+                    pz = __shfl_sync(0xffffffffu, z, src);
         float bx = 0.f, by = 0.f, bz = 0.f;
-        unsigned long long c0 = 0, c1 = 0, c2 = 0;
-        lane_scan<float, false, GUARD, false>(nodes, nullptr, s2root, nentries, redo, x, y, z, eps2, bx, by, bz,
-                                              c0, c1, c2, first_entry);
-        if (redo) { ax = bx; ay = by; az = bz; }
-        if (STATS) nredo = redo ? 1ull : 0ull;
+        if (!point_walk<GUARD>(nodes, GH_FIRST_ENTRY, nentries, s2root, px, py, pz, eps2, stack, lane, bx, by, bz)) {
+          bx = by = bz = 0.f;  // chain stack too small for this target: the serial scan, one active lane
+          unsigned long long c0 = 0, c1 = 0, c2 = 0;
+          lane_scan<float, false, GUARD, false>(nodes, nullptr, s2root, nentries, lane == src, x, y, z, eps2, bx, by,
+                                                bz, c0, c1, c2, GH_FIRST_ENTRY);
+          bx = __shfl_sync(0xffffffffu, bx, src);
+          by = __shfl_sync(0xffffffffu, by, src);
+          bz = __shfl_sync(0xffffffffu, bz, src);
+        }
+        if (lane == src) { ax = bx; ay = by; az = bz; }
       }
     }
   } else {
@@ -477,7 +549,7 @@ walk_group_kernel(const Node<float> *__restrict__ nodes, int nentries, TargetsVi
     nacc = nvis = 0;
     unsigned long long it2 = 0;
     lane_scan<float, STATS, GUARD, false>(nodes, nullptr, s2root, nentries, valid, x, y, z, eps2, ax, ay,
-                                          az, nacc, nvis, it2, first_entry);
+                                          az, nacc, nvis, it2, GH_FIRST_ENTRY);
   }
   if (valid) apply_epilogue(ep, ti, (double)ax, (double)ay, (double)az);
   if (STATS) {
@@ -498,5 +570,6 @@ walk_group_kernel(const Node<float> *__restrict__ nodes, int nentries, TargetsVi
 }
 #undef stack
 #undef ring4
+#undef GH_FIRST_ENTRY
 
 }  // namespace gh

@@ -146,6 +146,77 @@ class _Engine(object):
         return ms.value
 
 
+class _GroupEngine(object):
+    """All GPUs of this process stepping one system (gh_group_create_local: one engine per device,
+    ncclCommInitAll inside the library -- no launcher, no torch).  Targets are sharded evenly; for
+    the tree the particles are first laid out in Morton blocks dealt round-robin over the devices
+    (sharded.interleaved_layout) and mapped back at every snapshot."""
+
+    def __init__(self, n, precision, devices):
+        self.n, self.precision, self.devices = n, precision, list(devices)
+        self.lib = _lib.lib()
+        _lib.require_gpu()
+        g = C.c_void_p()
+        prec = _lib.GH_PREC_F64 if precision == 'fp64' else _lib.GH_PREC_F32
+        devs = (C.c_int * len(self.devices))(*self.devices)
+        _lib.check(self.lib.gh_group_create_local(C.byref(g), len(self.devices), devs, n, prec),
+                   "gh_group_create_local")
+        self.g = g
+        self.parts = []
+        for k in range(len(self.devices)):
+            h, b, c = C.c_void_p(), C.c_int64(), C.c_int64()
+            _lib.check(self.lib.gh_group_engine(g, k, C.byref(h), C.byref(b), C.byref(c)), "gh_group_engine")
+            self.parts.append((h, b.value, c.value))
+        self.perm = None
+
+    def close(self):
+        g, self.g = getattr(self, 'g', None), None
+        if g:
+            try:
+                self.lib.gh_group_destroy(g)
+            except Exception:  # interpreter shutdown
+                pass
+
+    __del__ = close
+
+    def set_potentials(self, pots):
+        for h, _, _ in self.parts:
+            _lib.check(self.lib.gh_engine_clear_potentials(h))
+            for p in pots:
+                prm = (C.c_double * 8)(*[float(v) for v in p.params()])
+                _lib.check(self.lib.gh_engine_add_potential(h, p.kind, prm, 8), "gh_engine_add_potential")
+
+    def upload(self, pos, vel, mass, tree):
+        from .sharded import interleaved_layout
+        pos = np.ascontiguousarray(pos, dtype=np.float64)
+        vel = np.ascontiguousarray(vel, dtype=np.float64)
+        mass = np.ascontiguousarray(mass, dtype=np.float64)
+        self.perm = interleaved_layout(pos, len(self.parts)) if tree else None
+        if self.perm is not None:
+            pos, vel, mass = pos[self.perm], vel[self.perm], np.ascontiguousarray(mass[self.perm])
+        origin = np.ascontiguousarray(pos.mean(axis=0))
+        for h, b, c in self.parts:
+            _lib.check(self.lib.gh_engine_set_origin(h, origin.ctypes.data_as(C.POINTER(C.c_double))))
+            p, w = np.ascontiguousarray(pos[b:b + c]), np.ascontiguousarray(vel[b:b + c])
+            _lib.check(self.lib.gh_engine_upload(h, _ptr(p), _ptr(w), _ptr(mass)), "gh_engine_upload")
+
+    def step(self, nsteps, dt, eps, theta, alg):
+        _lib.check(self.lib.gh_group_step(self.g, int(nsteps), dt, eps, theta, alg), "gh_group_step")
+
+    def download(self, pos_out, vel_out):
+        """State of all devices into (N,3) rows, in the caller's particle order."""
+        pos = pos_out if self.perm is None else np.empty_like(pos_out)
+        vel = vel_out if self.perm is None else np.empty_like(vel_out)
+        for h, b, c in self.parts:
+            p, w = np.empty((c, 3)), np.empty((c, 3))
+            _lib.check(self.lib.gh_engine_download(h, _ptr(p), _ptr(w)), "gh_engine_download")
+            pos[b:b + c] = p
+            vel[b:b + c] = w
+        if self.perm is not None:
+            pos_out[self.perm] = pos
+            vel_out[self.perm] = vel
+
+
 class Simulation(object):
     """Main class for N-body simulation (gravhopper.py:91-163).
 
@@ -154,7 +225,7 @@ class Simulation(object):
     """
 
     def __init__(self, dt=1 * u.Myr, eps=100 * u.pc, algorithm='tree', precision='fp64', theta=0.7,
-                 snapshot_every=1, device=0):
+                 snapshot_every=1, device=0, devices=None):
         self.ICarrays = False
         self.Np = 0
         self.Nsnap = 0
@@ -186,7 +257,19 @@ class Simulation(object):
             raise ValueError("snapshot_every must be >= 1.")
         self.params['snapshot_every'] = int(snapshot_every)
         self.params['device'] = int(device)
+        # devices: None / 1 = one GPU (`device`); an int N > 1 = GPUs 0..N-1; a list = those GPUs.
+        # run() then shards the targets over them inside this process (no torchrun needed).
+        if devices is None:
+            devs = [int(device)]
+        elif isinstance(devices, (list, tuple)):
+            devs = [int(d) for d in devices]
+        else:
+            devs = list(range(int(devices)))
+        if len(devs) < 1 or len(set(devs)) != len(devs):
+            raise ValueError("devices must name at least one GPU, each once.")
+        self.params['devices'] = devs
         self._engine = None
+        self._group = None
         self._plot_parms = None
 
     # ---- history arrays as Quantity views (gravhopper.py:135-143) ---------------------------
@@ -306,8 +389,11 @@ class Simulation(object):
         eps = self._eps_value()
         alg = self._alg_code()
         theta = self.params['theta']
-        eng = self._get_engine()
         s0 = self.timestep
+        if len(self.params['devices']) > 1 and not self._has_hooks() and self.Np >= len(self.params['devices']):
+            self._run_group(N, nnew, every, dt, eps, theta, alg, s0)
+            return
+        eng = self._get_engine()
         eng.upload(self._pos[s0], self._vel[s0], self._mass)
         eng.set_potentials(self.native_potentials)
         if not self._has_hooks():
@@ -345,6 +431,30 @@ class Simulation(object):
                     eng.download(x_now, v_now)
                     v_prev = v_now.copy()
             self.timestep = s0 + nnew
+
+    def _run_group(self, N, nnew, every, dt, eps, theta, alg, s0):
+        """run() over several GPUs of this process (Simulation(devices=...)): the state stays on the
+        devices between snapshots, each snapshot is one download of every device's slice."""
+        g = self._group
+        devs, prec = self.params['devices'], self.params['precision']
+        if g is None or g.n != self.Np or g.precision != prec or g.devices != devs:
+            if g is not None:
+                g.close()
+            g = _GroupEngine(self.Np, prec, devs)
+            self._group = g
+        g.upload(self._pos[s0], self._vel[s0], self._mass, tree=(alg == _lib.GH_ALG_TREE))
+        g.set_potentials(self.native_potentials)
+        done = 0
+        for k in range(nnew):
+            nst = min(every, N - done)
+            g.step(nst, dt, eps, theta, alg)
+            g.download(self._pos[s0 + 1 + k], self._vel[s0 + 1 + k])
+            t = self._times[s0 + k]
+            for _ in range(nst):
+                t = t + dt   # times[i] = times[i-1] + dt accumulated step by step (gravhopper.py:320)
+            self._times[s0 + 1 + k] = t
+            done += nst
+        self.timestep = s0 + nnew
 
     def init_run(self, Nsnap=None):
         """Initialize an N-body run (gravhopper.py:324-342)."""

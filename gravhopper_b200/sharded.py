@@ -86,9 +86,14 @@ def interleaved_layout(pos, world, block=None):
 
 
 class CudaShard(object):
-    """One rank's gh_engine over torch-owned source buffers."""
+    """One rank's engine.  native=True (default): the engine is a one-rank member of a gh_group whose
+    NCCL communicator lives inside libgravhopper_b200 (ncclCommInitRank; the 128-byte id travels
+    through torch.distributed) -- a step, collectives included, is ONE C call and the fp32 tree is
+    built distributed.  native=False: the engine reads torch-owned source buffers and the caller
+    all-gathers them with torch.distributed (redundant tree build; also what the gloo host-logic
+    tests exercise with a stand-in shard)."""
 
-    def __init__(self, n_total, begin, count, precision, device):
+    def __init__(self, n_total, begin, count, precision, device, rank=0, world=1, group=None, native=True):
         import torch
         self.torch = torch
         self.n, self.begin, self.count = n_total, begin, count
@@ -96,28 +101,55 @@ class CudaShard(object):
         self.device = torch.device("cuda", device)
         self.lib = _lib.lib()
         _lib.require_gpu()
-        h = C.c_void_p()
+        self.native = bool(native)
+        self.g = None
         prec = _lib.GH_PREC_F64 if precision == "fp64" else _lib.GH_PREC_F32
-        _lib.check(self.lib.gh_engine_create(C.byref(h), device, n_total, begin, count, prec),
-                   "gh_engine_create")
-        self.h = h
-        cols, dtype = (3, torch.float64) if precision == "fp64" else (4, torch.float32)
-        self.bufs = [torch.zeros((n_total, cols), dtype=dtype, device=self.device) for _ in range(2)]
-        torch.cuda.synchronize(self.device)
-        _lib.check(self.lib.gh_engine_bind_sources(self.h, C.c_void_p(self.bufs[0].data_ptr()),
-                                                   C.c_void_p(self.bufs[1].data_ptr())),
-                   "gh_engine_bind_sources")
+        h = C.c_void_p()
+        if self.native:
+            ident = (C.c_char * 128)()
+            if world > 1:
+                import torch.distributed as dist
+                box = [None]
+                if rank == 0:
+                    _lib.check(self.lib.gh_group_unique_id(ident), "gh_group_unique_id")
+                    box[0] = bytes(ident.raw)
+                src = 0 if group is None else dist.get_global_rank(group, 0)
+                dist.broadcast_object_list(box, src=src, group=group)
+                ident = (C.c_char * 128).from_buffer_copy(box[0])
+            g = C.c_void_p()
+            _lib.check(self.lib.gh_group_create_rank(C.byref(g), ident, rank, world, device, n_total, prec),
+                       "gh_group_create_rank")
+            self.g = g
+            b, c = C.c_int64(), C.c_int64()
+            _lib.check(self.lib.gh_group_engine(g, 0, C.byref(h), C.byref(b), C.byref(c)), "gh_group_engine")
+            if (b.value, c.value) != (begin, count):
+                raise _lib.GravHopperB200Error("partition mismatch between the library and the host logic")
+            self.h = h
+            self.bufs = None
+        else:
+            _lib.check(self.lib.gh_engine_create(C.byref(h), device, n_total, begin, count, prec),
+                       "gh_engine_create")
+            self.h = h
+            cols, dtype = (3, torch.float64) if precision == "fp64" else (4, torch.float32)
+            self.bufs = [torch.zeros((n_total, cols), dtype=dtype, device=self.device) for _ in range(2)]
+            torch.cuda.synchronize(self.device)
+            _lib.check(self.lib.gh_engine_bind_sources(self.h, C.c_void_p(self.bufs[0].data_ptr()),
+                                                       C.c_void_p(self.bufs[1].data_ptr())),
+                       "gh_engine_bind_sources")
         s = C.c_void_p()
         _lib.check(self.lib.gh_engine_stream(self.h, C.byref(s)))
         self.stream = torch.cuda.ExternalStream(s.value, device=self.device)
 
     def close(self):
         h, self.h = getattr(self, "h", None), None
-        if h:
-            try:
+        g, self.g = getattr(self, "g", None), None
+        try:
+            if g:
+                self.lib.gh_group_destroy(g)   # destroys its engine too
+            elif h:
                 self.lib.gh_engine_destroy(h)
-            except Exception:  # interpreter shutdown: the library may already be gone
-                pass
+        except Exception:  # interpreter shutdown: the library may already be gone
+            pass
 
     __del__ = close
 
@@ -142,6 +174,24 @@ class CudaShard(object):
     def step(self, dt, eps, theta, alg):
         _lib.check(self.lib.gh_engine_step(self.h, dt, eps, theta, alg, None, _lib.GH_MEM_HOST),
                    "gh_engine_step")
+
+    def group_step(self, nsteps, dt, eps, theta, alg):
+        """nsteps whole steps, NCCL exchanges included, in one asynchronous call (native only)."""
+        _lib.check(self.lib.gh_group_step(self.g, int(nsteps), dt, eps, theta, alg), "gh_group_step")
+
+    def set_tree_distributed(self, enable):
+        if self.g:
+            _lib.check(self.lib.gh_group_set_tree_distributed(self.g, 1 if enable else 0))
+
+    def phase_ms(self):
+        """Device ms of the last step's phases on this rank (see gh_group_phase_ms), or None."""
+        if not self.g:
+            return None
+        out = (C.c_float * 9)()
+        _lib.check(self.lib.gh_group_phase_ms(self.g, out), "gh_group_phase_ms")
+        names = ("source_allgather", "build_keys_select_sort", "exchange_boundary_keys", "build_levels_scans_moments",
+                 "exchange_tables", "stitch_emit", "entries_allgather", "target_sort_walk", "step")
+        return {k: float(v) for k, v in zip(names, out)}
 
     def download(self):
         pos = np.empty((self.count, 3))
@@ -177,7 +227,7 @@ class ShardedSimulation(object):
     (host arrays; synthetic ICs are generated identically on every rank) and keeps its slice."""
 
     def __init__(self, pos, vel, mass, dt, eps, algorithm="direct", theta=0.7, precision="fp64",
-                 rank=0, world=1, device=0, group=None, shard_factory=None, layout=True):
+                 rank=0, world=1, device=0, group=None, shard_factory=None, layout=True, native=None):
         import torch.distributed as dist
         self.dist = dist
         self.rank, self.world, self.group = rank, world, group
@@ -189,8 +239,13 @@ class ShardedSimulation(object):
             raise ValueError("algorithm must be 'tree' or 'direct'.")
         self.alg = _lib.GH_ALG_DIRECT if algorithm == "direct" else _lib.GH_ALG_TREE
         self.uneven = len(set(c for _, c in self.parts)) > 1
-        factory = shard_factory or (lambda n, b, c: CudaShard(n, b, c, precision, device))
+        if native is None:
+            import os
+            native = os.environ.get("GH_COMM", "native") != "torch"
+        factory = shard_factory or (lambda n, b, c: CudaShard(n, b, c, precision, device, rank=rank, world=world,
+                                                              group=group, native=native))
         self.shard = factory(self.n, self.begin, self.count)
+        self.native = bool(getattr(self.shard, "native", False))
         pos = np.asarray(pos, dtype=np.float64)
         vel = np.asarray(vel, dtype=np.float64)
         mass = np.asarray(mass, dtype=np.float64)
@@ -220,15 +275,40 @@ class ShardedSimulation(object):
                 self.dist.broadcast(buf[b:b + c], src=src, group=self.group)
 
     def step(self):
-        buf = self.shard.bufs[self.shard.source_index()]
-        with self.shard.stream_context():
-            self._all_gather(buf)
-        self.shard.step(self.dt, self.eps, self.theta, self.alg)
+        if self.native:
+            self.shard.group_step(1, self.dt, self.eps, self.theta, self.alg)
+        else:
+            buf = self.shard.bufs[self.shard.source_index()]
+            with self.shard.stream_context():
+                self._all_gather(buf)
+            self.shard.step(self.dt, self.eps, self.theta, self.alg)
         self.steps_done += 1
 
     def run(self, nsteps):
+        if self.native:
+            self.shard.group_step(int(nsteps), self.dt, self.eps, self.theta, self.alg)
+            self.steps_done += int(nsteps)
+            return
         for _ in range(int(nsteps)):
             self.step()
+
+    def phase_ms(self):
+        return self.shard.phase_ms() if hasattr(self.shard, "phase_ms") else None
+
+    def describe(self):
+        if self.world == 1:
+            return "one rank: all targets and sources on one GPU"
+        comm = "NCCL communicator inside libgravhopper_b200" if self.native else "torch.distributed"
+        if self.alg == _lib.GH_ALG_DIRECT:
+            return ("targets sharded over %d ranks, all-gather of x_half per step (%s), every rank tiles all sources"
+                    % (self.world, comm))
+        if self.native and self.shard.precision != "fp64":
+            return ("targets sharded over %d ranks (2048-particle Morton blocks dealt round-robin), all-gather of x_half "
+                    "per step (%s), DISTRIBUTED tree build: every rank sorts/scans/emits one Morton key range, two small "
+                    "exchanges stitch the ranges, the entry segments are all-gathered, every rank walks its own targets"
+                    % (self.world, comm))
+        return ("targets sharded over %d ranks, all-gather of x_half per step (%s), tree built redundantly per rank"
+                % (self.world, comm))
 
     def local_state(self):
         return self.shard.download()

@@ -103,6 +103,7 @@ template <class T> static inline T emu_exchange(T v, int src) {  // value of lan
 template <class T> static inline T __shfl_down_sync(unsigned, T v, int d) { return emu_exchange(v, emu::t_lane + d); }
 template <class T> static inline T __shfl_up_sync(unsigned, T v, int d) { return emu_exchange(v, emu::t_lane - d >= 0 ? emu::t_lane - d : -1); }
 template <class T> static inline T __shfl_sync(unsigned, T v, int src) { return emu_exchange(v, src & 31); }
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) { return emu_exchange(v, (emu::t_lane ^ m) & 31); }
 static inline unsigned __ballot_sync(unsigned, bool pred) {
   emu::t_warp->slot[emu::t_lane] = pred ? 1u : 0u;
   emu::t_warp->bar.arrive_and_wait();

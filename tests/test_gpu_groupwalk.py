@@ -153,11 +153,14 @@ def test_group_kernel_equals_the_cpu_model_of_its_criterion(oracle):
     x = np.ascontiguousarray(x)
     J.tree_walk("group")
     J.tree_stats(True)
+    default = J.tree_walk_hybrid()
+    J.tree_walk_hybrid(0.0)   # the plain criterion; the hybrid rule has its own test below
     try:
         a = J.tree_force(x, m, 0.05, 0.7, precision="fp32")
         st = J.tree_stats()
     finally:
         J.tree_stats(False)
+        J.tree_walk_hybrid(default)
     model, info = oracle.tree_force_group(x, m, 0.05, 0.7)
     assert info["fallback_groups"] == st["warp_entries_max"] == 0
     assert abs(st["accepted"] - info["list_sum"]) <= 1e-4 * info["list_sum"]
@@ -207,7 +210,7 @@ print("RESULT", sg["warp_entries_max"], sg["warps"])
 def test_partial_fallback_matches_the_model(oracle, tmp_path):
     # a 900-entry limit makes about half of the groups give up; the model applies the same rule
     # (limit checked when a 32-entry chunk is evaluated) and must pick the same groups
-    env = dict(os.environ, GH_WALK_LIST_LIMIT="900")
+    env = dict(os.environ, GH_WALK_LIST_LIMIT="900", GH_WALK_HYBRID="0")
     env.pop("GH_TREE_WALK", None)
     f = str(tmp_path / "g.npy")
     out = subprocess.run([sys.executable, "-c", _PARTIAL % ROOT, f], env=env, capture_output=True, text=True,
@@ -239,14 +242,12 @@ def test_groups_over_the_list_limit_reproduce_the_per_target_walk():
     assert err <= 1e-6         # (bit-identical when nvcc contracts both instances alike: line[1])
 
 
-@pytest.mark.skipif(os.environ.get("GH_TEST_HYBRID") != "1",
-                    reason="hybrid rule of the group walk: compiled, modelled on the CPU, not yet validated on a "
-                           "GPU (GPU budget of round 1 spent); run with GH_TEST_HYBRID=1")
 def test_hybrid_rule_matches_the_model_and_repairs_the_tail(oracle):
     n = 200000
     x, v, m = ic_raw.Hernquist(n, 1.0, 1e10, seed=42)
     x = np.ascontiguousarray(x)
     kappa = 0.1
+    default = J.tree_walk_hybrid()
     J.tree_walk("group")
     J.tree_stats(True)
     try:
@@ -255,7 +256,7 @@ def test_hybrid_rule_matches_the_model_and_repairs_the_tail(oracle):
         a = J.tree_force(x, m, 0.05, 0.7, precision="fp32")
         st = J.tree_stats()
     finally:
-        J.tree_walk_hybrid(0.0)
+        J.tree_walk_hybrid(default)
         J.tree_stats(False)
     model, info = oracle.tree_force_group(x, m, 0.05, 0.7, hybrid=kappa)
     assert info["hybrid_targets"] > 0

@@ -78,9 +78,6 @@ def test_device_output_feeds_the_force_path(oracle):
     assert abs(2 * ke / abs(pe) - 1.0) < 0.05  # virial equilibrium
 
 
-@pytest.mark.skipif(os.environ.get("GH_TEST_EXPDISK") != "1",
-                    reason="device-side expdisk: compiled and executed on the CPU (tests/test_ic_emu.py), not yet "
-                           "validated on a GPU (GPU budget of round 1 spent); run with GH_TEST_EXPDISK=1")
 def test_expdisk_same_distribution_as_host_generator():
     sigma0, Rd, z0, sigR = 200.0 * 1e6, 2.0, 0.2, 20.0
     rot = ic_raw.hernquist_vcirc(20.0, 4e11)

@@ -14,19 +14,23 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("world,n,alg,prec", [(2, 4096, "direct", "fp64"), (2, 4099, "direct", "fp64"),
-                                              (2, 4096, "tree", "fp64"), (2, 8192, "direct", "fp32"),
-                                              (2, 8192, "tree", "fp32")])
-def test_sharded_matches_single_gpu(tmp_path, world, n, alg, prec):
+# comm "native": NCCL communicator inside the library (fp32 tree: DISTRIBUTED build from the second
+# step on); "torch": torch.distributed all-gather + redundant build (the round-1 path)
+@pytest.mark.parametrize("world,n,alg,prec,steps,comm", [
+    (2, 4096, "direct", "fp64", 3, "native"), (2, 4099, "direct", "fp64", 3, "native"),
+    (2, 4096, "tree", "fp64", 3, "native"), (2, 8192, "direct", "fp32", 3, "native"),
+    (2, 8192, "tree", "fp32", 6, "native"), (2, 8195, "tree", "fp32", 4, "native"),
+    (2, 50000, "tree", "fp32", 5, "native"), (2, 8192, "tree", "fp32", 3, "torch"),
+    (2, 4096, "direct", "fp64", 3, "torch")])
+def test_sharded_matches_single_gpu(tmp_path, world, n, alg, prec, steps, comm):
     if _lib.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     from gravhopper_b200.sharded import ShardedSimulation
-    steps = 3
     out = str(tmp_path / "multi.npz")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", "29731",
            os.path.join(ROOT, "tests", "_sharded_worker.py"), out, str(n), alg, prec, str(steps)]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, GH_COMM=comm))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     got = np.load(out)
     x, v, m = ic_raw.Plummer(n, 1e-3, 1e6, seed=21)
@@ -36,3 +40,22 @@ def test_sharded_matches_single_gpu(tmp_path, world, n, alg, prec):
     tol = 1e-13 if prec == "fp64" else 1e-6
     assert np.abs(got["pos"] - pos).max() <= tol * np.abs(pos).max()
     assert np.abs(got["vel"] - vel).max() <= tol * np.abs(vel).max()
+
+
+def test_simulation_devices_argument_matches_one_gpu():
+    """Simulation(devices=2): single-process multi-GPU inside the drop-in class (ncclCommInitAll
+    behind the C ABI); same trajectories as one GPU."""
+    if _lib.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from gravhopper_b200 import Simulation
+    x, v, m = ic_raw.Plummer(6000, 1e-3, 1e6, seed=8)
+    res = {}
+    for alg, prec in (("direct", "fp64"), ("tree", "fp32")):
+        for ndev in (1, 2):
+            sim = Simulation(dt=0.005, eps=5e-5, algorithm=alg, precision=prec, devices=ndev)
+            sim.add_IC({"pos": x, "vel": v, "mass": m})
+            sim.run(5)
+            res[ndev] = (np.asarray(sim.positions.value)[-1].copy(), np.asarray(sim.velocities.value)[-1].copy())
+        tol = 1e-13 if prec == "fp64" else 1e-6
+        assert np.abs(res[2][0] - res[1][0]).max() <= tol * np.abs(res[1][0]).max(), (alg, prec)
+        assert np.abs(res[2][1] - res[1][1]).max() <= tol * np.abs(res[1][1]).max(), (alg, prec)

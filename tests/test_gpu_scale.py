@@ -37,6 +37,23 @@ def test_direct_fp32_1m_sampled_targets(plummer_1m, oracle):
     assert relerr(ap, a[sel]).max() <= 1e-6
 
 
+def test_direct_fp64_1m_sampled_targets(plummer_1m, oracle):
+    """Config 3's fp64 arm at full size: N = 2^20, the self evaluation of all
+    particles (1.1e12 pairs in fp64, ~1.1 s) checked on 4096 random targets against the oracle's
+    direct_summation_position (_jbgrav.c:299-353 restated); tolerance 1e-12 (north_star)."""
+    x, v, m = plummer_1m
+    eps = 5e-5
+    a = J.direct_summation(x, m, eps)
+    sel = np.random.default_rng(7).choice(len(m), 4096, replace=False)
+    ref = oracle.direct_summation_position(x, m, x[sel], eps, nthreads=0)
+    e = relerr(a[sel], ref)
+    assert e.max() <= 1e-12, e.max()
+    p = (m[:, None] * a).sum(axis=0)   # Newton's third law over all 2^20 particles
+    assert np.linalg.norm(p) <= 1e-12 * (m * np.linalg.norm(a, axis=1)).sum()
+    ap = J.direct_summation_position(x, m, x[sel], eps)
+    assert relerr(ap, a[sel]).max() <= 1e-13
+
+
 def test_direct_fp64_sampled_targets_200k(oracle):
     x, v, m = ic_raw.Hernquist(200000, 1.0, 1e10, seed=42)
     x = np.ascontiguousarray(x)
@@ -81,14 +98,14 @@ def test_tree_4m_hernquist_sampled(oracle, prec):
         assert relerr(a[sel], reft).max() <= 1e-12
         return
     eref, egpu = relerr(reft, refd), relerr(a[sel], refd)
-    # default fp32 walk = group walk: mean / median / p99 of the per-particle error are below the
-    # reference tree's.  The extreme tail is not: the 32 targets of a group share one list, so their
-    # errors are coherent instead of centred on each target, which shows for the ~0.01 % of
-    # particles inside the softened core whose net force nearly cancels.
+    # default fp32 walk = group walk + hybrid rule: mean / median / p99 of the per-particle error are
+    # below the reference tree's and the extreme tail is the reference's (the targets whose net force
+    # nearly cancels are re-evaluated with the reference's own criterion).  The full-distribution
+    # tail (p99.99 and max over all 4M particles) is test_tree_4m_tail_all_particles below.
     assert egpu.mean() <= eref.mean() * 1.02 + 1e-6
     assert np.median(egpu) <= np.median(eref) * 1.02 + 1e-6
     assert np.percentile(egpu, 99) <= np.percentile(eref, 99) * 1.05 + 1e-6
-    assert egpu.max() <= eref.max() * 2.0
+    assert egpu.max() <= eref.max() * 1.05 + 1e-6
     # the per-target walk applies _jbgrav.c:502 itself: the reference's node set, max included
     J.tree_walk("target")
     try:
@@ -103,11 +120,14 @@ def test_tree_4m_hernquist_sampled(oracle, prec):
     # (fp32 decisions reproduced), forces equal to fp32 rounding for all 4M particles except where a
     # borderline acceptance flips
     J.tree_stats(True)
+    default = J.tree_walk_hybrid()
+    J.tree_walk_hybrid(0.0)   # the plain criterion (the hybrid rule: tests/test_gpu_groupwalk.py)
     try:
         a = J.tree_force(x, m, eps, 0.7, precision="fp32")
         st = J.tree_stats()
     finally:
         J.tree_stats(False)
+        J.tree_walk_hybrid(default)
     model, info = oracle.tree_force_group(x, m, eps, 0.7)
     assert info["fallback_groups"] == 0 and st["warp_entries_max"] == 0
     assert abs(st["accepted"] - info["list_sum"]) <= 1e-5 * info["list_sum"]
@@ -116,6 +136,30 @@ def test_tree_4m_hernquist_sampled(oracle, prec):
     assert np.median(diff) <= 1e-5
     assert (diff > 1e-4).mean() <= 0.005
     assert diff.max() <= 2e-2
+
+
+def test_tree_4m_tail_all_particles():
+    """The tail of the default fp32 walk's error over ALL 4,194,304 particles: p99.9,
+    p99.99 and max of |a_tree - a_direct| / |a_direct| no worse than the reference criterion's
+    (the fp64 per-target walk accepts exactly the reference's node set, _jbgrav.c:487-541: checked
+    against the oracle in test_tree_4m_hernquist_sampled and tests/test_gpu_parity.py); the truth is
+    fp64 direct summation on the GPU (1.8e13 pairs, ~17 s)."""
+    import torch
+    n = 1 << 22
+    x, v, m = ic_raw.Hernquist(n, 1.0, 1e10, seed=42)
+    tx, tm = torch.from_numpy(np.ascontiguousarray(x)).cuda(), torch.from_numpy(m).cuda()
+    d = J.direct_summation(tx, tm, 0.05)
+    ref = J.tree_force(tx, tm, 0.05, 0.7)
+    a = J.tree_force(tx, tm, 0.05, 0.7, precision="fp32")
+    torch.cuda.synchronize()
+
+    def err(q):
+        return (torch.linalg.norm(q - d, dim=1) / torch.linalg.norm(d, dim=1)).cpu().numpy()
+    eref, egpu = err(ref), err(a)
+    assert egpu.mean() <= eref.mean() and np.median(egpu) <= np.median(eref)
+    for q in (99.0, 99.9, 99.99):
+        assert np.percentile(egpu, q) <= np.percentile(eref, q) * 1.05, q
+    assert egpu.max() <= eref.max() * 1.05
 
 
 def test_tree_galaxy_model_sampled(oracle):
