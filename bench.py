@@ -639,6 +639,8 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="headline workload only (no tree / fp64 blocks)")
+    ap.add_argument("--quick", action="store_true",
+                    help="experiments only: no parity check, no e2e, no cpu baseline (NOT a valid bench line)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -648,8 +650,12 @@ def main():
 
     ctx = Ctx(args)
     cpu = not args.no_cpu_baseline
-    line = run_block(ctx, args.workload, args.steps, args.warmup, cpu)
-    if args.workload == "direct" and not args.no_extras:
+    if args.quick:
+        line = run_block(ctx, args.workload, args.steps, args.warmup, False, with_e2e=False, with_parity=False)
+        line["quick"] = "experiment run: parity check, e2e and cpu baseline skipped -- not a bench line"
+    else:
+        line = run_block(ctx, args.workload, args.steps, args.warmup, cpu)
+    if args.workload == "direct" and not args.no_extras and not args.quick:
         # the other half of BASELINE.json's metric, at the same --gpus N: particle-steps/s of the tree
         tree = run_block(ctx, "tree", max(args.steps, 10), args.warmup, cpu)
         # configs[2]'s fp64 arm: ~1.07 s per step on one B200, so few steps

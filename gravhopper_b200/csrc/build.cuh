@@ -192,6 +192,7 @@ struct BuildCtl {
   D4 gP;         // moment prefix of all earlier ranks
   int xskip[LEVELS_HI + 1];   // cells of level l that start here and continue beyond this rank:
   D4 xP[LEVELS_HI + 1];       //   their skip link and the moment prefix at their end
+  int counts[DIST_MAX_RANKS];               // particles per rank (from the gathered RankRec1)
   uint64_t split[DIST_MAX_RANKS + 1];       // key ranges of this step
   uint64_t split_next[DIST_MAX_RANKS + 1];  // key ranges of the next step (from the gathered samples)
 };
@@ -259,7 +260,7 @@ select_count_kernel(const uint64_t *__restrict__ keys, int64_t n, const BuildCtl
 __global__ void __launch_bounds__(SEL_THREADS)
 select_compact_kernel(const uint64_t *__restrict__ keys, int64_t n, BuildCtl *__restrict__ ctl,
                       const int *__restrict__ tileoff /* exclusive scan of tilecnt, ntiles + 1 */, int ntiles,
-                      uint64_t *__restrict__ kout, int *__restrict__ vout) {
+                      uint64_t *__restrict__ kout, int *__restrict__ vout, int64_t ncap) {
   __shared__ int wcnt[SEL_THREADS / 32];
   const uint64_t lo = ctl->split[ctl->rank], hi = ctl->split[ctl->rank + 1];
   const bool last = ctl->rank == ctl->world - 1;
@@ -285,12 +286,20 @@ select_compact_kernel(const uint64_t *__restrict__ keys, int64_t n, BuildCtl *__
     const int64_t q = seg0 + r * 32 + lane;
     if (m[r] & (1u << lane)) {
       const int dst = off + __popc(m[r] & ((1u << lane) - 1u));
-      kout[dst] = k[r];
-      vout[dst] = (int)q;
+      if (dst < ncap) {
+        kout[dst] = k[r];
+        vout[dst] = (int)q;
+      }
     }
     off += __popc(m[r]);
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) ctl->n_local = tileoff[ntiles];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    // more particles in this rank's key range than its arrays hold: build what fits, raise the flag
+    // (the walk then does nothing and the host reports it at its next synchronisation)
+    const int tot = tileoff[ntiles];
+    if (tot > ncap) ctl->overflow = 1;
+    ctl->n_local = tot > ncap ? (int)ncap : tot;
+  }
 }
 
 // boundary keys of this rank's sorted range -> its slot of the gathered RankRec1 array
@@ -324,8 +333,10 @@ __global__ void neighbours_kernel(const RankRec1 *__restrict__ all, BuildCtl *__
   ctl->cnext = cnext;
   ctl->seg_next = seg_next;
   int first = ctl->end;  // the root entry is the first entry of the first non-empty rank
-  for (int q = 0; q < P; q++)
-    if (all[q].n > 0) { first = q * ctl->stride; break; }
+  for (int q = P - 1; q >= 0; q--) {
+    ctl->counts[q] = all[q].n;
+    if (all[q].n > 0) first = q * ctl->stride;
+  }
   ctl->first = first;
 }
 
@@ -365,11 +376,13 @@ __global__ void levels_kernel(const uint64_t *__restrict__ hi, const uint64_t *_
 // the emit kernel and the walk's target loads are all coalesced
 template <class Src>
 __global__ void gather_sorted_kernel(Src src, const int *__restrict__ idx, int64_t n,
-                                     double4 *__restrict__ out, const BuildCtl *__restrict__ ctl = nullptr) {
+                                     double4 *__restrict__ out, const BuildCtl *__restrict__ ctl = nullptr,
+                                     int *__restrict__ sidx_slot = nullptr) {
   int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (ctl) n = ctl->n_local;
   if (p >= n) return;
   const int64_t j = idx[p];
+  if (sidx_slot) sidx_slot[p] = (int)j;  // this rank's slot of the gathered sorted-index array
   double x, y, z;
   src.get(j, x, y, z);
   out[p] = make_double4(x, y, z, src.m(j));
@@ -729,5 +742,37 @@ __global__ void GH_EMIT_BOUNDS emit_kernel(const double4 *__restrict__ sp, const
   pack_node(E.node[e], cen, com);
 }
 
+
+// ---- distributed walk: kick and drift of the OWNED particles -------------------------------------
+// After the all-gather of the accelerations.  Sorted particle j of rank q's range was walked by rank
+// (kb + q) % world for block kb = j / blk; its acceleration sits in that rank's buffer at slot
+// q T blk + (kb / world) blk + j % blk (TargetsView, walk.cuh).  Two kernels so that the 170 bytes
+// of state the epilogue touches per particle are accessed in OWNED-index order (coalesced): the
+// first inverts the sorted-index array for the owned particles (one scattered 4-byte store each),
+// the second runs over the owned particles and fetches each one's acceleration (one scattered
+// 16-byte load each).
+__global__ void dist_inverse_kernel(const int *__restrict__ sidx_all, const BuildCtl *__restrict__ ctl, int world,
+                                    int ncap, int64_t ib, int64_t ni, int *__restrict__ inv /* ni */) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= (int64_t)world * ncap) return;
+  const int q = (int)(v / ncap), j = (int)(v % ncap);
+  if (j >= ctl->counts[q]) return;
+  const int64_t gi = sidx_all[v];
+  if (gi >= ib && gi < ib + ni) inv[gi - ib] = (int)v;
+}
+__global__ void dist_epilogue_kernel(const int *__restrict__ inv, const BuildCtl *__restrict__ ctl,
+                                     const float4 *__restrict__ acc_all, int world, int ncap, int blk, int T,
+                                     int64_t ni, Epilogue ep) {
+  if (ctl->overflow) return;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ni) return;
+  const int v = inv[i];
+  const int q = v / ncap, j = v % ncap;
+  const int kb = j / blk, o = j % blk;
+  const int w = (kb + q) % world, t = kb / world;
+  const int64_t slots = (int64_t)world * T * blk;  // target slots per rank
+  const float4 a = acc_all[(int64_t)w * slots + (int64_t)q * T * blk + (int64_t)t * blk + o];
+  apply_epilogue(ep, i, (double)a.x, (double)a.y, (double)a.z);
+}
 
 }  // namespace gh

@@ -62,7 +62,9 @@ struct DeviceBuffer {
 //   EP_STEP: the kick and both drifts of gravhopper.py:414-416 (+ the next step's :409),
 //            with the unit factors of jbgrav.py:48; products and sums are rounded separately
 //            (__dmul_rn/__dadd_rn) exactly as numpy evaluates the reference expressions.
-enum { EP_ACC = 0, EP_STEP = 1 };
+//   EP_ACC32: acc32_out[i] = (a_i, 0) in fp32 (distributed tree walk: accelerations of the targets a
+//            rank walked for other ranks, all-gathered before the owners' EP_STEP)
+enum { EP_ACC = 0, EP_STEP = 1, EP_ACC32 = 2 };
 
 // Device-native analytic external potentials: a tiny kernel evaluates them at
 // x_half into the step's external-acceleration buffer just before the force kernel, so a run in a
@@ -82,6 +84,8 @@ struct Epilogue {
   int mode;
   // EP_ACC
   double *acc_out;  // (nt,3)
+  // EP_ACC32
+  float4 *acc32_out;  // (nt)
   // EP_STEP (all indexed by the local target index i)
   const double *xhalf;   // (nt,3) x_half of this step
   const double *v_in;    // (nt,3) v_n
@@ -149,6 +153,10 @@ __device__ __forceinline__ void apply_epilogue(const Epilogue &ep, int64_t i, do
     ep.acc_out[3 * i + 0] = ax;
     ep.acc_out[3 * i + 1] = ay;
     ep.acc_out[3 * i + 2] = az;
+    return;
+  }
+  if (ep.mode == EP_ACC32) {
+    ep.acc32_out[i] = make_float4((float)ax, (float)ay, (float)az, 0.f);
     return;
   }
   double a[3] = {ax, ay, az};
@@ -245,10 +253,16 @@ int launch_tree(const TreeArgs &a, TreeWorkspace *ws, cudaStream_t stream,
 // Distributed build (fp32): this rank sorts / scans / emits only the particles of its key range
 // into segment [rank * stride, (rank + 1) * stride) of the global entry array.  The caller runs
 // phase 0, all-gathers exchange buffer 1, phase 1, all-gathers buffer 2, phase 2, all-gathers
-// buffer 3 (the entries), phase 3 (walk).  See build.cuh.
+// buffers 3 and 4 (the entries, the sorted particle indices), phase 3 (walk of this rank's share
+// of the global Morton order), all-gathers buffer 5 (accelerations), phase 4 (kick and drift of the
+// owned particles).  See build.cuh.
 struct TreeDist {
   int rank, world;
-  int64_t stride;
+  int64_t stride;  // entries a rank's segment holds
+  int64_t ncap;    // particles a rank's key range may hold (grids, scans and sort tables are sized for
+                   // this, not for all N); 0 = N.  More particles than this raise the overflow flag.
+  int blk;         // targets are dealt to the ranks in blocks of this many Morton-consecutive particles
+                   // of the GLOBAL sorted order (0 = 2048)
 };
 int launch_tree_phase(const TreeArgs &a, TreeWorkspace *ws, cudaStream_t stream, cudaEvent_t *force_events,
                       const TreeDist *dist, int phase);

@@ -72,7 +72,7 @@ const int *tree_maxent_ptr(TreeWorkspace *w);  // tree.cu
 
 using namespace gh;
 
-static constexpr int GROUP_EVENTS = 9;
+static constexpr int GROUP_EVENTS = 11;
 
 struct gh_group {
   int world = 1, rank0 = 0;
@@ -175,7 +175,7 @@ int tree_step_distributed(gh_group *g, double dt, double eps, double theta) {
       GH_CUDA(cudaStreamSynchronize(e->stream));
       int64_t entries = 0;
       if (tree_poll_overflow(e->tw, &entries) < 0) return engine_check_tree(e);
-      e->dist_stride = round_up(entries / g->world + entries / (4 * g->world) + 4096, 1024);
+      e->dist_stride = round_up(entries / g->world + entries / (6 * g->world) + 4096, 1024);
       e->dist_ready = true;
       e->dist_steps = 0;
     }
@@ -196,7 +196,7 @@ int tree_step_distributed(gh_group *g, double dt, double eps, double theta) {
                   "advancing there -- upload it again and rerun", (long long)m, (long long)e->dist_stride);
         return GH_ESTATE;
       }
-      if (10 * m > 9 * e->dist_stride) e->dist_stride = round_up(m + m / 3, 1024);
+      if (100 * m > 95 * e->dist_stride) e->dist_stride = round_up(m + m / 5, 1024);
     }
   }
   std::vector<StepArgs> sa(nl);
@@ -204,7 +204,11 @@ int tree_step_distributed(gh_group *g, double dt, double eps, double theta) {
     gh_engine *e = g->eng[k];
     EngineScope sc(e);
     GH_TRY(engine_step_args(e, dt, eps, theta, GH_ALG_TREE, nullptr, &sa[k]));
-    TreeDist d{g->rank0 + (int)k, g->world, e->dist_stride};
+    // a rank's key range holds N / world particles to within the sampling granularity of the
+    // splitters (1/64 of a rank's share): arrays, grids and the gathered buffers for 1.25x that
+    int64_t ncap = round_up(g->n / g->world + g->n / (4 * g->world) + 4096, 2048);
+    if (ncap > g->n) ncap = g->n;
+    TreeDist d{g->rank0 + (int)k, g->world, e->dist_stride, ncap, 0};
     GH_TRY(launch_tree_phase(sa[k].tree, e->tw, e->stream, nullptr, &d, 0));
   }
   mark(g, 2);
@@ -225,11 +229,20 @@ int tree_step_distributed(gh_group *g, double dt, double eps, double theta) {
   }
   mark(g, 6);
   GH_TRY(all_gather_slots(g, 3));
+  GH_TRY(all_gather_slots(g, 4));
   mark(g, 7);
   for (size_t k = 0; k < nl; k++) {
     gh_engine *e = g->eng[k];
     EngineScope sc(e);
     GH_TRY(launch_tree_phase(sa[k].tree, e->tw, e->stream, e->fev[e->fev_count % gh_engine::FEV_RING], nullptr, 3));
+  }
+  mark(g, 8);
+  GH_TRY(all_gather_slots(g, 5));
+  mark(g, 9);
+  for (size_t k = 0; k < nl; k++) {
+    gh_engine *e = g->eng[k];
+    EngineScope sc(e);
+    GH_TRY(launch_tree_phase(sa[k].tree, e->tw, e->stream, nullptr, nullptr, 4));
     const int slot = (int)(e->dist_steps % gh_engine::MAXENT_RING);
     GH_CUDA(cudaMemcpyAsync(&e->h_maxent[slot], tree_maxent_ptr(e->tw), sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     GH_CUDA(cudaEventRecord(e->maxent_ev[slot], e->stream));
@@ -402,7 +415,7 @@ int gh_group_step(gh_group *g, int64_t nsteps, double dt, double eps, double the
       }
       g->pev_dist = false;
     }
-    mark(g, 8);
+    mark(g, 10);
     g->pev_valid = true;
   }
   return GH_OK;
@@ -416,18 +429,18 @@ int gh_group_synchronize(gh_group *g) {
 
 /* ms of the last step on local engine 0: [0] source all-gather, [1] build A (bbox, keys, select,
  * sort), [2] exchange 1, [3] build B (levels, scans, moments), [4] exchange 2, [5] stitch + emit,
- * [6] entries all-gather, [7] target sort + walk, [8] whole step.  Non-distributed steps report
- * [0], [8] and the rest 0. */
-int gh_group_phase_ms(gh_group *g, float out[9]) {
+ * [6] entry + sorted-index all-gathers, [7] walk, [8] acceleration all-gather, [9] owners' kick and
+ * drift, [10] whole step.  Non-distributed steps report [0], [10] and the rest 0. */
+int gh_group_phase_ms(gh_group *g, float out[11]) {
   if (!g || !out) return GH_EINVAL;
   if (!g->pev_valid) { set_error("no step has run"); return GH_ESTATE; }
   cudaSetDevice(g->eng[0]->device);
-  GH_CUDA(cudaEventSynchronize(g->pev[8]));
-  for (int k = 0; k < 9; k++) out[k] = 0.f;
+  GH_CUDA(cudaEventSynchronize(g->pev[10]));
+  for (int k = 0; k < 11; k++) out[k] = 0.f;
   GH_CUDA(cudaEventElapsedTime(&out[0], g->pev[0], g->pev[1]));
-  GH_CUDA(cudaEventElapsedTime(&out[8], g->pev[0], g->pev[8]));
+  GH_CUDA(cudaEventElapsedTime(&out[10], g->pev[0], g->pev[10]));
   if (g->pev_dist)
-    for (int k = 1; k < 8; k++) GH_CUDA(cudaEventElapsedTime(&out[k], g->pev[k], g->pev[k + 1]));
+    for (int k = 1; k < 10; k++) GH_CUDA(cudaEventElapsedTime(&out[k], g->pev[k], g->pev[k + 1]));
   return GH_OK;
 }
 

@@ -201,7 +201,10 @@ static int chunked_scan(In in, int64_t n, T *P, DeviceBuffer *levels, int depth,
 // ---- radix sort ------------------------------------------------------------------------------
 static constexpr int RS_THREADS = 256;
 static constexpr int RS_WARPS = RS_THREADS / 32;
-static constexpr int RS_ROUNDS = 8;                      // keys per thread
+#ifndef GH_RS_ROUNDS
+#define GH_RS_ROUNDS 8
+#endif
+static constexpr int RS_ROUNDS = GH_RS_ROUNDS;           // keys per thread (8: 2048-key tiles; 12: 3072, 47 KB of smem)
 static constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;   // 2048 keys per CTA
 static constexpr int RS_RADIX = 256;
 
@@ -213,10 +216,23 @@ rs_hist_kernel(const uint64_t *__restrict__ keys, int64_t n, int shift, int *__r
   h[threadIdx.x] = 0;
   __syncthreads();
   const int64_t base = (int64_t)blockIdx.x * RS_TILE;
+  const int lane = threadIdx.x & 31;
+  // all loads first (independent), then one shared-memory atomic per DISTINCT digit of a warp's 32
+  // keys (MATCH.ANY): the high digits of Morton keys are the same for a whole tile, and 2048
+  // atomics on one address would serialise
+  uint64_t k[RS_ROUNDS];
 #pragma unroll
-  for (int k = 0; k < RS_ROUNDS; k++) {
-    const int64_t q = base + k * RS_THREADS + threadIdx.x;
-    if (q < n) atomicAdd(&h[(int)((keys[q] >> shift) & 0xff)], 1);
+  for (int r = 0; r < RS_ROUNDS; r++) {
+    const int64_t q = base + r * RS_THREADS + threadIdx.x;
+    k[r] = (q < n) ? keys[q] : 0;
+  }
+#pragma unroll
+  for (int r = 0; r < RS_ROUNDS; r++) {
+    const int64_t q = base + r * RS_THREADS + threadIdx.x;
+    const bool valid = q < n;
+    const unsigned d = valid ? (unsigned)((k[r] >> shift) & 0xff) : (0x100u + (unsigned)lane);
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    if (valid && lane == __ffs(peers) - 1) atomicAdd(&h[d], __popc(peers));
   }
   __syncthreads();
   const int c = h[threadIdx.x];

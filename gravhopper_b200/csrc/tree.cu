@@ -54,7 +54,8 @@ namespace gh {
 // What one evaluation leaves behind for its later phases (the distributed build interleaves the
 // phases with collectives the caller issues; a single-rank evaluation runs them back to back).
 struct TreePhaseState {
-  int64_t n = 0;            // sources (capacity of the sorted arrays)
+  int64_t n = 0;            // capacity of the sorted arrays: all sources (single rank) or TreeDist::ncap
+  int64_t nall = 0;         // all sources
   const uint64_t *shi = nullptr, *slo = nullptr;
   const int *sidx = nullptr;
   const int *ndev = nullptr;  // &ctl->n_local when the count lives on the device
@@ -63,11 +64,13 @@ struct TreePhaseState {
   int rank = 0, world = 1;
   int64_t ecap = 0;         // entries per segment (stride)
   int end = 0;              // world * stride
+  int blk = 2048, T = 0;    // distributed walk: block size of the deal, blocks per (rank, range)
+  int64_t slots = 0;        // target slots per rank = world * T * blk
 };
 struct TreeWorkspace {
   DeviceBuffer root, part, hi, lo, hi2, lo2, lo3, idx, idx2, clev, cnt, base, P;
   DeviceBuffer node, skip, misc, thi, tidx, thi2, tidx2, sorted, bsum, scanlv[4], cntlv[4];
-  DeviceBuffer ctl, rec1, rec2, keys_all, tilecnt, tileoff, tilelv[4];
+  DeviceBuffer ctl, rec1, rec2, keys_all, tilecnt, tileoff, tilelv[4], sidx_all, acc_all;
   RadixScratch rs;
   TreePhaseState ph;
   int64_t ecap = 0;          // entries the node buffer holds per segment (grow-only)
@@ -85,7 +88,7 @@ void tree_workspace_destroy(TreeWorkspace *w) {
   DeviceBuffer *all[] = {&w->root, &w->part, &w->hi, &w->lo, &w->hi2, &w->lo2, &w->lo3, &w->idx, &w->idx2,
                          &w->clev, &w->cnt, &w->base, &w->P, &w->node, &w->sorted, &w->bsum, &w->scanlv[0], &w->scanlv[1], &w->scanlv[2], &w->scanlv[3], &w->cntlv[0], &w->cntlv[1], &w->cntlv[2], &w->cntlv[3],
                          &w->skip, &w->misc, &w->thi, &w->tidx, &w->thi2, &w->tidx2, &w->ctl, &w->rec1, &w->rec2,
-                         &w->keys_all, &w->tilecnt, &w->tileoff, &w->tilelv[0], &w->tilelv[1], &w->tilelv[2], &w->tilelv[3]};
+                         &w->keys_all, &w->tilecnt, &w->tileoff, &w->sidx_all, &w->acc_all, &w->tilelv[0], &w->tilelv[1], &w->tilelv[2], &w->tilelv[3]};
   for (auto *b : all) b->release();
   w->rs.release();
   if (w->h_pinned) cudaFreeHost(w->h_pinned);
@@ -200,6 +203,7 @@ struct TreeRun {
     TreePhaseState &ph = w->ph;
     ph = TreePhaseState();
     ph.n = n;
+    ph.nall = n;
     ph.levels = (sizeof(Real) == 8) ? LEVELS_MAX : LEVELS_HI;
     ph.deep = ph.levels > LEVELS_HI;
     ph.dist = d != nullptr && d->world > 1;
@@ -274,9 +278,19 @@ struct TreeRun {
       GH_LAUNCH_CHECK();
       GH_TRY((chunked_scan<int, InArray<int>>(InArray<int>{w->tilecnt.as<int>()}, ntiles, w->tileoff.as<int>(),
                                                w->tilelv, 0, st)));
-      select_compact_kernel<<<ntiles, SEL_THREADS, 0, st>>>(kall, n, ctl, w->tileoff.as<int>(), ntiles, hi, idx);
+      // from here on everything is sized for the rank's share (ncap), not for all N
+      int64_t ncap = (d->ncap > 0 && d->ncap < n) ? d->ncap : n;
+      select_compact_kernel<<<ntiles, SEL_THREADS, 0, st>>>(kall, n, ctl, w->tileoff.as<int>(), ntiles, hi, idx, ncap);
       GH_LAUNCH_CHECK();
       ph.ndev = &ctl->n_local;
+      ph.n = ncap;
+      ph.blk = d->blk > 0 ? d->blk : 2048;
+      if (ph.blk % 32) { set_error("tree: the deal's block size must be a multiple of 32"); return GH_EINVAL; }
+      const int64_t nblk = (ncap + ph.blk - 1) / ph.blk;
+      ph.T = (int)((nblk + ph.world - 1) / ph.world);
+      ph.slots = (int64_t)ph.world * ph.T * ph.blk;
+      GH_TRY(w->sidx_all.reserve(sizeof(int) * (size_t)ph.world * (size_t)ncap));
+      GH_TRY(w->acc_all.reserve(sizeof(float4) * (size_t)ph.world * (size_t)ph.slots));
     } else {
       keys_kernel<<<nblk(n, 256), 256, 0, st>>>(src, n, root, ph.levels, hi, lo, idx);
       GH_LAUNCH_CHECK();
@@ -305,7 +319,7 @@ struct TreeRun {
       GH_LAUNCH_CHECK();
       ph.slo = lsorted;
     } else {
-      GH_TRY(radix_sort_pairs(hi, idx, hi2, idx2, n, 63, w->rs, st, &inB, ph.ndev));
+      GH_TRY(radix_sort_pairs(hi, idx, hi2, idx2, ph.n, 63, w->rs, st, &inB, ph.ndev));
       ph.shi = inB ? hi2 : hi;
       ph.sidx = inB ? idx2 : idx;
     }
@@ -342,7 +356,8 @@ struct TreeRun {
     // K7
     GH_TRY(w->sorted.reserve(sizeof(double4) * (size_t)n));
     double4 *sp = w->sorted.as<double4>();
-    gather_sorted_kernel<<<nblk(n, 256), 256, 0, st>>>(src, ph.sidx, n, sp, cd);
+    gather_sorted_kernel<<<nblk(n, 256), 256, 0, st>>>(src, ph.sidx, n, sp, cd,
+                                                       ph.dist ? w->sidx_all.as<int>() + (size_t)ph.rank * (size_t)n : nullptr);
     GH_LAUNCH_CHECK();
     GH_TRY(w->P.reserve(sizeof(Mom) * (size_t)(n + 1)));
     Mom *P = w->P.as<Mom>();
@@ -365,7 +380,7 @@ struct TreeRun {
     const int64_t n = ph.n;
     BuildCtl *ctl = w->ctl.as<BuildCtl>();
     if (ph.dist) {
-      stitch_kernel<<<1, 1, 0, st>>>(w->rec1.as<RankRec1>(), w->rec2.as<RankRec2>(), ctl, n);
+      stitch_kernel<<<1, 1, 0, st>>>(w->rec1.as<RankRec1>(), w->rec2.as<RankRec2>(), ctl, ph.nall);
       GH_LAUNCH_CHECK();
     }
     const bool rel_origin = (sizeof(Real) == 4);  // fp32 entries are stored relative to the root centre
@@ -403,7 +418,25 @@ struct TreeRun {
     tv.pos32 = tgt32;
     tv.order = nullptr;
     tv.order_offset = 0;
-    if (!ph.dist && a.targets_are_sources && ni == n) {
+    tv.dist_sidx = nullptr;
+    tv.dist_counts = nullptr;
+    tv.dist_rank = tv.dist_world = tv.dist_ncap = tv.dist_blk = tv.dist_T = 0;
+    Epilogue ep = a.ep;
+    int64_t nwalk = ni;
+    if (ph.dist) {
+      // this rank's share of the GLOBAL Morton order (blocks dealt round-robin over the ranks): groups
+      // of 32 are spatial neighbours whoever owns them; the accelerations go to this rank's slot of
+      // the gathered buffer and the owners apply the kick and the drift (phase 4)
+      if (!tgt32) { set_error("the distributed walk needs fp32 engine sources"); return GH_EINVAL; }
+      tv.pos32 = a.src32;
+      tv.dist_sidx = w->sidx_all.as<int>();
+      tv.dist_counts = ctl->counts;
+      tv.dist_rank = ph.rank; tv.dist_world = ph.world; tv.dist_ncap = (int)n; tv.dist_blk = ph.blk; tv.dist_T = ph.T;
+      memset(&ep, 0, sizeof(ep));
+      ep.mode = EP_ACC32;
+      ep.acc32_out = w->acc_all.as<float4>() + (size_t)ph.rank * (size_t)ph.slots;
+      nwalk = ph.slots;
+    } else if (a.targets_are_sources && ni == n) {
       tv.order = ph.sidx;
       tv.sorted = w->sorted.as<double4>();
     } else if (ni > 32) {
@@ -411,13 +444,7 @@ struct TreeRun {
       GH_TRY(w->thi2.reserve(sizeof(uint64_t) * ni));
       GH_TRY(w->tidx.reserve(sizeof(int) * ni));
       GH_TRY(w->tidx2.reserve(sizeof(int) * ni));
-      if (ph.dist && a.targets_are_sources) {
-        // the owned targets are sources [tgt_offset, tgt_offset + ni): their keys exist already
-        GH_CUDA(cudaMemcpyAsync(w->thi.ptr, w->keys_all.as<uint64_t>() + a.tgt_offset, sizeof(uint64_t) * ni,
-                                cudaMemcpyDeviceToDevice, st));
-        launch_counter()++;
-        iota_kernel<<<nblk(ni, 256), 256, 0, st>>>(w->tidx.as<int>(), ni);
-      } else if (tgt32) {
+      if (tgt32) {
         Src32 ts{tgt32};
         keys_kernel<<<nblk(ni, 256), 256, 0, st>>>(ts, ni, root, LEVELS_HI, w->thi.as<uint64_t>(),
                                                   (uint64_t *)nullptr, w->tidx.as<int>());
@@ -438,7 +465,7 @@ struct TreeRun {
     // fp32: see GH_F32_MIN_EPS2 (common.cuh)
     const bool tiny_eps = (sizeof(Real) == 4) ? !((float)eps2 >= GH_F32_MIN_EPS2) : (a.eps == 0.0);
     if (tiny_eps) eps2 = (Real)0;
-    const int64_t nwarps = (ni + 31) / 32;
+    const int64_t nwarps = (nwalk + 31) / 32;
     int wb = 128;
     if (const char *env = getenv("GH_WALK_BLOCK")) { int v = atoi(env); if (v == 32 || v == 64 || v == 128) wb = v; }
     const bool group = (sizeof(Real) == 4) && tree_walk_mode() == GH_WALK_GROUP;
@@ -450,12 +477,12 @@ struct TreeRun {
     bool prefetch = false;
     if (const char *env = getenv("GH_WALK_PREFETCH")) prefetch = atoi(env) != 0;
     if (group) {
-      GroupWalk<Real>::launch(E.node, nentries, tv, ni, root, (float)eps2, inv_theta2, a.ep, dstats,
+      GroupWalk<Real>::launch(E.node, nentries, tv, nwalk, root, (float)eps2, inv_theta2, ep, dstats,
                               a.want_stats, guard, (unsigned)nwarps, st, ovf);
     } else {
 #define GH_WALK(STATS, GUARD, PF)                                                                      \
-  walk_kernel<Real, STATS, GUARD, PF><<<blocks, wb, 0, st>>>(E.node, E.skip, nentries, tv, ni, root, \
-                                                            rel_origin, eps2, inv_theta2, a.ep, dstats, ovf)
+  walk_kernel<Real, STATS, GUARD, PF><<<blocks, wb, 0, st>>>(E.node, E.skip, nentries, tv, nwalk, root, \
+                                                            rel_origin, eps2, inv_theta2, ep, dstats, ovf)
 #define GH_WALK2(STATS, GUARD) do { if (prefetch) GH_WALK(STATS, GUARD, true); else GH_WALK(STATS, GUARD, false); } while (0)
       if (a.want_stats) { if (guard) GH_WALK2(true, true); else GH_WALK2(true, false); }
       else { if (guard) GH_WALK2(false, true); else GH_WALK2(false, false); }
@@ -486,7 +513,23 @@ struct TreeRun {
   }
 };
 
-// phase: 0 = A, 1 = B, 2 = C, 3 = D, -1 = all (single rank)
+// phase 4 of a distributed step: the owners' kick and drift from the gathered accelerations
+static int tree_phase_epilogue(const TreeArgs &a, TreeWorkspace *w, cudaStream_t st) {
+  TreePhaseState &ph = w->ph;
+  if (!ph.dist) return GH_OK;
+  const int64_t tot = (int64_t)ph.world * ph.n;
+  GH_TRY(w->tidx.reserve(sizeof(int) * (size_t)a.ni));
+  int *inv = w->tidx.as<int>();
+  dist_inverse_kernel<<<nblk(tot, 256), 256, 0, st>>>(w->sidx_all.as<int>(), w->ctl.as<BuildCtl>(), ph.world,
+                                                     (int)ph.n, a.tgt_offset, a.ni, inv);
+  GH_LAUNCH_CHECK();
+  dist_epilogue_kernel<<<nblk(a.ni, 256), 256, 0, st>>>(inv, w->ctl.as<BuildCtl>(), w->acc_all.as<float4>(), ph.world,
+                                                       (int)ph.n, ph.blk, ph.T, a.ni, a.ep);
+  GH_LAUNCH_CHECK();
+  return GH_OK;
+}
+
+// phase: 0 = A, 1 = B, 2 = C, 3 = D, 4 = distributed epilogue, -1 = all (single rank)
 static int tree_dispatch(const TreeArgs &a, TreeWorkspace *w, cudaStream_t st, cudaEvent_t *ev,
                          const TreeDist *d, int phase) {
 #define GH_TREE_PHASES(SRC, REAL, src, tgt)                                                    \
@@ -497,6 +540,7 @@ static int tree_dispatch(const TreeArgs &a, TreeWorkspace *w, cudaStream_t st, c
     if (phase == 3 || phase < 0) GH_TRY((TreeRun<SRC, REAL>::phase_d(a, src, tgt, w, st, ev))); \
     return GH_OK;                                                                              \
   } while (0)
+  if (phase == 4) return tree_phase_epilogue(a, w, st);
   if (a.prec == GH_PREC_F64) {
     Src64 s{a.src_pos, a.src_mass};
     GH_TREE_PHASES(Src64, double, s, nullptr);
@@ -554,6 +598,8 @@ int tree_exchange_buffer(TreeWorkspace *w, int which, void **ptr, int64_t *bytes
     case 1: *ptr = w->rec1.ptr; *bytes_per_rank = sizeof(RankRec1); return GH_OK;
     case 2: *ptr = w->rec2.ptr; *bytes_per_rank = sizeof(RankRec2); return GH_OK;
     case 3: *ptr = w->node.ptr; *bytes_per_rank = (int64_t)sizeof(Node<float>) * w->ph.ecap; return GH_OK;
+    case 4: *ptr = w->sidx_all.ptr; *bytes_per_rank = (int64_t)sizeof(int) * w->ph.n; return GH_OK;
+    case 5: *ptr = w->acc_all.ptr; *bytes_per_rank = (int64_t)sizeof(float4) * w->ph.slots; return GH_OK;
     default: return GH_EINVAL;
   }
 }

@@ -92,6 +92,15 @@ struct TargetsView {
   const float4 *pos32;   // (ni) or null  (already relative to the f32 engine origin)
   const int *order;      // sorted position -> local target index (null = identity)
   int64_t order_offset;  // subtracted from order[] values (self case with a slice)
+  // distributed walk (dist_sidx != null): the targets are this rank's share of the GLOBAL Morton
+  // order.  Rank q's sorted particles sit at dist_sidx[q * dist_ncap + j], j < dist_counts[q]
+  // (source indices; positions in pos32); blocks of dist_blk consecutive j are dealt round-robin:
+  // block kb of rank q's range belongs to rank (kb + q) % world.  Target slot s of this rank
+  // (= the index its acceleration is stored at) enumerates its blocks: q = s / (T blk),
+  // t = (s / blk) % T, kb = (rank - q) mod world + world t.
+  const int *dist_sidx;
+  const int *dist_counts;
+  int dist_rank, dist_world, dist_ncap, dist_blk, dist_T;
 };
 
 // One warp per 32 Morton-consecutive targets.  `i` (warp-uniform) runs through the pre-order
@@ -104,12 +113,27 @@ struct TargetsView {
 // monopole error).
 // Loads target p of the warp's 32 (relative to the fp32 origin when rel_origin).
 template <class Real>
-__device__ __forceinline__ void load_target(const TargetsView &tv, int64_t p, bool valid,
+__device__ __forceinline__ void load_target(const TargetsView &tv, int64_t p, bool &valid,
                                             const double *__restrict__ root, bool rel_origin,
                                             int64_t &ti, Real &x, Real &y, Real &z) {
   ti = 0;
   x = y = z = 0;
   if (!valid) return;
+  if (tv.dist_sidx) {
+    const int per = tv.dist_T * tv.dist_blk;
+    const int q = (int)(p / per), rem = (int)(p % per);
+    const int t = rem / tv.dist_blk, o = rem % tv.dist_blk;
+    const int kb = (tv.dist_rank - q + tv.dist_world) % tv.dist_world + tv.dist_world * t;
+    const int64_t j = (int64_t)kb * tv.dist_blk + o;
+    if (j >= tv.dist_counts[q]) { valid = false; return; }
+    const float4 tq = tv.pos32[tv.dist_sidx[(int64_t)q * tv.dist_ncap + j]];
+    ti = p;
+    const double ox = rel_origin ? root[0] : 0.0, oy = rel_origin ? root[1] : 0.0, oz = rel_origin ? root[2] : 0.0;
+    x = (Real)((double)tq.x - ox);
+    y = (Real)((double)tq.y - oy);
+    z = (Real)((double)tq.z - oz);
+    return;
+  }
   ti = tv.order ? (int64_t)tv.order[p] - tv.order_offset : p;
   const double ox = rel_origin ? root[0] : 0.0, oy = rel_origin ? root[1] : 0.0,
                oz = rel_origin ? root[2] : 0.0;
@@ -212,7 +236,7 @@ walk_kernel(const Node<Real> *__restrict__ nodes, const int *__restrict__ skips,
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t p = warp * 32 + lane;
-  const bool valid = p < ni;
+  bool valid = p < ni;
   int64_t ti;
   Real x, y, z;
   load_target<Real>(tv, p, valid, root, rel_origin, ti, x, y, z);
@@ -331,64 +355,6 @@ __device__ __forceinline__ float box_dist2(const Box &b, float cx, float cy, flo
   return dx * dx + dy * dy + dz * dz;
 }
 
-// The reference's per-target walk (_jbgrav.c:487-541) for ONE target, executed by the whole warp:
-// the group walk's chain-stack traversal with the point itself as the "box" (so the opening test
-// is the reference's own, side^2/theta^2 < |centre - x|^2), every lane tests one entry per
-// iteration and adds the monopole of the entry it accepted to its private partial sum; the 32
-// partial sums are added at the end (fixed order).  ~35 iterations instead of the ~1240 dependent
-// steps of lane_scan with one active lane: this is what the hybrid rule re-evaluates with.
-// Returns false (sums unusable) if the chain stack would overflow.
-template <bool GUARD>
-__device__ __forceinline__ bool point_walk(const Node<float> *__restrict__ nodes, int first_entry, int nentries,
-                                           float s2root, float px, float py, float pz, float eps2, int2 *stack,
-                                           int lane, float &ox, float &oy, float &oz) {
-  const unsigned gt = ~((1u << lane) - 1u) & ~(1u << lane);
-  float fx = 0.f, fy = 0.f, fz = 0.f;
-  __syncwarp();
-  if (lane == 0) stack[0] = make_int2(first_entry, nentries);
-  int sp = 1;
-  bool ok = true;
-  __syncwarp();
-  while (sp > 0) {
-    const int take = sp < 32 ? sp : 32;
-    const bool has = lane < take;
-    int first = 0, end = 0;
-    if (has) { const int2 it = stack[sp - 1 - lane]; first = it.x; end = it.y; }
-    sp -= take;
-    float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nb = na;
-    if (has) load_node32(nodes, first, na, nb);
-    __syncwarp();
-    float s2;
-    int sk;
-    unpack32(nb.z, s2root, s2, sk);
-    const float cx = na.x - px, cy = na.z - py, cz = nb.x - pz;
-    const float d2 = cx * cx + cy * cy + cz * cz;
-    const bool acc = has && (s2 < d2);  // leaves: s2 = -1
-    const bool open = has && !acc && (first + 1 < sk);
-    const bool rem = has && (sk < end);
-    const unsigned mr = __ballot_sync(0xffffffffu, rem);
-    const unsigned mo = __ballot_sync(0xffffffffu, open);
-    if (sp + __popc(mr) + __popc(mo) > GROUP_STACK) { ok = false; break; }
-    if (rem) stack[sp + __popc(mr & gt)] = make_int2(sk, end);
-    sp += __popc(mr);
-    if (open) stack[sp + __popc(mo & gt)] = make_int2(first + 1, sk);
-    sp += __popc(mo);
-    if (acc) {
-      const float ex = na.y - px, ey = na.w - py, ez = nb.y - pz;
-      const float w = nb.w * inv_cube<GUARD>(ex * ex + ey * ey + ez * ez + eps2);
-      fx += w * ex; fy += w * ey; fz += w * ez;
-    }
-    __syncwarp();
-  }
-  for (int o = 16; o > 0; o >>= 1) {
-    fx += __shfl_xor_sync(0xffffffffu, fx, o);
-    fy += __shfl_xor_sync(0xffffffffu, fy, o);
-    fz += __shfl_xor_sync(0xffffffffu, fz, o);
-  }
-  ox = fx; oy = fy; oz = fz;
-  return ok;
-}
-
 // Resident warps per SM the register allocation is capped for: 32 -> 64 registers per thread,
 // 24 -> 80, 20 -> 96, 16 -> 128 (scripts/gpu_variants.sh measures the alternatives).
 #ifndef GH_GW_WARPS_PER_SM
@@ -400,8 +366,7 @@ __device__ __forceinline__ bool point_walk(const Node<float> *__restrict__ nodes
 // average out the way the per-target walk's errors do, and the relative error of ~0.01 % of the
 // particles exceeds the reference tree's.  With HYBRID each lane compares |a| with a 1/16 sample
 // of sum m/(d^2+eps^2) over its list; lanes with |a| < kappa * sum repeat the evaluation with the
-// reference's own per-target criterion (point_walk: the whole warp on one flagged target at a
-// time).  Measured on B200 over all particles of the N = 4M Hernquist sphere
+// reference's own per-target criterion (lane_scan over the flagged lanes).  Measured on B200 over all particles of the N = 4M Hernquist sphere
 // (profiles/r02_hybrid_sweep_N4M.json): kappa = 0.1 re-evaluates 0.10 % of the targets (p99.99 of
 // the error 1.015x the reference tree's, max equal), 0.15 0.30 % (1.002x), 0.2 1.3 % (1.000x).
 __constant__ float c_hybrid_kappa2;
@@ -421,7 +386,7 @@ walk_group_kernel(const Node<float> *__restrict__ nodes, int nentries, TargetsVi
   const int wic = threadIdx.x >> 5;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t p = warp * 32 + lane;
-  const bool valid = p < ni;
+  bool valid = p < ni;
   int64_t ti;
   float x, y, z;
   load_target<float>(tv, p, valid, root, true, ti, x, y, z);
@@ -434,7 +399,7 @@ walk_group_kernel(const Node<float> *__restrict__ nodes, int nentries, TargetsVi
   // huge one (scripts/walk_sim.c: list p99 4770 -> 1507 entries at N = 4M, mean 1434 -> 1133).
   const float xn = __shfl_down_sync(0xffffffffu, x, 1), yn = __shfl_down_sync(0xffffffffu, y, 1),
               zn = __shfl_down_sync(0xffffffffu, z, 1);
-  const bool next_valid = lane < 31 && (p + 1 < ni);
+  const bool next_valid = (__shfl_down_sync(0xffffffffu, valid ? 1 : 0, 1) != 0) && valid && lane < 31;
   const float gap = next_valid ? (xn - x) * (xn - x) + (yn - y) * (yn - y) + (zn - z) * (zn - z) : -1.f;
   const int gmax = __reduce_max_sync(0xffffffffu, f2ord(gap));
   const int cut = __ffs(__ballot_sync(0xffffffffu, f2ord(gap) == gmax)) - 1;  // box A = lanes <= cut
@@ -524,24 +489,16 @@ walk_group_kernel(const Node<float> *__restrict__ nodes, int nentries, TargetsVi
     if (HYBRID) {
       const float S = 16.f * (sabs.x + sabs.y);
       const bool redo = valid && (ax * ax + ay * ay + az * az < c_hybrid_kappa2 * S * S);
-      unsigned todo = __ballot_sync(0xffffffffu, redo);
-      if (STATS) nredo = redo ? 1ull : 0ull;
-      while (todo) {  // one flagged target at a time, the whole warp on it (point_walk)
-        const int src = __ffs(todo) - 1;
-        todo &= todo - 1u;
-        const float px = __shfl_sync(0xffffffffu, x, src), py = __shfl_sync(0xffffffffu, y, src),
-                    pz = __shfl_sync(0xffffffffu, z, src);
+      if (__any_sync(0xffffffffu, redo)) {
+        // one serial scan for all flagged lanes of the group.  (Measured alternative, rejected: the
+        // whole warp on one flagged target at a time with the chain-stack traversal -- a single
+        // target's frontier is narrow, ~6 busy lanes over ~120 dependent iterations, 3x the cost.)
         float bx = 0.f, by = 0.f, bz = 0.f;
-        if (!point_walk<GUARD>(nodes, GH_FIRST_ENTRY, nentries, s2root, px, py, pz, eps2, stack, lane, bx, by, bz)) {
-          bx = by = bz = 0.f;  // chain stack too small for this target: the serial scan, one active lane
-          unsigned long long c0 = 0, c1 = 0, c2 = 0;
-          lane_scan<float, false, GUARD, false>(nodes, nullptr, s2root, nentries, lane == src, x, y, z, eps2, bx, by,
-                                                bz, c0, c1, c2, GH_FIRST_ENTRY);
-          bx = __shfl_sync(0xffffffffu, bx, src);
-          by = __shfl_sync(0xffffffffu, by, src);
-          bz = __shfl_sync(0xffffffffu, bz, src);
-        }
-        if (lane == src) { ax = bx; ay = by; az = bz; }
+        unsigned long long c0 = 0, c1 = 0, c2 = 0;
+        lane_scan<float, false, GUARD, false>(nodes, nullptr, s2root, nentries, redo, x, y, z, eps2, bx, by, bz,
+                                              c0, c1, c2, GH_FIRST_ENTRY);
+        if (redo) { ax = bx; ay = by; az = bz; }
+        if (STATS) nredo = redo ? 1ull : 0ull;
       }
     }
   } else {

@@ -187,10 +187,11 @@ class CudaShard(object):
         """Device ms of the last step's phases on this rank (see gh_group_phase_ms), or None."""
         if not self.g:
             return None
-        out = (C.c_float * 9)()
+        out = (C.c_float * 11)()
         _lib.check(self.lib.gh_group_phase_ms(self.g, out), "gh_group_phase_ms")
         names = ("source_allgather", "build_keys_select_sort", "exchange_boundary_keys", "build_levels_scans_moments",
-                 "exchange_tables", "stitch_emit", "entries_allgather", "target_sort_walk", "step")
+                 "exchange_tables", "stitch_emit", "entries_sortedindex_allgather", "walk", "acceleration_allgather",
+                 "owners_kick_drift", "step")
         return {k: float(v) for k, v in zip(names, out)}
 
     def download(self):
@@ -303,10 +304,11 @@ class ShardedSimulation(object):
             return ("targets sharded over %d ranks, all-gather of x_half per step (%s), every rank tiles all sources"
                     % (self.world, comm))
         if self.native and self.shard.precision != "fp64":
-            return ("targets sharded over %d ranks (2048-particle Morton blocks dealt round-robin), all-gather of x_half "
-                    "per step (%s), DISTRIBUTED tree build: every rank sorts/scans/emits one Morton key range, two small "
-                    "exchanges stitch the ranges, the entry segments are all-gathered, every rank walks its own targets"
-                    % (self.world, comm))
+            return ("state sharded over %d ranks, all-gather of x_half per step (%s), DISTRIBUTED tree build: every rank "
+                    "sorts/scans/emits one Morton key range, two small exchanges stitch the ranges, the entry segments "
+                    "and sorted indices are all-gathered, every rank walks its share of the GLOBAL Morton order "
+                    "(2048-particle blocks dealt round-robin), the accelerations are all-gathered and the owners kick "
+                    "and drift" % (self.world, comm))
         return ("targets sharded over %d ranks, all-gather of x_half per step (%s), tree built redundantly per rank"
                 % (self.world, comm))
 

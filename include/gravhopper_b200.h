@@ -299,8 +299,9 @@ int gh_group_synchronize(gh_group *g);
 int gh_group_set_tree_distributed(gh_group *g, int enable);
 /* Device time (ms) of the phases of the last step on local engine 0: [0] source all-gather,
  * [1] bbox + keys + select + sort, [2] boundary-key exchange, [3] levels + scans + moments,
- * [4] table exchange, [5] stitch + emit, [6] entry all-gather, [7] target sort + walk, [8] step. */
-int gh_group_phase_ms(gh_group *g, float out[9]);
+ * [4] table exchange, [5] stitch + emit, [6] entry + sorted-index all-gathers, [7] walk,
+ * [8] acceleration all-gather, [9] owners' kick and drift, [10] step. */
+int gh_group_phase_ms(gh_group *g, float out[11]);
 
 #ifdef __cplusplus
 }

@@ -12,12 +12,13 @@ VARIANTS = {
     # profiles/r01_sort_scatter_ab.txt)
     # "rs1": ["-DGH_RS_VARIANT=1"], "rs2": ["-DGH_RS_VARIANT=2"], "rs2b3": ["-DGH_RS_VARIANT=2", "-DGH_RS_MINBLOCKS=3"],
     # emit kernel: occupancy against registers
-    "emit8": ["-DGH_EMIT_MINBLOCKS=8"],
-    "emit10": ["-DGH_EMIT_MINBLOCKS=10"],
-    "emit12": ["-DGH_EMIT_MINBLOCKS=12"],
-    "emit16": ["-DGH_EMIT_MINBLOCKS=16"],
+    # "emit8": ["-DGH_EMIT_MINBLOCKS=8"], ... "emit16": no gain (profiles/r01_emit_occupancy_ab.txt)
+    # radix sort: keys per thread (tile size)
+    "rs12": ["-DGH_RS_ROUNDS=12"],
+    "rs10": ["-DGH_RS_ROUNDS=10"],
+    "rs6": ["-DGH_RS_ROUNDS=6"],
 }
-KERNEL = "emit_kernelINS_5Src64Ef"
+KERNEL = "rs_scatter_kernel"
 B.build()
 out = os.path.join(B.HERE, "variants")
 os.makedirs(out, exist_ok=True)

@@ -157,7 +157,12 @@ int emu_tree_build(int prec, const double *pos, const double *mass, int64_t n, d
 // concatenated.  Returns 0, or 2 when a rank raised the overflow flag.
 int emu_tree_build_dist(int world, const uint64_t *split, const double *pos, const double *mass, int64_t n,
                         double eps, double theta, float *nodes_out, int stride, double *sorted_out, int *order_out,
-                        double *root_out, int *counts_out, uint64_t *split_next_out, int *maxlevel_out) {
+                        double *root_out, int *counts_out, uint64_t *split_next_out, int *maxlevel_out,
+                        double *acc_out, int blk) {
+  // acc_out (nullable, (n,3)): ALSO run the distributed walk -- every rank walks its share of the
+  // global Morton order (blocks of `blk` dealt round-robin) into its slot of the gathered
+  // acceleration buffer, then every rank's dist_epilogue_kernel stores the accelerations of the
+  // particles it owns (contiguous even split of the source indices) into acc_out.
   const int levels = LEVELS_HI;
   Src64 src{pos, mass};
   std::vector<double> root(ROOT_DOUBLES), part(6 * 1024);
@@ -181,6 +186,7 @@ int emu_tree_build_dist(int world, const uint64_t *split, const double *pos, con
   std::vector<Rank> R(world);
   std::vector<RankRec1> rec1(world);
   std::vector<RankRec2> rec2(world);
+  std::vector<int> sidx_all((size_t)world * n, -1);  // the gathered sorted-index array (ncap = n)
   const int ntiles = (int)((n + SEL_TILE - 1) / SEL_TILE);
   // phase A
   for (int r = 0; r < world; r++) {
@@ -193,7 +199,7 @@ int emu_tree_build_dist(int world, const uint64_t *split, const double *pos, con
     std::vector<int> tilecnt(ntiles + 1), tileoff(ntiles + 2);
     emu::launch((unsigned)ntiles, SEL_THREADS, [&] { select_count_kernel(kall.data(), n, &k.ctl, tilecnt.data()); });
     emu_scan<int, InArray<int>>(InArray<int>{tilecnt.data()}, ntiles, tileoff.data());
-    emu::launch((unsigned)ntiles, SEL_THREADS, [&] { select_compact_kernel(kall.data(), n, &k.ctl, tileoff.data(), ntiles, k.hi.data(), k.idx.data()); });
+    emu::launch((unsigned)ntiles, SEL_THREADS, [&] { select_compact_kernel(kall.data(), n, &k.ctl, tileoff.data(), ntiles, k.hi.data(), k.idx.data(), n); });
     const bool inB = emu_sort(k.hi.data(), k.idx.data(), k.hi2.data(), k.idx2.data(), n, 63, &k.ctl.n_local);
     k.shi = inB ? k.hi2.data() : k.hi.data();
     k.sidx = inB ? k.idx2.data() : k.idx.data();
@@ -207,7 +213,7 @@ int emu_tree_build_dist(int world, const uint64_t *split, const double *pos, con
     emu::launch(nblk(n, 256), 256, [&] { levels_kernel(k.shi, nullptr, n, levels, k.clev.data(), k.cnt.data(), &k.ctl); }, true);
     emu_scan<int, InArray<int>>(InArray<int>{k.cnt.data()}, n, k.base.data(), &k.ctl.n_local);
     k.sp.assign(n, double4{0, 0, 0, 0});
-    emu::launch(nblk(n, 256), 256, [&] { gather_sorted_kernel<Src64>(src, k.sidx, n, k.sp.data(), &k.ctl); }, true);
+    emu::launch(nblk(n, 256), 256, [&] { gather_sorted_kernel<Src64>(src, k.sidx, n, k.sp.data(), &k.ctl, sidx_all.data() + (size_t)r * n); }, true);
     k.P.assign(n + 1, D4{{0, 0, 0, 0}});
     emu_scan<D4, InParticlesRel>(InParticlesRel{k.sp.data(), root.data()}, n, k.P.data(), &k.ctl.n_local);
     emu::launch(1, 32, [&] { rec2_kernel(k.shi, k.base.data(), k.P.data(), &k.ctl, rec2.data()); });
@@ -230,6 +236,49 @@ int emu_tree_build_dist(int world, const uint64_t *split, const double *pos, con
     std::memcpy(sorted_out + 4 * ofs, k.sp.data(), sizeof(double4) * (size_t)k.ctl.n_local);
     std::memcpy(order_out + ofs, k.sidx, sizeof(int) * (size_t)k.ctl.n_local);
     ofs += k.ctl.n_local;
+  }
+  if (acc_out) {
+    const int T = (int)(((n + blk - 1) / blk + world - 1) / world);
+    const int64_t slots = (int64_t)world * T * blk;
+    std::vector<float4> acc_all((size_t)world * slots, float4{0, 0, 0, 0});
+    std::vector<float4> pos32(n);
+    for (int64_t i = 0; i < n; i++)
+      pos32[i] = make_float4((float)pos[3 * i], (float)pos[3 * i + 1], (float)pos[3 * i + 2], (float)mass[i]);
+    const float eps2 = (float)(eps * eps);
+    for (int r = 0; r < world; r++) {  // walk
+      TargetsView tv;
+      std::memset(&tv, 0, sizeof(tv));
+      tv.pos32 = pos32.data();
+      tv.dist_sidx = sidx_all.data();
+      tv.dist_counts = R[r].ctl.counts;
+      tv.dist_rank = r; tv.dist_world = world; tv.dist_ncap = (int)n; tv.dist_blk = blk; tv.dist_T = T;
+      Epilogue ep;
+      std::memset(&ep, 0, sizeof(ep));
+      ep.mode = EP_ACC32;
+      ep.acc32_out = acc_all.data() + (size_t)r * slots;
+      const int *wc = &R[r].ctl.overflow;
+      emu::launch((unsigned)((slots + 31) / 32), 32, [&] {
+        walk_group_kernel<1, false, false, false>(E.node, world * stride, tv, slots, root.data(), eps2, inv_theta2, 3000,
+                                                  ep, nullptr, wc);
+      });
+    }
+    const int64_t base = n / world, rem = n % world;
+    int64_t ib = 0;
+    for (int r = 0; r < world; r++) {  // owners
+      const int64_t ni = base + (r < rem ? 1 : 0);
+      Epilogue ep;
+      std::memset(&ep, 0, sizeof(ep));
+      ep.mode = EP_ACC;
+      ep.acc_out = acc_out + 3 * ib;
+      std::vector<int> inv(ni, -1);
+      emu::launch(nblk((int64_t)world * n, 256), 256, [&] {
+        dist_inverse_kernel(sidx_all.data(), &R[r].ctl, world, (int)n, ib, ni, inv.data());
+      }, true);
+      emu::launch(nblk(ni, 256), 256, [&] {
+        dist_epilogue_kernel(inv.data(), &R[r].ctl, acc_all.data(), world, (int)n, blk, T, ni, ep);
+      }, true);
+      ib += ni;
+    }
   }
   for (int j = 0; j <= world; j++) split_next_out[j] = R[0].ctl.split_next[j];
   std::memcpy(root_out, root.data(), sizeof(double) * ROOT_DOUBLES);

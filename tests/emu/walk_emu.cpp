@@ -26,6 +26,7 @@ int emu_walk_group(const float *nodes, int nentries, const double *sorted4, cons
   // walkctl (nullable): {overflow flag, index of the root entry}, see walk_kernel
   using namespace gh;
   TargetsView tv;
+  std::memset(&tv, 0, sizeof(tv));
   tv.sorted = reinterpret_cast<const double4 *>(sorted4);
   tv.pos64 = nullptr;
   tv.pos32 = nullptr;
@@ -59,6 +60,7 @@ int emu_walk_target(const float *nodes, int nentries, const double *sorted4, con
                     unsigned long long *stats4, int flags) {
   using namespace gh;
   TargetsView tv;
+  std::memset(&tv, 0, sizeof(tv));
   tv.sorted = reinterpret_cast<const double4 *>(sorted4);
   tv.pos64 = nullptr;
   tv.pos32 = nullptr;
@@ -85,6 +87,7 @@ int emu_walk_target64(const double *nodes, const int *skips, int nentries, const
                       unsigned long long *stats4, int flags) {
   using namespace gh;
   TargetsView tv;
+  std::memset(&tv, 0, sizeof(tv));
   tv.sorted = nullptr;
   tv.pos64 = tpos;
   tv.pos32 = nullptr;

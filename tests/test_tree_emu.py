@@ -39,7 +39,7 @@ def temu():
     lib.emu_tree_build.argtypes = [C.c_int, vp, vp, C.c_int64, C.c_double, C.c_double, vp, vp, C.c_int, vp, vp,
                                    vp, vp, vp, C.c_int]
     lib.emu_tree_build_dist.argtypes = [C.c_int, vp, vp, vp, C.c_int64, C.c_double, C.c_double, vp, C.c_int, vp, vp,
-                                        vp, vp, vp, vp]
+                                        vp, vp, vp, vp, vp, C.c_int]
     return lib
 
 
@@ -132,7 +132,7 @@ def test_coincident_particles_do_not_break_the_build(temu, emu, oracle, prec):
 
 
 # ---- distributed build: P ranks, each sorting / scanning / emitting its key range --------
-def emu_build_dist(lib, world, split, x, m, eps, theta, stride):
+def emu_build_dist(lib, world, split, x, m, eps, theta, stride, walk_blk=0):
     n = len(m)
     x, m = np.ascontiguousarray(x, dtype=np.float64), np.ascontiguousarray(m, dtype=np.float64)
     split = np.ascontiguousarray(split, dtype=np.uint64)
@@ -144,10 +144,13 @@ def emu_build_dist(lib, world, split, x, m, eps, theta, stride):
     counts = np.zeros(2 * world, dtype=np.int32)
     split_next = np.zeros(world + 1, dtype=np.uint64)
     maxlevel = np.zeros(2, dtype=np.int32)
+    acc = np.zeros((n, 3)) if walk_blk else None
     rc = lib.emu_tree_build_dist(world, split.ctypes.data, x.ctypes.data, m.ctypes.data, n, eps, theta,
                                  nodes.ctypes.data, stride, sorted4.ctypes.data, order.ctypes.data, root.ctypes.data,
-                                 counts.ctypes.data, split_next.ctypes.data, maxlevel.ctypes.data)
-    return rc, nodes, sorted4, order, root, counts.reshape(world, 2), split_next, (int(maxlevel[0]), int(maxlevel[1]))
+                                 counts.ctypes.data, split_next.ctypes.data, maxlevel.ctypes.data,
+                                 None if acc is None else acc.ctypes.data, walk_blk)
+    out = (rc, nodes, sorted4, order, root, counts.reshape(world, 2), split_next, (int(maxlevel[0]), int(maxlevel[1])))
+    return out + (acc,) if walk_blk else out
 
 
 def compact_segments(nodes, counts, stride):
@@ -236,3 +239,39 @@ def test_segment_overflow_raises_the_flag_and_the_walk_stands_still(temu, emu):
     acc1, st1 = run_group(emu, tight[0], tight[2], tight[3], tight[4], 0.05, 0.7)
     acc, st = run_group(emu, padded, sorted4, order, root, 0.05, 0.7)
     assert st["accepted"] == st1["accepted"] and np.array_equal(acc, acc1)
+
+
+@pytest.mark.parametrize("world,blk,how", [(3, 64, "equal"), (4, 32, "random"), (4, 64, "empty")])
+def test_distributed_walk_deals_the_global_morton_order(temu, emu, world, blk, how):
+    """Every rank walks its share of the GLOBAL Morton order (blocks dealt round-robin), the
+    accelerations travel through the gathered buffer and the owners pick theirs up: the result per
+    particle is the single-rank group walk's (same groups of 32 when blk is a multiple of 32 and
+    the ranks' ranges start on group boundaries; otherwise equal to the tree's own accuracy)."""
+    from gravhopper_b200 import ic_raw
+    n = 1536
+    x, v, m = ic_raw.Hernquist(n, 1.0, 1e10, seed=12)
+    x = np.ascontiguousarray(x.astype(np.float32).astype(np.float64))   # exactly representable in fp32
+    m = m.astype(np.float32).astype(np.float64)
+    eps, theta = 0.05, 0.7
+    nodes1, _, sorted1, order1, root1, maxlevel1, keys = emu_build(temu, 32, x, m, eps, theta, want_keys=True)
+    acc1, st1 = run_group(emu, nodes1, sorted1, order1, root1, eps, theta)
+    single = np.zeros_like(acc1)
+    single[...] = acc1            # run_group returns accelerations in source order (order1 maps them)
+    split = np.zeros(world + 1, dtype=np.uint64)
+    split[world] = np.uint64(2 ** 64 - 1)
+    rng = np.random.default_rng(7)
+    if how == "equal":            # ranges of 512 particles: group boundaries coincide with the single rank's
+        split[1:world] = keys[(n * np.arange(1, world)) // world]
+    elif how == "random":
+        split[1:world] = np.sort(keys[rng.choice(n, world - 1, replace=False)] + np.uint64(1))
+    else:
+        split[1], split[2], split[3] = keys[0], keys[n // 2], keys[n // 2]
+    stride = int(len(nodes1) * 1.2)
+    rc, nodes, sorted4, order, root, counts, split_next, _, acc = emu_build_dist(temu, world, split, x, m, eps, theta,
+                                                                              stride, walk_blk=blk)
+    assert rc == 0 and np.isfinite(acc).all() and (np.abs(acc).sum(axis=1) > 0).all()
+    d = relerr(acc, single)
+    if how == "equal":
+        assert d.max() <= 2e-6     # identical groups, identical lists: fp32 rounding of the entries only
+    else:
+        assert np.median(d) <= 2e-3 and d.max() <= 0.2   # other groups of 32: the tree's own accuracy
