@@ -418,20 +418,24 @@ def parity_check(ctx, w, sim, pos_l, vel_l, mass_l):
     # reference tree on its own targets for the bar
     s_mean, cnt = ctx.allsum([float(e.sum()), float(len(e))])
     mx, = ctx.allmax([float(e.max())])
-    ref_mean = ref_max = 0.0
+    ref_mean = ref_max = own_max = 0.0
     if ctx.rank == 0:
         rt = O.tree_force_position(xh_all, mass_l, tgt, w["eps"], w["theta"], nthreads=nthreads)
         er = np.linalg.norm(rt - truth, axis=1) / np.linalg.norm(truth, axis=1)
-        ref_mean, ref_max = float(er.mean()), float(er.max())
-    ref_mean, ref_max = ctx.allmax([ref_mean, ref_max])
+        ref_mean, ref_max, own_max = float(er.mean()), float(er.max()), float(e.max())
+    ref_mean, ref_max, own_max = ctx.allmax([ref_mean, ref_max, own_max])
     mean = s_mean / cnt
+    # like for like: the mean over all ranks' targets against the reference tree's mean on rank 0's
+    # 256 (the mean is stable across samples); the MAX on the same 256 targets for both
     tol_mean, tol_max = 1.05 * ref_mean, 1.5 * ref_max
-    return {"mean_rel_err": mean, "max_rel_err": mx, "reference_tree_mean_rel_err": ref_mean,
-            "reference_tree_max_rel_err": ref_max, "tol": {"mean": tol_mean, "max": tol_max},
-            "ok": bool(mean <= tol_mean and mx <= tol_max), "targets_per_rank": len(sel),
-            "vs": "error against the oracle's direct summation at the same x_half (all ranks' targets), bar = the "
-                  "oracle's reference tree (theta = %.2f) on rank 0's targets: mean <= 1.05 x, max <= 1.5 x (samples "
-                  "of 256: the full-distribution tail checks are in tests/test_gpu_scale.py)" % w["theta"]}
+    return {"mean_rel_err": mean, "max_rel_err_all_ranks": mx, "max_rel_err": own_max,
+            "reference_tree_mean_rel_err": ref_mean, "reference_tree_max_rel_err": ref_max,
+            "tol": {"mean": tol_mean, "max": tol_max},
+            "ok": bool(mean <= tol_mean and own_max <= tol_max), "targets_per_rank": len(sel),
+            "vs": "error against the oracle's direct summation at the same x_half; bar = the oracle's reference tree "
+                  "(theta = %.2f): mean over all ranks' targets <= 1.05 x its mean on rank 0's targets, max on rank 0's "
+                  "targets <= 1.5 x its max on the same targets (samples of 256: the full-distribution tail checks are "
+                  "in tests/test_gpu_scale.py)" % w["theta"]}
 
 
 def run_block(ctx, kind, steps, warmup, with_cpu_baseline, with_e2e=True, with_parity=True):

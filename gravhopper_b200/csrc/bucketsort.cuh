@@ -1,0 +1,388 @@
+// bucketsort.cuh -- "splitter sort" of the tree build's (Morton key, index) pairs: the sort for the
+// steps of a RUNNING simulation, where the key distribution of step n is known from step n-1.
+//
+// The classic LSD radix sort (sortscan.cuh) moves every pair through global memory eight times
+// (63-bit keys, 8 bits per pass, three kernels per pass).  Here the key space is cut into B buckets
+// of ~1365 pairs by splitters taken from the previous step's sorted keys (every (n/B)-th key), and
+//   1. two stable partition passes (the classic pass kernels with the digit = low / high byte of
+//      the BUCKET id, found by binary search over the splitters) bring every pair into its bucket;
+//   2. one kernel sorts every bucket inside shared memory (one CTA per bucket: the same stable
+//      tile ranking as the scatter kernel, 8 bits per pass, only over the bits in which the
+//      bucket's bounds differ), so the pairs cross global memory 3 times instead of 8.
+// Buckets that outgrew the tile (2048 pairs; the splitters are refreshed every step, so this takes
+// a violent change of the system within one step) are sorted by their CTA with the classic pass
+// structure over global memory, tile after tile: slower, never wrong.  The result is the classic
+// sort's, bit for bit (both are stable).  Without valid splitters (first step, stateless calls)
+// the build uses the classic sort.
+#pragma once
+#include "sortscan.cuh"
+
+namespace gh {
+
+static constexpr int BS_TARGET = 1365;     // pairs per bucket the splitters aim at (2/3 of a tile)
+static constexpr int BS_MIN_BUCKETS = 257;  // below this the classic sort is used (launch bound anyway)
+static constexpr int BS_MAX_BUCKETS = 65536;
+
+// bucket of a key: the largest b with spl[b] <= key (spl[0] = 0, so every key has one)
+struct BucketOf {
+  const uint64_t *spl;
+  int nb;
+  __device__ __forceinline__ int operator()(uint64_t k) const {
+    int lo = 0, hi = nb - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (spl[mid] <= k) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+  }
+};
+struct BucketDigit {  // digit of a partition pass
+  BucketOf b;
+  int shift;
+  __device__ __forceinline__ unsigned operator()(uint64_t k) const { return (unsigned)((b(k) >> shift) & 0xff); }
+};
+struct BitsDigit {    // digit of a classic pass
+  int shift;
+  __device__ __forceinline__ unsigned operator()(uint64_t k) const { return (unsigned)((k >> shift) & 0xff); }
+};
+
+struct TileSmem {
+  int whist[RS_WARPS][RS_RADIX];  // per-warp digit counts, then per-warp digit bases
+  int dstart[RS_RADIX];           // start of digit d in the tile's sorted order
+  int gbase[RS_RADIX];            // (global passes) running start of digit d in the output
+  int wtot[RS_WARPS];
+  uint64_t skey[RS_TILE];
+  int sval[RS_TILE];
+};
+
+// Stable ranking of one tile (<= RS_TILE pairs, thread t / round r holds pair w*256 + r*32 + lane)
+// by digit.  On return lrank[r] is the pair's rank among the pairs of its digit inside its warp,
+// sm.whist[w][d] the number of pairs of digit d in warps < w, sm.dstart[d] the start of digit d in
+// the sorted tile; the return value is the tile's count of digit threadIdx.x.  (The body of
+// rs_scatter_kernel, shared here between the partition passes and the in-shared-memory sort.)
+template <class Digit>
+__device__ __forceinline__ int tile_rank(TileSmem &sm, const uint64_t (&key)[RS_ROUNDS], int count, Digit dg,
+                                         int (&lrank)[RS_ROUNDS], unsigned (&dig)[RS_ROUNDS]) {
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+#pragma unroll
+  for (int k = 0; k < RS_WARPS; k++) sm.whist[k][tid] = 0;
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < RS_ROUNDS; r++) {
+    const bool valid = w * (32 * RS_ROUNDS) + r * 32 + lane < count;
+    // invalid lanes get private pseudo-digits so that they match nobody
+    const unsigned d = valid ? dg(key[r]) : (0x100u + (unsigned)lane);
+    dig[r] = d;
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    const int leader = __ffs(peers) - 1;
+    int old = 0;
+    if (lane == leader && valid) {
+      old = sm.whist[w][d];
+      sm.whist[w][d] = old + __popc(peers);
+    }
+    old = __shfl_sync(0xffffffffu, old, leader);
+    lrank[r] = old + __popc(peers & ((1u << lane) - 1u));
+    __syncwarp();
+  }
+  __syncthreads();
+  int tot = 0;
+#pragma unroll
+  for (int k = 0; k < RS_WARPS; k++) {
+    const int c = sm.whist[k][tid];
+    sm.whist[k][tid] = tot;
+    tot += c;
+  }
+  const int incl = warp_scan<int>(tot, lane);
+  if (lane == 31) sm.wtot[w] = incl;
+  __syncthreads();
+  int woff = 0;
+#pragma unroll
+  for (int k = 0; k < RS_WARPS; k++) woff += (k < w) ? sm.wtot[k] : 0;
+  sm.dstart[tid] = woff + incl - tot;
+  __syncthreads();
+  return tot;
+}
+
+// place the tile's pairs into sm.skey / sm.sval in digit order (after tile_rank)
+__device__ __forceinline__ void tile_place(TileSmem &sm, const uint64_t (&key)[RS_ROUNDS], const int (&val)[RS_ROUNDS],
+                                           int count, const int (&lrank)[RS_ROUNDS], const unsigned (&dig)[RS_ROUNDS]) {
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+#pragma unroll
+  for (int r = 0; r < RS_ROUNDS; r++) {
+    if (w * (32 * RS_ROUNDS) + r * 32 + lane < count) {
+      const int d = (int)dig[r];
+      const int pos = sm.dstart[d] + sm.whist[w][d] + lrank[r];
+      sm.skey[pos] = key[r];
+      sm.sval[pos] = val[r];
+    }
+  }
+  __syncthreads();
+}
+
+// ---- partition passes: the classic three kernels with the bucket id's bytes as digits --------------
+__global__ void __launch_bounds__(RS_THREADS)
+bs_hist_kernel(const uint64_t *__restrict__ keys, int64_t n, BucketDigit dg, int *__restrict__ hist, int nblocks,
+               int *__restrict__ gtot /* [256], zeroed */, const int *__restrict__ ndev) {
+  __shared__ int h[RS_RADIX];
+  if (ndev) n = *ndev;
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * RS_TILE;
+  const int lane = threadIdx.x & 31;
+  uint64_t k[RS_ROUNDS];
+#pragma unroll
+  for (int r = 0; r < RS_ROUNDS; r++) {
+    const int64_t q = base + r * RS_THREADS + threadIdx.x;
+    k[r] = (q < n) ? keys[q] : 0;
+  }
+#pragma unroll
+  for (int r = 0; r < RS_ROUNDS; r++) {
+    const int64_t q = base + r * RS_THREADS + threadIdx.x;
+    const bool valid = q < n;
+    const unsigned d = valid ? dg(k[r]) : (0x100u + (unsigned)lane);
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    if (valid && lane == __ffs(peers) - 1) atomicAdd(&h[d], __popc(peers));
+  }
+  __syncthreads();
+  const int c = h[threadIdx.x];
+  hist[(int64_t)threadIdx.x * nblocks + blockIdx.x] = c;
+  if (c) atomicAdd(&gtot[threadIdx.x], c);
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+bs_scatter_kernel(const uint64_t *__restrict__ kin, const int *__restrict__ vin, uint64_t *__restrict__ kout,
+                  int *__restrict__ vout, int64_t n, BucketDigit dg, const int *__restrict__ offs,
+                  const int *__restrict__ gtot, int nblocks, const int *__restrict__ ndev) {
+  __shared__ TileSmem sm;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int64_t tile0 = (int64_t)blockIdx.x * RS_TILE;
+  if (ndev) n = *ndev;
+  if (tile0 >= n) return;
+  const int64_t left = n - tile0;
+  const int count = (int)(left < RS_TILE ? left : RS_TILE);
+  uint64_t key[RS_ROUNDS];
+  int val[RS_ROUNDS], lrank[RS_ROUNDS];
+  unsigned dig[RS_ROUNDS];
+#pragma unroll
+  for (int r = 0; r < RS_ROUNDS; r++) {
+    const int j = w * (32 * RS_ROUNDS) + r * 32 + lane;
+    key[r] = (j < count) ? kin[tile0 + j] : 0;
+    val[r] = (j < count) ? vin[tile0 + j] : 0;
+  }
+  tile_rank(sm, key, count, dg, lrank, dig);
+  {  // global start of digit d = pairs with a smaller digit + this CTA's offset inside the digit
+    const int g = gtot[tid];
+    const int gincl = warp_scan<int>(g, lane);
+    if (lane == 31) sm.wtot[w] = gincl;
+    __syncthreads();
+    int goff = 0;
+#pragma unroll
+    for (int k = 0; k < RS_WARPS; k++) goff += (k < w) ? sm.wtot[k] : 0;
+    sm.gbase[tid] = goff + gincl - g + offs[(int64_t)tid * nblocks + blockIdx.x];
+  }
+  __syncthreads();
+  tile_place(sm, key, val, count, lrank, dig);
+#pragma unroll
+  for (int k = 0; k < RS_ROUNDS; k++) {
+    const int j = k * RS_THREADS + tid;
+    if (j < count) {
+      const uint64_t kk = sm.skey[j];
+      const int d = (int)dg(kk);
+      const int64_t g = (int64_t)sm.gbase[d] + (j - sm.dstart[d]);
+      kout[g] = kk;
+      vout[g] = sm.sval[j];
+    }
+  }
+}
+
+// boff[b] = first position of the partitioned array whose bucket is >= b (b = 0 .. nb; boff[nb] = n)
+__global__ void bs_offsets_kernel(const uint64_t *__restrict__ keys, int64_t n, BucketOf bo, int *__restrict__ boff,
+                                  const int *__restrict__ ndev) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ndev) n = *ndev;
+  if (b > bo.nb) return;
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (bo(keys[mid]) < b) lo = mid + 1; else hi = mid;
+  }
+  boff[b] = (int)lo;
+}
+
+// ---- the buckets: one CTA each ---------------------------------------------------------------------
+// keys/vals: the partitioned array (sorted in place); kscr/vscr: scratch of the same size (only
+// the oversize path uses it).  Bits that are equal in the bucket's bounds need no pass.
+__global__ void __launch_bounds__(RS_THREADS)
+bs_bucket_kernel(uint64_t *__restrict__ keys, int *__restrict__ vals, uint64_t *__restrict__ kscr,
+                 int *__restrict__ vscr, const int *__restrict__ boff, const uint64_t *__restrict__ spl, int nb,
+                 int nbits) {
+  __shared__ TileSmem sm;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int b = blockIdx.x;
+  const int64_t s0 = boff[b], s1 = boff[b + 1];
+  const int64_t size = s1 - s0;
+  if (size <= 1) return;
+  // bits in which two keys of this bucket can differ
+  const uint64_t klo = spl[b], khi = (b + 1 < nb) ? spl[b + 1] - 1 : ~0ull;
+  int topbit = 64 - __clzll((long long)(klo ^ khi));  // 0 when all keys are equal
+  if (topbit > nbits) topbit = nbits;
+  const int npass = (topbit + 7) / 8;
+  if (npass == 0) return;
+  uint64_t key[RS_ROUNDS];
+  int val[RS_ROUNDS], lrank[RS_ROUNDS];
+  unsigned dig[RS_ROUNDS];
+  if (size <= RS_TILE) {
+    const int count = (int)size;
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS; r++) {
+      const int j = w * (32 * RS_ROUNDS) + r * 32 + lane;
+      key[r] = (j < count) ? keys[s0 + j] : 0;
+      val[r] = (j < count) ? vals[s0 + j] : 0;
+    }
+    for (int pass = 0; pass < npass; pass++) {
+      tile_rank(sm, key, count, BitsDigit{8 * pass}, lrank, dig);
+      tile_place(sm, key, val, count, lrank, dig);
+      if (pass + 1 < npass) {
+#pragma unroll
+        for (int r = 0; r < RS_ROUNDS; r++) {
+          const int j = w * (32 * RS_ROUNDS) + r * 32 + lane;
+          if (j < count) { key[r] = sm.skey[j]; val[r] = sm.sval[j]; }
+        }
+        __syncthreads();
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < RS_ROUNDS; k++) {
+      const int j = k * RS_THREADS + tid;
+      if (j < count) { keys[s0 + j] = sm.skey[j]; vals[s0 + j] = sm.sval[j]; }
+    }
+    return;
+  }
+  // oversize bucket: the classic pass structure over global memory, by this CTA alone.  An even
+  // number of passes, so that the result ends where it started.
+  __shared__ int ghist[RS_RADIX];
+  const int gp = (npass + 1) & ~1;
+  uint64_t *kin = keys + s0, *kout = kscr + s0;
+  int *vin = vals + s0, *vout = vscr + s0;
+  const int ntiles = (int)((size + RS_TILE - 1) / RS_TILE);
+  for (int pass = 0; pass < gp; pass++) {
+    const BitsDigit dg{8 * pass};
+    ghist[tid] = 0;
+    __syncthreads();
+    for (int64_t q = tid; q < size; q += RS_THREADS) atomicAdd(&ghist[dg(kin[q])], 1);
+    __syncthreads();
+    {  // exclusive scan of the digit counts -> running output offsets
+      const int g = ghist[tid];
+      const int gincl = warp_scan<int>(g, lane);
+      if (lane == 31) sm.wtot[w] = gincl;
+      __syncthreads();
+      int goff = 0;
+#pragma unroll
+      for (int k = 0; k < RS_WARPS; k++) goff += (k < w) ? sm.wtot[k] : 0;
+      __syncthreads();
+      ghist[tid] = goff + gincl - g;
+    }
+    __syncthreads();
+    for (int t = 0; t < ntiles; t++) {
+      const int64_t t0 = (int64_t)t * RS_TILE;
+      const int count = (int)((size - t0) < RS_TILE ? (size - t0) : RS_TILE);
+#pragma unroll
+      for (int r = 0; r < RS_ROUNDS; r++) {
+        const int j = w * (32 * RS_ROUNDS) + r * 32 + lane;
+        key[r] = (j < count) ? kin[t0 + j] : 0;
+        val[r] = (j < count) ? vin[t0 + j] : 0;
+      }
+      const int tot = tile_rank(sm, key, count, dg, lrank, dig);
+      tile_place(sm, key, val, count, lrank, dig);
+#pragma unroll
+      for (int k = 0; k < RS_ROUNDS; k++) {
+        const int j = k * RS_THREADS + tid;
+        if (j < count) {
+          const uint64_t kk = sm.skey[j];
+          const int d = (int)dg(kk);
+          const int64_t g = (int64_t)ghist[d] + (j - sm.dstart[d]);
+          kout[g] = kk;
+          vout[g] = sm.sval[j];
+        }
+      }
+      __syncthreads();
+      ghist[tid] += tot;  // this tile's pairs of digit tid are placed
+      __syncthreads();
+    }
+    uint64_t *tk = kin; kin = kout; kout = tk;
+    int *tv = vin; vin = vout; vout = tv;
+    __threadfence_block();
+    __syncthreads();
+  }
+}
+
+// spl[b] = the (b n / nb)-th sorted key (b = 1 .. nb-1), spl[0] = 0: the next step's buckets
+__global__ void bs_splitters_kernel(const uint64_t *__restrict__ sorted, int64_t n, int nb, uint64_t *__restrict__ spl,
+                                    const int *__restrict__ ndev) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ndev) n = *ndev;
+  if (b >= nb) return;
+  spl[b] = (b == 0 || n <= 0) ? 0ull : sorted[(n * b) / nb];
+}
+
+#ifndef GH_HOST_EMU
+struct SplitterState {
+  DeviceBuffer spl, boff;
+  int nb = 0;          // buckets the stored splitters describe (0 = none)
+  int64_t cap = 0;     // capacity (n) they were taken for
+  void release() { spl.release(); boff.release(); nb = 0; }
+};
+static inline int bs_buckets_for(int64_t n) {
+  int64_t nb = (n + BS_TARGET - 1) / BS_TARGET;
+  if (nb > BS_MAX_BUCKETS) nb = BS_MAX_BUCKETS;
+  return (int)nb;
+}
+
+// Stable sort of (key, value) pairs on key bits [0, nbits) with the buckets of `ss` (valid splitters
+// required: ss.nb >= BS_MIN_BUCKETS).  Result in (kA, vA); (kB, vB) is scratch.
+static int splitter_sort_pairs(uint64_t *kA, int *vA, uint64_t *kB, int *vB, int64_t n, int nbits, RadixScratch &rs,
+                               SplitterState &ss, cudaStream_t st, const int *ndev) {
+  if (n <= 1) return GH_OK;
+  const int nblocks = (int)((n + RS_TILE - 1) / RS_TILE);
+  GH_TRY(rs.hist.reserve(sizeof(int) * (size_t)RS_RADIX * (size_t)nblocks));
+  GH_TRY(rs.gtot.reserve(sizeof(int) * RS_RADIX * 8));
+  GH_TRY(ss.boff.reserve(sizeof(int) * (size_t)(ss.nb + 2)));
+  GH_CUDA(cudaMemsetAsync(rs.gtot.ptr, 0, sizeof(int) * RS_RADIX * 2, st));
+  const BucketOf bo{ss.spl.as<uint64_t>(), ss.nb};
+  uint64_t *kin = kA, *kout = kB;
+  int *vin = vA, *vout = vB;
+  for (int pass = 0; pass < 2; pass++) {
+    const BucketDigit dg{bo, 8 * pass};
+    int *gtot = rs.gtot.as<int>() + RS_RADIX * pass;
+    bs_hist_kernel<<<nblocks, RS_THREADS, 0, st>>>(kin, n, dg, rs.hist.as<int>(), nblocks, gtot, ndev);
+    GH_LAUNCH_CHECK();
+    rs_rowscan_kernel<<<RS_RADIX, RS_THREADS, 0, st>>>(rs.hist.as<int>(), nblocks);
+    GH_LAUNCH_CHECK();
+    bs_scatter_kernel<<<nblocks, RS_THREADS, 0, st>>>(kin, vin, kout, vout, n, dg, rs.hist.as<int>(), gtot, nblocks, ndev);
+    GH_LAUNCH_CHECK();
+    uint64_t *tk = kin; kin = kout; kout = tk;
+    int *tv = vin; vin = vout; vout = tv;
+  }
+  // two passes: the partitioned pairs are back in (kA, vA)
+  bs_offsets_kernel<<<(ss.nb + 1 + 255) / 256, 256, 0, st>>>(kA, n, bo, ss.boff.as<int>(), ndev);
+  GH_LAUNCH_CHECK();
+  bs_bucket_kernel<<<ss.nb, RS_THREADS, 0, st>>>(kA, vA, kB, vB, ss.boff.as<int>(), ss.spl.as<uint64_t>(), ss.nb, nbits);
+  GH_LAUNCH_CHECK();
+  return GH_OK;
+}
+
+// after a sort: the next step's splitters from the sorted keys (capacity n, real count possibly on
+// the device)
+static int splitter_refresh(SplitterState &ss, const uint64_t *sorted, int64_t n, cudaStream_t st, const int *ndev) {
+  const int nb = bs_buckets_for(n);
+  if (nb < BS_MIN_BUCKETS) { ss.nb = 0; return GH_OK; }
+  GH_TRY(ss.spl.reserve(sizeof(uint64_t) * (size_t)(nb + 1)));
+  bs_splitters_kernel<<<(nb + 255) / 256, 256, 0, st>>>(sorted, n, nb, ss.spl.as<uint64_t>(), ndev);
+  GH_LAUNCH_CHECK();
+  ss.nb = nb;
+  ss.cap = n;
+  return GH_OK;
+}
+#endif  // GH_HOST_EMU
+
+}  // namespace gh

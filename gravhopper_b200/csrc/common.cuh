@@ -245,6 +245,8 @@ struct TreeArgs {
   Epilogue ep;
   bool want_stats;
   bool sync_check;  // the caller synchronises anyway: check (and repair) an entry-array overflow
+  bool coherent;    // a step of a running simulation: the key distribution of the previous build in this
+                    // workspace describes this one (splitter sort, bucketsort.cuh)
 };
 // One evaluation never needs the host to learn a count from the device: the entry array has a
 // capacity, the walk ends its chains at the capacity, an overflow raises a device flag.
@@ -269,6 +271,7 @@ int launch_tree_phase(const TreeArgs &a, TreeWorkspace *ws, cudaStream_t stream,
 int tree_exchange_buffer(TreeWorkspace *ws, int which, void **ptr, int64_t *bytes_per_rank);
 int tree_splitters(TreeWorkspace *ws, int world, cudaStream_t stream);
 int tree_poll_overflow(TreeWorkspace *ws, int64_t *entries);
+void tree_forget_history(TreeWorkspace *ws);  // new state uploaded: the next build is not coherent with the last
 int tree_last_stats(TreeWorkspace *ws, int64_t out[8]);
 int tree_walk_mode();
 void set_tree_walk_mode(int mode);

@@ -557,6 +557,7 @@ int gh_engine_upload(gh_engine *e, const double *pos, const double *vel, const d
   e->uploaded = true;
   e->xhalf_valid = false;
   e->dist_ready = false;
+  tree_forget_history(e->tw);
   return GH_OK;
 }
 
@@ -571,6 +572,8 @@ int gh_engine_upload_device(gh_engine *e, const double *pos, const double *vel, 
   GH_CUDA(cudaStreamSynchronize(e->stream));
   e->uploaded = true;
   e->xhalf_valid = false;
+  e->dist_ready = false;
+  tree_forget_history(e->tw);
   return GH_OK;
 }
 
@@ -679,6 +682,7 @@ int engine_step_args(gh_engine *e, double dt, double eps, double theta, int algo
     a.ep = ep;
     a.targets_are_sources = true;
     a.tgt_offset = e->ib;
+    a.coherent = true;
     if (e->prec == GH_PREC_F64) {
       a.src_pos = reinterpret_cast<const double *>(e->src[e->scur]);
       a.src_mass = e->mass;

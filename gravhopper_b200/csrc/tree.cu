@@ -41,6 +41,7 @@
 // reference segfaults there, :401-413).
 #include "common.cuh"
 #include "sortscan.cuh"
+#include "bucketsort.cuh"
 #include "walk.cuh"
 #include "build.cuh"
 
@@ -72,6 +73,7 @@ struct TreeWorkspace {
   DeviceBuffer node, skip, misc, thi, tidx, thi2, tidx2, sorted, bsum, scanlv[4], cntlv[4];
   DeviceBuffer ctl, rec1, rec2, keys_all, tilecnt, tileoff, tilelv[4], sidx_all, acc_all;
   RadixScratch rs;
+  SplitterState ss;  // buckets of the splitter sort (bucketsort.cuh): valid from one coherent step to the next
   TreePhaseState ph;
   int64_t ecap = 0;          // entries the node buffer holds per segment (grow-only)
   int64_t node_slots = 0;    // entries allocated in `node`
@@ -91,6 +93,7 @@ void tree_workspace_destroy(TreeWorkspace *w) {
                          &w->keys_all, &w->tilecnt, &w->tileoff, &w->sidx_all, &w->acc_all, &w->tilelv[0], &w->tilelv[1], &w->tilelv[2], &w->tilelv[3]};
   for (auto *b : all) b->release();
   w->rs.release();
+  w->ss.release();
   if (w->h_pinned) cudaFreeHost(w->h_pinned);
   if (w->h_stats) cudaFreeHost(w->h_stats);
   if (w->readback) cudaEventDestroy(w->readback);
@@ -106,7 +109,7 @@ static inline unsigned nblk(int64_t n, int b) { return (unsigned)((n + b - 1) / 
 // walk selection: GH_WALK_GROUP (default; fp32 only) or GH_WALK_TARGET (the reference's per-target
 // criterion; always used in fp64).  Process-wide; GH_TREE_WALK=target|group sets the initial value.
 #ifndef GH_WALK_HYBRID_DEFAULT
-#define GH_WALK_HYBRID_DEFAULT 0.15f
+#define GH_WALK_HYBRID_DEFAULT 0.10f
 #endif
 static int g_walk_mode = -1;
 int tree_walk_mode() {
@@ -130,11 +133,12 @@ static int group_list_limit() {
   return v;
 }
 
-// kappa of the hybrid rule (see walk_group_kernel); 0 = off.  Default 0.15: measured on B200 over
+// kappa of the hybrid rule (see walk_group_kernel); 0 = off.  Default 0.10: measured on B200 over
 // ALL particles of the N = 4,194,304 Hernquist sphere (profiles/r02_hybrid_sweep_N4M.json) it
-// re-evaluates 0.30 % of the targets and brings p99.99 / max of the error against direct summation
-// to 1.002x / 1.000x the reference tree's (plain group walk: 1.12x p99.99), mean / median / p99
-// staying 11-13 % BELOW the reference's.  GH_WALK_HYBRID=<kappa> sets the initial value (0 = off),
+// re-evaluates 0.10 % of the targets and brings p99.9 / p99.99 / max of the error against direct
+// summation to 0.94x / 1.015x / 1.000x the reference tree's (plain group walk: 1.12x at p99.99),
+// mean / median / p99 staying 11-13 % BELOW the reference's, for ~2 % of the walk time (0.15:
+// 0.30 % of the targets, 1.002x, ~7 %; 0.2: 1.3 %, 1.000x).  GH_WALK_HYBRID=<kappa> sets the initial value (0 = off),
 // gh_set_tree_walk_hybrid() changes it.
 static float g_hybrid_kappa = -1.f;
 float group_hybrid_kappa() {
@@ -319,9 +323,24 @@ struct TreeRun {
       GH_LAUNCH_CHECK();
       ph.slo = lsorted;
     } else {
-      GH_TRY(radix_sort_pairs(hi, idx, hi2, idx2, ph.n, 63, w->rs, st, &inB, ph.ndev));
+      // A running simulation (a.coherent) sorts with the buckets the previous step left behind
+      // (bucketsort.cuh: 3 trips through global memory instead of 8); the first step after an
+      // upload, stateless calls and small systems use the classic LSD sort.  GH_SORT=classic|bucket.
+      static const int sort_mode = [] {
+        const char *env = getenv("GH_SORT");
+        return (env && !strcmp(env, "classic")) ? 0 : 1;
+      }();
+      const bool bucket = sort_mode == 1 && a.coherent && w->ss.nb >= BS_MIN_BUCKETS && w->ss.cap == ph.n;
+      if (bucket) {
+        GH_TRY(splitter_sort_pairs(hi, idx, hi2, idx2, ph.n, 63, w->rs, w->ss, st, ph.ndev));
+        inB = false;
+      } else {
+        GH_TRY(radix_sort_pairs(hi, idx, hi2, idx2, ph.n, 63, w->rs, st, &inB, ph.ndev));
+      }
       ph.shi = inB ? hi2 : hi;
       ph.sidx = inB ? idx2 : idx;
+      if (a.coherent && sort_mode == 1) GH_TRY(splitter_refresh(w->ss, ph.shi, ph.n, st, ph.ndev));
+      else w->ss.nb = 0;
     }
     if (ph.dist) {
       GH_TRY(w->rec1.reserve(sizeof(RankRec1) * (size_t)ph.world));
@@ -589,6 +608,8 @@ int tree_poll_overflow(TreeWorkspace *w, int64_t *entries) {
   if (entries) *entries = w->h_pinned[0];
   return w->h_pinned[2] ? -1 : 1;
 }
+
+void tree_forget_history(TreeWorkspace *w) { if (w) w->ss.nb = 0; }
 
 const int *tree_maxent_ptr(TreeWorkspace *w) { return &w->ctl.as<BuildCtl>()->maxent; }
 

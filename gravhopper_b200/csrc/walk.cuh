@@ -360,7 +360,7 @@ __device__ __forceinline__ float box_dist2(const Box &b, float cx, float cy, flo
 #ifndef GH_GW_WARPS_PER_SM
 #define GH_GW_WARPS_PER_SM 32
 #endif
-// HYBRID (the default, kappa = 0.15; GH_WALK_HYBRID=0 turns it off): the 32 targets of a group share one
+// HYBRID (the default, kappa = 0.10; GH_WALK_HYBRID=0 turns it off): the 32 targets of a group share one
 // list, so their truncation errors are one coherent vector; where a target's net force nearly
 // cancels (|a| << sum of |contributions|: the softened core of a cusp) that vector does not
 // average out the way the per-target walk's errors do, and the relative error of ~0.01 % of the

@@ -420,7 +420,7 @@ int gho_tree_force_group(const double *pos, const double *mass, int64_t np, doub
 }
 
 /* Design-study form of the model: the targets can be grouped along any given order (order_in, e.g.
- * a Hilbert curve instead of the depth-first/Morton order), in groups of group_size <= 32, with one
+ * a Hilbert curve instead of the depth-first/Morton order), in groups of group_size <= 64, with one
  * or two bounding boxes.  gho_tree_force_group is the kernel's configuration (NULL, 32, 1).
  * abs_out[np] (nullable) receives S = 16 x sum of m_e / (|d_e|^2 + eps^2) over the entries at
  * positions 0 and 1 of every 32-entry chunk of the target's list: the kernel's 1/16 sample of the
@@ -478,7 +478,7 @@ int gho_tree_force_group2(const double *pos, const double *mass, int64_t np, dou
 	free(stk);
 	if (order_out) memcpy(order_out, order, sizeof(int64_t) * (size_t)np);
 	if (order_in) memcpy(order, order_in, sizeof(int64_t) * (size_t)np);
-	if (group_size < 1 || group_size > 32) group_size = 32;
+	if (group_size < 1 || group_size > 64) group_size = 32;
 	const int GS = group_size;
 
 	const double inv_theta2 = 1.0 / (theta * theta);
@@ -498,7 +498,7 @@ int gho_tree_force_group2(const double *pos, const double *mass, int64_t np, dou
 			if (oom) continue;
 			const int64_t p0 = (int64_t)GS * g;
 			const int nv = (int)((np - p0) < GS ? (np - p0) : GS);
-			float x[32], y[32], z[32];
+			float x[64], y[64], z[64];
 			for (int l = 0; l < nv; l++) {
 				const double *q = &pos[3 * order[p0 + l]];
 				x[l] = (float)(q[0] - boxcenter[0]);

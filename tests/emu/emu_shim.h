@@ -137,6 +137,7 @@ static inline int __reduce_max_sync(unsigned, int v) {
   emu::t_warp->bar.arrive_and_wait();
   return r;
 }
+static inline void __threadfence_block() {}
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline int __clzll(long long v) { return v == 0 ? 64 : __builtin_clzll((unsigned long long)v); }

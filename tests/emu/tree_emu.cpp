@@ -6,6 +6,7 @@
 #include "emu_shim.h"
 
 #include "../../gravhopper_b200/csrc/build.cuh"
+#include "../../gravhopper_b200/csrc/bucketsort.cuh"
 
 #include <cstdlib>
 
@@ -133,7 +134,46 @@ static int build_impl(const double *pos, const double *mass, int64_t n, double e
   return 0;
 }
 
+// splitter_sort_pairs of bucketsort.cuh, launch for launch (result in kA / vA)
+static void emu_splitter_sort(uint64_t *kA, int *vA, uint64_t *kB, int *vB, int64_t n, int nbits, const uint64_t *spl,
+                              int nb, const int *ndev) {
+  const int nblocks = (int)((n + RS_TILE - 1) / RS_TILE);
+  std::vector<int> hist((size_t)RS_RADIX * nblocks), gtot((size_t)RS_RADIX * 2, 0), boff(nb + 2);
+  const BucketOf bo{spl, nb};
+  uint64_t *kin = kA, *kout = kB;
+  int *vin = vA, *vout = vB;
+  for (int pass = 0; pass < 2; pass++) {
+    const BucketDigit dg{bo, 8 * pass};
+    int *g = gtot.data() + RS_RADIX * pass;
+    emu::launch((unsigned)nblocks, RS_THREADS, [&] { bs_hist_kernel(kin, n, dg, hist.data(), nblocks, g, ndev); });
+    emu::launch(RS_RADIX, RS_THREADS, [&] { rs_rowscan_kernel(hist.data(), nblocks); });
+    emu::launch((unsigned)nblocks, RS_THREADS, [&] { bs_scatter_kernel(kin, vin, kout, vout, n, dg, hist.data(), g, nblocks, ndev); });
+    std::swap(kin, kout);
+    std::swap(vin, vout);
+  }
+  emu::launch((unsigned)((nb + 1 + 255) / 256), 256, [&] { bs_offsets_kernel(kA, n, bo, boff.data(), ndev); }, true);
+  emu::launch((unsigned)nb, RS_THREADS, [&] { bs_bucket_kernel(kA, vA, kB, vB, boff.data(), spl, nb, nbits); });
+}
+
 extern "C" {
+// keys[n] (63-bit), vals = 0..n-1.  The splitters are the (b n_spl / nb)-th keys of the sorted array
+// `spl_from` (n_spl keys: the same data = fresh splitters, other data = stale ones).  n_real <= n:
+// the device-side count.  Outputs the splitter sort's keys / vals; returns 0.
+int emu_splitter_sort_test(const uint64_t *keys, int64_t n, int64_t n_real, const uint64_t *spl_from, int64_t n_spl,
+                           int nb, uint64_t *keys_out, int *vals_out) {
+  std::vector<uint64_t> kA(keys, keys + n), kB(n);
+  std::vector<int> vA(n), vB(n);
+  for (int64_t i = 0; i < n; i++) vA[i] = (int)i;
+  std::vector<uint64_t> spl(nb + 1);
+  const int nsp = (int)n_spl;
+  emu::launch((unsigned)((nb + 255) / 256), 256, [&] { bs_splitters_kernel(spl_from, n_spl, nb, spl.data(), &nsp); }, true);
+  const int nr = (int)n_real;
+  emu_splitter_sort(kA.data(), vA.data(), kB.data(), vB.data(), n, 63, spl.data(), nb, &nr);
+  std::memcpy(keys_out, kA.data(), sizeof(uint64_t) * (size_t)n_real);
+  std::memcpy(vals_out, vA.data(), sizeof(int) * (size_t)n_real);
+  return 0;
+}
+
 // prec 32: Node<float> entries (8 floats each) into nodes_out; prec 64: Node<double> + skips_out.
 // info_out = {entries, deepest cell level}.  Returns 1 if nodes_cap is too small (info_out[0] = need).
 // info_out = {entries, deepest cell level, overflow flag}; keys_out (nullable): the sorted `hi` keys;

@@ -56,7 +56,7 @@ def test_argument_validation_without_gpu():
     assert lib.gh_engine_create(ctypes.byref(h), 0, 10, 5, 6, 64) == _lib.GH_EINVAL
     assert lib.gh_set_tree_walk_hybrid(-0.5) == _lib.GH_EINVAL and lib.gh_set_tree_walk_hybrid(2.0) == _lib.GH_EINVAL
     if not os.environ.get("GH_WALK_HYBRID"):
-        assert abs(lib.gh_get_tree_walk_hybrid() - 0.15) < 1e-6   # the hybrid rule is on by default
+        assert abs(lib.gh_get_tree_walk_hybrid() - 0.10) < 1e-6   # the hybrid rule is on by default
     prm = (ctypes.c_double * 4)(1.0, 2.0, 0.2, 20.0)
     assert lib.gh_ic_sample_expdisk(10, prm, None, None, None, None, 0, 1, None, None, None, 0, None) == _lib.GH_EINVAL
     p = ctypes.c_void_p()

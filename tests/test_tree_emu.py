@@ -38,6 +38,7 @@ def temu():
     vp = C.c_void_p
     lib.emu_tree_build.argtypes = [C.c_int, vp, vp, C.c_int64, C.c_double, C.c_double, vp, vp, C.c_int, vp, vp,
                                    vp, vp, vp, C.c_int]
+    lib.emu_splitter_sort_test.argtypes = [vp, C.c_int64, C.c_int64, vp, C.c_int64, C.c_int, vp, vp]
     lib.emu_tree_build_dist.argtypes = [C.c_int, vp, vp, vp, C.c_int64, C.c_double, C.c_double, vp, C.c_int, vp, vp,
                                         vp, vp, vp, vp, vp, C.c_int]
     return lib
@@ -275,3 +276,38 @@ def test_distributed_walk_deals_the_global_morton_order(temu, emu, world, blk, h
         assert d.max() <= 2e-6     # identical groups, identical lists: fp32 rounding of the entries only
     else:
         assert np.median(d) <= 2e-3 and d.max() <= 0.2   # other groups of 32: the tree's own accuracy
+
+
+# ---- splitter sort (csrc/bucketsort.cuh): the running simulation's sort ---------------------------------
+@pytest.mark.parametrize("case", ["fresh", "stale", "oversize", "duplicates", "partial"])
+def test_splitter_sort_equals_the_stable_sort(temu, case):
+    """Two partition passes by bucket id + one in-shared-memory sort per bucket give the stable
+    sort's result, bit for bit: with this step's own splitters, with another data set's (stale)
+    splitters, with buckets far beyond a tile (the CTA-local global-memory path), with many equal
+    keys, and with a device-side count below the capacity."""
+    rng = np.random.default_rng(11)
+    n = 9000
+    keys = rng.integers(0, 2 ** 63, size=n, dtype=np.uint64)
+    keys[rng.integers(0, n, 600)] >>= np.uint64(30)          # a dense corner: skewed, like Morton keys
+    nb, n_real = 300, n
+    spl_from = np.sort(keys)
+    if case == "stale":
+        other = rng.integers(0, 2 ** 63, size=5000, dtype=np.uint64)
+        spl_from = np.sort(other)
+    elif case == "oversize":                                  # all splitters in the upper half: bucket 0 holds ~4500
+        spl_from = np.sort(keys[keys > np.uint64(2 ** 62)])
+        nb = 260
+    elif case == "duplicates":
+        keys[:4000] = keys[rng.integers(0, 40, 4000)]         # 40 distinct values, 100 copies each
+        spl_from = np.sort(keys)
+    elif case == "partial":
+        n_real = 6500
+    out_k = np.zeros(n_real, dtype=np.uint64)
+    out_v = np.zeros(n_real, dtype=np.int32)
+    spl_from = np.ascontiguousarray(spl_from)
+    rc = temu.emu_splitter_sort_test(keys.ctypes.data, n, n_real, spl_from.ctypes.data, len(spl_from), nb,
+                                     out_k.ctypes.data, out_v.ctypes.data)
+    assert rc == 0
+    order = np.argsort(keys[:n_real], kind="stable")
+    assert np.array_equal(out_v, order.astype(np.int32))
+    assert np.array_equal(out_k, keys[:n_real][order])
