@@ -16,6 +16,7 @@ particle-steps/s (Barnes-Hut tree), both at 1/2/4/8 B200.  The default run measu
              pageable host buffers), roofline (walk against the FP32 FMA peak, build against the
              measured HBM peak), accuracy, parity_check and cpu_baseline.
   "fp64"     configs[2]'s fp64 arm: the same Plummer N = 2^20 through the fp64 direct kernel.
+  "galaxy"   (--gpus 8 only) BASELINE.json configs[4]: exponential disk + Hernquist halo, N = 10M, tree.
 
 With --gpus N > 1 (launched by torchrun, one rank per GPU) the targets are sharded N/P per rank and
 each step all-gathers the half-drifted positions over NCCL (strong scaling: total work fixed).
@@ -219,10 +220,12 @@ def tree_roofline(n, world, ms_per_step, kernel_ms, st, mode, accuracy, peaks, f
         bound = "issue (walk); fp32_fma peak quoted"
     if peak_how:
         how += "; peak: " + peak_how
-    # dram__bytes_read.sum + dram__bytes_write.sum of walk_group_kernel at N = 2^22 on one GPU from
-    # `ncu --set full` (profiles/r01_walk_group_f32_N4M_v2.txt): 591.8 MB + 192.3 MB; the
-    # algorithmic bytes are 32 B x 6.2M entries read once + 64 B x N targets/epilogue = 0.47 GB
-    traffic = 784.2e6 if (mode == "group" and n == (1 << 22) and world == 1) else None
+    # dram__bytes_read.sum + dram__bytes_write.sum of walk_group_kernel at N = 2^22 on one GPU in the
+    # engine path (this bench's), from `ncu --set full` (profiles/r02_walk_group_kernel_4194304.txt):
+    # 1010.1 MB + 478.5 MB.  Algorithmic: 32 B x 6.2M entries read once (0.20 GB) + 160 B x N of
+    # targets and fused kick/drift state (x_half, v, m read; x, v, x_half, float4 source written:
+    # 0.67 GB) = 0.87 GB; the excess is entry re-reads that miss L2 (hit rate 70 %)
+    traffic = 1488.6e6 if (mode == "group" and n == (1 << 22) and world == 1) else None
     # the build (everything of the step that is not the walk kernel) against the HBM roofline:
     # SURVEY 8d's algorithmic bytes per particle-step, 190 + 24 x radix passes (8) = 382 B
     build_ms = ms_per_step - kernel_ms
@@ -664,6 +667,10 @@ def main():
         tree = run_block(ctx, "tree", max(args.steps, 10), args.warmup, cpu)
         # configs[2]'s fp64 arm: ~1.07 s per step on one B200, so few steps
         f64 = run_block(ctx, "direct64", 2, 3, False, with_e2e=False)
+        # BASELINE.json configs[4] (galaxy model, N = 10M) is quoted on 8 GPUs only
+        galaxy = run_block(ctx, "galaxy", 10, 3, False, with_e2e=False) if ctx.world == 8 else None
+        if ctx.rank == 0 and galaxy is not None:
+            line["galaxy"] = galaxy
         if ctx.rank == 0:
             line["clocks"] = merge_clocks(merge_clocks(line.get("clocks"), tree.pop("clocks", None)),
                                           f64.pop("clocks", None))

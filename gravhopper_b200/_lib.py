@@ -68,6 +68,7 @@ PROTOTYPES = {
     "gh_engine_stream": (C.c_int, [_eng, C.POINTER(_vp)]),
     "gh_engine_tree_stats": (C.c_int, [_eng, C.POINTER(_i64)]),
     "gh_engine_launch_count": (C.c_int, [_eng, C.POINTER(_i64)]),
+    "gh_engine_history_pinned": (C.c_int, [_eng, C.POINTER(C.c_int)]),
     "gh_engine_last_force_ms": (C.c_int, [_eng, C.POINTER(C.c_float)]),
     "gh_engine_force_ms_mean": (C.c_int, [_eng, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
 }

@@ -5,6 +5,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -748,10 +749,20 @@ int gh_engine_run(gh_engine *e, int64_t nsteps, double dt, double eps, double th
   int64_t nsnap = 0;
   if (snapshot_every > 0) nsnap = nsteps / snapshot_every + ((nsteps % snapshot_every) ? 1 : 0);
   bool reg_p = false, reg_v = false;
-  if (nsnap > 0) {  // pin the caller's history arrays so the copies really overlap the steps
-    reg_p = cudaHostRegister(pos_hist, row * nsnap, cudaHostRegisterDefault) == cudaSuccess;
-    reg_v = cudaHostRegister(vel_hist, row * nsnap, cudaHostRegisterDefault) == cudaSuccess;
-    cudaGetLastError();
+  if (nsnap > 0) {
+    // pin the caller's history arrays so the copies really overlap the steps -- but never more than
+    // GH_PIN_HISTORY_MAX bytes (default 4 GiB) at a time: page-locking tens of GB is slow and can
+    // starve the host.  Beyond the cap, or when registration fails, the snapshots are ordinary
+    // staged copies (still asynchronous to the host thread, no longer overlapping the kernels);
+    // gh_engine_history_pinned() reports which it was.
+    size_t cap = (size_t)4 << 30;
+    if (const char *env = getenv("GH_PIN_HISTORY_MAX")) cap = (size_t)strtoull(env, nullptr, 10);
+    if (2 * row * (size_t)nsnap <= cap) {
+      reg_p = cudaHostRegister(pos_hist, row * nsnap, cudaHostRegisterDefault) == cudaSuccess;
+      reg_v = cudaHostRegister(vel_hist, row * nsnap, cudaHostRegisterDefault) == cudaSuccess;
+      cudaGetLastError();
+    }
+    e->history_pinned = reg_p && reg_v;
   }
   int rc = GH_OK;
   int64_t k = 0;
@@ -829,6 +840,11 @@ int gh_engine_state_ptrs(gh_engine *e, double **pos_dev, double **vel_dev) {
 int gh_engine_stream(gh_engine *e, void **stream) {
   if (!e || !stream) return GH_EINVAL;
   *stream = (void *)e->stream;
+  return GH_OK;
+}
+int gh_engine_history_pinned(gh_engine *e, int *pinned) {
+  if (!e || !pinned) return GH_EINVAL;
+  *pinned = e->history_pinned ? 1 : 0;
   return GH_OK;
 }
 int gh_engine_launch_count(gh_engine *e, int64_t *count) {

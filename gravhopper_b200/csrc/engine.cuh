@@ -39,6 +39,7 @@ struct gh_engine {
   int64_t launches = 0;
   double *d_energy = nullptr;
   PotentialSet pots;
+  bool history_pinned = false;  // the last gh_engine_run page-locked the caller's history arrays
   bool mixed_mass = false;  // the uploaded masses are not all equal (launch-shape hint, direct fp32)
   // distributed tree build (group.cu): bootstrapped by one redundant single-rank build, then
   // every rank builds its key range; stride = entries a rank's segment holds

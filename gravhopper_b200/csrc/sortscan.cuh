@@ -201,10 +201,19 @@ static int chunked_scan(In in, int64_t n, T *P, DeviceBuffer *levels, int depth,
 // ---- radix sort ------------------------------------------------------------------------------
 static constexpr int RS_THREADS = 256;
 static constexpr int RS_WARPS = RS_THREADS / 32;
+// measured at N = 4M (profiles/r02_sort_ab.txt): 12 / 10 / 8 / 6 / 5 / 4 keys per thread -> build
+// 1.72 / 1.59 / 1.46 / 1.40 / 1.59 / 1.53 ms with the splitter sort (the classic sort is flat
+// between 6 and 8)
 #ifndef GH_RS_ROUNDS
-#define GH_RS_ROUNDS 8
+#define GH_RS_ROUNDS 6
 #endif
-static constexpr int RS_ROUNDS = GH_RS_ROUNDS;           // keys per thread (8: 2048-key tiles; 12: 3072, 47 KB of smem)
+// ranking of a tile's keys: 0 = the leader of every digit group reads, adds and stores the running
+// count round by round; 1 = all ballots first, then one shared-memory atomic per round (see
+// tile_rank in bucketsort.cuh).  Measured (profiles/r02_sort_ab.txt): no gain (-0.04 ... +0.08 ms of build).
+#ifndef GH_RS_RANK
+#define GH_RS_RANK 0
+#endif
+static constexpr int RS_ROUNDS = GH_RS_ROUNDS;           // keys per thread (6: 1536-key tiles)
 static constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;   // 2048 keys per CTA
 static constexpr int RS_RADIX = 256;
 
@@ -299,7 +308,35 @@ rs_scatter_kernel(const uint64_t *__restrict__ kin, const int *__restrict__ vin,
 
   uint64_t key[RS_ROUNDS];
   int val[RS_ROUNDS], lrank[RS_ROUNDS];
-#if GH_RS_VARIANT == 0
+#if GH_RS_RANK == 1
+  unsigned peers[RS_ROUNDS], dg[RS_ROUNDS];
+  int old[RS_ROUNDS];
+#pragma unroll
+  for (int r = 0; r < RS_ROUNDS; r++) {
+    const int64_t q = seg0 + r * 32 + lane;
+    const bool valid = q < n;
+    key[r] = valid ? kin[q] : 0;
+    val[r] = valid ? vin[q] : 0;
+  }
+#pragma unroll
+  for (int r = 0; r < RS_ROUNDS; r++) {
+    const bool valid = seg0 + r * 32 + lane < n;
+    dg[r] = valid ? (unsigned)((key[r] >> shift) & 0xff) : (0x100u + (unsigned)lane);
+    peers[r] = __match_any_sync(0xffffffffu, dg[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < RS_ROUNDS; r++) {
+    const bool valid = seg0 + r * 32 + lane < n;
+    old[r] = 0;
+    if (valid && lane == __ffs(peers[r]) - 1) old[r] = atomicAdd(&whist[w][dg[r]], __popc(peers[r]));
+    __syncwarp();
+  }
+#pragma unroll
+  for (int r = 0; r < RS_ROUNDS; r++) {
+    const int base = __shfl_sync(0xffffffffu, old[r], __ffs(peers[r]) - 1);
+    lrank[r] = base + __popc(peers[r] & ((1u << lane) - 1u));
+  }
+#elif GH_RS_VARIANT == 0
   // one loop: load, ballot, update the running per-digit count, round by round
 #pragma unroll
   for (int r = 0; r < RS_ROUNDS; r++) {

@@ -411,9 +411,13 @@ class Simulation(object):
             self.timestep = s0 + nnew
         else:
             t = self._times[s0]
-            v_prev = self._vel[s0].copy()
-            x_now = np.empty((self.Np, 3))
-            v_now = np.empty((self.Np, 3))
+            # the velocities of the previous step only travel to the host when a velocity-dependent
+            # hook will read them (gravhopper.py:469-473); otherwise the state stays on the device
+            # between snapshots and only x_half (the hooks' positions) is downloaded per step
+            need_v = bool(self.extra_velocitydependent_force_functions)
+            v_prev = self._vel[s0].copy() if need_v else None
+            x_now = np.empty((self.Np, 3)) if need_v else None
+            v_now = np.empty((self.Np, 3)) if need_v else None
             k = 0
             for step in range(1, N + 1):
                 eng.prepare(dt)
@@ -424,10 +428,11 @@ class Simulation(object):
                 t = t + dt
                 if step % every == 0 or step == N:
                     eng.download(self._pos[s0 + 1 + k], self._vel[s0 + 1 + k])
-                    v_prev = self._vel[s0 + 1 + k].copy()
+                    if need_v:
+                        v_prev = self._vel[s0 + 1 + k].copy()
                     self._times[s0 + 1 + k] = t
                     k += 1
-                else:
+                elif need_v:
                     eng.download(x_now, v_now)
                     v_prev = v_now.copy()
             self.timestep = s0 + nnew
@@ -547,7 +552,8 @@ class Simulation(object):
         """Call the hooks exactly as the reference does (Quantities in, acceleration Quantity out)
         and return the summed external acceleration in km/s/Myr as a plain array."""
         pos = _q(xhalf, self.lenunit)
-        vel = _q(np.ascontiguousarray(vel_values), self.velunit)
+        # vel_values is None when no velocity-dependent hook is registered (nothing reads it)
+        vel = None if vel_values is None else _q(np.ascontiguousarray(vel_values), self.velunit)
         time = time_value * self.timeunit
         template = np.zeros((self.Np, 3)) * self.accelunit
         ext = self.calculate_extra_acceleration(pos, template, time=time, vel=vel)

@@ -261,6 +261,9 @@ int gh_engine_state_ptrs(gh_engine *e, double **pos_dev, double **vel_dev);
 int gh_engine_stream(gh_engine *e, void **stream);
 /* Tree statistics of the engine's last tree step (layout as gh_tree_last_stats). */
 int gh_engine_tree_stats(gh_engine *e, int64_t out[8]);
+/* 1 if the last gh_engine_run page-locked the caller's history arrays (snapshot copies overlap the
+ * steps), 0 if they exceeded GH_PIN_HISTORY_MAX (default 4 GiB) or registration failed (staged copies). */
+int gh_engine_history_pinned(gh_engine *e, int *pinned);
 /* Kernel launches issued by this engine since creation (bench.py's gpu_launches). */
 int gh_engine_launch_count(gh_engine *e, int64_t *count);
 /* Device time (ms, CUDA events on the engine's stream) of the force kernel of the last step. */

@@ -14,9 +14,13 @@ VARIANTS = {
     # emit kernel: occupancy against registers
     # "emit8": ["-DGH_EMIT_MINBLOCKS=8"], ... "emit16": no gain (profiles/r01_emit_occupancy_ab.txt)
     # radix sort: keys per thread (tile size)
-    "rs12": ["-DGH_RS_ROUNDS=12"],
-    "rs10": ["-DGH_RS_ROUNDS=10"],
+    # measured (profiles/r02_sort_ab.txt): 12 / 10 / 8 / 6 keys per thread -> build 1.72 / 1.59 / 1.46 / 1.40 ms
     "rs6": ["-DGH_RS_ROUNDS=6"],
+    "rs8": ["-DGH_RS_ROUNDS=8"],
+    # ranking: ballots first + one shared-memory atomic per round
+    "rk6": ["-DGH_RS_ROUNDS=6", "-DGH_RS_RANK=1"],
+    "rk8": ["-DGH_RS_ROUNDS=8", "-DGH_RS_RANK=1"],
+    "rk10": ["-DGH_RS_ROUNDS=10", "-DGH_RS_RANK=1"],
 }
 KERNEL = "rs_scatter_kernel"
 B.build()

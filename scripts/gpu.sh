@@ -34,7 +34,7 @@ for task in "$@"; do
               python scripts/profile_kernels.py $a1 $a2 $a3 > gpurun_out/${TAG}_ncu_$k.log 2>&1; tail -1 gpurun_out/${TAG}_ncu_$k.log ;;
     ab) GH_AB_ENV="$a2" bash scripts/gpu_ab.sh ${a1//,/ } ;;
     ncu) timeout 900 ncu --set full --clock-control none --import-source on -k regex:$a1 -s ${a4:-1} -c 1 -f -o gpurun_out/${TAG}_${a1}_${a3} \
-              python scripts/profile_kernels.py $a2 $a3 > gpurun_out/${TAG}_ncu_$k.log 2>&1; tail -1 gpurun_out/${TAG}_ncu_$k.log ;;
+              python scripts/profile_kernels.py $a2 $a3 4 > gpurun_out/${TAG}_ncu_$k.log 2>&1; tail -1 gpurun_out/${TAG}_ncu_$k.log ;;
     sweep) timeout 600 python scripts/gpu_hybrid_sweep.py ${a1:-4194304} ${a2//,/ } > gpurun_out/${TAG}_sweep_$k.log 2>&1; tail -8 gpurun_out/${TAG}_sweep_$k.log | cut -c1-300 ;;
     py) timeout 900 python $a1 > gpurun_out/${TAG}_py_$k.log 2>&1; echo "rc=$?"; tail -15 gpurun_out/${TAG}_py_$k.log | cut -c1-300 ;;
     *) echo "unknown task $what" ;;

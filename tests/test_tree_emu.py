@@ -172,11 +172,10 @@ def compact_segments(nodes, counts, stride):
     return out
 
 
-@pytest.mark.parametrize("world,how", [(2, "equal"), (3, "equal"), (8, "equal"), (4, "random"), (4, "empty"),
-                                       (5, "tiny")])
+@pytest.mark.parametrize("world,how", [(2, "equal"), (8, "equal"), (4, "random"), (4, "empty"), (5, "tiny")])
 def test_distributed_build_is_the_single_rank_tree(temu, emu, world, how):
     from gravhopper_b200 import ic_raw
-    n = 2500
+    n = 1800
     x, v, m = ic_raw.Hernquist(n, 1.0, 1e10, seed=5)
     x = np.ascontiguousarray(x)
     eps, theta = 0.05, 0.7
@@ -242,7 +241,7 @@ def test_segment_overflow_raises_the_flag_and_the_walk_stands_still(temu, emu):
     assert st["accepted"] == st1["accepted"] and np.array_equal(acc, acc1)
 
 
-@pytest.mark.parametrize("world,blk,how", [(3, 64, "equal"), (4, 32, "random"), (4, 64, "empty")])
+@pytest.mark.parametrize("world,blk,how", [(3, 64, "equal"), (4, 32, "random")])
 def test_distributed_walk_deals_the_global_morton_order(temu, emu, world, blk, how):
     """Every rank walks its share of the GLOBAL Morton order (blocks dealt round-robin), the
     accelerations travel through the gathered buffer and the owners pick theirs up: the result per
