@@ -176,3 +176,14 @@ def tree_walk_hybrid(kappa=None):
         _lib.check(L.gh_set_tree_walk_hybrid(float(kappa)))
         return None
     return float(L.gh_get_tree_walk_hybrid())
+
+
+def tree_quadrupoles(enable=None):
+    """Set / query the opt-in quadrupole extension of the tree (an accuracy upgrade BEYOND the
+    reference, which is monopole only): accepted cells also contribute their traceless quadrupole.
+    Off by default; with it on, tree evaluations use the per-target walk in either precision."""
+    L = _lib.lib()
+    if enable is not None:
+        _lib.check(L.gh_set_tree_quadrupoles(1 if enable else 0))
+        return None
+    return bool(L.gh_get_tree_quadrupoles())

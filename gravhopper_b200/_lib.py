@@ -39,6 +39,8 @@ PROTOTYPES = {
     "gh_set_tree_stats": (C.c_int, [C.c_int]),
     "gh_set_tree_walk": (C.c_int, [C.c_int]),
     "gh_get_tree_walk": (C.c_int, []),
+    "gh_set_tree_quadrupoles": (C.c_int, [C.c_int]),
+    "gh_get_tree_quadrupoles": (C.c_int, []),
     "gh_set_tree_walk_hybrid": (C.c_int, [C.c_double]),
     "gh_get_tree_walk_hybrid": (C.c_double, []),
     "gh_ic_sample": (C.c_int, [C.c_int, _i64, _dp, C.c_int, _vp, _vp, C.c_int, C.c_uint64, _vp, _vp, _vp,

@@ -425,6 +425,23 @@ struct InParticlesRel {
     return r;
   }
 };
+// opt-in quadrupoles: second moments about the root centre, plain double.  A cell's central second
+// moment is the difference of two prefixes minus M c c^T: for the smallest cells that difference
+// cancels to ~1e-16 N m R^2 / (m_cell size^2) relative accuracy -- percent level for a two-particle
+// cell at N = 4M, whose quadrupole term is itself ~(size/d)^2 < theta^2/4 of a monopole that is one
+// of ~600: far below the monopole truncation error the extension removes.
+struct InSecondRel {
+  const double4 *sp;
+  const double *root;
+  __device__ __forceinline__ D6 operator()(int64_t q) const {
+    const double4 t = sp[q];
+    const double dx = t.x - root[0], dy = t.y - root[1], dz = t.z - root[2];
+    D6 r;
+    r.c[0] = t.w * dx * dx; r.c[1] = t.w * dy * dy; r.c[2] = t.w * dz * dz;
+    r.c[3] = t.w * dx * dy; r.c[4] = t.w * dx * dz; r.c[5] = t.w * dy * dz;
+    return r;
+  }
+};
 // moments of sorted particles [p, b]: mass and first moments (fp64: absolute coordinates,
 // double-double difference; fp32: relative to the root centre, plain difference)
 __device__ __forceinline__ void moment_diff(const DD4 *__restrict__ P, int64_t p, int64_t b, double mh[4]) {
@@ -611,7 +628,10 @@ __global__ void GH_EMIT_BOUNDS emit_kernel(const double4 *__restrict__ sp, const
                             const typename MomentOf<Real>::type *__restrict__ P, int64_t n,
                             const double *__restrict__ root, bool rel_origin, double inv_theta2,
                             Entries<Real> E, int *__restrict__ maxlevel, BuildCtl *__restrict__ ctl,
-                            bool dist) {
+                            bool dist, const D6 *__restrict__ P2 = nullptr, Real *__restrict__ quad = nullptr) {
+  // P2 / quad (nullable, single rank only): the opt-in quadrupole extension.  quad[6 e ..] receives
+  // the traceless quadrupole (xx, yy, zz, xy, xz, yz) of cell entry e about its centre of mass,
+  // zeros for leaves.
   int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (dist) n = ctl->n_local;
   if (p >= n) return;
@@ -692,6 +712,23 @@ __global__ void GH_EMIT_BOUNDS emit_kernel(const double4 *__restrict__ sp, const
           com.z = (Real)(mh[3] / mh[0] - oz);
         }
         com.w = (Real)mh[0];
+        if (quad && e < seg_cap) {
+          const D6 se = P2[b + 1], ss = P2[p];
+          // centre of mass relative to the root centre (fp32 moments already are)
+          const double c0 = mh[1] / mh[0] - (sizeof(Real) == 4 ? 0.0 : root[0]);
+          const double c1 = mh[2] / mh[0] - (sizeof(Real) == 4 ? 0.0 : root[1]);
+          const double c2 = mh[3] / mh[0] - (sizeof(Real) == 4 ? 0.0 : root[2]);
+          const double cxx = (se.c[0] - ss.c[0]) - mh[0] * c0 * c0, cyy = (se.c[1] - ss.c[1]) - mh[0] * c1 * c1,
+                       czz = (se.c[2] - ss.c[2]) - mh[0] * c2 * c2;
+          const double tr = cxx + cyy + czz;
+          Real *qd = quad + 6 * (size_t)e;
+          qd[0] = (Real)(3.0 * cxx - tr);
+          qd[1] = (Real)(3.0 * cyy - tr);
+          qd[2] = (Real)(3.0 * czz - tr);
+          qd[3] = (Real)(3.0 * ((se.c[3] - ss.c[3]) - mh[0] * c0 * c1));
+          qd[4] = (Real)(3.0 * ((se.c[4] - ss.c[4]) - mh[0] * c0 * c2));
+          qd[5] = (Real)(3.0 * ((se.c[5] - ss.c[5]) - mh[0] * c1 * c2));
+        }
         cen.x = (Real)(cc[0] - ox);
         cen.y = (Real)(cc[1] - oy);
         cen.z = (Real)(cc[2] - oz);
@@ -733,6 +770,11 @@ __global__ void GH_EMIT_BOUNDS emit_kernel(const double4 *__restrict__ sp, const
   cen.x = cen.y = cen.z = (Real)0;
   const int after = (p + 1 < n) ? e + 1 : seg_next;
   if (e >= seg_cap) { ctl->overflow = 1; return; }
+  if (quad) {
+    Real *qd = quad + 6 * (size_t)e;
+#pragma unroll
+    for (int k = 0; k < 6; k++) qd[k] = (Real)0;
+  }
   if (sizeof(Real) == 4) {
     cen.w = (Real)__int_as_float((int)(((unsigned)LEAF_LEVEL << SKIP_BITS) | (unsigned)after));
   } else {

@@ -275,6 +275,8 @@ void tree_forget_history(TreeWorkspace *ws);  // new state uploaded: the next bu
 int tree_last_stats(TreeWorkspace *ws, int64_t out[8]);
 int tree_walk_mode();
 void set_tree_walk_mode(int mode);
+int tree_quadrupoles();
+void set_tree_quadrupoles(int on);
 float group_hybrid_kappa();
 void set_group_hybrid_kappa(double kappa);
 

@@ -338,6 +338,12 @@ int gh_set_tree_walk(int mode) {
 }
 int gh_get_tree_walk(void) { return tree_walk_mode(); }
 
+int gh_set_tree_quadrupoles(int enable) {
+  set_tree_quadrupoles(enable);
+  return GH_OK;
+}
+int gh_get_tree_quadrupoles(void) { return tree_quadrupoles(); }
+
 int gh_set_tree_walk_hybrid(double kappa) {
   if (!(kappa >= 0.0) || kappa > 1.0) { set_error("gh_set_tree_walk_hybrid: kappa must be in [0, 1]"); return GH_EINVAL; }
   set_group_hybrid_kappa(kappa);

@@ -401,7 +401,9 @@ int gh_group_step(gh_group *g, int64_t nsteps, double dt, double eps, double the
     if (!e->uploaded) { set_error("engine has no state: upload first"); return GH_ESTATE; }
     if (!e->xhalf_valid || dt != e->dt_built) GH_TRY(gh_engine_prepare(e, dt));
   }
-  const bool dist = algorithm == GH_ALG_TREE && g->world > 1 && g->prec == GH_PREC_F32 && g->tree_dist;
+  // (quadrupoles, an opt-in accuracy upgrade, use the single-rank build and the per-target walk)
+  const bool dist = algorithm == GH_ALG_TREE && g->world > 1 && g->prec == GH_PREC_F32 && g->tree_dist &&
+                    !tree_quadrupoles();
   for (int64_t s = 0; s < nsteps; s++) {
     mark(g, 0);
     GH_TRY(all_gather_sources(g));

@@ -106,6 +106,38 @@ template <> struct ScanOps<D4> {
   }
 };
 
+// second moments (m dx dx, m dy dy, m dz dz, m dx dy, m dx dz, m dy dz) about the root centre: the scan
+// element of the opt-in quadrupole extension (plain double, see emit_kernel)
+struct D6 {
+  double c[6];
+};
+template <> struct ScanOps<D6> {
+  static __device__ __forceinline__ D6 zero() {
+    D6 r;
+#pragma unroll
+    for (int k = 0; k < 6; k++) r.c[k] = 0.0;
+    return r;
+  }
+  static __device__ __forceinline__ D6 add(const D6 &a, const D6 &b) {
+    D6 r;
+#pragma unroll
+    for (int k = 0; k < 6; k++) r.c[k] = __dadd_rn(a.c[k], b.c[k]);
+    return r;
+  }
+  static __device__ __forceinline__ D6 shfl_up(const D6 &v, int d) {
+    D6 r;
+#pragma unroll
+    for (int k = 0; k < 6; k++) r.c[k] = __shfl_up_sync(0xffffffffu, v.c[k], d);
+    return r;
+  }
+  static __device__ __forceinline__ D6 shfl(const D6 &v, int src) {
+    D6 r;
+#pragma unroll
+    for (int k = 0; k < 6; k++) r.c[k] = __shfl_sync(0xffffffffu, v.c[k], src);
+    return r;
+  }
+};
+
 // inclusive scan across the 32 lanes (fixed order: Hillis-Steele, lower lanes on the left)
 template <class T>
 __device__ __forceinline__ T warp_scan(T v, int lane) {

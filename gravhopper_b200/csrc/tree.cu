@@ -65,6 +65,7 @@ struct TreePhaseState {
   int rank = 0, world = 1;
   int64_t ecap = 0;         // entries per segment (stride)
   int end = 0;              // world * stride
+  bool quad = false;        // this evaluation carries quadrupoles (single rank, per-target walk)
   int blk = 2048, T = 0;    // distributed walk: block size of the deal, blocks per (rank, range)
   int64_t slots = 0;        // target slots per rank = world * T * blk
 };
@@ -72,6 +73,7 @@ struct TreeWorkspace {
   DeviceBuffer root, part, hi, lo, hi2, lo2, lo3, idx, idx2, clev, cnt, base, P;
   DeviceBuffer node, skip, misc, thi, tidx, thi2, tidx2, sorted, bsum, scanlv[4], cntlv[4];
   DeviceBuffer ctl, rec1, rec2, keys_all, tilecnt, tileoff, tilelv[4], sidx_all, acc_all;
+  DeviceBuffer P2, quad, scanlv2[4];  // opt-in quadrupoles: second-moment prefixes, per-entry tensors
   RadixScratch rs;
   SplitterState ss;  // buckets of the splitter sort (bucketsort.cuh): valid from one coherent step to the next
   TreePhaseState ph;
@@ -90,7 +92,8 @@ void tree_workspace_destroy(TreeWorkspace *w) {
   DeviceBuffer *all[] = {&w->root, &w->part, &w->hi, &w->lo, &w->hi2, &w->lo2, &w->lo3, &w->idx, &w->idx2,
                          &w->clev, &w->cnt, &w->base, &w->P, &w->node, &w->sorted, &w->bsum, &w->scanlv[0], &w->scanlv[1], &w->scanlv[2], &w->scanlv[3], &w->cntlv[0], &w->cntlv[1], &w->cntlv[2], &w->cntlv[3],
                          &w->skip, &w->misc, &w->thi, &w->tidx, &w->thi2, &w->tidx2, &w->ctl, &w->rec1, &w->rec2,
-                         &w->keys_all, &w->tilecnt, &w->tileoff, &w->sidx_all, &w->acc_all, &w->tilelv[0], &w->tilelv[1], &w->tilelv[2], &w->tilelv[3]};
+                         &w->keys_all, &w->tilecnt, &w->tileoff, &w->sidx_all, &w->acc_all, &w->P2, &w->quad,
+                         &w->scanlv2[0], &w->scanlv2[1], &w->scanlv2[2], &w->scanlv2[3], &w->tilelv[0], &w->tilelv[1], &w->tilelv[2], &w->tilelv[3]};
   for (auto *b : all) b->release();
   w->rs.release();
   w->ss.release();
@@ -150,6 +153,20 @@ float group_hybrid_kappa() {
   return g_hybrid_kappa;
 }
 void set_group_hybrid_kappa(double k) { g_hybrid_kappa = (k > 0.0 && k <= 1.0) ? (float)k : 0.f; }
+
+// Opt-in accuracy upgrade beyond the reference: traceless quadrupoles of the
+// accepted cells.  Off by default (the reference is monopole only, _jbgrav.c:522-524); with it the
+// evaluation uses the per-target walk (the reference's accepted node set) and a single-rank build.
+// GH_TREE_QUADRUPOLES=1 sets the initial value, gh_set_tree_quadrupoles() changes it.
+static int g_quadrupoles = -1;
+int tree_quadrupoles() {
+  if (g_quadrupoles < 0) {
+    const char *env = getenv("GH_TREE_QUADRUPOLES");
+    g_quadrupoles = (env && atoi(env) != 0) ? 1 : 0;
+  }
+  return g_quadrupoles;
+}
+void set_tree_quadrupoles(int on) { g_quadrupoles = on ? 1 : 0; }
 
 template <class Real> struct GroupWalk {
   static void launch(const Node<Real> *, int, const TargetsView &, int64_t, const double *, float, double,
@@ -211,6 +228,8 @@ struct TreeRun {
     ph.levels = (sizeof(Real) == 8) ? LEVELS_MAX : LEVELS_HI;
     ph.deep = ph.levels > LEVELS_HI;
     ph.dist = d != nullptr && d->world > 1;
+    ph.quad = tree_quadrupoles() != 0;
+    if (ph.dist && ph.quad) { set_error("quadrupoles need the single-rank (redundant) tree build"); return GH_EINVAL; }
     if (ph.dist && ph.deep) { set_error("the distributed tree build is fp32 only"); return GH_EINVAL; }
     if (ph.dist && d->world > DIST_MAX_RANKS) { set_error("at most %d ranks", DIST_MAX_RANKS); return GH_EINVAL; }
     ph.rank = ph.dist ? d->rank : 0;
@@ -390,6 +409,10 @@ struct TreeRun {
       rec2_kernel<<<1, 32, 0, st>>>(ph.shi, base, reinterpret_cast<const D4 *>(P), ctl, w->rec2.as<RankRec2>());
       GH_LAUNCH_CHECK();
     }
+    if (ph.quad) {
+      GH_TRY(w->P2.reserve(sizeof(D6) * (size_t)(n + 1)));
+      GH_TRY((chunked_scan<D6, InSecondRel>(InSecondRel{sp, root}, n, w->P2.as<D6>(), w->scanlv2, 0, st)));
+    }
     return GH_OK;
   }
 
@@ -407,10 +430,13 @@ struct TreeRun {
     const double inv_theta2 = 1.0 / (a.theta * a.theta);  // theta = 0 -> inf: cells are never accepted
     int *maxlevel = w->misc.as<int>();
     GH_CUDA(cudaMemsetAsync(w->misc.ptr, 0, 64, st));
+    if (ph.quad) GH_TRY(w->quad.reserve(sizeof(Real) * 6 * (size_t)ph.end));
     emit_kernel<Src, Real><<<nblk(n, 128), 128, 0, st>>>(w->sorted.as<double4>(), ph.shi, ph.slo,
                                                        w->clev.as<signed char>(), w->base.as<int>(),
                                                        w->P.as<Mom>(), n, w->root.as<double>(), rel_origin,
-                                                       inv_theta2, E, maxlevel, ctl, ph.dist);
+                                                       inv_theta2, E, maxlevel, ctl, ph.dist,
+                                                       ph.quad ? w->P2.as<D6>() : nullptr,
+                                                       ph.quad ? w->quad.as<Real>() : nullptr);
     GH_LAUNCH_CHECK();
     return GH_OK;
   }
@@ -487,7 +513,7 @@ struct TreeRun {
     const int64_t nwarps = (nwalk + 31) / 32;
     int wb = 128;
     if (const char *env = getenv("GH_WALK_BLOCK")) { int v = atoi(env); if (v == 32 || v == 64 || v == 128) wb = v; }
-    const bool group = (sizeof(Real) == 4) && tree_walk_mode() == GH_WALK_GROUP;
+    const bool group = (sizeof(Real) == 4) && tree_walk_mode() == GH_WALK_GROUP && !ph.quad;
     const unsigned blocks = (unsigned)((nwarps + wb / 32 - 1) / (wb / 32));
     if (ev) GH_CUDA(cudaEventRecord(ev[0], st));
     const bool guard = tiny_eps;
@@ -502,10 +528,15 @@ struct TreeRun {
 #define GH_WALK(STATS, GUARD, PF)                                                                      \
   walk_kernel<Real, STATS, GUARD, PF><<<blocks, wb, 0, st>>>(E.node, E.skip, nentries, tv, nwalk, root, \
                                                             rel_origin, eps2, inv_theta2, ep, dstats, ovf)
-#define GH_WALK2(STATS, GUARD) do { if (prefetch) GH_WALK(STATS, GUARD, true); else GH_WALK(STATS, GUARD, false); } while (0)
+#define GH_WALKQ(STATS, GUARD)                                                                                 \
+  walk_kernel<Real, STATS, GUARD, false, true><<<blocks, wb, 0, st>>>(E.node, E.skip, nentries, tv, nwalk, root, \
+                                                                     rel_origin, eps2, inv_theta2, ep, dstats, ovf, \
+                                                                     w->quad.as<Real>())
+#define GH_WALK2(STATS, GUARD) do { if (ph.quad) GH_WALKQ(STATS, GUARD); else if (prefetch) GH_WALK(STATS, GUARD, true); else GH_WALK(STATS, GUARD, false); } while (0)
       if (a.want_stats) { if (guard) GH_WALK2(true, true); else GH_WALK2(true, false); }
       else { if (guard) GH_WALK2(false, true); else GH_WALK2(false, false); }
 #undef GH_WALK2
+#undef GH_WALKQ
 #undef GH_WALK
     }
     GH_LAUNCH_CHECK();

@@ -86,6 +86,25 @@ __device__ __forceinline__ float inv_cube(float s) {
   return y * y * y;
 }
 
+// y = s^-1/2 (the quadrupole term needs y^5 and y^7 besides the monopole's y^3)
+template <bool GUARD>
+__device__ __forceinline__ double inv_sqrt(double s) {
+  double y = rsqrt64_t(s);
+  if (GUARD) y = (s > 0.0) ? y : 0.0;
+  return y;
+}
+template <bool GUARD>
+__device__ __forceinline__ float inv_sqrt(float s) {
+  float y;
+#ifdef GH_HOST_EMU
+  y = 1.0f / sqrtf(s);
+#else
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(s));
+#endif
+  if (GUARD) y = (s > 0.f) ? y : 0.f;
+  return y;
+}
+
 struct TargetsView {
   const double4 *sorted;  // non-null: target p IS sorted source p (self evaluation of all sources)
   const double *pos64;   // (ni,3) or null
@@ -156,13 +175,15 @@ __device__ __forceinline__ void load_target(const TargetsView &tv, int64_t p, bo
 
 // The per-target scan of one warp (see above): every lane applies the reference's own opening
 // test, so the accepted node set is the reference's.
-template <class Real, bool STATS, bool GUARD, bool PREFETCH>
+// QUAD (opt-in): every accepted CELL also contributes its traceless quadrupole
+// (quad[6 i ..], written by emit_kernel): a += -(Q e) y^5 + 5/2 (e.Q.e) y^7 e, e = COM - x.
+template <class Real, bool STATS, bool GUARD, bool PREFETCH, bool QUAD = false>
 __device__ __forceinline__ void lane_scan(const Node<Real> *__restrict__ nodes,
                                           const int *__restrict__ skips, Real s2root, int nentries,
                                           bool valid, Real x, Real y, Real z, Real eps2, Real &ax, Real &ay,
                                           Real &az, unsigned long long &nacc,
                                           unsigned long long &nvis, unsigned long long &niter,
-                                          int first_entry = 0) {
+                                          int first_entry = 0, const Real *__restrict__ quad = nullptr) {
   int until = valid ? 0 : INT_MAX;
   int i = first_entry;
   while (i < nentries) {
@@ -209,10 +230,31 @@ __device__ __forceinline__ void lane_scan(const Node<Real> *__restrict__ nodes,
     }
     const bool acc = active && pass;
     const bool open = active && !pass;
+    if (QUAD) {
+      const Real yy = inv_sqrt<GUARD>(s);
+      const Real y2 = yy * yy, y3 = y2 * yy;
+      const Real w = acc ? nb.w * y3 : (Real)0;
+      ax += w * ex;
+      ay += w * ey;
+      az += w * ez;
+      if (nb.z >= (Real)0) {  // a cell (leaves carry s2 = -1): warp-uniform, one broadcast load
+        const Real *q = quad + 6 * (size_t)i;
+        const Real qxx = q[0], qyy = q[1], qzz = q[2], qxy = q[3], qxz = q[4], qyz = q[5];
+        const Real qex = qxx * ex + qxy * ey + qxz * ez, qey = qxy * ex + qyy * ey + qyz * ez,
+                   qez = qxz * ex + qyz * ey + qzz * ez;
+        const Real eqe = ex * qex + ey * qey + ez * qez;
+        const Real y5 = acc ? y3 * y2 : (Real)0, y7 = y5 * y2;
+        const Real g = (Real)2.5 * eqe * y7;
+        ax += g * ex - qex * y5;
+        ay += g * ey - qey * y5;
+        az += g * ez - qez * y5;
+      }
+    } else {
     const Real w = acc ? nb.w * inv_cube<GUARD>(s) : (Real)0;
     ax += w * ex;
     ay += w * ey;
     az += w * ez;
+    }
     until = acc ? sk : until;
     if (STATS) { nvis += active; nacc += acc; }
     const int next = open ? i + 1 : until;
@@ -220,12 +262,12 @@ __device__ __forceinline__ void lane_scan(const Node<Real> *__restrict__ nodes,
   }
 }
 
-template <class Real, bool STATS, bool GUARD, bool PREFETCH>
+template <class Real, bool STATS, bool GUARD, bool PREFETCH, bool QUAD = false>
 __global__ void __launch_bounds__(128, 8)
 walk_kernel(const Node<Real> *__restrict__ nodes, const int *__restrict__ skips, int nentries,
             TargetsView tv, int64_t ni, const double *__restrict__ root, bool rel_origin, Real eps2,
             double inv_theta2, Epilogue ep, unsigned long long *__restrict__ stats,
-            const int *__restrict__ walkctl = nullptr) {
+            const int *__restrict__ walkctl = nullptr, const Real *__restrict__ quad = nullptr) {
   // `nentries` is the index every chain ends at (the capacity of the entry array, not its fill:
   // the build never tells the host how many entries it wrote).  walkctl (BuildCtl::overflow,
   // ::first): a build whose entries did not fit sets [0]; the walk then leaves the state alone and
@@ -243,8 +285,8 @@ walk_kernel(const Node<Real> *__restrict__ nodes, const int *__restrict__ skips,
   Real ax = 0, ay = 0, az = 0;
   unsigned long long nacc = 0, nvis = 0, niter = 0;
   const Real s2root = (Real)(root[3] * root[3] * inv_theta2);
-  lane_scan<Real, STATS, GUARD, PREFETCH>(nodes, skips, s2root, nentries, valid, x, y, z, eps2, ax, ay,
-                                          az, nacc, nvis, niter, first_entry);
+  lane_scan<Real, STATS, GUARD, PREFETCH, QUAD>(nodes, skips, s2root, nentries, valid, x, y, z, eps2, ax, ay,
+                                                az, nacc, nvis, niter, first_entry, quad);
   if (valid) apply_epilogue(ep, ti, (double)ax, (double)ay, (double)az);
   if (STATS) {
     for (int o = 16; o > 0; o >>= 1) {

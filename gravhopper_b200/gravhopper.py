@@ -225,7 +225,7 @@ class Simulation(object):
     """
 
     def __init__(self, dt=1 * u.Myr, eps=100 * u.pc, algorithm='tree', precision='fp64', theta=0.7,
-                 snapshot_every=1, device=0, devices=None):
+                 snapshot_every=1, device=0, devices=None, quadrupoles=False):
         self.ICarrays = False
         self.Np = 0
         self.Nsnap = 0
@@ -257,6 +257,8 @@ class Simulation(object):
             raise ValueError("snapshot_every must be >= 1.")
         self.params['snapshot_every'] = int(snapshot_every)
         self.params['device'] = int(device)
+        # quadrupoles: opt-in accuracy upgrade beyond the reference (tree only; see _jbgrav.tree_quadrupoles)
+        self.params['quadrupoles'] = bool(quadrupoles)
         # devices: None / 1 = one GPU (`device`); an int N > 1 = GPUs 0..N-1; a list = those GPUs.
         # run() then shards the targets over them inside this process (no torchrun needed).
         if devices is None:
@@ -373,6 +375,17 @@ class Simulation(object):
     def run(self, N=1):
         """Run N timesteps.  Initializes a simulation that has not yet been run, or continues from
         the last snapshot if it has (gravhopper.py:293-320)."""
+        if self.params.get('quadrupoles'):
+            from . import _jbgrav
+            was = _jbgrav.tree_quadrupoles()
+            _jbgrav.tree_quadrupoles(True)   # process-wide switch of the library, restored afterwards
+            try:
+                return self._run(N)
+            finally:
+                _jbgrav.tree_quadrupoles(was)
+        return self._run(N)
+
+    def _run(self, N=1):
         N = int(N)
         every = self.params['snapshot_every']
         nnew = N // every + (1 if N % every else 0)

@@ -358,6 +358,112 @@ int gho_tree_force(const double *pos, const double *mass, int64_t np, const doub
 }
 
 /* ------------------------------------------------------------------------------------------
+ * CPU MODEL OF THE PRODUCT'S OPT-IN QUADRUPOLE EXTENSION.  NOT a reference
+ * function: the reference evaluates monopoles only (_jbgrav.c:522-524).  Same octree, same
+ * opening test (_jbgrav.c:502) and so the same accepted node set as gho_accel; every accepted
+ * CELL additionally contributes its traceless quadrupole about its centre of mass,
+ *   Q_ij = sum_k m_k (3 r_ki r_kj - r_k^2 delta_ij),  r_k = x_k - COM,
+ *   a += -(Q e) y^5 + 5/2 (e.Q.e) y^7 e,   e = COM - x,  y = (|e|^2 + eps^2)^-1/2
+ * (the gradient of -1/2 e.Q.e / r^5 with r^2 softened like the monopole).  Leaves have Q = 0.
+ * The central second moments are built bottom-up with the parallel-axis rule, in double. */
+static void gho_quad_build(const gho_tree *t, int64_t ni, double *C /* 6 per node: xx yy zz xy xz yz */)
+{
+	const gho_node *nd = &t->nodes[ni];
+	double *c = &C[6 * ni];
+	for (int k = 0; k < 6; k++) c[k] = 0.0;
+	if (nd->leaf >= 0) return;
+	for (int j = 0; j < 8; j++) {
+		const int64_t ch = nd->branches[j];
+		if (ch < 0) continue;
+		gho_quad_build(t, ch, C);
+		const gho_node *cn = &t->nodes[ch];
+		const double dx = cn->COM[0] - nd->COM[0], dy = cn->COM[1] - nd->COM[1], dz = cn->COM[2] - nd->COM[2];
+		const double *cc = &C[6 * ch];
+		c[0] += cc[0] + cn->mass * dx * dx;
+		c[1] += cc[1] + cn->mass * dy * dy;
+		c[2] += cc[2] + cn->mass * dz * dz;
+		c[3] += cc[3] + cn->mass * dx * dy;
+		c[4] += cc[4] + cn->mass * dx * dz;
+		c[5] += cc[5] + cn->mass * dy * dz;
+	}
+}
+
+static void gho_accel_quad(const gho_tree *t, const double *C, int64_t ni, const double *pos, double eps,
+                           double theta, double *force)
+{
+	const gho_node *nd = &t->nodes[ni];
+	const double eps2 = eps * eps;
+	double node_dist = 0.0;
+	for (int i = 0; i < 3; i++) node_dist += (nd->center[i] - pos[i]) * (nd->center[i] - pos[i]);
+	node_dist = sqrt(node_dist);
+	if ((nd->leaf >= 0) || ((nd->size / node_dist) < theta)) {
+		double e[3], s = eps2;
+		for (int i = 0; i < 3; i++) { e[i] = nd->COM[i] - pos[i]; s += e[i] * e[i]; }
+		const double y = (s == 0.0) ? 0.0 : 1.0 / sqrt(s);
+		const double y3 = y * y * y;
+		for (int i = 0; i < 3; i++) force[i] = e[i] * nd->mass * y3;
+		if (nd->leaf < 0) {
+			const double *c = &C[6 * ni];
+			const double tr = c[0] + c[1] + c[2];
+			const double qxx = 3.0 * c[0] - tr, qyy = 3.0 * c[1] - tr, qzz = 3.0 * c[2] - tr;
+			const double qxy = 3.0 * c[3], qxz = 3.0 * c[4], qyz = 3.0 * c[5];
+			const double qe[3] = {qxx * e[0] + qxy * e[1] + qxz * e[2], qxy * e[0] + qyy * e[1] + qyz * e[2],
+			                      qxz * e[0] + qyz * e[1] + qzz * e[2]};
+			const double eqe = e[0] * qe[0] + e[1] * qe[1] + e[2] * qe[2];
+			const double y5 = y3 * y * y, y7 = y5 * y * y;
+			for (int i = 0; i < 3; i++) force[i] += -qe[i] * y5 + 2.5 * eqe * y7 * e[i];
+		}
+	} else {
+		double bf[3];
+		for (int i = 0; i < 3; i++) force[i] = 0.0;
+		for (int j = 0; j < 8; j++)
+			if (nd->branches[j] >= 0) {
+				gho_accel_quad(t, C, nd->branches[j], pos, eps, theta, bf);
+				for (int i = 0; i < 3; i++) force[i] += bf[i];
+			}
+	}
+}
+
+int gho_tree_force_quad(const double *pos, const double *mass, int64_t np, const double *fpos, int64_t nf,
+                        double eps, double theta, double *acc, int nthreads)
+{
+	double min[3], max[3], boxsize, boxcenter[3];
+	if (np < 1) return GHO_OK;
+	for (int i = 0; i < 3; i++) { min[i] = pos[i]; max[i] = min[i]; }
+	for (int64_t i = 1; i < np; i++)
+		for (int j = 0; j < 3; j++) {
+			double q = pos[3 * i + j];
+			if (q < min[j]) min[j] = q;
+			if (q > max[j]) max[j] = q;
+		}
+	boxsize = max[0] - min[0] + eps;
+	for (int i = 1; i < 3; i++)
+		if ((max[i] - min[i]) > boxsize) boxsize = max[i] - min[i] + eps;
+	for (int i = 0; i < 3; i++) boxcenter[i] = 0.5 * (min[i] + max[i]);
+	gho_tree t;
+	t.cap = 2 * np + 64; t.n = 0; t.pos = pos; t.mass = mass; t.err = 0; t.maxdepth = 0;
+	t.nodes = (gho_node *)malloc(sizeof(gho_node) * (size_t)t.cap);
+	if (!t.nodes) return GHO_ENOMEM;
+	int64_t root = gho_node_new(&t, boxcenter, boxsize);
+	for (int64_t i = 0; i < np && !t.err; i++) gho_add(&t, root, i, 0);
+	if (t.err) { free(t.nodes); return t.err; }
+	gho_finalize_all(&t);
+	double *C = (double *)malloc(sizeof(double) * 6 * (size_t)t.n);
+	if (!C) { free(t.nodes); return GHO_ENOMEM; }
+	gho_quad_build(&t, root, C);
+	gho_set_threads(nthreads);
+#pragma omp parallel for schedule(dynamic, 64)
+	for (int64_t i = 0; i < nf; i++) {
+		double f[3];
+		gho_accel_quad(&t, C, root, &fpos[3 * i], eps, theta, f);
+		acc[3 * i] = f[0]; acc[3 * i + 1] = f[1]; acc[3 * i + 2] = f[2];
+	}
+	free(C);
+	free(t.nodes);
+	return GHO_OK;
+}
+
+/* ------------------------------------------------------------------------------------------
  * CPU MODEL OF THE PRODUCT'S GROUP WALK (walk_group_kernel, gravhopper_b200/csrc/tree.cu).
  * This is NOT a reference function: the reference walks the tree once per target (gho_accel
  * above).  The product's default fp32 walk shares one traversal between the 32 depth-first

@@ -52,6 +52,7 @@ def _lib():
         lib.gho_direct_position.argtypes = [dp, dp, i64, dp, i64, C.c_double, dp, C.c_int]
         lib.gho_tree_force.argtypes = [dp, dp, i64, dp, i64, C.c_double, C.c_double, dp,
                                        C.POINTER(i64), C.c_int]
+        lib.gho_tree_force_quad.argtypes = [dp, dp, i64, dp, i64, C.c_double, C.c_double, dp, C.c_int]
         lib.gho_tree_force_group.argtypes = [dp, dp, i64, C.c_double, C.c_double, C.c_int, C.c_int, dp,
                                              C.POINTER(i64), C.POINTER(C.c_int32), C.POINTER(i64), C.c_int]
         lib.gho_tree_force_group2.argtypes = lib.gho_tree_force_group.argtypes + [C.POINTER(i64), C.c_int, C.c_int, dp,
@@ -118,6 +119,16 @@ def tree_force_position(pos, mass, force_pos, eps, theta, nthreads=1, return_sta
 
 def tree_force(pos, mass, eps, theta, nthreads=1, return_stats=False):
     return tree_force_position(pos, mass, pos, eps, theta, nthreads, return_stats)
+
+
+def tree_force_quad(pos, mass, force_pos, eps, theta, nthreads=0):
+    """CPU model of the PRODUCT's opt-in quadrupole extension (not a reference function): the
+    reference's octree and accepted node set, monopole + traceless quadrupole per accepted cell."""
+    pos, mass, fpos = _f64(pos), _f64(mass), _f64(force_pos)
+    acc = np.empty_like(fpos)
+    _check(_lib().gho_tree_force_quad(_p(pos), _p(mass), pos.shape[0], _p(fpos), fpos.shape[0], float(eps),
+                                      float(theta), _p(acc), nthreads), "gho_tree_force_quad")
+    return acc
 
 
 def tree_force_group(pos, mass, eps, theta, list_limit=3000, stack_limit=320, nthreads=0, order=None,

@@ -60,7 +60,7 @@ static bool emu_sort(uint64_t *kA, int *vA, uint64_t *kB, int *vB, int64_t n, in
 template <class Real>
 static int build_impl(const double *pos, const double *mass, int64_t n, double eps, double theta, void *nodes_out,
                       int *skips_out, int nodes_cap, double *sorted_out, int *order_out, double *root_out,
-                      int *info_out, uint64_t *keys_out, int seg_cap) {
+                      int *info_out, uint64_t *keys_out, int seg_cap, void *quad_out) {
   using Mom = typename MomentOf<Real>::type;
   const int levels = (sizeof(Real) == 8) ? LEVELS_MAX : LEVELS_HI;
   const bool deep = levels > LEVELS_HI;
@@ -121,9 +121,13 @@ static int build_impl(const double *pos, const double *mass, int64_t n, double e
   BuildCtl ctl;
   std::memset(&ctl, 0, sizeof(ctl));
   emu::launch(1, 1, [&] { ctl_init_single(&ctl, (int)n, seg_cap > 0 ? seg_cap : nentries); }, true);
+  std::vector<D6> P2(quad_out ? n + 1 : 0);
+  if (quad_out)  // opt-in quadrupoles: second-moment prefixes, per-entry tensors (6 Reals per entry)
+    emu_scan<D6, InSecondRel>(InSecondRel{sp.data(), root.data()}, n, P2.data());
   emu::launch(nblk(n, 128), 128, [&] {
     emit_kernel<Src64, Real>(sp.data(), shi, slo, clev.data(), base.data(), P.data(), n, root.data(), rel_origin,
-                             inv_theta2, E, &maxlevel, &ctl, false);
+                             inv_theta2, E, &maxlevel, &ctl, false, quad_out ? P2.data() : nullptr,
+                             reinterpret_cast<Real *>(quad_out));
   }, true);
   info_out[1] = maxlevel;
   info_out[2] = ctl.overflow;
@@ -180,12 +184,13 @@ int emu_splitter_sort_test(const uint64_t *keys, int64_t n, int64_t n_real, cons
 // seg_cap > 0: capacity of the segment (chains end there; entries beyond it raise the overflow flag).
 int emu_tree_build(int prec, const double *pos, const double *mass, int64_t n, double eps, double theta,
                    void *nodes_out, int *skips_out, int nodes_cap, double *sorted_out, int *order_out,
-                   double *root_out, int *info_out, uint64_t *keys_out, int seg_cap) {
+                   double *root_out, int *info_out, uint64_t *keys_out, int seg_cap, void *quad_out) {
+  // quad_out (nullable): 6 values per entry, the opt-in quadrupole tensors
   if (prec == 32)
     return build_impl<float>(pos, mass, n, eps, theta, nodes_out, skips_out, nodes_cap, sorted_out, order_out,
-                             root_out, info_out, keys_out, seg_cap);
+                             root_out, info_out, keys_out, seg_cap, quad_out);
   return build_impl<double>(pos, mass, n, eps, theta, nodes_out, skips_out, nodes_cap, sorted_out, order_out,
-                            root_out, info_out, keys_out, seg_cap);
+                            root_out, info_out, keys_out, seg_cap, quad_out);
 }
 
 // The DISTRIBUTED fp32 build (tree.cu phases A-C with TreeDist) for `world` ranks run one after the

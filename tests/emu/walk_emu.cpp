@@ -84,7 +84,8 @@ int emu_walk_target(const float *nodes, int nentries, const double *sorted4, con
 // positions (nt,3) in the given order (order == nullptr: identity).
 int emu_walk_target64(const double *nodes, const int *skips, int nentries, const double *tpos, const int *order,
                       int64_t ni, const double *root, double eps2, double inv_theta2, double *acc_out,
-                      unsigned long long *stats4, int flags) {
+                      unsigned long long *stats4, int flags, const double *quad) {
+  // quad (nullable): 6 doubles per entry -> the opt-in quadrupole instantiation of the kernel
   using namespace gh;
   TargetsView tv;
   std::memset(&tv, 0, sizeof(tv));
@@ -99,7 +100,9 @@ int emu_walk_target64(const double *nodes, const int *skips, int nentries, const
   ep.acc_out = acc_out;
   const Node<double> *nd = reinterpret_cast<const Node<double> *>(nodes);
   const int64_t nwarps = (ni + 31) / 32;
-  if (flags & 2)
+  if (quad)
+    run_warps(nwarps, [&] { walk_kernel<double, true, false, false, true>(nd, skips, nentries, tv, ni, root, false, eps2, inv_theta2, ep, stats4, nullptr, quad); });
+  else if (flags & 2)
     run_warps(nwarps, [&] { walk_kernel<double, true, true, false>(nd, skips, nentries, tv, ni, root, false, eps2, inv_theta2, ep, stats4); });
   else
     run_warps(nwarps, [&] { walk_kernel<double, true, false, false>(nd, skips, nentries, tv, ni, root, false, eps2, inv_theta2, ep, stats4); });

@@ -63,6 +63,30 @@ def test_argument_validation_without_gpu():
     assert lib.gh_host_alloc(ctypes.byref(p), 0) == _lib.GH_EINVAL and lib.gh_host_free(None) == _lib.GH_OK
 
 
+def test_group_argument_validation_without_gpu():
+    """Engine groups (multi-GPU): bad arguments are rejected before any CUDA or NCCL call; NCCL itself
+    is found at run time (dlopen), never linked."""
+    lib = _lib.lib()
+    g = ctypes.c_void_p()
+    assert lib.gh_group_create_local(ctypes.byref(g), 0, None, 100, 32) == _lib.GH_EINVAL      # no device
+    assert lib.gh_group_create_local(ctypes.byref(g), 4, None, 3, 32) == _lib.GH_EINVAL        # fewer particles than ranks
+    assert lib.gh_group_create_rank(ctypes.byref(g), None, 5, 4, 0, 100, 32) == _lib.GH_EINVAL  # rank >= world
+    assert lib.gh_group_create_rank(ctypes.byref(g), None, 0, 2, 0, 100, 32) == _lib.GH_EINVAL  # world > 1 needs an id
+    assert lib.gh_group_unique_id(None) == _lib.GH_EINVAL
+    assert lib.gh_group_step(None, 1, 0.1, 0.1, 0.7, 0) == _lib.GH_EINVAL
+    assert lib.gh_group_destroy(None) == _lib.GH_OK
+    out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "nccl" not in out
+    v = ctypes.c_int()
+    if lib.gh_nccl_version(ctypes.byref(v)) == _lib.GH_OK:   # a libnccl.so.2 is on this machine
+        assert v.value >= 20000
+    # the opt-in quadrupole switch: off unless asked for
+    if not os.environ.get("GH_TREE_QUADRUPOLES"):
+        assert lib.gh_get_tree_quadrupoles() == 0
+    assert lib.gh_set_tree_quadrupoles(1) == _lib.GH_OK and lib.gh_get_tree_quadrupoles() == 1
+    assert lib.gh_set_tree_quadrupoles(0) == _lib.GH_OK and lib.gh_get_tree_quadrupoles() == 0
+
+
 def test_reference_error_messages():
     """Shape errors: same type and text as _jbgrav.c:92,98,106,228,235,244,253,260."""
     with pytest.raises(RuntimeError, match="Position array is not Nx3."):

@@ -1,0 +1,83 @@
+"""Opt-in quadrupoles: an accuracy upgrade BEYOND the reference, off by default.
+With it on, the tree keeps the reference's octree and accepted node set (per-target walk) and every
+accepted cell also contributes its traceless quadrupole; checked against the CPU model
+oracle.tree_force_quad and against direct summation."""
+import numpy as np
+import pytest
+
+from gravhopper_b200 import _jbgrav as J, ic_raw
+
+pytestmark = pytest.mark.gpu
+
+
+def relerr(a, b):
+    return np.linalg.norm(a - b, axis=1) / np.linalg.norm(b, axis=1)
+
+
+@pytest.fixture()
+def quadrupoles():
+    assert J.tree_quadrupoles() is False          # the default is the reference's monopole tree
+    J.tree_quadrupoles(True)
+    try:
+        yield
+    finally:
+        J.tree_quadrupoles(False)
+
+
+def test_quadrupole_tree_equals_its_model_and_beats_the_monopole_tree(oracle, quadrupoles):
+    n = 20000
+    x, v, m = ic_raw.Hernquist(n, 1.0, 1e10, seed=3)
+    x = np.ascontiguousarray(x)
+    eps, theta = 0.05, 0.7
+    d = oracle.direct_summation(x, m, eps, nthreads=0)
+    model = oracle.tree_force_quad(x, m, x, eps, theta)
+    a64 = J.tree_force(x, m, eps, theta)
+    # plain-double second-moment prefixes: the smallest cells' tensors cancel to ~1e-16 N m R^2
+    assert relerr(a64, model).max() <= 1e-7
+    J.tree_quadrupoles(False)
+    mono64 = J.tree_force(x, m, eps, theta)
+    mono32 = J.tree_force(x, m, eps, theta, precision="fp32")
+    J.tree_quadrupoles(True)
+    a32 = J.tree_force(x, m, eps, theta, precision="fp32")
+    # fp32: tensors and decisions in single precision (measured max 2.6e-4: a borderline acceptance)
+    assert relerr(a32, model).max() <= 2e-3 and np.median(relerr(a32, model)) <= 1e-5
+    e64, e32, em = relerr(a64, d), relerr(a32, d), relerr(mono64, d)
+    assert e64.mean() <= 0.35 * em.mean() and e32.mean() <= 0.35 * em.mean()   # measured ~0.27
+    assert np.percentile(e64, 99) <= np.percentile(em, 99) and e64.max() <= em.max() * 1.05
+    assert e32.mean() <= 0.5 * relerr(mono32, d).mean()
+    # separate targets
+    t = np.ascontiguousarray(x[:777] * 1.5 + 0.01)
+    ap = J.tree_force_position(x, m, t, eps, theta)
+    assert relerr(ap, oracle.tree_force_quad(x, m, t, eps, theta)).max() <= 1e-7
+
+
+def test_quadrupoles_off_is_the_reference_tree_again(oracle):
+    x, v, m = ic_raw.Plummer(3000, 1e-3, 1e6, seed=9)
+    x = np.ascontiguousarray(x)
+    before = J.tree_force(x, m, 5e-5, 0.7)
+    J.tree_quadrupoles(True)
+    try:
+        with_q = J.tree_force(x, m, 5e-5, 0.7)
+    finally:
+        J.tree_quadrupoles(False)
+    after = J.tree_force(x, m, 5e-5, 0.7)
+    assert np.array_equal(before, after) and not np.array_equal(before, with_q)
+    assert relerr(after, oracle.tree_force(x, m, 5e-5, 0.7)).max() <= 1e-12
+
+
+def test_simulation_runs_with_quadrupoles(oracle):
+    """Simulation(..., quadrupoles=True): the fused step uses the extension; one step equals the
+    oracle's leapfrog arithmetic with the quadrupole model's accelerations."""
+    from gravhopper_b200 import Simulation
+    x, v, m = ic_raw.Plummer(2000, 1e-3, 1e6, seed=4)
+    dt, eps = 0.005, 5e-5
+    sim = Simulation(dt=dt, eps=eps, algorithm="tree", quadrupoles=True)
+    sim.add_IC({"pos": x, "vel": v, "mass": m})
+    sim.run(1)
+    assert J.tree_quadrupoles() is False          # restored after the run
+    xh = oracle.half_drift(x, v, dt)
+    a = oracle.tree_force_quad(xh, m, xh, eps, 0.7) * oracle.C_ACC
+    v1 = v + a * dt
+    x1 = xh + ((0.5 * v1) * dt) * oracle.KPC_PER_KMS_MYR
+    assert np.abs(np.asarray(sim.velocities.value)[1] - v1).max() <= 1e-9 * np.abs(v1).max()
+    assert np.abs(np.asarray(sim.positions.value)[1] - x1).max() <= 1e-12 * np.abs(x1).max()

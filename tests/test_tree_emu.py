@@ -37,14 +37,14 @@ def temu():
     lib = C.CDLL(LIB)
     vp = C.c_void_p
     lib.emu_tree_build.argtypes = [C.c_int, vp, vp, C.c_int64, C.c_double, C.c_double, vp, vp, C.c_int, vp, vp,
-                                   vp, vp, vp, C.c_int]
+                                   vp, vp, vp, C.c_int, vp]
     lib.emu_splitter_sort_test.argtypes = [vp, C.c_int64, C.c_int64, vp, C.c_int64, C.c_int, vp, vp]
     lib.emu_tree_build_dist.argtypes = [C.c_int, vp, vp, vp, C.c_int64, C.c_double, C.c_double, vp, C.c_int, vp, vp,
                                         vp, vp, vp, vp, vp, C.c_int]
     return lib
 
 
-def emu_build(lib, prec, x, m, eps, theta, want_keys=False, seg_cap=0):
+def emu_build(lib, prec, x, m, eps, theta, want_keys=False, seg_cap=0, want_quad=False):
     n = len(m)
     x, m = np.ascontiguousarray(x, dtype=np.float64), np.ascontiguousarray(m, dtype=np.float64)
     cap = 44 * n + 64  # chains of single-child cells included (<= levels per particle)
@@ -55,12 +55,15 @@ def emu_build(lib, prec, x, m, eps, theta, want_keys=False, seg_cap=0):
     root = np.zeros(10)
     info = np.zeros(3, dtype=np.int32)
     keys = np.zeros(n, dtype=np.uint64)
+    quad = np.zeros((cap, 6), dtype=nodes.dtype) if want_quad else None
     rc = lib.emu_tree_build(prec, x.ctypes.data, m.ctypes.data, n, eps, theta, nodes.ctypes.data, skips.ctypes.data,
                             cap, sorted4.ctypes.data, order.ctypes.data, root.ctypes.data, info.ctypes.data,
-                            keys.ctypes.data, seg_cap)
+                            keys.ctypes.data, seg_cap, None if quad is None else quad.ctypes.data)
     assert rc == 0
     ne = int(info[0])
     out = (np.ascontiguousarray(nodes[:ne]), np.ascontiguousarray(skips[:ne]), sorted4, order, root, int(info[1]))
+    if want_quad:
+        return out + (np.ascontiguousarray(quad[:ne]),)
     if seg_cap:
         return out + (int(info[2]),)
     return out + (keys,) if want_keys else out
@@ -85,7 +88,7 @@ def test_fp64_build_is_the_reference_octree_and_walks_to_the_oracle(temu, emu, o
         acc = np.zeros_like(tpos)
         st = np.zeros(4, dtype=np.uint64)
         emu.emu_walk_target64(nodes.ctypes.data, skips.ctypes.data, len(nodes), tpos.ctypes.data, None, len(tpos),
-                              root.ctypes.data, eps * eps, 1.0 / theta ** 2, acc.ctypes.data, st.ctypes.data, 1)
+                              root.ctypes.data, eps * eps, 1.0 / theta ** 2, acc.ctypes.data, st.ctypes.data, 1, None)
         ref, s2 = oracle.tree_force_position(x, m, tpos, eps, theta, return_stats=True)
         assert int(st[0]) == s2["accepted"] and int(st[1]) == s2["visited"]
         assert relerr(acc, ref).max() <= 1e-12
@@ -125,7 +128,7 @@ def test_coincident_particles_do_not_break_the_build(temu, emu, oracle, prec):
         acc = np.zeros_like(tpos)
         st = np.zeros(4, dtype=np.uint64)
         emu.emu_walk_target64(nodes.ctypes.data, skips.ctypes.data, len(nodes), tpos.ctypes.data, None, len(tpos),
-                              root.ctypes.data, eps * eps, float("inf"), acc.ctypes.data, st.ctypes.data, 1)
+                              root.ctypes.data, eps * eps, float("inf"), acc.ctypes.data, st.ctypes.data, 1, None)
         assert relerr(acc, d).max() <= 1e-12
     else:
         acc, st = run_group(emu, nodes, sorted4, order, root, eps, 0.0)
@@ -310,3 +313,28 @@ def test_splitter_sort_equals_the_stable_sort(temu, case):
     order = np.argsort(keys[:n_real], kind="stable")
     assert np.array_equal(out_v, order.astype(np.int32))
     assert np.array_equal(out_k, keys[:n_real][order])
+
+
+def test_quadrupole_extension_equals_its_cpu_model(temu, emu, oracle, golden):
+    """Opt-in quadrupoles (beyond the reference): emit_kernel's per-cell traceless
+    tensors from the second-moment prefixes + walk_kernel<double, QUAD> reproduce
+    oracle.tree_force_quad (the reference's octree and node set, quadrupoles built bottom-up with
+    the parallel-axis rule), and the error against direct summation drops well below the monopole
+    tree's at the same theta."""
+    x, m, eps = golden["c1_pos"][:1500], golden["c1_mass"][:1500], float(golden["c1_eps"])
+    theta = 0.7
+    nodes, skips, sorted4, order, root, maxlevel, quad = emu_build(temu, 64, x, m, eps, theta, want_quad=True)
+    leaves = nodes[:, 6] < 0
+    assert not quad[leaves].any() and np.abs(quad[~leaves, 0] + quad[~leaves, 1] + quad[~leaves, 2]).max() <= \
+        1e-9 * np.abs(quad).max()                                   # traceless
+    tpos = np.ascontiguousarray(x)
+    acc = np.zeros_like(tpos)
+    st = np.zeros(4, dtype=np.uint64)
+    emu.emu_walk_target64(nodes.ctypes.data, skips.ctypes.data, len(nodes), tpos.ctypes.data, None, len(tpos),
+                          root.ctypes.data, eps * eps, 1.0 / theta ** 2, acc.ctypes.data, st.ctypes.data, 1,
+                          quad.ctypes.data)
+    model = oracle.tree_force_quad(x, m, x, eps, theta)
+    assert relerr(acc, model).max() <= 1e-9
+    d = oracle.direct_summation(x, m, eps)
+    mono = oracle.tree_force(x, m, eps, theta)
+    assert relerr(acc, d).mean() <= 0.5 * relerr(mono, d).mean()

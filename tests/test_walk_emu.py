@@ -41,7 +41,7 @@ def emu():
     lib.emu_walk_group.argtypes = [vp, C.c_int, vp, vp, i64, vp, C.c_float, C.c_double, C.c_int, C.c_float, vp,
                                    vp, C.c_int, vp]
     lib.emu_walk_target.argtypes = [vp, C.c_int, vp, vp, i64, vp, C.c_float, C.c_double, vp, vp, C.c_int]
-    lib.emu_walk_target64.argtypes = [vp, vp, C.c_int, vp, vp, i64, vp, C.c_double, C.c_double, vp, vp, C.c_int]
+    lib.emu_walk_target64.argtypes = [vp, vp, C.c_int, vp, vp, i64, vp, C.c_double, C.c_double, vp, vp, C.c_int, vp]
     return lib
 
 
@@ -201,7 +201,7 @@ def test_fp64_walk_kernel_source_equals_the_reference_tree(emu, oracle, golden, 
         st = np.zeros(4, dtype=np.uint64)
         emu.emu_walk_target64(nodes.ctypes.data, skips.ctypes.data, len(nodes), tpos.ctypes.data, None, len(tpos),
                               rootblk.ctypes.data, eps * eps, 1.0 / (theta * theta), acc.ctypes.data,
-                              st.ctypes.data, 1 | (2 if eps == 0.0 else 0))
+                              st.ctypes.data, 1 | (2 if eps == 0.0 else 0), None)
         ref, so = oracle.tree_force_position(x, m, tpos, eps, theta, return_stats=True)
         assert len(nodes) == so["nodes"]
         assert int(st[0]) == so["accepted"] and int(st[1]) == so["visited"]
