@@ -349,7 +349,10 @@ struct TreeRun {
         const char *env = getenv("GH_SORT");
         return (env && !strcmp(env, "classic")) ? 0 : 1;
       }();
-      const bool bucket = sort_mode == 1 && a.coherent && w->ss.nb >= BS_MIN_BUCKETS && w->ss.cap == ph.n;
+      // Single rank only: a rank's key range moves by ~1 % of its particles per step, and the keys
+      // it gains all land in the first or last bucket, which then takes the slow oversize path
+      // (measured at 8 GPUs: 0.7 ms of skew at the next exchange).
+      const bool bucket = sort_mode == 1 && a.coherent && !ph.dist && w->ss.nb >= BS_MIN_BUCKETS && w->ss.cap == ph.n;
       if (bucket) {
         GH_TRY(splitter_sort_pairs(hi, idx, hi2, idx2, ph.n, 63, w->rs, w->ss, st, ph.ndev));
         inB = false;
@@ -358,7 +361,7 @@ struct TreeRun {
       }
       ph.shi = inB ? hi2 : hi;
       ph.sidx = inB ? idx2 : idx;
-      if (a.coherent && sort_mode == 1) GH_TRY(splitter_refresh(w->ss, ph.shi, ph.n, st, ph.ndev));
+      if (a.coherent && sort_mode == 1 && !ph.dist) GH_TRY(splitter_refresh(w->ss, ph.shi, ph.n, st, ph.ndev));
       else w->ss.nb = 0;
     }
     if (ph.dist) {
