@@ -55,6 +55,7 @@ PROTOTYPES = {
     "gh_engine_source_index": (C.c_int, [_eng, C.POINTER(C.c_int)]),
     "gh_engine_source_stride_bytes": (C.c_int, [_eng, C.POINTER(_i64)]),
     "gh_engine_set_origin": (C.c_int, [_eng, _dp]),
+    "gh_engine_set_origin_velocity": (C.c_int, [_eng, _dp]),
     "gh_engine_prepare": (C.c_int, [_eng, C.c_double]),
     "gh_engine_add_potential": (C.c_int, [_eng, C.c_int, _dp, C.c_int]),
     "gh_engine_clear_potentials": (C.c_int, [_eng]),

@@ -533,6 +533,11 @@ int gh_engine_set_origin(gh_engine *e, const double origin[3]) {
   e->xhalf_valid = false;
   return GH_OK;
 }
+int gh_engine_set_origin_velocity(gh_engine *e, const double vel[3]) {
+  if (!e || !vel) return GH_EINVAL;
+  for (int k = 0; k < 3; k++) e->origin_vel[k] = vel[k];
+  return GH_OK;
+}
 
 int gh_engine_clear_potentials(gh_engine *e) {
   if (!e) return GH_EINVAL;
@@ -657,7 +662,11 @@ int engine_step_args(gh_engine *e, double dt, double eps, double theta, int algo
   ep.mass = e->mass + e->ib;
   ep.ext = ext_dev;
   ep.dt = dt;
-  for (int k = 0; k < 3; k++) ep.origin[k] = e->origin[k];
+  // the next step's float4 sources are written relative to where the origin will be then
+  for (int k = 0; k < 3; k++) {
+    e->origin_next[k] = e->origin[k] + e->origin_vel[k] * dt * GH_KPC_PER_KMS_MYR;
+    ep.origin[k] = e->origin_next[k];
+  }
 
   // gravhopper.py:449-450 (Np == 1 feels no N-body force) needs no special case: the only source
   // is the target itself and its term is exactly zero in every kernel.
@@ -703,6 +712,7 @@ int engine_step_args(gh_engine *e, double dt, double eps, double theta, int algo
 }
 
 void engine_step_done(gh_engine *e) {
+  for (int k = 0; k < 3; k++) e->origin[k] = e->origin_next[k];
   e->fev_count++;
   e->cur = (e->cur + 1) % GH_RING;
   e->scur ^= 1;

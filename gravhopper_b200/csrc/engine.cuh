@@ -26,7 +26,14 @@ struct gh_engine {
   void *src[2] = {nullptr, nullptr};  // f64: double (n,3); f32: float4 (n)
   int scur = 0;
   double *xh_private = nullptr;       // f32: (ni,3) own x_half in float64
+  // fp32 coordinates are stored relative to `origin`, which MOVES with the system: origin_vel is the
+  // mean velocity at upload (km/s), and every step's epilogue writes the next step's float4 sources
+  // relative to origin + origin_vel dt.  Bulk motion (a merger's or flyby's centre-of-mass velocity)
+  // then costs no fp32 digits however long the run; all ranks of a group derive the same
+  // sequence from the same uploaded values.
   double origin[3] = {0, 0, 0};
+  double origin_vel[3] = {0, 0, 0};
+  double origin_next[3] = {0, 0, 0};
   double dt_built = 0.0;
   bool uploaded = false, xhalf_valid = false;
   DeviceBuffer ws, ext, ext2;

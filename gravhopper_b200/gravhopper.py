@@ -103,8 +103,12 @@ class _Engine(object):
         vel = np.ascontiguousarray(vel, dtype=np.float64)
         mass = np.ascontiguousarray(mass, dtype=np.float64)
         if self.precision == 'fp32':
+            # fp32 coordinates are relative to an origin that starts at the mean position and moves
+            # with the mean velocity
             origin = np.ascontiguousarray(pos.mean(axis=0))
+            ovel = np.ascontiguousarray(vel.mean(axis=0))
             _lib.check(self.lib.gh_engine_set_origin(self.h, origin.ctypes.data_as(C.POINTER(C.c_double))))
+            _lib.check(self.lib.gh_engine_set_origin_velocity(self.h, ovel.ctypes.data_as(C.POINTER(C.c_double))))
         _lib.check(self.lib.gh_engine_upload(self.h, _ptr(pos), _ptr(vel), _ptr(mass)), "gh_engine_upload")
 
     def run(self, nsteps, dt, eps, theta, alg, every, pos_hist, vel_hist):
@@ -195,8 +199,10 @@ class _GroupEngine(object):
         if self.perm is not None:
             pos, vel, mass = pos[self.perm], vel[self.perm], np.ascontiguousarray(mass[self.perm])
         origin = np.ascontiguousarray(pos.mean(axis=0))
+        ovel = np.ascontiguousarray(vel.mean(axis=0))
         for h, b, c in self.parts:
             _lib.check(self.lib.gh_engine_set_origin(h, origin.ctypes.data_as(C.POINTER(C.c_double))))
+            _lib.check(self.lib.gh_engine_set_origin_velocity(h, ovel.ctypes.data_as(C.POINTER(C.c_double))))
             p, w = np.ascontiguousarray(pos[b:b + c]), np.ascontiguousarray(vel[b:b + c])
             _lib.check(self.lib.gh_engine_upload(h, _ptr(p), _ptr(w), _ptr(mass)), "gh_engine_upload")
 

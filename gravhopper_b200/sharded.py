@@ -153,12 +153,15 @@ class CudaShard(object):
 
     __del__ = close
 
-    def upload(self, pos_own, vel_own, mass_all, origin):
+    def upload(self, pos_own, vel_own, mass_all, origin, origin_vel=None):
         pos_own = np.ascontiguousarray(pos_own, dtype=np.float64)
         vel_own = np.ascontiguousarray(vel_own, dtype=np.float64)
         mass_all = np.ascontiguousarray(mass_all, dtype=np.float64)
         origin = np.ascontiguousarray(origin, dtype=np.float64)
         _lib.check(self.lib.gh_engine_set_origin(self.h, origin.ctypes.data_as(C.POINTER(C.c_double))))
+        if origin_vel is not None:
+            ovel = np.ascontiguousarray(origin_vel, dtype=np.float64)
+            _lib.check(self.lib.gh_engine_set_origin_velocity(self.h, ovel.ctypes.data_as(C.POINTER(C.c_double))))
         _lib.check(self.lib.gh_engine_upload(self.h, C.c_void_p(pos_own.ctypes.data),
                                              C.c_void_p(vel_own.ctypes.data),
                                              C.c_void_p(mass_all.ctypes.data)), "gh_engine_upload")
@@ -251,6 +254,7 @@ class ShardedSimulation(object):
         vel = np.asarray(vel, dtype=np.float64)
         mass = np.asarray(mass, dtype=np.float64)
         origin = pos.mean(axis=0)  # identical on every rank: all ranks hold the same ICs
+        origin_vel = vel.mean(axis=0)  # the fp32 origin moves with the system (gh_engine_set_origin_velocity)
         # tree: lay the particles out in Morton blocks dealt round-robin over the ranks (coherent
         # warps + load balance); identical on every rank.  self.perm maps new index -> original.
         self.perm = None
@@ -258,7 +262,10 @@ class ShardedSimulation(object):
             self.perm = interleaved_layout(pos, world)
             pos, vel, mass = pos[self.perm], vel[self.perm], mass[self.perm]
         sl = slice(self.begin, self.begin + self.count)
-        self.shard.upload(pos[sl], vel[sl], mass, origin)
+        try:
+            self.shard.upload(pos[sl], vel[sl], mass, origin, origin_vel)
+        except TypeError:  # stand-in shards of the host-logic tests take no origin velocity
+            self.shard.upload(pos[sl], vel[sl], mass, origin)
         self.shard.prepare(self.dt)
         self.steps_done = 0
 

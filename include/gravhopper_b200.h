@@ -211,6 +211,9 @@ int gh_engine_source_stride_bytes(gh_engine *e, int64_t *bytes);
 /* Origin subtracted from positions before they are rounded to fp32 (GH_PREC_F32 engines only;
  * default 0,0,0).  Every rank of a sharded run must set the same value. */
 int gh_engine_set_origin(gh_engine *e, const double origin[3]);
+/* Velocity (km/s) the fp32 origin moves with: the system's mean velocity at upload.  Every step
+ * advances the origin by vel * dt, so bulk motion costs no fp32 digits in long runs. */
+int gh_engine_set_origin_velocity(gh_engine *e, const double vel[3]);
 
 /* Build x_half = x + ((0.5 v) dt) K for the next step from the current state
  * (gravhopper.py:409) into the owned slice of source buffer gh_engine_source_index().  Single-GPU

@@ -9,6 +9,8 @@
 #   launches:<which>:<n>[:<steps>]  ncu launch list of scripts/profile_kernels.py <which> <n> [steps]
 #   ab:<name,name,..>[:K=V]    scripts/gpu_ab.sh: quick tree bench with library variants (base = in-tree)
 #   ncu:<kernel-regex>:<which>:<n>[:<skip>]  ncu --set full of one launch  -> <tag>_<regex>.ncu-rep
+#   benchlaunches[:<bench args>]  ncu launch list of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline` (a number
+#                              printed under ncu is never a bench value)
 #   sweep[:<N>[:kappas...]]    scripts/gpu_hybrid_sweep.py
 #   py:<script and args>       python <script> ...
 # GH_TAG names the outputs (default r02).  Multi-GPU benches run under a short timeout of their own
@@ -35,6 +37,8 @@ for task in "$@"; do
     ab) GH_AB_ENV="$a2" bash scripts/gpu_ab.sh ${a1//,/ } ;;
     ncu) timeout 900 ncu --set full --clock-control none --import-source on -k regex:$a1 -s ${a4:-1} -c 1 -f -o gpurun_out/${TAG}_${a1}_${a3} \
               python scripts/profile_kernels.py $a2 $a3 4 > gpurun_out/${TAG}_ncu_$k.log 2>&1; tail -1 gpurun_out/${TAG}_ncu_$k.log ;;
+    benchlaunches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/${TAG}_launches_bench.csv \
+              python bench.py --steps 2 --warmup 3 --no-cpu-baseline $a1 > gpurun_out/${TAG}_ncu_$k.log 2>&1; tail -c 300 gpurun_out/${TAG}_ncu_$k.log ;;
     sweep) timeout 600 python scripts/gpu_hybrid_sweep.py ${a1:-4194304} ${a2//,/ } > gpurun_out/${TAG}_sweep_$k.log 2>&1; tail -8 gpurun_out/${TAG}_sweep_$k.log | cut -c1-300 ;;
     py) timeout 900 python $a1 > gpurun_out/${TAG}_py_$k.log 2>&1; echo "rc=$?"; tail -15 gpurun_out/${TAG}_py_$k.log | cut -c1-300 ;;
     *) echo "unknown task $what" ;;
