@@ -239,5 +239,10 @@ def test_fp32_origin_moves_with_the_system():
         sim.add_IC({"pos": x, "vel": v + boost, "mass": m})
         sim.run(steps)
         out[name] = np.asarray(sim.positions.value)[-1] - boost * (steps * dt) * 1.022712165045695e-3
-    scale = np.abs(out["rest"] - out["rest"].mean(axis=0)).max()
-    assert np.abs(out["moving"] - out["rest"]).max() <= 2e-5 * scale
+    # scale = the typical radius (1e-3 kpc).  Expected difference: fp32 force rounding (1e-6) x the
+    # force's share of ten steps' motion (1e-2) = 1e-8 of it; a fixed origin 0.5 kpc away would cost
+    # 3e-8 kpc of coordinate resolution, i.e. 1e-3 force errors and 1e-5 here
+    scale = np.median(np.linalg.norm(out["rest"] - out["rest"].mean(axis=0), axis=1))
+    diff = np.linalg.norm(out["moving"] - out["rest"], axis=1)
+    assert np.median(diff) <= 1e-6 * scale          # a fixed origin would give ~1e-5
+    assert diff.max() <= 1e-4 * scale               # measured 3.3e-6: one close pair amplifies the rounding
