@@ -42,13 +42,14 @@ def test_sharded_matches_single_gpu(tmp_path, world, n, alg, prec, steps, comm):
     # interaction lists -- differ: the runs agree to the tree's own approximation error (~1e-2 of
     # the force, i.e. ~1e-5 of the positions after a few of these short steps), not to rounding
     if prec == "fp32" and alg == "tree":
-        # (individual particles in close encounters see force differences of ~10 % between two
-        # groupings -- the reference tree's own max error at theta = 0.7 is 0.15 -- hence percentiles)
-        for a, b in ((got["pos"], pos), (got["vel"], vel)):
+        # Measured (tests/_sharded_debug.py, N = 8192, 6 steps, 2 GPUs): positions median 1.7e-6 / p99
+        # 1.4e-5 / max 4.4e-5 of max|x|, velocities median 9.2e-5 / p99 7.2e-4 / max 1.9e-3 of max|v| --
+        # already 4e-5 after ONE step: the force differs by the group walk's own error (~3e-3) and the
+        # kick is ~1 % of max|v|.  The redundant-build path (GH_TREE_DIST=0) differs by the same amount.
+        for (a, b), (med, p99, mx) in zip(((got["pos"], pos), (got["vel"], vel)),
+                                          ((2e-5, 2e-4, 2e-3), (1e-3, 1e-2, 5e-2))):
             d = np.abs(a - b).max(axis=1) / np.abs(b).max()
-            # measured: median 1.6e-6 (velocities, 6 steps at N = 8192): a force difference of ~3e-3 (the
-            # group walk's own mean error there) times the kick a dt ~ 0.06 |v| of these steps
-            assert np.median(d) <= 2e-5 and np.percentile(d, 99) <= 1e-3 and d.max() <= 5e-2
+            assert np.median(d) <= med and np.percentile(d, 99) <= p99 and d.max() <= mx
         return
     tol = 1e-13 if prec == "fp64" else 1e-6
     assert np.abs(got["pos"] - pos).max() <= tol * np.abs(pos).max()
@@ -74,4 +75,5 @@ def test_simulation_devices_argument_matches_one_gpu():
             if prec == "fp64":
                 assert d.max() <= 1e-13, (alg, prec)
             else:  # fp32 tree: see test_sharded_matches_single_gpu
-                assert np.median(d) <= 2e-5 and np.percentile(d, 99) <= 1e-3 and d.max() <= 5e-2, (alg, prec)
+                med, p99, mx = ((2e-5, 2e-4, 2e-3), (1e-3, 1e-2, 5e-2))[k]
+                assert np.median(d) <= med and np.percentile(d, 99) <= p99 and d.max() <= mx, (alg, prec)
