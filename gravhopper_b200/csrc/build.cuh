@@ -310,7 +310,10 @@ __global__ void rec1_kernel(const uint64_t *__restrict__ shi, const BuildCtl *__
   r.n = ctl->n_local;
   r.kfirst = r.n > 0 ? shi[0] : 0;
   r.klast = r.n > 0 ? shi[r.n - 1] : 0;
-  r.pad[0] = r.pad[1] = r.pad[2] = 0;
+  // pad[0]: this rank's key range held more particles than its arrays (select_compact_kernel): every
+  // rank must know, or the others would walk a tree with particles missing
+  r.pad[0] = ctl->overflow;
+  r.pad[1] = r.pad[2] = 0;
   all[ctl->rank] = r;
 }
 
@@ -336,6 +339,7 @@ __global__ void neighbours_kernel(const RankRec1 *__restrict__ all, BuildCtl *__
   for (int q = P - 1; q >= 0; q--) {
     ctl->counts[q] = all[q].n;
     if (all[q].n > 0) first = q * ctl->stride;
+    if (all[q].pad[0]) ctl->overflow = 1;  // some rank's range overflowed: nobody walks this step
   }
   ctl->first = first;
 }
@@ -556,6 +560,7 @@ __global__ void stitch_kernel(const RankRec1 *__restrict__ r1, const RankRec2 *_
   // a segment that does not fit anywhere stops the walk on EVERY rank (all see the same records)
   int maxent = 0;
   for (int q = 0; q < P; q++) maxent = r2[q].nentries > maxent ? r2[q].nentries : maxent;
+  if (ctl->overflow) maxent = 0x7fffffff;  // (a particle-count overflow, see rec1_kernel) the host's signal
   ctl->maxent = maxent;
   if (maxent > stride) ctl->overflow = 1;
   // cells of level l <= cnext that contain my last particle continue into the next non-empty rank

@@ -192,8 +192,13 @@ int tree_step_distributed(gh_group *g, double dt, double eps, double theta) {
       GH_CUDA(cudaEventSynchronize(e->maxent_ev[slot]));
       const int64_t m = e->h_maxent[slot];
       if (m > e->dist_stride) {
-        set_error("tree: a rank's entry segment overflowed (%lld entries, segment %lld); the state stopped "
-                  "advancing there -- upload it again and rerun", (long long)m, (long long)e->dist_stride);
+        if (m == 0x7fffffff)
+          set_error("tree: a rank's key range held more particles than its arrays (1.25x its share): the system "
+                    "changed too violently within one step; the state stopped advancing there -- upload it again "
+                    "and rerun (GH_TREE_DIST=0 builds redundantly)");
+        else
+          set_error("tree: a rank's entry segment overflowed (%lld entries, segment %lld); the state stopped "
+                    "advancing there -- upload it again and rerun", (long long)m, (long long)e->dist_stride);
         return GH_ESTATE;
       }
       if (100 * m > 95 * e->dist_stride) e->dist_stride = round_up(m + m / 5, 1024);
