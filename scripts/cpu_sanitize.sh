@@ -14,7 +14,7 @@ trap restore EXIT
 if [ "$mode" = asan ]; then flags="-fsanitize=address,undefined -fno-omit-frame-pointer"; units="walk tree direct ic"
 else flags="-fsanitize=thread"; units="walk tree direct"; fi
 for f in $units; do
-  g++ -O1 -g -std=c++20 -shared -fPIC -pthread $flags -I"${CUDA_HOME:-/usr/local/cuda}/include" -o tests/emu/lib${f}_emu.so tests/emu/${f}_emu.cpp
+  g++ -O1 -g -std=c++20 -shared -fPIC -pthread -DGH_EMU_THREADS $flags -I"${CUDA_HOME:-/usr/local/cuda}/include" -o tests/emu/lib${f}_emu.so tests/emu/${f}_emu.cpp
 done
 touch tests/emu/lib*_emu.so
 tests=""; for f in $units; do tests="$tests tests/test_${f}_emu.py"; done
