@@ -63,9 +63,10 @@ struct TileSmem {
 // sm.whist[w][d] the number of pairs of digit d in warps < w, sm.dstart[d] the start of digit d in
 // the sorted tile; the return value is the tile's count of digit threadIdx.x.  (The body of
 // rs_scatter_kernel, shared here between the partition passes and the in-shared-memory sort.)
-template <class Digit>
-__device__ __forceinline__ int tile_rank(TileSmem &sm, const uint64_t (&key)[RS_ROUNDS], int count, Digit dg,
-                                         int (&lrank)[RS_ROUNDS], unsigned (&dig)[RS_ROUNDS]) {
+// tile_rank_digits: the digits are the caller's (dig[r] of an invalid pair = 0x100 + lane, a private
+// pseudo-digit that matches nobody); tile_rank computes them from the keys.
+__device__ __forceinline__ int tile_rank_digits(TileSmem &sm, int count, int (&lrank)[RS_ROUNDS],
+                                                const unsigned (&dig)[RS_ROUNDS]) {
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 #pragma unroll
   for (int k = 0; k < RS_WARPS; k++) sm.whist[k][tid] = 0;
@@ -79,8 +80,6 @@ __device__ __forceinline__ int tile_rank(TileSmem &sm, const uint64_t (&key)[RS_
   int old[RS_ROUNDS];
 #pragma unroll
   for (int r = 0; r < RS_ROUNDS; r++) {
-    const bool valid = w * (32 * RS_ROUNDS) + r * 32 + lane < count;
-    dig[r] = valid ? dg(key[r]) : (0x100u + (unsigned)lane);
     peers[r] = __match_any_sync(0xffffffffu, dig[r]);
   }
 #pragma unroll
@@ -99,9 +98,7 @@ __device__ __forceinline__ int tile_rank(TileSmem &sm, const uint64_t (&key)[RS_
 #pragma unroll
   for (int r = 0; r < RS_ROUNDS; r++) {
     const bool valid = w * (32 * RS_ROUNDS) + r * 32 + lane < count;
-    // invalid lanes get private pseudo-digits so that they match nobody
-    const unsigned d = valid ? dg(key[r]) : (0x100u + (unsigned)lane);
-    dig[r] = d;
+    const unsigned d = dig[r];
     const unsigned peers = __match_any_sync(0xffffffffu, d);
     const int leader = __ffs(peers) - 1;
     int old = 0;
@@ -131,6 +128,18 @@ __device__ __forceinline__ int tile_rank(TileSmem &sm, const uint64_t (&key)[RS_
   sm.dstart[tid] = woff + incl - tot;
   __syncthreads();
   return tot;
+}
+template <class Digit>
+__device__ __forceinline__ int tile_rank(TileSmem &sm, const uint64_t (&key)[RS_ROUNDS], int count, Digit dg,
+                                         int (&lrank)[RS_ROUNDS], unsigned (&dig)[RS_ROUNDS]) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = 0; r < RS_ROUNDS; r++) {
+    const bool valid = w * (32 * RS_ROUNDS) + r * 32 + lane < count;
+    // invalid lanes get private pseudo-digits so that they match nobody
+    dig[r] = valid ? dg(key[r]) : (0x100u + (unsigned)lane);
+  }
+  return tile_rank_digits(sm, count, lrank, dig);
 }
 
 // place the tile's pairs into sm.skey / sm.sval in digit order (after tile_rank)
@@ -346,6 +355,330 @@ bs_bucket_kernel(uint64_t *__restrict__ keys, int *__restrict__ vals, uint64_t *
   }
 }
 
+// ---- "place": the splitter sort with ONE trip into the buckets ---------------------------------------
+// The two partition passes above cost 2 x (histogram + row scan + ranked scatter) + the offsets
+// search, and every kernel of them repeats the 12-step splitter search per key.  Here:
+//   bp_count_kernel   bucket id of every key, ONCE (coarse splitter table in shared memory + one
+//                     128-byte line of the full table), stored as 16 bits; counts per bucket with
+//                     global reductions (no return value);
+//   bp_scan_kernel    exclusive scan of the counts = bucket offsets and running cursors (one CTA);
+//   bp_place_kernel   every pair goes straight to cursor[bucket]++ (global atomic with return);
+//   bp_bucket_kernel  one CTA per bucket sorts it inside shared memory.
+// The atomics make the order INSIDE a bucket arbitrary, so the bucket kernel cannot lean on
+// stability; it does not need to.  It ranks by the top BP_SUBBITS bits of (key - bucket start) that can
+// differ inside the bucket (<= 3 passes of 8 bits instead of up to 8 over the whole key), then puts the
+// rare runs of pairs that tie in those bits into (key, value) order by insertion (one thread per run).
+// A bucket with a run longer than BP_MAX_RUN (many particles in a tiny corner of the bucket's key
+// range, or coincident ones) is sorted again the long way: LSD passes over the value bits, then over
+// every key bit that can differ.  Either way the result is ordered by (key, value): exactly the
+// stable sort of pairs whose values ascend in the input, which is what the build feeds it
+// (keys_kernel: value = particle index).  Oversize buckets: the global-memory pass structure of
+// bs_bucket_kernel with the value passes in front.
+static constexpr int BP_THREADS = 256;
+static constexpr int BP_ROUNDS = 8;      // pairs per thread in the count / place kernels
+static constexpr int BP_COARSE = 16;     // every 16th splitter is staged in shared memory (16 x 8 B = one line)
+static constexpr int BP_SUBBITS = 24;
+static constexpr int BP_MAX_RUN = 16;
+
+__device__ __forceinline__ int bp_bucket_of(const uint64_t *coarse, int nc, const uint64_t *__restrict__ spl, int nb,
+                                            uint64_t k) {
+  int lo = 0, hi = nc - 1;  // largest j with coarse[j] <= k (coarse[0] = spl[0] = 0)
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (coarse[mid] <= k) lo = mid; else hi = mid - 1;
+  }
+  int b0 = lo * BP_COARSE, b1 = b0 + BP_COARSE - 1;
+  if (b1 > nb - 1) b1 = nb - 1;
+  while (b0 < b1) {  // largest b in the line with spl[b] <= k
+    const int mid = (b0 + b1 + 1) >> 1;
+    if (spl[mid] <= k) b0 = mid; else b1 = mid - 1;
+  }
+  return b0;
+}
+
+__global__ void __launch_bounds__(BP_THREADS)
+bp_count_kernel(const uint64_t *__restrict__ keys, int64_t n, const uint64_t *__restrict__ spl, int nb,
+                unsigned short *__restrict__ bid, int *__restrict__ count /* [nb], zeroed */,
+                const int *__restrict__ ndev) {
+  __shared__ uint64_t coarse[BS_MAX_BUCKETS / BP_COARSE];
+  if (ndev) n = *ndev;
+  const int nc = (nb + BP_COARSE - 1) / BP_COARSE;
+  for (int j = threadIdx.x; j < nc; j += BP_THREADS) coarse[j] = spl[j * BP_COARSE];
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * (BP_THREADS * BP_ROUNDS);
+  uint64_t k[BP_ROUNDS];
+#pragma unroll
+  for (int r = 0; r < BP_ROUNDS; r++) {
+    const int64_t q = base + r * BP_THREADS + threadIdx.x;
+    k[r] = (q < n) ? keys[q] : 0;
+  }
+#pragma unroll
+  for (int r = 0; r < BP_ROUNDS; r++) {
+    const int64_t q = base + r * BP_THREADS + threadIdx.x;
+    if (q < n) {
+      const int b = bp_bucket_of(coarse, nc, spl, nb, k[r]);
+      bid[q] = (unsigned short)b;
+      atomicAdd(&count[b], 1);
+    }
+  }
+}
+
+// boff[b] = pairs in buckets < b (b = 0 .. nb), cursor[b] = boff[b].  One CTA.
+__global__ void __launch_bounds__(RS_THREADS)
+bp_scan_kernel(const int *__restrict__ count, int nb, int *__restrict__ boff, int *__restrict__ cursor) {
+  __shared__ int wtot[RS_WARPS];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int carry = 0;
+  for (int b0 = 0; b0 < nb; b0 += RS_THREADS) {
+    const int b = b0 + threadIdx.x;
+    const int v = (b < nb) ? count[b] : 0;
+    const int incl = warp_scan<int>(v, lane);
+    if (lane == 31) wtot[w] = incl;
+    __syncthreads();
+    int woff = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < RS_WARPS; k++) {
+      woff += (k < w) ? wtot[k] : 0;
+      tot += wtot[k];
+    }
+    if (b < nb) { const int e = carry + woff + incl - v; boff[b] = e; cursor[b] = e; }
+    carry += tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) boff[nb] = carry;
+}
+
+__global__ void __launch_bounds__(BP_THREADS)
+bp_place_kernel(const uint64_t *__restrict__ kin, const int *__restrict__ vin, const unsigned short *__restrict__ bid,
+                int64_t n, int *__restrict__ cursor, uint64_t *__restrict__ kout, int *__restrict__ vout,
+                const int *__restrict__ ndev) {
+  if (ndev) n = *ndev;
+  const int64_t base = (int64_t)blockIdx.x * (BP_THREADS * BP_ROUNDS);
+  uint64_t k[BP_ROUNDS];
+  int v[BP_ROUNDS], pos[BP_ROUNDS];
+#pragma unroll
+  for (int r = 0; r < BP_ROUNDS; r++) {
+    const int64_t q = base + r * BP_THREADS + threadIdx.x;
+    pos[r] = -1;
+    if (q < n) {
+      k[r] = kin[q];
+      v[r] = vin[q];
+      pos[r] = atomicAdd(&cursor[bid[q]], 1);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < BP_ROUNDS; r++)
+    if (pos[r] >= 0) { kout[pos[r]] = k[r]; vout[pos[r]] = v[r]; }
+}
+
+#ifdef GH_HOST_EMU
+// which way the buckets went (tests/test_tree_emu.py): [0] compact ranking, [1] the long way,
+// [2] oversize, [3] runs ordered by insertion
+static long long g_bp_stats[4] = {0, 0, 0, 0};
+#define GH_BP_STAT(k) __atomic_fetch_add(&g_bp_stats[k], 1ll, __ATOMIC_RELAXED)
+#else
+#define GH_BP_STAT(k) ((void)0)
+#endif
+struct SubDigit {  // digit of (key - bucket start)
+  uint64_t klo;
+  int shift;
+  __device__ __forceinline__ unsigned operator()(uint64_t k) const {
+    return shift < 64 ? (unsigned)(((k - klo) >> shift) & 0xff) : 0u;
+  }
+};
+// k[0 .. count) is ordered by (k - klo) >> shift.  If a run of pairs that agree in those bits starts
+// at j: its length (counting stops at cap + 1), else 0.
+__device__ __forceinline__ int bp_run_length(const uint64_t *k, int count, int j, uint64_t klo, int shift, int cap) {
+  const uint64_t s = (k[j] - klo) >> shift;
+  if (j > 0 && ((k[j - 1] - klo) >> shift) == s) return 0;
+  int len = 1;
+  while (j + len < count && len <= cap && ((k[j + len] - klo) >> shift) == s) len++;
+  return len;
+}
+// insertion sort of the run [j, j + len) by (key, value)
+__device__ __forceinline__ void bp_sort_run(uint64_t *k, int *v, int j, int len) {
+  for (int a = 1; a < len; a++) {
+    const uint64_t ka = k[j + a];
+    const int va = v[j + a];
+    int t = a;
+    while (t > 0 && (k[j + t - 1] > ka || (k[j + t - 1] == ka && v[j + t - 1] > va))) {
+      k[j + t] = k[j + t - 1];
+      v[j + t] = v[j + t - 1];
+      t--;
+    }
+    k[j + t] = ka;
+    v[j + t] = va;
+  }
+}
+
+// keys/vals: the placed pairs (sorted in place); kscr/vscr: scratch of the same size (oversize path).
+// nbits: key bits in use; vbits: bits of the largest value.
+__global__ void __launch_bounds__(RS_THREADS)
+bp_bucket_kernel(uint64_t *__restrict__ keys, int *__restrict__ vals, uint64_t *__restrict__ kscr,
+                 int *__restrict__ vscr, const int *__restrict__ boff, const uint64_t *__restrict__ spl, int nb,
+                 int nbits, int vbits) {
+  __shared__ TileSmem sm;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int b = blockIdx.x;
+  const int64_t s0 = boff[b], s1 = boff[b + 1];
+  const int64_t size = s1 - s0;
+  if (size <= 1) return;
+  // (key - klo) of this bucket's pairs lies in [0, span]: `sbits` bits can differ
+  const uint64_t klo = spl[b];
+  const uint64_t kmax = (nbits >= 64) ? ~0ull : ((1ull << nbits) - 1ull);
+  const uint64_t khi = (b + 1 < nb) ? spl[b + 1] - 1 : kmax;
+  const uint64_t span = khi >= klo ? khi - klo : 0;
+  const int sbits = 64 - __clzll((long long)span);  // 0: all keys are equal
+  const int nvp = (vbits + 7) / 8;
+  uint64_t key[RS_ROUNDS];
+  int val[RS_ROUNDS], lrank[RS_ROUNDS];
+  unsigned dig[RS_ROUNDS];
+  if (size <= RS_TILE) {
+    const int count = (int)size;
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS; r++) {
+      const int j = w * (32 * RS_ROUNDS) + r * 32 + lane;
+      key[r] = (j < count) ? keys[s0 + j] : 0;
+      val[r] = (j < count) ? vals[s0 + j] : 0;
+    }
+    bool full = sbits == 0;
+    if (!full) {
+      const int shift0 = sbits > BP_SUBBITS ? sbits - BP_SUBBITS : 0;
+      const int npass = (sbits - shift0 + 7) / 8;
+      for (int pass = 0; pass < npass; pass++) {
+        tile_rank(sm, key, count, SubDigit{klo, shift0 + 8 * pass}, lrank, dig);
+        tile_place(sm, key, val, count, lrank, dig);
+        if (pass + 1 < npass) {
+#pragma unroll
+          for (int r = 0; r < RS_ROUNDS; r++) {
+            const int j = w * (32 * RS_ROUNDS) + r * 32 + lane;
+            if (j < count) { key[r] = sm.skey[j]; val[r] = sm.sval[j]; }
+          }
+          __syncthreads();
+        }
+      }
+      // runs that tie in the ranked bits: short ones are ordered here, a long one sends the bucket
+      // the long way
+      int ok = 1;
+      int len[RS_ROUNDS];
+#pragma unroll
+      for (int k = 0; k < RS_ROUNDS; k++) {
+        const int j = k * RS_THREADS + tid;
+        len[k] = (j < count) ? bp_run_length(sm.skey, count, j, klo, shift0, BP_MAX_RUN) : 0;
+        if (len[k] > BP_MAX_RUN) ok = 0;
+      }
+      full = !__syncthreads_and(ok);
+      if (!full) {
+#pragma unroll
+        for (int k = 0; k < RS_ROUNDS; k++)
+          if (len[k] >= 2) { GH_BP_STAT(3); bp_sort_run(sm.skey, sm.sval, k * RS_THREADS + tid, len[k]); }
+        __syncthreads();
+      }
+      if (full) {
+#pragma unroll
+        for (int r = 0; r < RS_ROUNDS; r++) {
+          const int j = w * (32 * RS_ROUNDS) + r * 32 + lane;
+          if (j < count) { key[r] = sm.skey[j]; val[r] = sm.sval[j]; }
+        }
+        __syncthreads();
+      }
+    }
+    if (tid == 0) GH_BP_STAT(full ? 1 : 0);
+    if (full) {  // block-uniform: value passes, then every key bit that can differ
+      const int nkp = (sbits + 7) / 8;
+      for (int pass = 0; pass < nvp + nkp; pass++) {
+#pragma unroll
+        for (int r = 0; r < RS_ROUNDS; r++) {
+          const bool valid = w * (32 * RS_ROUNDS) + r * 32 + lane < count;
+          const unsigned d = pass < nvp ? (unsigned)((val[r] >> (8 * pass)) & 0xff)
+                                        : SubDigit{klo, 8 * (pass - nvp)}(key[r]);
+          dig[r] = valid ? d : (0x100u + (unsigned)lane);
+        }
+        tile_rank_digits(sm, count, lrank, dig);
+        tile_place(sm, key, val, count, lrank, dig);
+        if (pass + 1 < nvp + nkp) {
+#pragma unroll
+          for (int r = 0; r < RS_ROUNDS; r++) {
+            const int j = w * (32 * RS_ROUNDS) + r * 32 + lane;
+            if (j < count) { key[r] = sm.skey[j]; val[r] = sm.sval[j]; }
+          }
+          __syncthreads();
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < RS_ROUNDS; k++) {
+      const int j = k * RS_THREADS + tid;
+      if (j < count) { keys[s0 + j] = sm.skey[j]; vals[s0 + j] = sm.sval[j]; }
+    }
+    return;
+  }
+  // oversize bucket: stable passes over global memory, tile after tile, by this CTA alone -- first
+  // over the value bits, then over the key bits that can differ.  An even number of passes, so
+  // that the result ends where it started (the extra pass sees equal digits).
+  __shared__ int ghist[RS_RADIX];
+  if (tid == 0) GH_BP_STAT(2);
+  const int nkp = (sbits + 7) / 8;
+  const int gp = (nvp + nkp + 1) & ~1;
+  uint64_t *kin = keys + s0, *kout = kscr + s0;
+  int *vin = vals + s0, *vout = vscr + s0;
+  const int ntiles = (int)((size + RS_TILE - 1) / RS_TILE);
+  for (int pass = 0; pass < gp; pass++) {
+    const SubDigit kd{klo, 8 * (pass - nvp)};
+    const int vshift = 8 * pass;
+    ghist[tid] = 0;
+    __syncthreads();
+    for (int64_t q = tid; q < size; q += RS_THREADS)
+      atomicAdd(&ghist[pass < nvp ? (unsigned)((vin[q] >> vshift) & 0xff) : kd(kin[q])], 1);
+    __syncthreads();
+    {  // exclusive scan of the digit counts -> running output offsets
+      const int g = ghist[tid];
+      const int gincl = warp_scan<int>(g, lane);
+      if (lane == 31) sm.wtot[w] = gincl;
+      __syncthreads();
+      int goff = 0;
+#pragma unroll
+      for (int k = 0; k < RS_WARPS; k++) goff += (k < w) ? sm.wtot[k] : 0;
+      __syncthreads();
+      ghist[tid] = goff + gincl - g;
+    }
+    __syncthreads();
+    for (int t = 0; t < ntiles; t++) {
+      const int64_t t0 = (int64_t)t * RS_TILE;
+      const int count = (int)((size - t0) < RS_TILE ? (size - t0) : RS_TILE);
+#pragma unroll
+      for (int r = 0; r < RS_ROUNDS; r++) {
+        const int j = w * (32 * RS_ROUNDS) + r * 32 + lane;
+        key[r] = (j < count) ? kin[t0 + j] : 0;
+        val[r] = (j < count) ? vin[t0 + j] : 0;
+        const unsigned d = pass < nvp ? (unsigned)((val[r] >> vshift) & 0xff) : kd(key[r]);
+        dig[r] = (j < count) ? d : (0x100u + (unsigned)lane);
+      }
+      const int tot = tile_rank_digits(sm, count, lrank, dig);
+      tile_place(sm, key, val, count, lrank, dig);
+#pragma unroll
+      for (int k = 0; k < RS_ROUNDS; k++) {
+        const int j = k * RS_THREADS + tid;
+        if (j < count) {
+          const uint64_t kk = sm.skey[j];
+          const int vv = sm.sval[j];
+          const int d = (int)(pass < nvp ? (unsigned)((vv >> vshift) & 0xff) : kd(kk));
+          const int64_t g = (int64_t)ghist[d] + (j - sm.dstart[d]);
+          kout[g] = kk;
+          vout[g] = vv;
+        }
+      }
+      __syncthreads();
+      ghist[tid] += tot;  // this tile's pairs of digit tid are placed
+      __syncthreads();
+    }
+    uint64_t *tk = kin; kin = kout; kout = tk;
+    int *tv = vin; vin = vout; vout = tv;
+    __threadfence_block();
+    __syncthreads();
+  }
+}
+
 // spl[b] = the (b n / nb)-th sorted key (b = 1 .. nb-1), spl[0] = 0: the next step's buckets
 __global__ void bs_splitters_kernel(const uint64_t *__restrict__ sorted, int64_t n, int nb, uint64_t *__restrict__ spl,
                                     const int *__restrict__ ndev) {
@@ -357,10 +690,10 @@ __global__ void bs_splitters_kernel(const uint64_t *__restrict__ sorted, int64_t
 
 #ifndef GH_HOST_EMU
 struct SplitterState {
-  DeviceBuffer spl, boff;
+  DeviceBuffer spl, boff, bid, cnt;
   int nb = 0;          // buckets the stored splitters describe (0 = none)
   int64_t cap = 0;     // capacity (n) they were taken for
-  void release() { spl.release(); boff.release(); nb = 0; }
+  void release() { spl.release(); boff.release(); bid.release(); cnt.release(); nb = 0; }
 };
 static inline int bs_buckets_for(int64_t n) {
   int64_t nb = (n + BS_TARGET - 1) / BS_TARGET;
@@ -397,6 +730,32 @@ static int splitter_sort_pairs(uint64_t *kA, int *vA, uint64_t *kB, int *vB, int
   bs_offsets_kernel<<<(ss.nb + 1 + 255) / 256, 256, 0, st>>>(kA, n, bo, ss.boff.as<int>(), ndev);
   GH_LAUNCH_CHECK();
   bs_bucket_kernel<<<ss.nb, RS_THREADS, 0, st>>>(kA, vA, kB, vB, ss.boff.as<int>(), ss.spl.as<uint64_t>(), ss.nb, nbits);
+  GH_LAUNCH_CHECK();
+  return GH_OK;
+}
+
+// The "place" form (see bp_count_kernel).  Result in (kB, vB); (kA, vA) is clobbered (scratch of the
+// oversize path).  The values of the input must ascend (vA[q] < vA[q+1]): the result is then the
+// stable sort's.
+static int splitter_place_sort_pairs(uint64_t *kA, int *vA, uint64_t *kB, int *vB, int64_t n, int nbits,
+                                     SplitterState &ss, cudaStream_t st, const int *ndev) {
+  if (n <= 1) return GH_OK;
+  GH_TRY(ss.bid.reserve(sizeof(unsigned short) * (size_t)n));
+  GH_TRY(ss.cnt.reserve(sizeof(int) * (size_t)(2 * ss.nb + 2)));
+  GH_TRY(ss.boff.reserve(sizeof(int) * (size_t)(ss.nb + 2)));
+  int *count = ss.cnt.as<int>(), *cursor = count + ss.nb + 1;
+  GH_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * (size_t)ss.nb, st));
+  const unsigned nblocks = (unsigned)((n + BP_THREADS * BP_ROUNDS - 1) / (BP_THREADS * BP_ROUNDS));
+  const uint64_t *spl = ss.spl.as<uint64_t>();
+  bp_count_kernel<<<nblocks, BP_THREADS, 0, st>>>(kA, n, spl, ss.nb, ss.bid.as<unsigned short>(), count, ndev);
+  GH_LAUNCH_CHECK();
+  bp_scan_kernel<<<1, RS_THREADS, 0, st>>>(count, ss.nb, ss.boff.as<int>(), cursor);
+  GH_LAUNCH_CHECK();
+  bp_place_kernel<<<nblocks, BP_THREADS, 0, st>>>(kA, vA, ss.bid.as<unsigned short>(), n, cursor, kB, vB, ndev);
+  GH_LAUNCH_CHECK();
+  int vbits = 1;
+  while (vbits < 31 && (int64_t(1) << vbits) < n) vbits++;
+  bp_bucket_kernel<<<ss.nb, RS_THREADS, 0, st>>>(kB, vB, kA, vA, ss.boff.as<int>(), spl, ss.nb, nbits, vbits);
   GH_LAUNCH_CHECK();
   return GH_OK;
 }

@@ -111,6 +111,10 @@ static inline unsigned nblk(int64_t n, int b) { return (unsigned)((n + b - 1) / 
 
 // walk selection: GH_WALK_GROUP (default; fp32 only) or GH_WALK_TARGET (the reference's per-target
 // criterion; always used in fp64).  Process-wide; GH_TREE_WALK=target|group sets the initial value.
+// sort of a running simulation's steps (tree_impl): 1 = bucket, 2 = place (bucketsort.cuh); GH_SORT overrides
+#ifndef GH_SORT_DEFAULT
+#define GH_SORT_DEFAULT 1
+#endif
 #ifndef GH_WALK_HYBRID_DEFAULT
 #define GH_WALK_HYBRID_DEFAULT 0.10f
 #endif
@@ -345,15 +349,21 @@ struct TreeRun {
       // A running simulation (a.coherent) sorts with the buckets the previous step left behind
       // (bucketsort.cuh: 3 trips through global memory instead of 8); the first step after an
       // upload, stateless calls and small systems use the classic LSD sort.  GH_SORT=classic|bucket.
-      static const int sort_mode = [] {
+      static const int sort_mode = [] {  // 0 classic, 1 bucket (two partition passes), 2 place (count + place)
         const char *env = getenv("GH_SORT");
-        return (env && !strcmp(env, "classic")) ? 0 : 1;
+        if (env && !strcmp(env, "classic")) return 0;
+        if (env && !strcmp(env, "place")) return 2;
+        if (env && !strcmp(env, "bucket")) return 1;
+        return GH_SORT_DEFAULT;
       }();
       // Single rank only: a rank's key range moves by ~1 % of its particles per step, and the keys
       // it gains all land in the first or last bucket, which then takes the slow oversize path
       // (measured at 8 GPUs: 0.7 ms of skew at the next exchange).
-      const bool bucket = sort_mode == 1 && a.coherent && !ph.dist && w->ss.nb >= BS_MIN_BUCKETS && w->ss.cap == ph.n;
-      if (bucket) {
+      const bool bucket = sort_mode >= 1 && a.coherent && !ph.dist && w->ss.nb >= BS_MIN_BUCKETS && w->ss.cap == ph.n;
+      if (bucket && sort_mode == 2) {
+        GH_TRY(splitter_place_sort_pairs(hi, idx, hi2, idx2, ph.n, 63, w->ss, st, ph.ndev));
+        inB = true;
+      } else if (bucket) {
         GH_TRY(splitter_sort_pairs(hi, idx, hi2, idx2, ph.n, 63, w->rs, w->ss, st, ph.ndev));
         inB = false;
       } else {
@@ -361,7 +371,7 @@ struct TreeRun {
       }
       ph.shi = inB ? hi2 : hi;
       ph.sidx = inB ? idx2 : idx;
-      if (a.coherent && sort_mode == 1 && !ph.dist) GH_TRY(splitter_refresh(w->ss, ph.shi, ph.n, st, ph.ndev));
+      if (a.coherent && sort_mode >= 1 && !ph.dist) GH_TRY(splitter_refresh(w->ss, ph.shi, ph.n, st, ph.ndev));
       else w->ss.nb = 0;
     }
     if (ph.dist) {

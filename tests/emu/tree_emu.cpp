@@ -159,12 +159,29 @@ static void emu_splitter_sort(uint64_t *kA, int *vA, uint64_t *kB, int *vB, int6
   emu::launch((unsigned)nb, RS_THREADS, [&] { bs_bucket_kernel(kA, vA, kB, vB, boff.data(), spl, nb, nbits); });
 }
 
+// splitter_place_sort_pairs of bucketsort.cuh, launch for launch (result in kB / vB)
+static void emu_place_sort(uint64_t *kA, int *vA, uint64_t *kB, int *vB, int64_t n, int nbits, const uint64_t *spl,
+                           int nb, const int *ndev) {
+  std::vector<unsigned short> bid((size_t)n);
+  std::vector<int> count(nb + 1, 0), cursor(nb + 1, 0), boff(nb + 2, 0);
+  const unsigned nblocks = (unsigned)((n + BP_THREADS * BP_ROUNDS - 1) / (BP_THREADS * BP_ROUNDS));
+  emu::launch(nblocks, BP_THREADS, [&] { bp_count_kernel(kA, n, spl, nb, bid.data(), count.data(), ndev); });
+  emu::launch(1, RS_THREADS, [&] { bp_scan_kernel(count.data(), nb, boff.data(), cursor.data()); });
+  emu::launch(nblocks, BP_THREADS, [&] { bp_place_kernel(kA, vA, bid.data(), n, cursor.data(), kB, vB, ndev); });
+  int vbits = 1;
+  while (vbits < 31 && (int64_t(1) << vbits) < n) vbits++;
+  emu::launch((unsigned)nb, RS_THREADS, [&] { bp_bucket_kernel(kB, vB, kA, vA, boff.data(), spl, nb, nbits, vbits); });
+}
+
 extern "C" {
 // keys[n] (63-bit), vals = 0..n-1.  The splitters are the (b n_spl / nb)-th keys of the sorted array
 // `spl_from` (n_spl keys: the same data = fresh splitters, other data = stale ones).  n_real <= n:
 // the device-side count.  Outputs the splitter sort's keys / vals; returns 0.
+// stats_out (nullable, 4): which way the "place" form's buckets went (g_bp_stats of bucketsort.cuh).
+// place != 0: the "place" form (one counting and one placing pass, compact in-bucket ranking).
 int emu_splitter_sort_test(const uint64_t *keys, int64_t n, int64_t n_real, const uint64_t *spl_from, int64_t n_spl,
-                           int nb, uint64_t *keys_out, int *vals_out) {
+                           int nb, uint64_t *keys_out, int *vals_out, int place, long long *stats_out) {
+  for (int k = 0; k < 4; k++) g_bp_stats[k] = 0;
   std::vector<uint64_t> kA(keys, keys + n), kB(n);
   std::vector<int> vA(n), vB(n);
   for (int64_t i = 0; i < n; i++) vA[i] = (int)i;
@@ -172,6 +189,13 @@ int emu_splitter_sort_test(const uint64_t *keys, int64_t n, int64_t n_real, cons
   const int nsp = (int)n_spl;
   emu::launch((unsigned)((nb + 255) / 256), 256, [&] { bs_splitters_kernel(spl_from, n_spl, nb, spl.data(), &nsp); }, true);
   const int nr = (int)n_real;
+  if (place) {
+    emu_place_sort(kA.data(), vA.data(), kB.data(), vB.data(), n, 63, spl.data(), nb, &nr);
+    std::memcpy(keys_out, kB.data(), sizeof(uint64_t) * (size_t)n_real);
+    std::memcpy(vals_out, vB.data(), sizeof(int) * (size_t)n_real);
+    if (stats_out) for (int k = 0; k < 4; k++) stats_out[k] = g_bp_stats[k];
+    return 0;
+  }
   emu_splitter_sort(kA.data(), vA.data(), kB.data(), vB.data(), n, 63, spl.data(), nb, &nr);
   std::memcpy(keys_out, kA.data(), sizeof(uint64_t) * (size_t)n_real);
   std::memcpy(vals_out, vA.data(), sizeof(int) * (size_t)n_real);

@@ -209,12 +209,14 @@ def test_splitter_sort_steps_equal_classic_sort_steps(tmp_path):
     """A running fp32 tree simulation sorts its Morton keys with the buckets the previous step left
     behind (csrc/bucketsort.cuh); the result is the classic LSD sort's, so six steps of N = 400,000
     (293 buckets; dt = 1 Myr moves every particle out of its bucket every step) give bit-identical
-    positions under GH_SORT=bucket and GH_SORT=classic."""
+    positions under GH_SORT=bucket, GH_SORT=place (one counting + one placing pass with atomics: the
+    order inside a bucket is arbitrary on entry, the in-bucket sort orders by (key, index)) and
+    GH_SORT=classic."""
     import os
     import subprocess
     import sys
     out = {}
-    for mode in ("bucket", "classic"):
+    for mode in ("bucket", "place", "classic"):
         f = str(tmp_path / (mode + ".npy"))
         env = dict(os.environ, GH_SORT=mode)
         r = subprocess.run([sys.executable, "-c", _SORT_RUN % ROOT, f], env=env, capture_output=True, text=True,
@@ -223,6 +225,7 @@ def test_splitter_sort_steps_equal_classic_sort_steps(tmp_path):
         out[mode] = np.load(f)
     assert np.isfinite(out["bucket"]).all()
     assert np.array_equal(out["bucket"], out["classic"])
+    assert np.array_equal(out["place"], out["classic"])
 
 
 def test_fp32_origin_moves_with_the_system():

@@ -27,7 +27,7 @@ LIB = os.path.join(ROOT, "tests", "emu", "libtree_emu.so")
 def temu():
     csrc = os.path.join(ROOT, "gravhopper_b200", "csrc")
     deps = [SRC, os.path.join(ROOT, "tests", "emu", "emu_shim.h")] + \
-           [os.path.join(csrc, f) for f in ("build.cuh", "sortscan.cuh", "walk.cuh", "common.cuh")]
+           [os.path.join(csrc, f) for f in ("build.cuh", "sortscan.cuh", "bucketsort.cuh", "walk.cuh", "common.cuh")]
     if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
         cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
         out = subprocess.run(["g++", "-O1", "-std=c++20", "-shared", "-fPIC", "-pthread", "-I" + cuda_inc,
@@ -38,7 +38,7 @@ def temu():
     vp = C.c_void_p
     lib.emu_tree_build.argtypes = [C.c_int, vp, vp, C.c_int64, C.c_double, C.c_double, vp, vp, C.c_int, vp, vp,
                                    vp, vp, vp, C.c_int, vp]
-    lib.emu_splitter_sort_test.argtypes = [vp, C.c_int64, C.c_int64, vp, C.c_int64, C.c_int, vp, vp]
+    lib.emu_splitter_sort_test.argtypes = [vp, C.c_int64, C.c_int64, vp, C.c_int64, C.c_int, vp, vp, C.c_int, vp]
     lib.emu_tree_build_dist.argtypes = [C.c_int, vp, vp, vp, C.c_int64, C.c_double, C.c_double, vp, C.c_int, vp, vp,
                                         vp, vp, vp, vp, vp, C.c_int]
     return lib
@@ -281,12 +281,16 @@ def test_distributed_walk_deals_the_global_morton_order(temu, emu, world, blk, h
 
 
 # ---- splitter sort (csrc/bucketsort.cuh): the running simulation's sort ---------------------------------
-@pytest.mark.parametrize("case", ["fresh", "stale", "oversize", "duplicates", "partial"])
-def test_splitter_sort_equals_the_stable_sort(temu, case):
-    """Two partition passes by bucket id + one in-shared-memory sort per bucket give the stable
-    sort's result, bit for bit: with this step's own splitters, with another data set's (stale)
-    splitters, with buckets far beyond a tile (the CTA-local global-memory path), with many equal
-    keys, and with a device-side count below the capacity."""
+@pytest.mark.parametrize("place", [0, 1], ids=["partition", "place"])
+@pytest.mark.parametrize("case", ["fresh", "stale", "oversize", "duplicates", "partial", "clump", "lowbits", "equal", "adjacent"])
+def test_splitter_sort_equals_the_stable_sort(temu, case, place):
+    """Both forms of the splitter sort -- two partition passes by bucket id + one in-shared-memory
+    sort per bucket; one counting + one placing pass with atomics + a compact ranking per bucket --
+    give the stable sort's result, bit for bit: with this step's own splitters, with another data
+    set's (stale) splitters, with buckets far beyond a tile (the CTA-local global-memory path), with
+    many equal keys (also of two adjacent values), with a device-side count below the capacity, with a tight clump in a corner of
+    a bucket's key range (long runs of ties in the ranked bits: the long way), with keys that differ
+    only below the ranked bits (short runs: insertion), and with buckets of identical keys."""
     rng = np.random.default_rng(11)
     n = 9000
     keys = rng.integers(0, 2 ** 63, size=n, dtype=np.uint64)
@@ -304,15 +308,48 @@ def test_splitter_sort_equals_the_stable_sort(temu, case):
         spl_from = np.sort(keys)
     elif case == "partial":
         n_real = 6500
+    elif case == "clump":
+        # 700 keys within 2^20 of each other inside buckets that span ~2^55 (stale, coarse splitters)
+        keys[:700] = np.uint64(2 ** 61) + rng.integers(0, 2 ** 20, 700, dtype=np.uint64)
+        keys[700:1400] = np.uint64(3 * 2 ** 60) + rng.integers(0, 4, 700, dtype=np.uint64)   # and heavy ties
+        spl_from = np.sort(rng.integers(0, 2 ** 63, size=5000, dtype=np.uint64))
+        nb = 257
+    elif case == "lowbits":
+        # pairs / triples that agree in all but their lowest bits, spread over the whole key space
+        base = rng.integers(0, 2 ** 62, size=3000, dtype=np.uint64) << np.uint64(1)
+        keys = np.concatenate([base, base + np.uint64(1), base[:1500] + np.uint64(1), base[:1500]])
+        rng.shuffle(keys)
+        n = n_real = len(keys)
+        spl_from = np.sort(keys)
+    elif case == "equal":
+        keys[:] = keys[rng.integers(0, 3, n)]                 # three distinct values: buckets of one value
+        spl_from = np.sort(keys)
+    elif case == "adjacent":
+        # 1000 copies each of two ADJACENT key values: the bucket of the first spans no bits at all
+        keys[:1000] = np.uint64(5 * 2 ** 60)
+        keys[1000:2000] = np.uint64(5 * 2 ** 60 + 1)
+        spl_from = np.sort(keys)
+    keys = np.ascontiguousarray(keys)
     out_k = np.zeros(n_real, dtype=np.uint64)
     out_v = np.zeros(n_real, dtype=np.int32)
     spl_from = np.ascontiguousarray(spl_from)
+    stats = np.zeros(4, dtype=np.int64)
     rc = temu.emu_splitter_sort_test(keys.ctypes.data, n, n_real, spl_from.ctypes.data, len(spl_from), nb,
-                                     out_k.ctypes.data, out_v.ctypes.data)
+                                     out_k.ctypes.data, out_v.ctypes.data, place, stats.ctypes.data)
     assert rc == 0
     order = np.argsort(keys[:n_real], kind="stable")
-    assert np.array_equal(out_v, order.astype(np.int32))
     assert np.array_equal(out_k, keys[:n_real][order])
+    assert np.array_equal(out_v, order.astype(np.int32))
+    if place:  # the cases reach the paths they were made for
+        compact, long_way, oversize, runs = stats
+        print(case, stats)
+        assert compact > 0 or case == "equal"
+        if case in ("clump", "duplicates", "adjacent"):
+            assert long_way > 0
+        if case in ("oversize", "equal"):
+            assert oversize > 0
+        if case == "lowbits":
+            assert runs > 100 and long_way == 0
 
 
 def test_quadrupole_extension_equals_its_cpu_model(temu, emu, oracle, golden):
