@@ -790,6 +790,147 @@ __global__ void GH_EMIT_BOUNDS emit_kernel(const double4 *__restrict__ sp, const
 }
 
 
+// ---- K6b emit, fp32 tree, warp-cooperative ("warp" form) ---------------------------------------------
+// emit_kernel gives every particle a thread that loops over the cells the particle opens: ncu at
+// N = 4M counts 6.4 active lanes per instruction (only a third of the particles open cells, and
+// their loops have different lengths), 1170 instructions per warp.  Here a warp owns 32 sorted
+// particles, writes their 32 leaves together, numbers the cells they open (a warp scan of the
+// counts) and deals those cells to its lanes -- one cell per lane, the same arithmetic as
+// emit_kernel's (centre: closed form at the first level the owner opens, then the owner's descent;
+// end of the cell: the same search; moments: the same differences), so the entries are
+// bit-identical (tests/emu compares the two kernels' arrays).  fp32 entries only, no quadrupoles.
+__global__ void __launch_bounds__(128)
+emit32_warp_kernel(const double4 *__restrict__ sp, const uint64_t *__restrict__ hi,
+                   const signed char *__restrict__ clev, const int *__restrict__ base /* n+1 */,
+                   const D4 *__restrict__ P, int64_t n, const double *__restrict__ root, Entries<float> E,
+                   int *__restrict__ maxlevel, BuildCtl *__restrict__ ctl, bool dist) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wbase = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
+  if (dist) n = ctl->n_local;
+  if (wbase >= n) return;  // the whole warp
+  const int64_t p = wbase + lane;
+  const bool valid = p < n;
+  const int seg = ctl->seg, seg_next = ctl->seg_next, seg_cap = ctl->seg + ctl->stride;
+  const int c = valid ? (int)clev[p] : -1;
+  int cprev = __shfl_up_sync(0xffffffffu, c, 1);
+  if (lane == 0) cprev = (p > 0) ? (int)clev[p - 1] : ctl->cprev;
+  const int ncell = (valid && c > cprev) ? c - cprev : 0;
+  const int e0 = valid ? seg + base[p] : 0;
+  const uint64_t h0 = valid ? hi[p] : 0;
+  if (valid) {
+    // the particle's own leaf: COM = particle position (:473-475), always accepted (:502)
+    const double4 self = sp[p];
+    float4 com, cen;
+    com.x = (float)(self.x - root[0]);
+    com.y = (float)(self.y - root[1]);
+    com.z = (float)(self.z - root[2]);
+    com.w = (float)self.w;
+    cen.x = cen.y = cen.z = 0.f;
+    const int e = e0 + ncell;
+    const int after = (p + 1 < n) ? e + 1 : seg_next;
+    if (e >= seg_cap) {
+      ctl->overflow = 1;
+    } else {
+      cen.w = __int_as_float((int)(((unsigned)LEAF_LEVEL << SKIP_BITS) | (unsigned)after));
+      pack_node(E.node[e], cen, com);
+    }
+  }
+  const int wmax = __reduce_max_sync(0xffffffffu, ncell > 0 ? c : 0);
+  if (lane == 0 && wmax > 0) atomicMax(maxlevel, wmax);
+
+  // the cells: task t of the warp = cell number t - off of the lane whose inclusive count first exceeds t
+  const int incl = warp_scan<int>(ncell, lane);
+  const int off = incl - ncell;
+  const int T = __shfl_sync(0xffffffffu, incl, 31);
+  for (int t0 = 0; t0 < T; t0 += 32) {
+    const int t = t0 + lane;
+    const bool act = t < T;
+    int lo_l = 0, hi_l = 31;
+#pragma unroll
+    for (int s = 0; s < 5; s++) {
+      const int mid = (lo_l + hi_l) >> 1;
+      const int v = __shfl_sync(0xffffffffu, incl, mid);
+      if (v > t) hi_l = mid; else lo_l = mid + 1;
+    }
+    const int owner = lo_l < 31 ? lo_l : 31;
+    const int o_off = __shfl_sync(0xffffffffu, off, owner);
+    const int o_cprev = __shfl_sync(0xffffffffu, cprev, owner);
+    const int o_e0 = __shfl_sync(0xffffffffu, e0, owner);
+    const uint64_t o_h = __shfl_sync(0xffffffffu, h0, owner);
+    if (!act) continue;
+    const int level = o_cprev + 1 + (t - o_off);
+    const int64_t pt = wbase + owner;
+    // centre and side of the cell: as emit_kernel forms them for its particle
+    double cc[3] = {root[0], root[1], root[2]};
+    double size = root[3];
+    int l0 = 0;
+    if (o_cprev >= 0) {
+      l0 = o_cprev + 1;
+      const double sL = ldexp(size, -l0);
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const uint64_t ik = compact3(o_h >> k) >> (LEVELS_HI - l0);
+        cc[k] = root[k] - 0.5 * size + ((double)ik + 0.5) * sL;
+      }
+      size = sL;
+    }
+    for (int l = l0 + 1; l <= level; l++) {  // the owner's descent (:406,:441-462)
+      const unsigned d = (unsigned)((o_h >> (3 * (LEVELS_HI - l))) & 7u);
+      const double quarter = __dmul_rn(0.5, __dmul_rn(0.5, size));
+#pragma unroll
+      for (int k = 0; k < 3; k++) cc[k] = __dadd_rn(cc[k], ((d >> k) & 1u) ? quarter : -quarter);
+      size = __dmul_rn(0.5, size);
+    }
+    // last sorted particle b sharing `level` octant levels with pt (emit_kernel's search)
+    int64_t lo_i = pt + 1, step = 1, hi_i;
+    bool found = false;
+    for (int u = 0; u < 12 && lo_i < n; u++) {
+      if (clev[lo_i] < level) { found = true; break; }
+      lo_i++;
+    }
+    if (lo_i >= n) { lo_i = n - 1; found = true; }
+    hi_i = lo_i;
+    if (!found) for (;;) {
+      const int64_t q = lo_i + step;
+      if (q >= n) { hi_i = n - 1; break; }
+      if (same_prefix(hi[q], 0, o_h, 0, level)) { lo_i = q; step <<= 1; }
+      else { hi_i = q - 1; break; }
+    }
+    while (!found && lo_i < hi_i) {
+      const int64_t mid = (lo_i + hi_i + 1) >> 1;
+      if (same_prefix(hi[mid], 0, o_h, 0, level)) lo_i = mid;
+      else hi_i = mid - 1;
+    }
+    const int64_t b = lo_i;
+    const bool beyond = (b == n - 1) && (ctl->cnext >= level);
+    double mh[4];
+    int skipidx;
+    if (beyond) {
+      moment_diff_beyond(P, pt, ctl, level, mh);
+      skipidx = ctl->xskip[level];
+    } else {
+      moment_diff(P, pt, b, mh);
+      skipidx = (b + 1 < n) ? seg + base[b + 1] : seg_next;
+    }
+    float4 com, cen;
+    com.x = (float)(mh[1] / mh[0]);
+    com.y = (float)(mh[2] / mh[0]);
+    com.z = (float)(mh[3] / mh[0]);
+    com.w = (float)mh[0];
+    cen.x = (float)(cc[0] - root[0]);
+    cen.y = (float)(cc[1] - root[1]);
+    cen.z = (float)(cc[2] - root[2]);
+    const int e = o_e0 + (level - (o_cprev + 1));
+    if (e < seg_cap) {
+      cen.w = __int_as_float((int)(((unsigned)level << SKIP_BITS) | (unsigned)skipidx));
+      pack_node(E.node[e], cen, com);
+    } else {
+      ctl->overflow = 1;
+    }
+  }
+}
+
+
 // ---- distributed walk: kick and drift of the OWNED particles -------------------------------------
 // After the all-gather of the accelerations.  Sorted particle j of rank q's range was walked by rank
 // (kb + q) % world for block kb = j / blk; its acceleration sits in that rank's buffer at slot

@@ -115,6 +115,10 @@ static inline unsigned nblk(int64_t n, int b) { return (unsigned)((n + b - 1) / 
 #ifndef GH_SORT_DEFAULT
 #define GH_SORT_DEFAULT 1
 #endif
+// emit of the fp32 tree: 0 = one thread per particle, 1 = warp-cooperative; GH_EMIT overrides
+#ifndef GH_EMIT_DEFAULT
+#define GH_EMIT_DEFAULT 0
+#endif
 #ifndef GH_WALK_HYBRID_DEFAULT
 #define GH_WALK_HYBRID_DEFAULT 0.10f
 #endif
@@ -216,6 +220,22 @@ static int64_t entry_capacity(TreeWorkspace *w, int64_t n, bool fp32) {
   if (fp32 && want >= (1 << SKIP_BITS)) want = (1 << SKIP_BITS) - 1;
   return want;
 }
+
+// emit of the fp32 tree, warp-cooperative form (emit32_warp_kernel); false: not this precision
+template <class Real> struct Emit32 {
+  static bool launch(const double4 *, const uint64_t *, const signed char *, const int *, const void *, int64_t,
+                     const double *, void *, int *, BuildCtl *, bool, cudaStream_t) { return false; }
+};
+template <> struct Emit32<float> {
+  static bool launch(const double4 *sp, const uint64_t *shi, const signed char *clev, const int *base, const void *P,
+                     int64_t n, const double *root, void *nodes, int *maxlevel, BuildCtl *ctl, bool dist,
+                     cudaStream_t st) {
+    Entries<float> E{static_cast<Node<float> *>(nodes), nullptr};
+    emit32_warp_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(sp, shi, clev, base, static_cast<const D4 *>(P), n, root,
+                                                                    E, maxlevel, ctl, dist);
+    return true;
+  }
+};
 
 template <class Src, class Real>
 struct TreeRun {
@@ -444,6 +464,20 @@ struct TreeRun {
     int *maxlevel = w->misc.as<int>();
     GH_CUDA(cudaMemsetAsync(w->misc.ptr, 0, 64, st));
     if (ph.quad) GH_TRY(w->quad.reserve(sizeof(Real) * 6 * (size_t)ph.end));
+    // fp32 entries without quadrupoles: the warp-cooperative form (build.cuh), same array bit for bit.
+    // GH_EMIT=thread|warp.
+    static const int emit_mode = [] {
+      const char *env = getenv("GH_EMIT");
+      if (env && !strcmp(env, "thread")) return 0;
+      if (env && !strcmp(env, "warp")) return 1;
+      return GH_EMIT_DEFAULT;
+    }();
+    if (emit_mode == 1 && !ph.quad &&
+        Emit32<Real>::launch(w->sorted.as<double4>(), ph.shi, w->clev.as<signed char>(), w->base.as<int>(), w->P.ptr, n,
+                             w->root.as<double>(), w->node.ptr, maxlevel, ctl, ph.dist, st)) {
+      GH_LAUNCH_CHECK();
+      return GH_OK;
+    }
     emit_kernel<Src, Real><<<nblk(n, 128), 128, 0, st>>>(w->sorted.as<double4>(), ph.shi, ph.slo,
                                                        w->clev.as<signed char>(), w->base.as<int>(),
                                                        w->P.as<Mom>(), n, w->root.as<double>(), rel_origin,

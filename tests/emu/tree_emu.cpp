@@ -131,6 +131,23 @@ static int build_impl(const double *pos, const double *mass, int64_t n, double e
   }, true);
   info_out[1] = maxlevel;
   info_out[2] = ctl.overflow;
+  if (sizeof(Real) == 4 && !quad_out) {
+    // the warp-cooperative form of the emit (emit32_warp_kernel) must write the same array, bit for bit
+    const int filled = ctl.stride < nentries ? ctl.stride : nentries;
+    std::vector<Node<float>> alt((size_t)filled + 1);
+    std::memset(alt.data(), 0xff, sizeof(Node<float>) * alt.size());
+    BuildCtl ctl2;
+    std::memset(&ctl2, 0, sizeof(ctl2));
+    emu::launch(1, 1, [&] { ctl_init_single(&ctl2, (int)n, seg_cap > 0 ? seg_cap : nentries); }, true);
+    int maxlevel2 = 0;
+    Entries<float> E2{alt.data(), nullptr};
+    emu::launch(nblk(n, 128), 128, [&] {
+      emit32_warp_kernel(sp.data(), shi, clev.data(), base.data(), reinterpret_cast<const D4 *>(P.data()), n, root.data(),
+                         E2, &maxlevel2, &ctl2, false);
+    });
+    if (maxlevel2 != maxlevel || ctl2.overflow != ctl.overflow) return 7;
+    if (std::memcmp(alt.data(), nodes_out, sizeof(Node<float>) * (size_t)filled) != 0) return 7;
+  }
   if (keys_out) std::memcpy(keys_out, shi, sizeof(uint64_t) * (size_t)n);
   std::memcpy(sorted_out, sp.data(), sizeof(double4) * (size_t)n);
   std::memcpy(order_out, sidx, sizeof(int) * (size_t)n);
@@ -299,6 +316,23 @@ int emu_tree_build_dist(int world, const uint64_t *split, const double *pos, con
       emit_kernel<Src64, float>(k.sp.data(), k.shi, nullptr, k.clev.data(), k.base.data(), k.P.data(), n, root.data(),
                                 true, inv_theta2, E, &maxlevel, &k.ctl, true);
     }, true);
+    {  // the warp-cooperative form writes the same segment
+      std::vector<Node<float>> alt((size_t)world * stride);
+      std::memset(alt.data(), 0xff, sizeof(Node<float>) * alt.size());
+      BuildCtl c2 = k.ctl;
+      c2.overflow = 0;
+      // (the thread form raised the flag itself or inherited none: stitch sets it before the emit)
+      int ml2 = 0;
+      Entries<float> E2{alt.data(), nullptr};
+      BuildCtl before = k.ctl;
+      (void)before;
+      emu::launch(nblk(n, 128), 128, [&] {
+        emit32_warp_kernel(k.sp.data(), k.shi, k.clev.data(), k.base.data(), k.P.data(), n, root.data(), E2, &ml2, &c2, true);
+      });
+      const int fill = k.ctl.nentries < stride ? k.ctl.nentries : stride;
+      if (std::memcmp(alt.data() + (size_t)r * stride, E.node + (size_t)r * stride, sizeof(Node<float>) * (size_t)fill) != 0) return 7;
+      if (ml2 > maxlevel) return 7;
+    }
     if (k.ctl.overflow) rc = 2;
     counts_out[2 * r] = k.ctl.n_local;
     counts_out[2 * r + 1] = k.ctl.nentries;

@@ -211,21 +211,25 @@ def test_splitter_sort_steps_equal_classic_sort_steps(tmp_path):
     (293 buckets; dt = 1 Myr moves every particle out of its bucket every step) give bit-identical
     positions under GH_SORT=bucket, GH_SORT=place (one counting + one placing pass with atomics: the
     order inside a bucket is arbitrary on entry, the in-bucket sort orders by (key, index)) and
-    GH_SORT=classic."""
+    GH_SORT=classic; and under GH_EMIT=warp (the warp-cooperative form of the emit kernel, which
+    writes the same entry array) as under GH_EMIT=thread."""
     import os
     import subprocess
     import sys
     out = {}
-    for mode in ("bucket", "place", "classic"):
-        f = str(tmp_path / (mode + ".npy"))
-        env = dict(os.environ, GH_SORT=mode)
+    modes = {"classic": dict(GH_SORT="classic", GH_EMIT="thread"), "bucket": dict(GH_SORT="bucket", GH_EMIT="thread"),
+             "place": dict(GH_SORT="place", GH_EMIT="thread"), "warp": dict(GH_SORT="classic", GH_EMIT="warp"),
+             "place+warp": dict(GH_SORT="place", GH_EMIT="warp")}
+    for mode, envs in modes.items():
+        f = str(tmp_path / (mode.replace("+", "_") + ".npy"))
+        env = dict(os.environ, **envs)
         r = subprocess.run([sys.executable, "-c", _SORT_RUN % ROOT, f], env=env, capture_output=True, text=True,
                            timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
         out[mode] = np.load(f)
-    assert np.isfinite(out["bucket"]).all()
-    assert np.array_equal(out["bucket"], out["classic"])
-    assert np.array_equal(out["place"], out["classic"])
+    assert np.isfinite(out["classic"]).all()
+    for mode in modes:
+        assert np.array_equal(out[mode], out["classic"]), mode
 
 
 def test_fp32_origin_moves_with_the_system():
