@@ -377,7 +377,10 @@ bs_bucket_kernel(uint64_t *__restrict__ keys, int *__restrict__ vals, uint64_t *
 static constexpr int BP_THREADS = 256;
 static constexpr int BP_ROUNDS = 8;      // pairs per thread in the count / place kernels
 static constexpr int BP_COARSE = 16;     // every 16th splitter is staged in shared memory (16 x 8 B = one line)
-static constexpr int BP_SUBBITS = 24;
+#ifndef GH_BP_SUBBITS
+#define GH_BP_SUBBITS 24
+#endif
+static constexpr int BP_SUBBITS = GH_BP_SUBBITS;
 static constexpr int BP_MAX_RUN = 16;
 
 __device__ __forceinline__ int bp_bucket_of(const uint64_t *coarse, int nc, const uint64_t *__restrict__ spl, int nb,
@@ -513,7 +516,10 @@ __device__ __forceinline__ void bp_sort_run(uint64_t *k, int *v, int j, int len)
 
 // keys/vals: the placed pairs (sorted in place); kscr/vscr: scratch of the same size (oversize path).
 // nbits: key bits in use; vbits: bits of the largest value.
-__global__ void __launch_bounds__(RS_THREADS)
+#ifndef GH_BP_MINBLOCKS
+#define GH_BP_MINBLOCKS 4  // 64 registers: as many resident CTAs as bs_bucket_kernel (the ranking is latency bound)
+#endif
+__global__ void __launch_bounds__(RS_THREADS, GH_BP_MINBLOCKS)
 bp_bucket_kernel(uint64_t *__restrict__ keys, int *__restrict__ vals, uint64_t *__restrict__ kscr,
                  int *__restrict__ vscr, const int *__restrict__ boff, const uint64_t *__restrict__ spl, int nb,
                  int nbits, int vbits) {

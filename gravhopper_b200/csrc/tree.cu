@@ -469,10 +469,12 @@ struct TreeRun {
     static const int emit_mode = [] {
       const char *env = getenv("GH_EMIT");
       if (env && !strcmp(env, "thread")) return 0;
-      if (env && !strcmp(env, "warp")) return 1;
+      if (env && !strcmp(env, "warp")) return 2;
       return GH_EMIT_DEFAULT;
     }();
-    if (emit_mode == 1 && !ph.quad &&
+    // (as a default, 1, the warp form is used by single-rank builds only -- the distributed build's
+    // use of it is validated on the CPU with the kernel source, GH_EMIT=warp selects it there too)
+    if ((emit_mode == 2 || (emit_mode == 1 && !ph.dist)) && !ph.quad &&
         Emit32<Real>::launch(w->sorted.as<double4>(), ph.shi, w->clev.as<signed char>(), w->base.as<int>(), w->P.ptr, n,
                              w->root.as<double>(), w->node.ptr, maxlevel, ctl, ph.dist, st)) {
       GH_LAUNCH_CHECK();

@@ -15,14 +15,14 @@ VARIANTS = {
     # "emit8": ["-DGH_EMIT_MINBLOCKS=8"], ... "emit16": no gain (profiles/r01_emit_occupancy_ab.txt)
     # radix sort: keys per thread (tile size)
     # measured (profiles/r02_sort_ab.txt): 12 / 10 / 8 / 6 keys per thread -> build 1.72 / 1.59 / 1.46 / 1.40 ms
-    "rs6": ["-DGH_RS_ROUNDS=6"],
+    # "rs6"/"rs8", "rk6"/"rk8"/"rk10" (GH_RS_RANK=1): see profiles/r02_sort_ab.txt
+    # "place" form of the splitter sort: bits ranked first inside a bucket, tile size
+    "sb16": ["-DGH_BP_SUBBITS=16"],
+    "sb32": ["-DGH_BP_SUBBITS=32"],
     "rs8": ["-DGH_RS_ROUNDS=8"],
-    # ranking: ballots first + one shared-memory atomic per round
-    "rk6": ["-DGH_RS_ROUNDS=6", "-DGH_RS_RANK=1"],
-    "rk8": ["-DGH_RS_ROUNDS=8", "-DGH_RS_RANK=1"],
-    "rk10": ["-DGH_RS_ROUNDS=10", "-DGH_RS_RANK=1"],
+    "rs8sb16": ["-DGH_RS_ROUNDS=8", "-DGH_BP_SUBBITS=16"],
 }
-KERNEL = "rs_scatter_kernel"
+KERNEL = "bp_bucket_kernel"
 B.build()
 out = os.path.join(B.HERE, "variants")
 os.makedirs(out, exist_ok=True)

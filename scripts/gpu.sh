@@ -7,7 +7,7 @@
 #   bench[:<bench args>]       python bench.py [args]                      -> <tag>_bench_<n>.json
 #   mbench:<N>[:<bench args>]  torchrun --nproc-per-node N bench.py --gpus N [args]
 #   launches:<which>:<n>[:<steps>]  ncu launch list of scripts/profile_kernels.py <which> <n> [steps]
-#   ab:<name,name,..>[:K=V]    scripts/gpu_ab.sh: quick tree bench with library variants (base = in-tree)
+#   ab:<name,name,..>[:K=V,K=V[:label]]  scripts/gpu_ab.sh: quick tree bench with library variants (base = in-tree)
 #   ncu:<kernel-regex>:<which>:<n>[:<skip>]  ncu --set full of one launch  -> <tag>_<regex>.ncu-rep
 #   benchlaunches[:<bench args>]  ncu launch list of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline` (a number
 #                              printed under ncu is never a bench value)
@@ -34,7 +34,7 @@ for task in "$@"; do
            tail -3 gpurun_out/${TAG}_mbench${a1}_$k.err | cut -c1-300; tail -1 gpurun_out/${TAG}_mbench${a1}_$k.json | cut -c1-300 ;;
     launches) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches_${a1}_${a2}.csv \
               python scripts/profile_kernels.py $a1 $a2 $a3 > gpurun_out/${TAG}_ncu_$k.log 2>&1; tail -1 gpurun_out/${TAG}_ncu_$k.log ;;
-    ab) GH_AB_ENV="$a2" bash scripts/gpu_ab.sh ${a1//,/ } ;;
+    ab) GH_AB_ENV="${a2//,/ }" GH_AB_LABEL="$a3" bash scripts/gpu_ab.sh ${a1//,/ } ;;
     ncu) timeout 900 ncu --set full --clock-control none --import-source on -k regex:$a1 -s ${a4:-1} -c 1 -f -o gpurun_out/${TAG}_${a1}_${a3} \
               python scripts/profile_kernels.py $a2 $a3 4 > gpurun_out/${TAG}_ncu_$k.log 2>&1; tail -1 gpurun_out/${TAG}_ncu_$k.log ;;
     benchlaunches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/${TAG}_launches_bench.csv \
