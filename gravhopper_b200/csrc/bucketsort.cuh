@@ -474,6 +474,115 @@ bp_place_kernel(const uint64_t *__restrict__ kin, const int *__restrict__ vin, c
     if (pos[r] >= 0) { kout[pos[r]] = k[r]; vout[pos[r]] = v[r]; }
 }
 
+// ---- "place", shared-memory form --------------------------------------------------------------------
+// Measured on B200 (N = 4M, 3072 buckets): the global reductions of bp_count_kernel and the global
+// atomics of bp_place_kernel run at ~18 G/s -- 1365 updates per address -- and cost 230 + 250 us,
+// no better than the two partition passes they replace.  Same idea with the contention moved into
+// shared memory: G CTAs each own a contiguous chunk of the input, count their chunk's pairs per
+// bucket in a shared-memory histogram (bp2_count_kernel -> one row of a G x nb table), a column
+// scan turns the table into every CTA's first slot inside every bucket (bp2_colscan_kernel +
+// bp_scan_kernel for the bucket offsets), and bp2_place_kernel hands out slots with shared-memory
+// atomics on its own row.  No global atomic at all.  Needs nb <= BP2_MAX_NB (histogram + coarse
+// splitters in 48 KB of static shared memory): N <= 14M at 1365 pairs per bucket; beyond that the
+// partition passes are used.
+static constexpr int BP2_THREADS = 512;
+static constexpr int BP2_MAX_NB = 10240;
+static constexpr int BP2_UNROLL = 8;
+
+// pairs per CTA: a multiple of the CTA size, G chunks cover n
+static inline __host__ __device__ int64_t bp2_chunk(int64_t n, int G) {
+  const int64_t c = (n + G - 1) / G;
+  return ((c + BP2_THREADS - 1) / BP2_THREADS) * BP2_THREADS;
+}
+
+__global__ void __launch_bounds__(BP2_THREADS)
+bp2_count_kernel(const uint64_t *__restrict__ keys, int64_t n, const uint64_t *__restrict__ spl, int nb,
+                 unsigned short *__restrict__ bid, int *__restrict__ ghist /* [gridDim.x][nb] */,
+                 const int *__restrict__ ndev) {
+  __shared__ uint64_t coarse[BP2_MAX_NB / BP_COARSE];
+  __shared__ int hist[BP2_MAX_NB];
+  const int64_t chunk = bp2_chunk(n, (int)gridDim.x);  // from the capacity: the same on every launch of a step
+  if (ndev) n = *ndev;
+  const int nc = (nb + BP_COARSE - 1) / BP_COARSE;
+  for (int j = threadIdx.x; j < nc; j += BP2_THREADS) coarse[j] = spl[j * BP_COARSE];
+  for (int j = threadIdx.x; j < nb; j += BP2_THREADS) hist[j] = 0;
+  __syncthreads();
+  const int64_t q0 = (int64_t)blockIdx.x * chunk;
+  int64_t q1 = q0 + chunk;
+  if (q1 > n) q1 = n;
+  for (int64_t qb = q0; qb < q1; qb += BP2_THREADS * BP2_UNROLL) {
+    uint64_t k[BP2_UNROLL];
+#pragma unroll
+    for (int u = 0; u < BP2_UNROLL; u++) {
+      const int64_t q = qb + u * BP2_THREADS + threadIdx.x;
+      k[u] = (q < q1) ? keys[q] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < BP2_UNROLL; u++) {
+      const int64_t q = qb + u * BP2_THREADS + threadIdx.x;
+      if (q < q1) {
+        const int b = bp_bucket_of(coarse, nc, spl, nb, k[u]);
+        bid[q] = (unsigned short)b;
+        atomicAdd(&hist[b], 1);
+      }
+    }
+  }
+  __syncthreads();
+  int *row = ghist + (int64_t)blockIdx.x * nb;
+  for (int j = threadIdx.x; j < nb; j += BP2_THREADS) row[j] = hist[j];
+}
+
+// column b of the table: ghist[c][b] <- pairs of bucket b in CTAs < c; tot[b] = pairs of bucket b
+__global__ void bp2_colscan_kernel(int *__restrict__ ghist, int G, int nb, int *__restrict__ tot) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  int run = 0;
+  for (int c0 = 0; c0 < G; c0 += 8) {  // eight rows at a time: the loads of a batch are independent
+    int v[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) v[u] = (c0 + u < G) ? ghist[(int64_t)(c0 + u) * nb + b] : 0;
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+      if (c0 + u < G) {
+        ghist[(int64_t)(c0 + u) * nb + b] = run;
+        run += v[u];
+      }
+  }
+  tot[b] = run;
+}
+
+__global__ void __launch_bounds__(BP2_THREADS)
+bp2_place_kernel(const uint64_t *__restrict__ kin, const int *__restrict__ vin, const unsigned short *__restrict__ bid,
+                 int64_t n, const int *__restrict__ ghist, const int *__restrict__ boff, int nb,
+                 uint64_t *__restrict__ kout, int *__restrict__ vout, const int *__restrict__ ndev) {
+  __shared__ int cur[BP2_MAX_NB];
+  const int64_t chunk = bp2_chunk(n, (int)gridDim.x);
+  if (ndev) n = *ndev;
+  const int *row = ghist + (int64_t)blockIdx.x * nb;
+  for (int j = threadIdx.x; j < nb; j += BP2_THREADS) cur[j] = boff[j] + row[j];
+  __syncthreads();
+  const int64_t q0 = (int64_t)blockIdx.x * chunk;
+  int64_t q1 = q0 + chunk;
+  if (q1 > n) q1 = n;
+  for (int64_t qb = q0; qb < q1; qb += BP2_THREADS * BP2_UNROLL) {
+    uint64_t k[BP2_UNROLL];
+    int v[BP2_UNROLL], b[BP2_UNROLL];
+#pragma unroll
+    for (int u = 0; u < BP2_UNROLL; u++) {
+      const int64_t q = qb + u * BP2_THREADS + threadIdx.x;
+      b[u] = -1;
+      if (q < q1) { k[u] = kin[q]; v[u] = vin[q]; b[u] = (int)bid[q]; }
+    }
+#pragma unroll
+    for (int u = 0; u < BP2_UNROLL; u++)
+      if (b[u] >= 0) {
+        const int pos = atomicAdd(&cur[b[u]], 1);
+        kout[pos] = k[u];
+        vout[pos] = v[u];
+      }
+  }
+}
+
 #ifdef GH_HOST_EMU
 // which way the buckets went (tests/test_tree_emu.py): [0] compact ranking, [1] the long way,
 // [2] oversize, [3] runs ordered by insertion
@@ -758,6 +867,32 @@ static int splitter_place_sort_pairs(uint64_t *kA, int *vA, uint64_t *kB, int *v
   bp_scan_kernel<<<1, RS_THREADS, 0, st>>>(count, ss.nb, ss.boff.as<int>(), cursor);
   GH_LAUNCH_CHECK();
   bp_place_kernel<<<nblocks, BP_THREADS, 0, st>>>(kA, vA, ss.bid.as<unsigned short>(), n, cursor, kB, vB, ndev);
+  GH_LAUNCH_CHECK();
+  int vbits = 1;
+  while (vbits < 31 && (int64_t(1) << vbits) < n) vbits++;
+  bp_bucket_kernel<<<ss.nb, RS_THREADS, 0, st>>>(kB, vB, kA, vA, ss.boff.as<int>(), spl, ss.nb, nbits, vbits);
+  GH_LAUNCH_CHECK();
+  return GH_OK;
+}
+
+// The shared-memory form of "place" (bp2_*): same contract as splitter_place_sort_pairs.  G: CTAs of
+// the count / place kernels (a couple per SM).
+static int splitter_place2_sort_pairs(uint64_t *kA, int *vA, uint64_t *kB, int *vB, int64_t n, int nbits,
+                                      SplitterState &ss, int G, cudaStream_t st, const int *ndev) {
+  if (n <= 1) return GH_OK;
+  if (ss.nb > BP2_MAX_NB) { set_error("place2: %d buckets exceed the shared-memory histogram", ss.nb); return GH_EINVAL; }
+  GH_TRY(ss.bid.reserve(sizeof(unsigned short) * (size_t)n));
+  GH_TRY(ss.cnt.reserve(sizeof(int) * ((size_t)G * (size_t)ss.nb + (size_t)(2 * ss.nb + 2))));
+  GH_TRY(ss.boff.reserve(sizeof(int) * (size_t)(ss.nb + 2)));
+  int *ghist = ss.cnt.as<int>(), *tot = ghist + (size_t)G * (size_t)ss.nb, *cursor = tot + ss.nb + 1;
+  const uint64_t *spl = ss.spl.as<uint64_t>();
+  bp2_count_kernel<<<G, BP2_THREADS, 0, st>>>(kA, n, spl, ss.nb, ss.bid.as<unsigned short>(), ghist, ndev);
+  GH_LAUNCH_CHECK();
+  bp2_colscan_kernel<<<(ss.nb + 127) / 128, 128, 0, st>>>(ghist, G, ss.nb, tot);
+  GH_LAUNCH_CHECK();
+  bp_scan_kernel<<<1, RS_THREADS, 0, st>>>(tot, ss.nb, ss.boff.as<int>(), cursor);
+  GH_LAUNCH_CHECK();
+  bp2_place_kernel<<<G, BP2_THREADS, 0, st>>>(kA, vA, ss.bid.as<unsigned short>(), n, ghist, ss.boff.as<int>(), ss.nb, kB, vB, ndev);
   GH_LAUNCH_CHECK();
   int vbits = 1;
   while (vbits < 31 && (int64_t(1) << vbits) < n) vbits++;

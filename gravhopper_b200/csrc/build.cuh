@@ -355,20 +355,127 @@ __device__ __forceinline__ int common_levels(uint64_t h0, uint64_t l0, uint64_t 
   return LEVELS_MAX;
 }
 
+// ---- level-min tables: where a cell ends, without touching the keys ------------------------------------
+// The cell of level L that starts at sorted particle p ends at the first q >= p with clev[q] < L.
+// lm.t[0][q] = clev[q] + 1 as an unsigned byte (0 beyond the last particle); lm.t[k][j] = the
+// minimum of lm.t[k-1][32 j .. 32 j + 31]: 1/31 of a byte per particle in total.  cell_end climbs
+// until a group to the right holds a smaller value and descends to it: two 16-byte loads and ~60
+// integer instructions per table level, <= 2 * levels of them (emit_kernel's gallop + bisection over
+// the 8-byte keys costs up to 40 dependent loads for the big cells, and a warp waits for its
+// slowest lane).
+static constexpr int LM_MAX_TABLES = 7;  // 32^7 particles
+struct LevelMin {
+  unsigned char *t[LM_MAX_TABLES];
+  int64_t n[LM_MAX_TABLES];  // entries of table k (n[0] = particles, capacity); allocated in multiples of 32
+  int ntab;                  // 0: no tables
+};
+static inline __host__ __device__ int64_t lm_padded(int64_t n) { return ((n + 31) / 32) * 32; }
+// sizes of the tables for n particles; returns the bytes needed when every table starts at a multiple of
+// 256 (table 0 is padded to the levels_kernel grid: a multiple of 256 entries)
+static inline size_t lm_layout(int64_t n, LevelMin &lm, size_t off[LM_MAX_TABLES]) {
+  size_t bytes = 0;
+  lm.ntab = 0;
+  int64_t m = n;
+  for (int k = 0; k < LM_MAX_TABLES; k++) {
+    lm.n[k] = m;
+    off[k] = bytes;
+    const int64_t padded = (k == 0) ? ((m + 255) / 256) * 256 : lm_padded(m);
+    bytes += (size_t)((padded + 255) / 256) * 256;
+    lm.ntab = k + 1;
+    if (m <= 32) break;
+    m = (m + 31) / 32;
+  }
+  return bytes;
+}
+// first entry j >= from of group g (32 entries) of a table with value < t (t4 = t in every byte), or 32
+__device__ __forceinline__ int lm_first(const unsigned char *__restrict__ tab, int64_t g, int from, unsigned t4) {
+  const uint4 *gp = reinterpret_cast<const uint4 *>(tab + g * 32);
+  const uint4 a = gp[0], b = gp[1];
+  const unsigned w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  unsigned bits = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    // values are <= 43 < 128: (u | 0x80) - t keeps bit 7 of a byte exactly when u >= t, no borrows
+    const unsigned x = (w[i] | 0x80808080u) - t4;
+    const unsigned y = (~x & 0x80808080u) >> 7;            // 0x01 in the bytes with u < t
+    bits |= ((y * 0x01020408u) >> 24) << (4 * i);          // byte j -> bit j
+  }
+  bits = from < 32 ? (bits & ~((1u << from) - 1u)) : 0u;
+  return bits ? __ffs((int)bits) - 1 : 32;
+}
+// last sorted particle of the level-`level` cell that starts at p (n: particles of this rank)
+__device__ __forceinline__ int64_t cell_end(const LevelMin &lm, int64_t p, int level, int64_t n) {
+  const unsigned t4 = (unsigned)(level + 1) * 0x01010101u;
+  int q = lm_first(lm.t[0], p >> 5, (int)(p & 31) + 1, t4);
+  int64_t idx;
+  if (q < 32) {
+    idx = (p & ~(int64_t)31) + q;
+  } else {
+    idx = p >> 5;
+    int k = 1;
+    for (;;) {
+      if (k >= lm.ntab) return n - 1;  // nothing smaller to the right
+      const int64_t g = idx >> 5;
+      q = lm_first(lm.t[k], g, (int)(idx & 31) + 1, t4);
+      if (q < 32) { idx = (g << 5) + q; break; }
+      idx = g;
+      k++;
+    }
+    while (k > 0) {
+      k--;
+      q = lm_first(lm.t[k], idx, 0, t4);
+      if (q >= 32) return n - 1;  // (inconsistent tables: cannot happen)
+      idx = (idx << 5) + q;
+    }
+  }
+  return idx < n ? idx : n - 1;
+}
+// tables 2 .. ntab-1 from table 1 (one CTA; the sizes shrink by 32 per level)
+__global__ void levelmin_top_kernel(const __grid_constant__ LevelMin lm) {
+  for (int k = 2; k < lm.ntab; k++) {
+    const unsigned char *in = lm.t[k - 1];
+    unsigned char *out = lm.t[k];
+    const int64_t nk = lm.n[k], np = lm_padded(nk);
+    for (int64_t j = threadIdx.x; j < np; j += blockDim.x) {
+      unsigned m = 0;
+      if (j < nk) {
+        m = 255;
+        for (int i = 0; i < 32; i++) { const unsigned v = in[32 * j + i]; m = v < m ? v : m; }
+      }
+      out[j] = (unsigned char)m;
+    }
+    __syncthreads();
+  }
+}
+
 // cnt[p] = (cells opened at sorted position p) + 1 leaf;  clev[p] = c[p] (c[n-1] = -1)
 // ctl (nullable): this rank's particle count and the levels shared across its range boundaries
+// lm (ntab > 0): also the level-min tables 0 and 1 (every thread of the grid takes part: the grid
+// covers a multiple of 256 positions, positions beyond the last particle hold 0)
 __global__ void levels_kernel(const uint64_t *__restrict__ hi, const uint64_t *__restrict__ lo,
                               int64_t n, int levels, signed char *__restrict__ clev,
-                              int *__restrict__ cnt, const BuildCtl *__restrict__ ctl = nullptr) {
+                              int *__restrict__ cnt, const BuildCtl *__restrict__ ctl = nullptr,
+                              const __grid_constant__ LevelMin lm = LevelMin{{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr},
+                                                                             {0, 0, 0, 0, 0, 0, 0}, 0}) {
   int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (ctl) n = ctl->n_local;
-  if (p >= n) return;
-  int cprev = ctl ? ctl->cprev : -1, c = ctl ? ctl->cnext : -1;
-  if (p > 0) cprev = common_levels(hi[p - 1], lo ? lo[p - 1] : 0, hi[p], lo ? lo[p] : 0, levels);
-  if (p + 1 < n) c = common_levels(hi[p], lo ? lo[p] : 0, hi[p + 1], lo ? lo[p + 1] : 0, levels);
-  clev[p] = (signed char)c;
-  int open = c - cprev;
-  cnt[p] = (open > 0 ? open : 0) + 1;
+  int c = -1;
+  if (p < n) {
+    int cprev = ctl ? ctl->cprev : -1;
+    c = ctl ? ctl->cnext : -1;
+    if (p > 0) cprev = common_levels(hi[p - 1], lo ? lo[p - 1] : 0, hi[p], lo ? lo[p] : 0, levels);
+    if (p + 1 < n) c = common_levels(hi[p], lo ? lo[p] : 0, hi[p + 1], lo ? lo[p + 1] : 0, levels);
+    clev[p] = (signed char)c;
+    int open = c - cprev;
+    cnt[p] = (open > 0 ? open : 0) + 1;
+  }
+  if (lm.ntab > 0) {
+    lm.t[0][p] = (unsigned char)(c + 1);
+    if (lm.ntab > 1) {
+      const int m = __reduce_min_sync(0xffffffffu, c + 1);
+      if ((threadIdx.x & 31) == 0) lm.t[1][p >> 5] = (unsigned char)m;
+    }
+  }
 }
 
 // ---- K7 double-double moments -------------------------------------------------------------------
@@ -803,7 +910,8 @@ __global__ void __launch_bounds__(128)
 emit32_warp_kernel(const double4 *__restrict__ sp, const uint64_t *__restrict__ hi,
                    const signed char *__restrict__ clev, const int *__restrict__ base /* n+1 */,
                    const D4 *__restrict__ P, int64_t n, const double *__restrict__ root, Entries<float> E,
-                   int *__restrict__ maxlevel, BuildCtl *__restrict__ ctl, bool dist) {
+                   int *__restrict__ maxlevel, BuildCtl *__restrict__ ctl, bool dist,
+                   const __grid_constant__ LevelMin lm) {
   const int lane = threadIdx.x & 31;
   const int64_t wbase = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
   if (dist) n = ctl->n_local;
@@ -881,9 +989,12 @@ emit32_warp_kernel(const double4 *__restrict__ sp, const uint64_t *__restrict__ 
       for (int k = 0; k < 3; k++) cc[k] = __dadd_rn(cc[k], ((d >> k) & 1u) ? quarter : -quarter);
       size = __dmul_rn(0.5, size);
     }
-    // last sorted particle b sharing `level` octant levels with pt (emit_kernel's search)
+    // last sorted particle b sharing `level` octant levels with pt: from the level-min tables, or
+    // (no tables) emit_kernel's search over the keys
     int64_t lo_i = pt + 1, step = 1, hi_i;
     bool found = false;
+    if (lm.ntab > 0) { lo_i = cell_end(lm, pt, level, n); found = true; }
+    else
     for (int u = 0; u < 12 && lo_i < n; u++) {
       if (clev[lo_i] < level) { found = true; break; }
       lo_i++;

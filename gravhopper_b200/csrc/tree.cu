@@ -66,6 +66,7 @@ struct TreePhaseState {
   int64_t ecap = 0;         // entries per segment (stride)
   int end = 0;              // world * stride
   bool quad = false;        // this evaluation carries quadrupoles (single rank, per-target walk)
+  LevelMin lm = LevelMin{{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, {0, 0, 0, 0, 0, 0, 0}, 0};  // level-min tables (warp emit)
   int blk = 2048, T = 0;    // distributed walk: block size of the deal, blocks per (rank, range)
   int64_t slots = 0;        // target slots per rank = world * T * blk
 };
@@ -73,6 +74,7 @@ struct TreeWorkspace {
   DeviceBuffer root, part, hi, lo, hi2, lo2, lo3, idx, idx2, clev, cnt, base, P;
   DeviceBuffer node, skip, misc, thi, tidx, thi2, tidx2, sorted, bsum, scanlv[4], cntlv[4];
   DeviceBuffer ctl, rec1, rec2, keys_all, tilecnt, tileoff, tilelv[4], sidx_all, acc_all;
+  DeviceBuffer lmin;  // level-min tables of the common levels (build.cuh)
   DeviceBuffer P2, quad, scanlv2[4];  // opt-in quadrupoles: second-moment prefixes, per-entry tensors
   RadixScratch rs;
   SplitterState ss;  // buckets of the splitter sort (bucketsort.cuh): valid from one coherent step to the next
@@ -92,7 +94,7 @@ void tree_workspace_destroy(TreeWorkspace *w) {
   DeviceBuffer *all[] = {&w->root, &w->part, &w->hi, &w->lo, &w->hi2, &w->lo2, &w->lo3, &w->idx, &w->idx2,
                          &w->clev, &w->cnt, &w->base, &w->P, &w->node, &w->sorted, &w->bsum, &w->scanlv[0], &w->scanlv[1], &w->scanlv[2], &w->scanlv[3], &w->cntlv[0], &w->cntlv[1], &w->cntlv[2], &w->cntlv[3],
                          &w->skip, &w->misc, &w->thi, &w->tidx, &w->thi2, &w->tidx2, &w->ctl, &w->rec1, &w->rec2,
-                         &w->keys_all, &w->tilecnt, &w->tileoff, &w->sidx_all, &w->acc_all, &w->P2, &w->quad,
+                         &w->keys_all, &w->tilecnt, &w->tileoff, &w->sidx_all, &w->acc_all, &w->P2, &w->quad, &w->lmin,
                          &w->scanlv2[0], &w->scanlv2[1], &w->scanlv2[2], &w->scanlv2[3], &w->tilelv[0], &w->tilelv[1], &w->tilelv[2], &w->tilelv[3]};
   for (auto *b : all) b->release();
   w->rs.release();
@@ -224,18 +226,36 @@ static int64_t entry_capacity(TreeWorkspace *w, int64_t n, bool fp32) {
 // emit of the fp32 tree, warp-cooperative form (emit32_warp_kernel); false: not this precision
 template <class Real> struct Emit32 {
   static bool launch(const double4 *, const uint64_t *, const signed char *, const int *, const void *, int64_t,
-                     const double *, void *, int *, BuildCtl *, bool, cudaStream_t) { return false; }
+                     const double *, void *, int *, BuildCtl *, bool, const LevelMin &, cudaStream_t) { return false; }
 };
 template <> struct Emit32<float> {
   static bool launch(const double4 *sp, const uint64_t *shi, const signed char *clev, const int *base, const void *P,
                      int64_t n, const double *root, void *nodes, int *maxlevel, BuildCtl *ctl, bool dist,
-                     cudaStream_t st) {
+                     const LevelMin &lm, cudaStream_t st) {
     Entries<float> E{static_cast<Node<float> *>(nodes), nullptr};
     emit32_warp_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(sp, shi, clev, base, static_cast<const D4 *>(P), n, root,
-                                                                    E, maxlevel, ctl, dist);
+                                                                    E, maxlevel, ctl, dist, lm);
     return true;
   }
 };
+
+// 0 = one thread per particle, 1 = warp-cooperative for single-rank fp32 builds, 2 = warp-cooperative
+// for every fp32 build (GH_EMIT=thread|warp; the distributed build's use of the warp form is
+// validated on the CPU with the kernel source)
+static int emit_mode() {
+  static const int mode = [] {
+    const char *env = getenv("GH_EMIT");
+    if (env && !strcmp(env, "thread")) return 0;
+    if (env && !strcmp(env, "warp")) return 2;
+    return GH_EMIT_DEFAULT;
+  }();
+  return mode;
+}
+template <class Real>
+static bool use_warp_emit(const TreePhaseState &ph) {
+  const int m = emit_mode();
+  return sizeof(Real) == 4 && !ph.quad && (m == 2 || (m == 1 && !ph.dist));
+}
 
 template <class Src, class Real>
 struct TreeRun {
@@ -369,10 +389,11 @@ struct TreeRun {
       // A running simulation (a.coherent) sorts with the buckets the previous step left behind
       // (bucketsort.cuh: 3 trips through global memory instead of 8); the first step after an
       // upload, stateless calls and small systems use the classic LSD sort.  GH_SORT=classic|bucket.
-      static const int sort_mode = [] {  // 0 classic, 1 bucket (two partition passes), 2 place (count + place)
+      static const int sort_mode = [] {  // 0 classic, 1 bucket (two partition passes), 2 place (global atomics), 3 place2 (shared-memory histograms)
         const char *env = getenv("GH_SORT");
         if (env && !strcmp(env, "classic")) return 0;
         if (env && !strcmp(env, "place")) return 2;
+        if (env && !strcmp(env, "place2")) return 3;
         if (env && !strcmp(env, "bucket")) return 1;
         return GH_SORT_DEFAULT;
       }();
@@ -380,7 +401,15 @@ struct TreeRun {
       // it gains all land in the first or last bucket, which then takes the slow oversize path
       // (measured at 8 GPUs: 0.7 ms of skew at the next exchange).
       const bool bucket = sort_mode >= 1 && a.coherent && !ph.dist && w->ss.nb >= BS_MIN_BUCKETS && w->ss.cap == ph.n;
-      if (bucket && sort_mode == 2) {
+      if (bucket && sort_mode == 3 && w->ss.nb <= BP2_MAX_NB) {
+        // a couple of CTAs per SM, each with a contiguous chunk of the keys
+        int dev = 0, sms = 0;
+        GH_CUDA(cudaGetDevice(&dev));
+        GH_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        static const int per_sm = [] { const char *e = getenv("GH_BP2_CTAS_PER_SM"); const int v = e ? atoi(e) : 2; return v >= 1 && v <= 4 ? v : 2; }();
+        GH_TRY(splitter_place2_sort_pairs(hi, idx, hi2, idx2, ph.n, 63, w->ss, sms * per_sm, st, ph.ndev));
+        inB = true;
+      } else if (bucket && sort_mode == 2) {
         GH_TRY(splitter_place_sort_pairs(hi, idx, hi2, idx2, ph.n, 63, w->ss, st, ph.ndev));
         inB = true;
       } else if (bucket) {
@@ -419,8 +448,23 @@ struct TreeRun {
     GH_TRY(w->base.reserve(sizeof(int) * (n + 1)));
     signed char *clev = w->clev.as<signed char>();
     int *cnt = w->cnt.as<int>(), *base = w->base.as<int>();
-    levels_kernel<<<nblk(n, 256), 256, 0, st>>>(ph.shi, ph.slo, n, ph.levels, clev, cnt, cd);
+    // the warp form of the emit finds the cells' ends in level-min tables of the common levels
+    // (GH_EMIT_SEARCH=keys keeps the search over the keys)
+    static const bool lm_on = [] { const char *e = getenv("GH_EMIT_SEARCH"); return !(e && !strcmp(e, "keys")); }();
+    ph.lm.ntab = 0;
+    if (lm_on && use_warp_emit<Real>(ph)) {
+      size_t off[LM_MAX_TABLES];
+      const size_t bytes = lm_layout(n, ph.lm, off);
+      GH_TRY(w->lmin.reserve(bytes));
+      for (int k = 0; k < ph.lm.ntab; k++) ph.lm.t[k] = w->lmin.as<unsigned char>() + off[k];
+      if (ph.lm.ntab > 1) GH_CUDA(cudaMemsetAsync(ph.lm.t[1], 0, bytes - off[1], st));
+    }
+    levels_kernel<<<nblk(n, 256), 256, 0, st>>>(ph.shi, ph.slo, n, ph.levels, clev, cnt, cd, ph.lm);
     GH_LAUNCH_CHECK();
+    if (ph.lm.ntab > 2) {
+      levelmin_top_kernel<<<1, 1024, 0, st>>>(ph.lm);
+      GH_LAUNCH_CHECK();
+    }
     GH_TRY((chunked_scan<int, InArray<int>>(InArray<int>{cnt}, n, base, w->cntlv, 0, st, ph.ndev)));
     if (!ph.dist) GH_CUDA(cudaMemcpyAsync(&w->h_pinned[0], base + n, sizeof(int), cudaMemcpyDeviceToHost, st));
 
@@ -464,19 +508,10 @@ struct TreeRun {
     int *maxlevel = w->misc.as<int>();
     GH_CUDA(cudaMemsetAsync(w->misc.ptr, 0, 64, st));
     if (ph.quad) GH_TRY(w->quad.reserve(sizeof(Real) * 6 * (size_t)ph.end));
-    // fp32 entries without quadrupoles: the warp-cooperative form (build.cuh), same array bit for bit.
-    // GH_EMIT=thread|warp.
-    static const int emit_mode = [] {
-      const char *env = getenv("GH_EMIT");
-      if (env && !strcmp(env, "thread")) return 0;
-      if (env && !strcmp(env, "warp")) return 2;
-      return GH_EMIT_DEFAULT;
-    }();
-    // (as a default, 1, the warp form is used by single-rank builds only -- the distributed build's
-    // use of it is validated on the CPU with the kernel source, GH_EMIT=warp selects it there too)
-    if ((emit_mode == 2 || (emit_mode == 1 && !ph.dist)) && !ph.quad &&
+    // fp32 entries without quadrupoles: the warp-cooperative form (build.cuh), same array bit for bit
+    if (use_warp_emit<Real>(ph) &&
         Emit32<Real>::launch(w->sorted.as<double4>(), ph.shi, w->clev.as<signed char>(), w->base.as<int>(), w->P.ptr, n,
-                             w->root.as<double>(), w->node.ptr, maxlevel, ctl, ph.dist, st)) {
+                             w->root.as<double>(), w->node.ptr, maxlevel, ctl, ph.dist, ph.lm, st)) {
       GH_LAUNCH_CHECK();
       return GH_OK;
     }

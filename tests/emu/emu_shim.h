@@ -26,6 +26,7 @@
 
 #define GH_HOST_EMU 1
 #define __launch_bounds__(...)
+#define __grid_constant__
 #include <cuda_runtime.h>
 #undef __shared__
 #ifdef GH_EMU_THREADS

@@ -57,6 +57,21 @@ static bool emu_sort(uint64_t *kA, int *vA, uint64_t *kB, int *vB, int64_t n, in
   return inB;
 }
 
+// level-min tables for n particles (tree.cu phase B): storage + the view the kernels take
+struct EmuLevelMin {
+  std::vector<unsigned char> buf;
+  LevelMin lm;
+  explicit EmuLevelMin(int64_t n) {
+    size_t off[LM_MAX_TABLES];
+    const size_t bytes = lm_layout(n, lm, off);
+    buf.assign(bytes + 64, 0);
+    unsigned char *base = buf.data();
+    base += (32 - (reinterpret_cast<uintptr_t>(base) & 31)) & 31;
+    for (int k = 0; k < lm.ntab; k++) lm.t[k] = base + off[k];
+  }
+  void finish() { if (lm.ntab > 2) emu::launch(1, 1024, [&] { levelmin_top_kernel(lm); }); }
+};
+
 template <class Real>
 static int build_impl(const double *pos, const double *mass, int64_t n, double eps, double theta, void *nodes_out,
                       int *skips_out, int nodes_cap, double *sorted_out, int *order_out, double *root_out,
@@ -99,7 +114,9 @@ static int build_impl(const double *pos, const double *mass, int64_t n, double e
 
   std::vector<signed char> clev(n);
   std::vector<int> cnt(n + 1), base(n + 1);
-  emu::launch(nblk(n, 256), 256, [&] { levels_kernel(shi, slo, n, levels, clev.data(), cnt.data()); }, true);
+  EmuLevelMin elm(n);
+  emu::launch(nblk(n, 256), 256, [&] { levels_kernel(shi, slo, n, levels, clev.data(), cnt.data(), nullptr, elm.lm); });
+  elm.finish();
   emu_scan<int, InArray<int>>(InArray<int>{cnt.data()}, n, base.data());
 
   std::vector<double4> sp(n);
@@ -141,12 +158,20 @@ static int build_impl(const double *pos, const double *mass, int64_t n, double e
     emu::launch(1, 1, [&] { ctl_init_single(&ctl2, (int)n, seg_cap > 0 ? seg_cap : nentries); }, true);
     int maxlevel2 = 0;
     Entries<float> E2{alt.data(), nullptr};
-    emu::launch(nblk(n, 128), 128, [&] {
-      emit32_warp_kernel(sp.data(), shi, clev.data(), base.data(), reinterpret_cast<const D4 *>(P.data()), n, root.data(),
-                         E2, &maxlevel2, &ctl2, false);
-    });
-    if (maxlevel2 != maxlevel || ctl2.overflow != ctl.overflow) return 7;
-    if (std::memcmp(alt.data(), nodes_out, sizeof(Node<float>) * (size_t)filled) != 0) return 7;
+    for (int tables = 0; tables < 2; tables++) {  // cell ends from the keys, then from the level-min tables
+      LevelMin none = elm.lm;
+      none.ntab = 0;
+      const LevelMin use = tables ? elm.lm : none;
+      std::memset(alt.data(), 0xff, sizeof(Node<float>) * alt.size());
+      maxlevel2 = 0;
+      ctl2.overflow = 0;
+      emu::launch(nblk(n, 128), 128, [&] {
+        emit32_warp_kernel(sp.data(), shi, clev.data(), base.data(), reinterpret_cast<const D4 *>(P.data()), n, root.data(),
+                           E2, &maxlevel2, &ctl2, false, use);
+      });
+      if (maxlevel2 != maxlevel || ctl2.overflow != ctl.overflow) return 7 + tables;
+      if (std::memcmp(alt.data(), nodes_out, sizeof(Node<float>) * (size_t)filled) != 0) return 7 + tables;
+    }
   }
   if (keys_out) std::memcpy(keys_out, shi, sizeof(uint64_t) * (size_t)n);
   std::memcpy(sorted_out, sp.data(), sizeof(double4) * (size_t)n);
@@ -190,11 +215,26 @@ static void emu_place_sort(uint64_t *kA, int *vA, uint64_t *kB, int *vB, int64_t
   emu::launch((unsigned)nb, RS_THREADS, [&] { bp_bucket_kernel(kB, vB, kA, vA, boff.data(), spl, nb, nbits, vbits); });
 }
 
+// splitter_place2_sort_pairs of bucketsort.cuh, launch for launch (result in kB / vB)
+static void emu_place2_sort(uint64_t *kA, int *vA, uint64_t *kB, int *vB, int64_t n, int nbits, const uint64_t *spl,
+                            int nb, int G, const int *ndev) {
+  std::vector<unsigned short> bid((size_t)n);
+  std::vector<int> ghist((size_t)G * nb, -1), tot(nb + 1, 0), cursor(nb + 1, 0), boff(nb + 2, 0);
+  emu::launch((unsigned)G, BP2_THREADS, [&] { bp2_count_kernel(kA, n, spl, nb, bid.data(), ghist.data(), ndev); });
+  emu::launch((unsigned)((nb + 127) / 128), 128, [&] { bp2_colscan_kernel(ghist.data(), G, nb, tot.data()); }, true);
+  emu::launch(1, RS_THREADS, [&] { bp_scan_kernel(tot.data(), nb, boff.data(), cursor.data()); });
+  emu::launch((unsigned)G, BP2_THREADS, [&] { bp2_place_kernel(kA, vA, bid.data(), n, ghist.data(), boff.data(), nb, kB, vB, ndev); });
+  int vbits = 1;
+  while (vbits < 31 && (int64_t(1) << vbits) < n) vbits++;
+  emu::launch((unsigned)nb, RS_THREADS, [&] { bp_bucket_kernel(kB, vB, kA, vA, boff.data(), spl, nb, nbits, vbits); });
+}
+
 extern "C" {
 // keys[n] (63-bit), vals = 0..n-1.  The splitters are the (b n_spl / nb)-th keys of the sorted array
 // `spl_from` (n_spl keys: the same data = fresh splitters, other data = stale ones).  n_real <= n:
 // the device-side count.  Outputs the splitter sort's keys / vals; returns 0.
 // stats_out (nullable, 4): which way the "place" form's buckets went (g_bp_stats of bucketsort.cuh).
+// place == 1: the "place" form with global atomics; place >= 2: its shared-memory form with G = place CTAs.
 // place != 0: the "place" form (one counting and one placing pass, compact in-bucket ranking).
 int emu_splitter_sort_test(const uint64_t *keys, int64_t n, int64_t n_real, const uint64_t *spl_from, int64_t n_spl,
                            int nb, uint64_t *keys_out, int *vals_out, int place, long long *stats_out) {
@@ -207,7 +247,8 @@ int emu_splitter_sort_test(const uint64_t *keys, int64_t n, int64_t n_real, cons
   emu::launch((unsigned)((nb + 255) / 256), 256, [&] { bs_splitters_kernel(spl_from, n_spl, nb, spl.data(), &nsp); }, true);
   const int nr = (int)n_real;
   if (place) {
-    emu_place_sort(kA.data(), vA.data(), kB.data(), vB.data(), n, 63, spl.data(), nb, &nr);
+    if (place >= 2) emu_place2_sort(kA.data(), vA.data(), kB.data(), vB.data(), n, 63, spl.data(), nb, place, &nr);  // G = place
+    else emu_place_sort(kA.data(), vA.data(), kB.data(), vB.data(), n, 63, spl.data(), nb, &nr);
     std::memcpy(keys_out, kB.data(), sizeof(uint64_t) * (size_t)n_real);
     std::memcpy(vals_out, vB.data(), sizeof(int) * (size_t)n_real);
     if (stats_out) for (int k = 0; k < 4; k++) stats_out[k] = g_bp_stats[k];
@@ -216,6 +257,31 @@ int emu_splitter_sort_test(const uint64_t *keys, int64_t n, int64_t n_real, cons
   emu_splitter_sort(kA.data(), vA.data(), kB.data(), vB.data(), n, 63, spl.data(), nb, &nr);
   std::memcpy(keys_out, kA.data(), sizeof(uint64_t) * (size_t)n_real);
   std::memcpy(vals_out, vA.data(), sizeof(int) * (size_t)n_real);
+  return 0;
+}
+
+// cell_end (build.cuh) on a given array of common levels: tables 0 and 1 as levels_kernel leaves them
+// (built here on the host), the upper tables by levelmin_top_kernel; out[i] = cell_end(p[i], level[i]).
+int emu_cell_end_test(const signed char *clev, int64_t n, const int64_t *p, const int *level, int64_t nq, int64_t *out,
+                      int *ntab_out) {
+  EmuLevelMin elm(n);
+  for (int64_t q = 0; q < n; q++) elm.lm.t[0][q] = (unsigned char)(clev[q] + 1);
+  if (elm.lm.ntab > 1)
+    for (int64_t j = 0; j < elm.lm.n[1]; j++) {
+      unsigned m = 255;
+      for (int i = 0; i < 32; i++) {
+        const int64_t q = 32 * j + i;
+        const unsigned v = q < n ? (unsigned)(clev[q] + 1) : 0u;
+        m = v < m ? v : m;
+      }
+      elm.lm.t[1][j] = (unsigned char)m;
+    }
+  elm.finish();
+  *ntab_out = elm.lm.ntab;
+  emu::launch((unsigned)((nq + 255) / 256), 256, [&] {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq) out[i] = cell_end(elm.lm, p[i], level[i], n);
+  }, true);
   return 0;
 }
 
@@ -268,6 +334,7 @@ int emu_tree_build_dist(int world, const uint64_t *split, const double *pos, con
     std::vector<D4> P;
     const uint64_t *shi;
     const int *sidx;
+    std::unique_ptr<EmuLevelMin> elm;
   };
   std::vector<Rank> R(world);
   std::vector<RankRec1> rec1(world);
@@ -296,7 +363,9 @@ int emu_tree_build_dist(int world, const uint64_t *split, const double *pos, con
     Rank &k = R[r];
     emu::launch(1, 1, [&] { neighbours_kernel(rec1.data(), &k.ctl); }, true);
     k.clev.assign(n, 0); k.cnt.assign(n + 1, 0); k.base.assign(n + 1, 0);
-    emu::launch(nblk(n, 256), 256, [&] { levels_kernel(k.shi, nullptr, n, levels, k.clev.data(), k.cnt.data(), &k.ctl); }, true);
+    k.elm.reset(new EmuLevelMin(n));
+    emu::launch(nblk(n, 256), 256, [&] { levels_kernel(k.shi, nullptr, n, levels, k.clev.data(), k.cnt.data(), &k.ctl, k.elm->lm); });
+    k.elm->finish();
     emu_scan<int, InArray<int>>(InArray<int>{k.cnt.data()}, n, k.base.data(), &k.ctl.n_local);
     k.sp.assign(n, double4{0, 0, 0, 0});
     emu::launch(nblk(n, 256), 256, [&] { gather_sorted_kernel<Src64>(src, k.sidx, n, k.sp.data(), &k.ctl, sidx_all.data() + (size_t)r * n); }, true);
@@ -326,12 +395,18 @@ int emu_tree_build_dist(int world, const uint64_t *split, const double *pos, con
       Entries<float> E2{alt.data(), nullptr};
       BuildCtl before = k.ctl;
       (void)before;
-      emu::launch(nblk(n, 128), 128, [&] {
-        emit32_warp_kernel(k.sp.data(), k.shi, k.clev.data(), k.base.data(), k.P.data(), n, root.data(), E2, &ml2, &c2, true);
-      });
       const int fill = k.ctl.nentries < stride ? k.ctl.nentries : stride;
-      if (std::memcmp(alt.data() + (size_t)r * stride, E.node + (size_t)r * stride, sizeof(Node<float>) * (size_t)fill) != 0) return 7;
-      if (ml2 > maxlevel) return 7;
+      for (int tables = 0; tables < 2; tables++) {
+        LevelMin use = k.elm->lm;
+        if (!tables) use.ntab = 0;
+        std::memset(alt.data(), 0xff, sizeof(Node<float>) * alt.size());
+        ml2 = 0;
+        emu::launch(nblk(n, 128), 128, [&] {
+          emit32_warp_kernel(k.sp.data(), k.shi, k.clev.data(), k.base.data(), k.P.data(), n, root.data(), E2, &ml2, &c2, true, use);
+        });
+        if (std::memcmp(alt.data() + (size_t)r * stride, E.node + (size_t)r * stride, sizeof(Node<float>) * (size_t)fill) != 0) return 7 + tables;
+        if (ml2 > maxlevel) return 7 + tables;
+      }
     }
     if (k.ctl.overflow) rc = 2;
     counts_out[2 * r] = k.ctl.n_local;

@@ -218,8 +218,8 @@ def test_splitter_sort_steps_equal_classic_sort_steps(tmp_path):
     import sys
     out = {}
     modes = {"classic": dict(GH_SORT="classic", GH_EMIT="thread"), "bucket": dict(GH_SORT="bucket", GH_EMIT="thread"),
-             "place": dict(GH_SORT="place", GH_EMIT="thread"), "warp": dict(GH_SORT="classic", GH_EMIT="warp"),
-             "place+warp": dict(GH_SORT="place", GH_EMIT="warp")}
+             "place": dict(GH_SORT="place", GH_EMIT="warp"), "warp": dict(GH_SORT="classic", GH_EMIT="warp"),
+             "place2": dict(GH_SORT="place2", GH_EMIT="thread"), "place2+warp": dict(GH_SORT="place2", GH_EMIT="warp")}
     for mode, envs in modes.items():
         f = str(tmp_path / (mode.replace("+", "_") + ".npy"))
         env = dict(os.environ, **envs)

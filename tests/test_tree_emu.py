@@ -41,6 +41,7 @@ def temu():
     lib.emu_splitter_sort_test.argtypes = [vp, C.c_int64, C.c_int64, vp, C.c_int64, C.c_int, vp, vp, C.c_int, vp]
     lib.emu_tree_build_dist.argtypes = [C.c_int, vp, vp, vp, C.c_int64, C.c_double, C.c_double, vp, C.c_int, vp, vp,
                                         vp, vp, vp, vp, vp, C.c_int]
+    lib.emu_cell_end_test.argtypes = [vp, C.c_int64, vp, vp, C.c_int64, vp, vp]
     return lib
 
 
@@ -281,7 +282,7 @@ def test_distributed_walk_deals_the_global_morton_order(temu, emu, world, blk, h
 
 
 # ---- splitter sort (csrc/bucketsort.cuh): the running simulation's sort ---------------------------------
-@pytest.mark.parametrize("place", [0, 1], ids=["partition", "place"])
+@pytest.mark.parametrize("place", [0, 1, 5, 37], ids=["partition", "place", "place2-5ctas", "place2-37ctas"])
 @pytest.mark.parametrize("case", ["fresh", "stale", "oversize", "duplicates", "partial", "clump", "lowbits", "equal", "adjacent"])
 def test_splitter_sort_equals_the_stable_sort(temu, case, place):
     """Both forms of the splitter sort -- two partition passes by bucket id + one in-shared-memory
@@ -375,3 +376,37 @@ def test_quadrupole_extension_equals_its_cpu_model(temu, emu, oracle, golden):
     d = oracle.direct_summation(x, m, eps)
     mono = oracle.tree_force(x, m, eps, theta)
     assert relerr(acc, d).mean() <= 0.5 * relerr(mono, d).mean()
+
+
+@pytest.mark.parametrize("n", [31, 32, 33, 1024, 40000, 1100000])
+def test_cell_end_from_level_min_tables(temu, n):
+    """cell_end (build.cuh): the end of the level-L cell that starts at p is the first q > p whose
+    common level drops below L (or the last particle), found in the level-min tables by climbing and
+    descending -- against a brute-force scan, for arrays that need 1 to 5 table levels, with long
+    plateaus (big cells) and with queries near the end."""
+    rng = np.random.default_rng(n)
+    clev = rng.integers(3, 22, size=n).astype(np.int8)
+    # long stretches above a level (big cells) and a few deep drops
+    for _ in range(12):
+        a = int(rng.integers(0, n)); b = min(n, a + int(rng.integers(1, max(2, n // 3))))
+        clev[a:b] = np.maximum(clev[a:b], rng.integers(6, 15))
+    clev[rng.integers(0, n, size=max(1, n // 5000))] = rng.integers(0, 3)
+    clev[n - 1] = -1
+    nq = 4000 if n < 100000 else 500
+    p = rng.integers(0, n, size=nq).astype(np.int64)
+    p[:50] = np.maximum(0, n - 1 - np.arange(50) % n)
+    level = np.array([rng.integers(0, clev[q] + 1) if clev[q] >= 0 else 0 for q in p], dtype=np.int32)
+    out = np.zeros(nq, dtype=np.int64)
+    ntab = C.c_int(0)
+    temu.emu_cell_end_test(clev.ctypes.data, n, p.ctypes.data, level.ctypes.data, nq, out.ctypes.data, C.byref(ntab))
+    expect_tabs = 1
+    m = n
+    while m > 32:
+        m = (m + 31) // 32
+        expect_tabs += 1
+    assert ntab.value == expect_tabs
+    # brute force: next position to the right whose level is below L
+    for i in range(nq):
+        tail = clev[int(p[i]) + 1:] < int(level[i])
+        q = int(p[i]) + 1 + int(np.argmax(tail)) if tail.any() else n
+        assert out[i] == min(q, n - 1), (i, p[i], level[i])
