@@ -80,7 +80,7 @@ __device__ __forceinline__ int tile_rank_digits(TileSmem &sm, int count, int (&l
   int old[RS_ROUNDS];
 #pragma unroll
   for (int r = 0; r < RS_ROUNDS; r++) {
-    peers[r] = __match_any_sync(0xffffffffu, dig[r]);
+    peers[r] = warp_match_digit(dig[r]);
   }
 #pragma unroll
   for (int r = 0; r < RS_ROUNDS; r++) {
@@ -99,7 +99,7 @@ __device__ __forceinline__ int tile_rank_digits(TileSmem &sm, int count, int (&l
   for (int r = 0; r < RS_ROUNDS; r++) {
     const bool valid = w * (32 * RS_ROUNDS) + r * 32 + lane < count;
     const unsigned d = dig[r];
-    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    const unsigned peers = warp_match_digit(d);
     const int leader = __ffs(peers) - 1;
     int old = 0;
     if (lane == leader && valid) {
@@ -179,7 +179,7 @@ bs_hist_kernel(const uint64_t *__restrict__ keys, int64_t n, BucketDigit dg, int
     const int64_t q = base + r * RS_THREADS + threadIdx.x;
     const bool valid = q < n;
     const unsigned d = valid ? dg(k[r]) : (0x100u + (unsigned)lane);
-    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    const unsigned peers = warp_match_digit(d);
     if (valid && lane == __ffs(peers) - 1) atomicAdd(&h[d], __popc(peers));
   }
   __syncthreads();

@@ -231,6 +231,30 @@ static int chunked_scan(In in, int64_t n, T *P, DeviceBuffer *levels, int depth,
 #endif  // GH_HOST_EMU
 
 // ---- radix sort ------------------------------------------------------------------------------
+// lanes of the warp that hold the same digit (0 .. 255; values >= 0x100 mark lanes without a pair:
+// they match nobody).  GH_RS_MATCH = 0: one MATCH.ANY; 1 (default): nine ballots and eight selects.
+// ncu of the ranking kernels shows MATCH.ANY as the limiter -- sm__throughput 85 % at 18 % issue
+// utilisation, `short_scoreboard` the top stall, ~90 cycles of an SM per MATCH by the kernels'
+// MATCH counts -- while the ballot form costs ~30 issue slots the kernels have to spare.
+#ifndef GH_RS_MATCH
+#define GH_RS_MATCH 1
+#endif
+__device__ __forceinline__ unsigned warp_match_digit(unsigned d) {
+#if GH_RS_MATCH == 0
+  return __match_any_sync(0xffffffffu, d);
+#else
+  const bool valid = d < 0x100u;
+  unsigned peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const bool bit = (d >> k) & 1u;
+    const unsigned bk = __ballot_sync(0xffffffffu, bit);
+    peers &= bit ? bk : ~bk;
+  }
+  return valid ? peers : (1u << (threadIdx.x & 31));
+#endif
+}
+
 static constexpr int RS_THREADS = 256;
 static constexpr int RS_WARPS = RS_THREADS / 32;
 // measured at N = 4M (profiles/r02_sort_ab.txt): 12 / 10 / 8 / 6 / 5 / 4 keys per thread -> build
@@ -272,7 +296,7 @@ rs_hist_kernel(const uint64_t *__restrict__ keys, int64_t n, int shift, int *__r
     const int64_t q = base + r * RS_THREADS + threadIdx.x;
     const bool valid = q < n;
     const unsigned d = valid ? (unsigned)((k[r] >> shift) & 0xff) : (0x100u + (unsigned)lane);
-    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    const unsigned peers = warp_match_digit(d);
     if (valid && lane == __ffs(peers) - 1) atomicAdd(&h[d], __popc(peers));
   }
   __syncthreads();
@@ -354,7 +378,7 @@ rs_scatter_kernel(const uint64_t *__restrict__ kin, const int *__restrict__ vin,
   for (int r = 0; r < RS_ROUNDS; r++) {
     const bool valid = seg0 + r * 32 + lane < n;
     dg[r] = valid ? (unsigned)((key[r] >> shift) & 0xff) : (0x100u + (unsigned)lane);
-    peers[r] = __match_any_sync(0xffffffffu, dg[r]);
+    peers[r] = warp_match_digit(dg[r]);
   }
 #pragma unroll
   for (int r = 0; r < RS_ROUNDS; r++) {
@@ -378,7 +402,7 @@ rs_scatter_kernel(const uint64_t *__restrict__ kin, const int *__restrict__ vin,
     val[r] = valid ? vin[q] : 0;
     // invalid lanes get private pseudo-digits so that they match nobody
     const unsigned d = valid ? (unsigned)((key[r] >> shift) & 0xff) : (0x100u + (unsigned)lane);
-    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    const unsigned peers = warp_match_digit(d);
     const int leader = __ffs(peers) - 1;
     int old = 0;
     if (lane == leader && valid) {
@@ -408,7 +432,7 @@ rs_scatter_kernel(const uint64_t *__restrict__ kin, const int *__restrict__ vin,
     const bool valid = seg0 + r * 32 + lane < n;
     // invalid lanes get private pseudo-digits so that they match nobody
     const unsigned d = valid ? (unsigned)((key[r] >> shift) & 0xff) : (0x100u + (unsigned)lane);
-    peers[r] = __match_any_sync(0xffffffffu, d);
+    peers[r] = warp_match_digit(d);
   }
 #if GH_RS_VARIANT == 2
 #pragma unroll

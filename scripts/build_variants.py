@@ -17,10 +17,12 @@ VARIANTS = {
     # measured (profiles/r02_sort_ab.txt): 12 / 10 / 8 / 6 keys per thread -> build 1.72 / 1.59 / 1.46 / 1.40 ms
     # "rs6"/"rs8", "rk6"/"rk8"/"rk10" (GH_RS_RANK=1): see profiles/r02_sort_ab.txt
     # "place" form of the splitter sort: bits ranked first inside a bucket, tile size
-    "sb16": ["-DGH_BP_SUBBITS=16"],
-    "sb32": ["-DGH_BP_SUBBITS=32"],
+    # measured with the global-atomic form (gpurun_out/ab_*_place_warp.json): sb16 -0.024 ms, sb32 +0.027 ms,
+    # rs8 -0.005 ms of build
+    # "sb16": ["-DGH_BP_SUBBITS=16"], "sb32": ["-DGH_BP_SUBBITS=32"], "rs8sb16": [...]
     "rs8": ["-DGH_RS_ROUNDS=8"],
-    "rs8sb16": ["-DGH_RS_ROUNDS=8", "-DGH_BP_SUBBITS=16"],
+    # ranking with MATCH.ANY instead of ballots
+    "match0": ["-DGH_RS_MATCH=0"],
 }
 KERNEL = "bp_bucket_kernel"
 B.build()
