@@ -532,23 +532,49 @@ bp2_count_kernel(const uint64_t *__restrict__ keys, int64_t n, const uint64_t *_
   for (int j = threadIdx.x; j < nb; j += BP2_THREADS) row[j] = hist[j];
 }
 
-// column b of the table: ghist[c][b] <- pairs of bucket b in CTAs < c; tot[b] = pairs of bucket b
-__global__ void bp2_colscan_kernel(int *__restrict__ ghist, int G, int nb, int *__restrict__ tot) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nb) return;
-  int run = 0;
-  for (int c0 = 0; c0 < G; c0 += 8) {  // eight rows at a time: the loads of a batch are independent
-    int v[8];
+// column b of the table: ghist[c][b] <- pairs of bucket b in CTAs < c; tot[b] = pairs of bucket b.
+// A CTA of 256 threads owns 32 columns; warp w sums rows [w R, (w+1) R), R = ceil(G / 8) (lanes =
+// columns: every row access is one 128-byte line), the eight partial sums are prefixed through
+// shared memory, and the warp walks its rows again writing the running offsets.
+__global__ void __launch_bounds__(256) bp2_colscan_kernel(int *__restrict__ ghist, int G, int nb, int *__restrict__ tot) {
+  __shared__ int psum[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int b = blockIdx.x * 32 + lane;
+  const int R = (G + 7) / 8;
+  const int c0 = w * R, c1 = (c0 + R < G) ? c0 + R : G;
+  int sum = 0;
+  if (b < nb) {
+    for (int cb = c0; cb < c1; cb += 8) {  // eight rows at a time: independent loads
+      int v[8];
 #pragma unroll
-    for (int u = 0; u < 8; u++) v[u] = (c0 + u < G) ? ghist[(int64_t)(c0 + u) * nb + b] : 0;
+      for (int u = 0; u < 8; u++) v[u] = (cb + u < c1) ? ghist[(int64_t)(cb + u) * nb + b] : 0;
 #pragma unroll
-    for (int u = 0; u < 8; u++)
-      if (c0 + u < G) {
-        ghist[(int64_t)(c0 + u) * nb + b] = run;
-        run += v[u];
-      }
+      for (int u = 0; u < 8; u++) sum += v[u];
+    }
   }
-  tot[b] = run;
+  psum[w][lane] = sum;
+  __syncthreads();
+  int run = 0, total = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const int s = psum[k][lane];
+    run += (k < w) ? s : 0;
+    total += s;
+  }
+  if (b < nb) {
+    for (int cb = c0; cb < c1; cb += 8) {
+      int v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) v[u] = (cb + u < c1) ? ghist[(int64_t)(cb + u) * nb + b] : 0;
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+        if (cb + u < c1) {
+          ghist[(int64_t)(cb + u) * nb + b] = run;
+          run += v[u];
+        }
+    }
+    if (w == 0) tot[b] = total;
+  }
 }
 
 __global__ void __launch_bounds__(BP2_THREADS)
@@ -888,7 +914,7 @@ static int splitter_place2_sort_pairs(uint64_t *kA, int *vA, uint64_t *kB, int *
   const uint64_t *spl = ss.spl.as<uint64_t>();
   bp2_count_kernel<<<G, BP2_THREADS, 0, st>>>(kA, n, spl, ss.nb, ss.bid.as<unsigned short>(), ghist, ndev);
   GH_LAUNCH_CHECK();
-  bp2_colscan_kernel<<<(ss.nb + 127) / 128, 128, 0, st>>>(ghist, G, ss.nb, tot);
+  bp2_colscan_kernel<<<(ss.nb + 31) / 32, 256, 0, st>>>(ghist, G, ss.nb, tot);
   GH_LAUNCH_CHECK();
   bp_scan_kernel<<<1, RS_THREADS, 0, st>>>(tot, ss.nb, ss.boff.as<int>(), cursor);
   GH_LAUNCH_CHECK();

@@ -438,9 +438,16 @@ __global__ void levelmin_top_kernel(const __grid_constant__ LevelMin lm) {
     const int64_t nk = lm.n[k], np = lm_padded(nk);
     for (int64_t j = threadIdx.x; j < np; j += blockDim.x) {
       unsigned m = 0;
-      if (j < nk) {
+      if (j < nk) {  // minimum of 32 bytes: two 16-byte loads
+        const uint4 *gp = reinterpret_cast<const uint4 *>(in + 32 * j);
+        const uint4 a = gp[0], b = gp[1];
+        const unsigned w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
         m = 255;
-        for (int i = 0; i < 32; i++) { const unsigned v = in[32 * j + i]; m = v < m ? v : m; }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+#pragma unroll
+          for (int s = 0; s < 32; s += 8) { const unsigned v = (w[i] >> s) & 0xffu; m = v < m ? v : m; }
+        }
       }
       out[j] = (unsigned char)m;
     }

@@ -113,13 +113,16 @@ static inline unsigned nblk(int64_t n, int b) { return (unsigned)((n + b - 1) / 
 
 // walk selection: GH_WALK_GROUP (default; fp32 only) or GH_WALK_TARGET (the reference's per-target
 // criterion; always used in fp64).  Process-wide; GH_TREE_WALK=target|group sets the initial value.
-// sort of a running simulation's steps (tree_impl): 1 = bucket, 2 = place (bucketsort.cuh); GH_SORT overrides
+// sort of a running simulation's steps (tree_impl; bucketsort.cuh): 1 = bucket (two partition passes),
+// 2 = place (global atomics), 3 = place2 (shared-memory histograms; the default: measured at N = 4M
+// build 1.34 -> 1.11 ms against bucket, gpurun_out/ab_*); GH_SORT=classic|bucket|place|place2 overrides
 #ifndef GH_SORT_DEFAULT
-#define GH_SORT_DEFAULT 1
+#define GH_SORT_DEFAULT 3
 #endif
-// emit of the fp32 tree: 0 = one thread per particle, 1 = warp-cooperative; GH_EMIT overrides
+// emit of the fp32 tree: 0 = one thread per particle, 1 = warp-cooperative (single-rank builds; the
+// default: -0.14 ms of build at N = 4M); GH_EMIT=thread|warp overrides
 #ifndef GH_EMIT_DEFAULT
-#define GH_EMIT_DEFAULT 0
+#define GH_EMIT_DEFAULT 1
 #endif
 #ifndef GH_WALK_HYBRID_DEFAULT
 #define GH_WALK_HYBRID_DEFAULT 0.10f

@@ -221,7 +221,7 @@ static void emu_place2_sort(uint64_t *kA, int *vA, uint64_t *kB, int *vB, int64_
   std::vector<unsigned short> bid((size_t)n);
   std::vector<int> ghist((size_t)G * nb, -1), tot(nb + 1, 0), cursor(nb + 1, 0), boff(nb + 2, 0);
   emu::launch((unsigned)G, BP2_THREADS, [&] { bp2_count_kernel(kA, n, spl, nb, bid.data(), ghist.data(), ndev); });
-  emu::launch((unsigned)((nb + 127) / 128), 128, [&] { bp2_colscan_kernel(ghist.data(), G, nb, tot.data()); }, true);
+  emu::launch((unsigned)((nb + 31) / 32), 256, [&] { bp2_colscan_kernel(ghist.data(), G, nb, tot.data()); });
   emu::launch(1, RS_THREADS, [&] { bp_scan_kernel(tot.data(), nb, boff.data(), cursor.data()); });
   emu::launch((unsigned)G, BP2_THREADS, [&] { bp2_place_kernel(kA, vA, bid.data(), n, ghist.data(), boff.data(), nb, kB, vB, ndev); });
   int vbits = 1;
