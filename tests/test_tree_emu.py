@@ -283,13 +283,13 @@ def test_distributed_walk_deals_the_global_morton_order(temu, emu, world, blk, h
 
 # ---- splitter sort (csrc/bucketsort.cuh): the running simulation's sort ---------------------------------
 @pytest.mark.parametrize("place", [0, 1, 5, 37], ids=["partition", "place", "place2-5ctas", "place2-37ctas"])
-@pytest.mark.parametrize("case", ["fresh", "stale", "oversize", "duplicates", "partial", "clump", "lowbits", "equal", "adjacent"])
+@pytest.mark.parametrize("case", ["fresh", "stale", "oversize", "duplicates", "partial", "clump", "lowbits", "equal", "adjacent", "manybuckets"])
 def test_splitter_sort_equals_the_stable_sort(temu, case, place):
     """Both forms of the splitter sort -- two partition passes by bucket id + one in-shared-memory
     sort per bucket; one counting + one placing pass with atomics + a compact ranking per bucket --
     give the stable sort's result, bit for bit: with this step's own splitters, with another data
     set's (stale) splitters, with buckets far beyond a tile (the CTA-local global-memory path), with
-    many equal keys (also of two adjacent values), with a device-side count below the capacity, with a tight clump in a corner of
+    many equal keys (also of two adjacent values), with thousands of small buckets, with a device-side count below the capacity, with a tight clump in a corner of
     a bucket's key range (long runs of ties in the ranked bits: the long way), with keys that differ
     only below the ranked bits (short runs: insertion), and with buckets of identical keys."""
     rng = np.random.default_rng(11)
@@ -325,6 +325,13 @@ def test_splitter_sort_equals_the_stable_sort(temu, case, place):
     elif case == "equal":
         keys[:] = keys[rng.integers(0, 3, n)]                 # three distinct values: buckets of one value
         spl_from = np.sort(keys)
+    elif case == "manybuckets":
+        # 9000 buckets of ~7 pairs: the shared-memory histograms of the place2 form near their limit
+        n = n_real = 60000
+        keys = rng.integers(0, 2 ** 63, size=n, dtype=np.uint64)
+        keys[rng.integers(0, n, 6000)] >>= np.uint64(25)
+        spl_from = np.sort(keys)
+        nb = 9000
     elif case == "adjacent":
         # 1000 copies each of two ADJACENT key values: the bucket of the first spans no bits at all
         keys[:1000] = np.uint64(5 * 2 ** 60)
