@@ -233,7 +233,9 @@ def tree_roofline(n, world, ms_per_step, kernel_ms, st, mode, accuracy, peaks, f
     build_gbs = 382.0 * n / (build_ms * 1e-3) / 1e9
     build_roofline = {"bound": "hbm", "achieved": build_gbs, "peak": hbm_peak, "unit": "GB/s",
                       "frac": build_gbs / hbm_peak, "ms": build_ms,
-                      "how": "382 B per particle (SURVEY 8d: 190 + 24 x 8 radix passes) x N / (ms_per_step - walk "
+                      "how": "382 B per particle (SURVEY 8d's accounting: 190 + 24 x 8 radix passes; the running "
+                             "simulation's splitter sort moves the pairs through memory 3 times, not 8, so this is "
+                             "the algorithmic figure, not the build's traffic) x N / (ms_per_step - walk "
                              "kernel ms; with --gpus N > 1 this includes the NCCL exchanges); peak = %s"
                              % ("MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks.get("hbm_gbs")
                                 else "6.65 TB/s (of fallback, B200_PROFILING.md)")}
