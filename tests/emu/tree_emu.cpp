@@ -390,11 +390,8 @@ int emu_tree_build_dist(int world, const uint64_t *split, const double *pos, con
       std::memset(alt.data(), 0xff, sizeof(Node<float>) * alt.size());
       BuildCtl c2 = k.ctl;
       c2.overflow = 0;
-      // (the thread form raised the flag itself or inherited none: stitch sets it before the emit)
       int ml2 = 0;
       Entries<float> E2{alt.data(), nullptr};
-      BuildCtl before = k.ctl;
-      (void)before;
       const int fill = k.ctl.nentries < stride ? k.ctl.nentries : stride;
       for (int tables = 0; tables < 2; tables++) {
         LevelMin use = k.elm->lm;
