@@ -14,6 +14,13 @@
 // structure over global memory, tile after tile: slower, never wrong.  The result is the classic
 // sort's, bit for bit (both are stable).  Without valid splitters (first step, stateless calls)
 // the build uses the classic sort.
+//
+// Three forms of step 1 live here (GH_SORT selects; DESIGN 4.3 has the measurements):
+//   bucket  (bs_*)   the two partition passes described above;
+//   place   (bp_*)   bucket id once per key, counts and slots by GLOBAL atomics -- measured no faster;
+//   place2  (bp2_*)  the same through per-CTA shared-memory histograms, no global atomics: the default.
+// The place forms leave the order inside a bucket arbitrary; their bucket kernel (bp_bucket_kernel)
+// orders by (key, value) instead of relying on stability, ranking only the top bits that can differ.
 #pragma once
 #include "sortscan.cuh"
 

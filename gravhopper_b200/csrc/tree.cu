@@ -17,8 +17,10 @@
 //                       z-major so that key order == the reference's branch order (:441-450);
 //                       levels 1-21 in `hi`, 22-42 in `lo`
 //   K5  sort            stable LSD radix sort of (lo, hi) with the particle index: hand-written,
-//                       8 bits per pass, MATCH.ANY ranking, shared-memory staged coalesced
-//                       scatter (sortscan.cuh); no library kernels anywhere in the build
+//                       8 bits per pass, ballot ranking, shared-memory staged coalesced
+//                       scatter (sortscan.cuh); a running fp32 simulation sorts with buckets
+//                       taken from the previous step's order instead (bucketsort.cuh), same
+//                       result bit for bit; no library kernels anywhere in the build
 //   K6a common levels   c[p] = number of octant levels shared by sorted neighbours p, p+1.
 //                       A cell of level l starts at p  <=>  c[p-1] < l <= c[p]; therefore the
 //                       depth-first (pre-order) position of every cell and leaf is a prefix sum
@@ -29,7 +31,9 @@
 //                       double-double difference is exact to ~1e-30, so no cancellation)
 //   K6b emit            per particle: walk down its key, write one entry per opened cell
 //                       (centre, side, COM, mass, skip = pre-order index after the subtree, found
-//                       by galloping search for the end of the key-prefix run) and its leaf entry
+//                       by galloping search for the end of the key-prefix run) and its leaf entry;
+//                       fp32 single-rank builds use the warp-cooperative form (a warp's opened
+//                       cells dealt one per lane, cell ends from level-min tables; build.cuh)
 //   K8  walk            one warp per 32 Morton-consecutive targets; the warp scans the
 //                       pre-order array once, skipping a subtree when every lane has either
 //                       accepted the cell or is already past it; each lane applies ITS OWN
